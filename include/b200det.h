@@ -1,0 +1,208 @@
+/*
+ * b200det.h -- C-ABI of libb200det.so: B200 (sm_100a) kernels for the detection
+ * post-backbone hot path of pengfeidip/pytorch-faster-rcnn.
+ *
+ * The reference has no FFI: the path sits behind plain Python call sites and the
+ * lib.builder.MODULES registry.  Each entry point below therefore
+ * cites the reference *Python* function it replaces (file:line under the
+ * reference root); INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - boxes are column-major [4, n] fp32 (row 0 = x1, 1 = y1, 2 = x2, 3 = y2), the
+ *    reference layout (lib/utils.py:52); "ld" is the row pitch in elements;
+ *  - batched entry points are image-major: tensor[b] starts at b * (rows * ld);
+ *  - `stream` is a cudaStream_t passed as void*;
+ *  - return 0 on success, B2D_ERR_ARG (-1) for argument errors, else a positive
+ *    cudaError_t; b2d_last_error_string() describes the last failure;
+ *  - no entry point allocates, synchronises or throws; scratch memory is passed
+ *    in by the caller (sizes from the b2d_*_workspace_bytes queries).
+ */
+#ifndef B200DET_H_
+#define B200DET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B2D_API __attribute__((visibility("default")))
+#else
+#define B2D_API
+#endif
+
+#define B2D_OK 0
+#define B2D_ERR_ARG (-1)
+#define B2D_MAX_LEVELS 8
+#define B2D_MAX_ANCHORS 16
+
+/* One pyramid level of an anchor head (lib/heads/anchor_head.py:33-36,66-67). */
+typedef struct b2d_level {
+    int H, W, A;        /* grid size, anchors per cell */
+    int center_lt;      /* lib/anchor.py:82 */
+    float stride;       /* == base size */
+    float ws[B2D_MAX_ANCHORS], hs[B2D_MAX_ANCHORS]; /* lib/anchor.py:92-99, fp32 */
+    long long offset;   /* first flattened anchor of this level (level-major concat) */
+} b2d_level;
+
+typedef struct b2d_pyramid {
+    int num_levels;
+    int _pad;
+    long long total;    /* anchors per image over all levels */
+    b2d_level lv[B2D_MAX_LEVELS];
+} b2d_pyramid;
+
+B2D_API const char* b2d_last_error_string(void);
+B2D_API int b2d_version(void);
+
+/* ---- K1: AnchorCreator.__call__ (lib/anchor.py:107-129) -> out [4, A, H, W] */
+B2D_API int b2d_anchor_grid(float* out, const float* ws, const float* hs, int A, int H, int W, float stride,
+                    int center_lt, void* stream);
+/* inside_anchor_mask (lib/region.py:19-29); anchors [4,n] -> mask u8[n]; border<0 => all 1 */
+B2D_API int b2d_inside_anchor_mask(uint8_t* mask, const float* anchors, long long n, float img_h, float img_w,
+                           float border, void* stream);
+/* inside_grid_mask (lib/region.py:10-16) -> flags fp32 [A,H,W]; in_h/in_w computed by the host */
+B2D_API int b2d_inside_grid_mask(float* flags, int A, int H, int W, int in_h, int in_w, void* stream);
+
+/* ---- a3: calc_iou / elem_iou (lib/utils.py:151-182) */
+B2D_API int b2d_calc_iou(float* out /*[N,K]*/, const float* a /*[4,N]*/, long long N, const float* b /*[4,K]*/,
+                 long long K, void* stream);
+B2D_API int b2d_elem_iou(float* out /*[N]*/, const float* a, const float* b, long long N, void* stream);
+
+/* ---- K2: MaxIoUAssigner.__call__ (lib/region.py:75-107), batched over B images.
+ * Box source: explicit `boxes` [B][4][box_ld] with optional per-image counts, or
+ * (boxes == NULL) the anchors of `pyr` generated in registers and masked by
+ * inside_anchor_mask & inside_grid_mask against img_hw[b] = (img_h, img_w)
+ * (lib/heads/anchor_head.py:92-100); masked-out anchors get label -1, iou 0.
+ * gt [B][4][gt_ld], gt_count int32[B] (every count must be >= 1).
+ * prepend_gt != 0 reproduces lib/bbox.py:27-29: outputs get gt_count[b] leading
+ * rows (labels 1..K, iou 1) and the boxes follow; out_ld is the row pitch of
+ * labels/max_iou.  census int32[B][4] = {#pos, #neg, #pos appended, 0}; pos_list
+ * int32[B][pos_cap] receives the indices (into the output row) of positives in
+ * unspecified order (may be NULL).  workspace: B * gt_ld * 4 bytes. */
+B2D_API int b2d_assign_max_iou(int64_t* labels, float* max_iou, long long out_ld, const float* boxes,
+                       long long box_ld, const int* box_count, long long N, const b2d_pyramid* pyr_host,
+                       const float* img_hw, float border, const float* gt, int gt_ld, const int* gt_count,
+                       int B, float pos_iou, float neg_iou, float min_pos_iou, int prepend_gt, int* census,
+                       int* pos_list, int pos_cap, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a5: device-RNG sampler (RandomSampler semantics, lib/region.py:43-57,112-126;
+ * the RNG stream is this library's own, see DESIGN.md "Samplers").  One image per
+ * block.  chosen int32[B][max_num] ascending (padded with -1), n_chosen int32[B].
+ * labels int64[B][ld]; count int32[B] (NULL => n for all); census/pos_list from
+ * b2d_assign_max_iou or b2d_label_census. */
+B2D_API int b2d_sample_labels(int* chosen, int* n_chosen, const int64_t* labels, long long ld, const int* count,
+                      const int* count_add /* optional int32[B] added to count */, long long n, const int* census, const int* pos_list, int pos_cap, int B, int max_num,
+                      int pos_num, unsigned long long seed, void* stream);
+/* census + positive list of an arbitrary labels vector (for the sampler classes) */
+B2D_API int b2d_label_census(int* census, int* pos_list, int pos_cap, const int64_t* labels, long long ld,
+                     const int* count, long long n, int B, void* stream);
+/* out[b][i] = -1 everywhere except out[b][chosen] = labels[b][chosen] (lib/region.py:120-126) */
+B2D_API int b2d_scatter_sampled(int64_t* out, const int64_t* labels, long long ld, long long n, const int* chosen,
+                        const int* n_chosen, int max_num, int B, void* stream);
+
+/* ---- K8: bbox2param (lib/utils.py:47-70) / param2bbox (:83-92) elementwise, [4,n] */
+B2D_API int b2d_bbox2param(float* out, const float* base, const float* bbox, long long n, const float* means_host,
+                   const float* stds_host, void* stream);
+B2D_API int b2d_param2bbox(float* out, const float* base, const float* param, long long n, const float* means_host,
+                   const float* stds_host, int clamp, float img_h, float img_w, void* stream);
+B2D_API int b2d_clamp_bbox(float* out, const float* bbox, long long n, float img_h, float img_w, void* stream);
+
+/* ---- fused target gather + encode for the sampled rows (lib/anchor.py:44-73,
+ * lib/bbox.py:55-77).  Candidate i of image b is: GT i (if prepend_gt and i < K),
+ * else box (i - K) taken from `boxes` or generated from `pyr`.  Outputs are
+ * [B][4][max_num] / [B][max_num] with n_chosen[b] valid columns. */
+B2D_API int b2d_encode_targets(float* tar_box, float* tar_gt, float* tar_param, int64_t* tar_label, int64_t* tar_is_gt,
+                       const int* chosen, const int* n_chosen, int max_num, const int64_t* labels,
+                       long long label_ld, const float* boxes, long long box_ld, const b2d_pyramid* pyr_host,
+                       const float* gt, int gt_ld, const int* gt_count, const int64_t* gt_label,
+                       int prepend_gt, const float* means_host, const float* stds_host, int B, void* stream);
+
+/* gather of the head outputs at the sampled anchors (lib/anchor.py:49-56), batched:
+ * cls_ptrs_host[l] -> [B, C, n_l], reg_ptrs_host[l] -> [B, 4, n_l] (the views of
+ * lib/heads/anchor_head.py:82-83) -> tar_cls [B][C][max_num], tar_reg [B][4][max_num]. */
+B2D_API int b2d_gather_head_outputs(float* tar_cls, float* tar_reg, const void* const* cls_ptrs_host,
+                            const void* const* reg_ptrs_host, const b2d_pyramid* pyr_host, int cls_channels,
+                            const int* chosen, const int* n_chosen, int max_num, int B, void* stream);
+
+/* ---- K3: fused RPN proposal selection, all images and levels per launch
+ * (RPNHead.predict_single_image, lib/heads/rpn_head.py:68-120; AnchorHead
+ * .predict_single_image top-k part, lib/heads/anchor_head.py:224-248).
+ * cls_ptrs_host[l] -> [B, A*C, H, W] logits, reg_ptrs_host[l] -> [B, 4A, H, W]
+ * (channel = coord*A + a, lib/heads/anchor_head.py:82-83).  score_mode: 0 = one
+ * sigmoid channel, 1 = two-channel softmax (score = p[1]), 2 = max over C sigmoid
+ * channels.  Outputs: props [B][4][max_num], scores [B][max_num], count int32[B]
+ * (plus, if non-NULL, prov int32[B][max_num] = flattened anchor index). */
+typedef struct b2d_rpn_cfg {
+    int pre_nms, post_nms, max_num; /* <= 0 means "no limit" like the reference */
+    int score_mode, num_cls_channels;
+    float nms_thr_f;                /* largest fp32 <= the python-double threshold */
+    float min_size;                 /* scale_factor * min_bbox_size */
+    float means[4], stds[4];
+    int do_nms;                     /* 0: stop after decode (AnchorHead path) */
+} b2d_rpn_cfg;
+
+B2D_API size_t b2d_rpn_proposals_workspace_bytes(const b2d_pyramid* pyr_host, int B, const b2d_rpn_cfg* cfg_host);
+B2D_API int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const void* const* cls_ptrs_host,
+                      const void* const* reg_ptrs_host, const b2d_pyramid* pyr_host, const float* img_hw,
+                      int B, const b2d_rpn_cfg* cfg_host, void* workspace, size_t ws_bytes, void* stream);
+
+/* generic segmented top-k (descending, ties -> lowest index): values [S][ld] with
+ * per-segment counts -> idx int32[S][k] (padded -1), out_count int32[S]. */
+B2D_API size_t b2d_topk_workspace_bytes(long long n_max, int S, int k);
+B2D_API int b2d_topk(int* idx, int* out_count, const float* values, long long ld, const int* counts, long long n,
+             int S, int k, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- K4: NMS (torchvision.ops.nms CPU semantics: stable descending score order,
+ * areas without +1, suppress iff (double)iou > thr).  Segmented: boxes [S][n_ld][4]
+ * ROW-major (the torchvision boundary, lib/heads/rpn_head.py:103), scores [S][n_ld],
+ * counts int32[S] (NULL => n).  keep int64[S][n_ld] original indices in score order,
+ * keep_count int32[S].  presorted != 0 skips the sort. */
+B2D_API size_t b2d_nms_workspace_bytes(long long n_max, int S);
+B2D_API int b2d_nms(int64_t* keep, int* keep_count, const float* boxes, const float* scores, long long n_ld,
+            const int* counts, long long n, int S, float thr_f, int max_keep, int presorted, void* workspace,
+            size_t ws_bytes, void* stream);
+
+/* ---- K5/K6: FPN level-mapped RoIAlign (BasicRoIExtractor, lib/region.py:243-306 +
+ * torchvision RoIAlign aligned=False).  rois [4, R] column-major, roi_img int32[R]
+ * (NULL => image 0).  feat_ptrs_host[l] -> level l features, fp32 NCHW [B,C,H,W]
+ * (layout 0) or NHWC [B,H,W,C] (layout 1) or bf16 NHWC (layout 2).  Level map:
+ * floor(log2(sqrt((w+1)(h+1))/finest_scale + 1e-6)) clamped (lib/region.py:256-264);
+ * levels int32[R] if non-NULL overrides the map.  out [R, C, PH, PW] fp32. */
+typedef struct b2d_roi_cfg {
+    int num_levels, C, PH, PW, sampling_ratio, aligned, layout;
+    float finest_scale;
+    int H[B2D_MAX_LEVELS], W[B2D_MAX_LEVELS];
+    float spatial_scale[B2D_MAX_LEVELS];
+} b2d_roi_cfg;
+
+B2D_API int b2d_roi_align_fwd(float* out, const void* const* feat_ptrs_host, const float* rois, long long roi_ld,
+                      const int* roi_img, const int* levels, long long R, const b2d_roi_cfg* cfg_host,
+                      void* stream);
+/* image-major variant for the fused pipeline: rois [B][4][ld] with counts int32[B];
+ * out [B*ld, C, PH, PW]; rows past counts[b] are left untouched. */
+B2D_API int b2d_roi_align_fwd_batched(float* out, const void* const* feat_ptrs_host, const float* rois, long long ld,
+                              const int* counts, int B, const b2d_roi_cfg* cfg_host, void* stream);
+B2D_API size_t b2d_roi_align_bwd_workspace_bytes(long long R, int B, const b2d_roi_cfg* cfg_host);
+B2D_API int b2d_roi_align_bwd(void* const* grad_feat_ptrs_host, const float* grad_out, const float* rois,
+                      long long roi_ld, const int* roi_img, const int* levels, long long R, int B,
+                      const b2d_roi_cfg* cfg_host, void* workspace, size_t ws_bytes, void* stream);
+B2D_API int b2d_roi_levels(int* levels, const float* rois, long long roi_ld, long long R, float finest_scale,
+                   int num_levels, void* stream);
+
+/* ---- K7: RoIPool (torchvision.ops.roi_pool semantics), single level, NCHW fp32.
+ * argmax int32 [R,C,PH,PW] (index into the H*W plane, -1 = empty). */
+B2D_API int b2d_roi_pool_fwd(float* out, int* argmax, const float* feat, int B, int C, int H, int W, const float* rois,
+                     long long roi_ld, const int* roi_img, long long R, float spatial_scale, int PH, int PW,
+                     void* stream);
+B2D_API int b2d_roi_pool_bwd(float* grad_feat, const float* grad_out, const int* argmax, int B, int C, int H, int W,
+                     const float* rois, long long roi_ld, const int* roi_img, long long R, float spatial_scale,
+                     int PH, int PW, void* workspace, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DET_H_ */

@@ -1,0 +1,262 @@
+// nms.cu -- K4: bitmask NMS with torchvision.ops.nms *CPU* semantics
+// (stable descending score order, areas without +1, suppress iff (double)iou > thr;
+// reference call sites lib/heads/rpn_head.py:103, lib/region.py:207, lib/utils.py:220).
+//
+//   k_nms_sort  (generic entry only) per-segment bitonic sort of (score, index)
+//   k_nms_mask  64x64 tiles of the upper triangle: column boxes live in registers,
+//               row boxes are staged in shared memory and broadcast, the 64-bit
+//               suppression word of a row is assembled with two __ballot_sync
+//   k_nms_scan  one block per segment: 64-box chunks; the intra-chunk dependency is
+//               resolved by warp 0 from the diagonal words (register/shuffle only),
+//               then every thread ORs the kept rows into its own word of the
+//               removed-set.  Latency-bound by design.
+//
+// The fp32 threshold passed in is the largest float <= the caller's double
+// threshold, which makes `iou > thr_f` identical to torchvision's CPU comparison
+// `(double)iou > thr` for every float iou.
+#include <cstring>
+
+#include "common.cuh"
+#include "pipeline.cuh"
+
+namespace b2d {
+
+struct NmsSegs {
+    int L;                              // levels per image (1 for the generic entry)
+    long long box_per_img, box_off[kMaxLevels];
+    long long mask_per_img, mask_off[kMaxLevels];
+    int wp[kMaxLevels];                 // mask row pitch in words
+    const float4* boxes;                // score-sorted boxes
+    const int* counts;                  // int[S]
+    uint64_t* mask;
+    float thr;
+};
+
+__device__ __forceinline__ bool suppresses(const float4& a, float aa, const float4& b, float ab, float thr) {
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.0f, xx2 - xx1), h = fmaxf(0.0f, yy2 - yy1);
+    const float inter = w * h;
+    if (inter == 0.0f && thr >= 0.0f) return false;      // 0/u is 0 or NaN: never > thr
+    const float ovr = inter / ((aa + ab) - inter);
+    return ovr > thr;
+}
+
+__global__ void __launch_bounds__(64) k_nms_mask(NmsSegs s, int wmax) {
+    __shared__ float4 s_row[64];
+    const int seg = blockIdx.y;
+    const int l = seg % s.L, b = seg / s.L;
+    const int n = s.counts[seg];
+    // decode the upper-triangular tile index
+    int t = blockIdx.x, rb = 0;
+    while (t >= wmax - rb) { t -= wmax - rb; ++rb; }
+    const int cb = rb + t;
+    const int r0 = rb * 64, c0 = cb * 64;
+    if (r0 >= n || c0 >= n) return;
+    const float4* boxes = s.boxes + (long long)b * s.box_per_img + s.box_off[l];
+    uint64_t* mask = s.mask + (long long)b * s.mask_per_img + s.mask_off[l];
+    const int wp = s.wp[l];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    s_row[threadIdx.x] = (r0 + (int)threadIdx.x < n) ? boxes[r0 + threadIdx.x] : zero;
+    const int j0 = c0 + lane, j1 = c0 + 32 + lane;
+    const float4 cb0 = j0 < n ? boxes[j0] : zero, cb1 = j1 < n ? boxes[j1] : zero;
+    const float a0 = (cb0.z - cb0.x) * (cb0.w - cb0.y), a1 = (cb1.z - cb1.x) * (cb1.w - cb1.y);
+    __syncthreads();
+    uint64_t myword = 0;
+    const int rows = min(32, n - (r0 + w * 32));
+    for (int rr = 0; rr < rows; ++rr) {
+        const int i = r0 + w * 32 + rr;
+        const float4 rbx = s_row[w * 32 + rr];
+        const float ra = (rbx.z - rbx.x) * (rbx.w - rbx.y);
+        const bool p0 = (j0 < n) && (j0 > i) && suppresses(rbx, ra, cb0, a0, s.thr);
+        const bool p1 = (j1 < n) && (j1 > i) && suppresses(rbx, ra, cb1, a1, s.thr);
+        const unsigned lo = __ballot_sync(0xffffffffu, p0), hi = __ballot_sync(0xffffffffu, p1);
+        if (lane == rr) myword = ((uint64_t)hi << 32) | lo;
+    }
+    const int row = r0 + w * 32 + lane;
+    if (lane < rows) mask[(long long)row * wp + cb] = myword;
+}
+
+// mode 0: write positions into keep_pos (RPN pipeline); mode 1: write int64 original indices.
+__global__ void __launch_bounds__(256) k_nms_scan(NmsSegs s, int max_keep, int* __restrict__ keep_pos,
+                                                  int* __restrict__ keep_count, int64_t* __restrict__ keep64,
+                                                  const int* __restrict__ sorted_idx, long long keep_ld) {
+    __shared__ uint64_t s_removed[kSortCap / 64];
+    __shared__ uint64_t s_keepw[kSortCap / 64];
+    __shared__ uint64_t s_keep;
+    const int seg = blockIdx.x;
+    const int l = seg % s.L, b = seg / s.L;
+    const int n = s.counts[seg];
+    const int W = (n + 63) / 64;
+    const uint64_t* mask = s.mask + (long long)b * s.mask_per_img + s.mask_off[l];
+    const int wp = s.wp[l];
+    const int lane = threadIdx.x & 31;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        uint64_t r = 0;
+        if (w == W - 1 && (n & 63)) r = ~0ull << (n & 63);   // rows past n are "removed"
+        s_removed[w] = r; s_keepw[w] = 0;
+    }
+    __syncthreads();
+    int kept_total = 0;
+    for (int c = 0; c < W; ++c) {
+        if (threadIdx.x < 32) {
+            const int row0 = c * 64 + lane, row1 = row0 + 32;
+            const uint64_t d0 = row0 < n ? mask[(long long)row0 * wp + c] : 0ull;
+            const uint64_t d1 = row1 < n ? mask[(long long)row1 * wp + c] : 0ull;
+            uint64_t cur = s_removed[c], keep = 0;
+#pragma unroll
+            for (int bit = 0; bit < 32; ++bit) {
+                const uint64_t word = __shfl_sync(0xffffffffu, d0, bit);
+                const uint64_t alive = ((cur >> bit) & 1ull) ^ 1ull;
+                keep |= alive << bit;
+                cur |= word & (0ull - alive);
+            }
+#pragma unroll
+            for (int bit = 0; bit < 32; ++bit) {
+                const uint64_t word = __shfl_sync(0xffffffffu, d1, bit);
+                const uint64_t alive = ((cur >> (bit + 32)) & 1ull) ^ 1ull;
+                keep |= alive << (bit + 32);
+                cur |= word & (0ull - alive);
+            }
+            if (max_keep > 0 && kept_total + __popcll(keep) > max_keep) {
+                int room = max_keep - kept_total;        // keep only the first `room` set bits
+                uint64_t trimmed = 0, rest = keep;
+                while (room-- > 0) { const uint64_t low = rest & (0ull - rest); trimmed |= low; rest ^= low; }
+                keep = trimmed;
+            }
+            if (lane == 0) { s_keep = keep; s_keepw[c] = keep; }
+        }
+        __syncthreads();
+        const uint64_t keep = s_keep;
+        kept_total += __popcll(keep);
+        const bool done = (max_keep > 0 && kept_total >= max_keep);
+        if (!done) {
+            for (int w = c + 1 + threadIdx.x; w < W; w += blockDim.x) {
+                uint64_t acc = s_removed[w], rest = keep;
+                while (rest) {
+                    const int bit = __ffsll((long long)rest) - 1;
+                    rest &= rest - 1;
+                    acc |= mask[(long long)(c * 64 + bit) * wp + w];
+                }
+                s_removed[w] = acc;
+            }
+        }
+        __syncthreads();
+        if (done) break;
+    }
+    // ordered write-out
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        int pos = 0;
+        for (int q = 0; q < w; ++q) pos += __popcll(s_keepw[q]);
+        uint64_t rest = s_keepw[w];
+        while (rest) {
+            const int bit = __ffsll((long long)rest) - 1;
+            rest &= rest - 1;
+            const int r = w * 64 + bit;
+            if (keep64) keep64[(long long)seg * keep_ld + pos] = (int64_t)sorted_idx[(long long)seg * keep_ld + r];
+            else keep_pos[(long long)b * s.box_per_img + s.box_off[l] + pos] = r;
+            ++pos;
+        }
+    }
+    if (threadIdx.x == 0) keep_count[seg] = kept_total;
+}
+
+// generic entry: sort (score desc, index asc) and gather boxes into score order
+__global__ void __launch_bounds__(kSelThreads) k_nms_sort(float4* __restrict__ sorted_box, int* __restrict__ sorted_idx,
+                                                          const float4* __restrict__ boxes,
+                                                          const float* __restrict__ scores, long long n_ld,
+                                                          const int* __restrict__ counts, long long n, int presorted) {
+    extern __shared__ uint64_t s_buf[];
+    const int s = blockIdx.x;
+    const int m = counts ? counts[s] : (int)n;
+    if (!presorted) {
+        int p2 = 1;
+        while (p2 < m) p2 <<= 1;
+        for (int i = threadIdx.x; i < p2; i += blockDim.x)
+            s_buf[i] = i < m ? make_comp(f2key(scores[(long long)s * n_ld + i]), (uint32_t)i) : 0ull;
+        __syncthreads();
+        bitonic_sort_desc(s_buf, p2);
+    }
+    for (int r = threadIdx.x; r < m; r += blockDim.x) {
+        const int i = presorted ? r : (int)comp_idx(s_buf[r]);
+        sorted_box[(long long)s * n_ld + r] = boxes[(long long)s * n_ld + i];
+        sorted_idx[(long long)s * n_ld + r] = i;
+    }
+}
+
+__global__ void k_fill_i32(int* p, int v, int m) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) p[i] = v;
+}
+
+int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st) {
+    NmsSegs s;
+    memset(&s, 0, sizeof(s));
+    s.L = p.L; s.box_per_img = p.sel_per_img; s.mask_per_img = p.mask_per_img;
+    int wmax = 1;
+    for (int l = 0; l < p.L; ++l) {
+        s.box_off[l] = p.sel_off[l]; s.mask_off[l] = p.mask_off[l];
+        s.wp[l] = (p.kcap[l] + 63) / 64;
+        wmax = max(wmax, s.wp[l]);
+    }
+    s.boxes = p.sel_box; s.counts = p.sel_count; s.mask = p.mask; s.thr = p.nms_thr;
+    const int S = p.B * p.L;
+    dim3 grid(wmax * (wmax + 1) / 2, S);
+    k_nms_mask<<<grid, 64, 0, st>>>(s, wmax);
+    const int threads = min(256, max(32, ((wmax + 31) / 32) * 32));
+    k_nms_scan<<<S, threads, 0, st>>>(s, p.post_nms, p.keep_pos, p.keep_count, nullptr, nullptr, 0);
+    return check_launch("rpn_nms");
+}
+
+}  // namespace b2d
+
+using namespace b2d;
+
+extern "C" {
+
+size_t b2d_nms_workspace_bytes(long long n_max, int S) {
+    if (n_max < 0 || S < 1) return 0;
+    const size_t n = (size_t)(n_max > 0 ? n_max : 1);
+    const size_t wp = (n + 63) / 64;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    return al((size_t)S * n * 16) + al((size_t)S * n * 4) + al((size_t)S * n * wp * 8) + al((size_t)S * 4);
+}
+
+int b2d_nms(int64_t* keep, int* keep_count, const float* boxes, const float* scores, long long n_ld,
+            const int* counts, long long n, int S, float thr_f, int max_keep, int presorted, void* workspace,
+            size_t ws_bytes, void* stream) {
+    B2D_REQUIRE(keep && keep_count && boxes && scores && S >= 1 && n >= 0 && n_ld >= n, "nms: bad args");
+    B2D_REQUIRE(n <= kSortCap, "nms: at most 16384 boxes per segment");
+    B2D_REQUIRE(workspace && ws_bytes >= b2d_nms_workspace_bytes(n_ld, S), "nms: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { cudaMemsetAsync(keep_count, 0, sizeof(int) * S, st); return B2D_OK; }
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const int wp = (int)((n_ld + 63) / 64);
+    char* base = (char*)workspace;
+    float4* sorted_box = (float4*)base; base += al((size_t)S * n_ld * 16);
+    int* sorted_idx = (int*)base; base += al((size_t)S * n_ld * 4);
+    uint64_t* mask = (uint64_t*)base; base += al((size_t)S * n_ld * wp * 8);
+    int* cnt = (int*)base;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_nms_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
+        attr_set = true;
+    }
+    if (counts) cudaMemcpyAsync(cnt, counts, sizeof(int) * S, cudaMemcpyDeviceToDevice, st);
+    else k_fill_i32<<<cdiv(S, 256), 256, 0, st>>>(cnt, (int)n, S);
+    k_nms_sort<<<S, kSelThreads, kSortCap * 8, st>>>(sorted_box, sorted_idx, (const float4*)boxes, scores, n_ld, cnt, n,
+                                                     presorted);
+    NmsSegs s;
+    memset(&s, 0, sizeof(s));
+    s.L = 1; s.box_per_img = n_ld; s.mask_per_img = (long long)n_ld * wp; s.wp[0] = wp;
+    s.boxes = sorted_box; s.counts = cnt; s.mask = mask; s.thr = thr_f;
+    const int wmax = (int)((n + 63) / 64);
+    dim3 grid(wmax * (wmax + 1) / 2, S);
+    k_nms_mask<<<grid, 64, 0, st>>>(s, wmax);
+    const int threads = min(256, max(32, ((wmax + 31) / 32) * 32));
+    k_nms_scan<<<S, threads, 0, st>>>(s, max_keep, nullptr, keep_count, keep, sorted_idx, n_ld);
+    return check_launch("nms");
+}
+
+}  // extern "C"

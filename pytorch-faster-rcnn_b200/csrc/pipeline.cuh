@@ -1,0 +1,37 @@
+// pipeline.cuh -- launch descriptor shared by select.cu (K3) and nms.cu (K4) for
+// the fused RPN proposal path.
+#pragma once
+#include "common.cuh"
+
+namespace b2d {
+
+constexpr int kHistBits = 12;
+constexpr int kHistBins = 1 << kHistBits;
+constexpr int kChunk = 16384;          // elements per block in k_hist / k_compact
+constexpr int kSortCap = 16384;        // u64 entries of the in-smem bitonic sort (128 KB)
+constexpr int kSelThreads = 1024;
+
+struct RpnLaunch {
+    b2d_pyramid pyr;
+    const float* cls[kMaxLevels];
+    const float* reg[kMaxLevels];
+    const float* img_hw;
+    int B, L;
+    int n[kMaxLevels], kcap[kMaxLevels];
+    long long sel_off[kMaxLevels], sel_per_img;
+    long long mask_off[kMaxLevels], mask_per_img;
+    int pre_nms, post_nms, max_num, score_mode, cls_ch, do_nms, out_ld;
+    int raw;                            // 1: plain segmented top-k (no anchors / deltas / decode)
+    float nms_thr, min_size, ms[8];
+    // workspace
+    uint32_t* hist; int* cand_count; int* sel_count; int* keep_count; int* thr_bin;
+    size_t zero_bytes;
+    uint64_t* cand; uint64_t* cand2;
+    float4* sel_box; uint32_t* sel_key; int* sel_idx; int* keep_pos;
+    uint64_t* mask;
+};
+
+// nms.cu: suppression mask + scan over the sel_* arrays of every segment
+int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st);
+
+}  // namespace b2d

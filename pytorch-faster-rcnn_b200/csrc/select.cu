@@ -1,0 +1,519 @@
+// select.cu -- K3: fused RPN proposal selection for all (image, level) segments:
+//   k_hist      12-bit radix histogram of the monotone logit keys   (multi-block)
+//   k_compact   threshold bin from the histogram + candidate compaction (multi-block)
+//   k_select    per segment: exact top-k by radix narrowing + in-smem bitonic sort,
+//               anchor generation in registers, delta decode, clip, min-size filter
+//   (NMS: nms.cu)
+//   k_merge     per image: concat levels, global top-max_num, sigmoid, [4,k] output
+// Reference: RPNHead.predict_single_image (lib/heads/rpn_head.py:68-120).
+//
+// Selection and ordering use the *logit* (sigmoid is monotone), ties broken by the
+// lowest index; torch.topk's tie order is unspecified, so this is the
+// documented contract and parity is asserted on tie-free inputs.
+#include <cstring>
+
+#include "common.cuh"
+#include "pipeline.cuh"
+
+namespace b2d {
+
+__device__ __forceinline__ float load_logit(const float* __restrict__ cls, int n, int i, int mode, int C) {
+    if (mode == 0) return cls[i];
+    if (mode == 1) return cls[n + i] - cls[i];            // softmax[1] == sigmoid(l1 - l0)
+    float m = cls[i];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, cls[(long long)c * n + i]);
+    return m;
+}
+
+__device__ __forceinline__ const float* seg_cls(const RpnLaunch& p, int b, int l) {
+    const b2d_level& lv = p.pyr.lv[l];
+    const long long n = (long long)lv.A * lv.H * lv.W;
+    return p.cls[l] + (long long)b * n * p.cls_ch;
+}
+__device__ __forceinline__ const float* seg_reg(const RpnLaunch& p, int b, int l) {
+    const b2d_level& lv = p.pyr.lv[l];
+    const long long n = (long long)lv.A * lv.H * lv.W;
+    return p.reg[l] + (long long)b * n * 4;
+}
+
+// ---------------------------------------------------------------- k_hist
+__global__ void __launch_bounds__(256) k_hist(RpnLaunch p) {
+    __shared__ uint32_t s_h[kHistBins];
+    const int seg = blockIdx.y, b = seg / p.L, l = seg - b * p.L;
+    const int n = p.n[l], k = p.kcap[l];
+    if (k >= n) return;                                  // no selection on this level
+    const int start = blockIdx.x * kChunk;
+    if (start >= n) return;
+    for (int t = threadIdx.x; t < kHistBins; t += blockDim.x) s_h[t] = 0;
+    __syncthreads();
+    const float* cls = seg_cls(p, b, l);
+    const int end = min(start + kChunk, n);
+    for (int i = start + threadIdx.x; i < end; i += blockDim.x) {
+        const uint32_t key = f2key(load_logit(cls, n, i, p.score_mode, p.cls_ch));
+        atomicAdd(&s_h[key >> (32 - kHistBits)], 1u);
+    }
+    __syncthreads();
+    uint32_t* gh = p.hist + (long long)seg * kHistBins;
+    for (int t = threadIdx.x; t < kHistBins; t += blockDim.x)
+        if (s_h[t]) atomicAdd(&gh[t], s_h[t]);
+}
+
+// Find the largest bin t with sum_{bin >= t} hist[bin] >= k.  blockDim.x == 256.
+__device__ int find_threshold_bin(const uint32_t* __restrict__ gh, int k, uint32_t* s_tmp /*256*/) {
+    constexpr int per = kHistBins / 256;
+    uint32_t loc[per];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int q = 0; q < per; ++q) { loc[q] = gh[threadIdx.x * per + q]; sum += loc[q]; }
+    s_tmp[threadIdx.x] = sum;
+    __syncthreads();
+    // suffix sums over 256 partials (small: serial by warp 0 lanes over 8 each + shuffle would also do)
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int t = 255; t >= 0; --t) { const uint32_t v = s_tmp[t]; s_tmp[t] = run; run += v; }
+    }
+    __syncthreads();
+    const uint32_t above = s_tmp[threadIdx.x];            // count in bins owned by higher threads
+    __shared__ int s_bin;
+    if (threadIdx.x == 0) s_bin = 0;
+    __syncthreads();
+    if (above < (uint32_t)k && above + sum >= (uint32_t)k) {
+        uint32_t run = above;
+        for (int q = per - 1; q >= 0; --q) {
+            run += loc[q];
+            if (run >= (uint32_t)k) { s_bin = threadIdx.x * per + q; break; }
+        }
+    }
+    __syncthreads();
+    return s_bin;
+}
+
+// ---------------------------------------------------------------- k_compact
+__global__ void __launch_bounds__(256) k_compact(RpnLaunch p) {
+    __shared__ uint32_t s_tmp[256];
+    const int seg = blockIdx.y, b = seg / p.L, l = seg - b * p.L;
+    const int n = p.n[l], k = p.kcap[l];
+    if (k >= n) return;
+    const int start = blockIdx.x * kChunk;
+    if (start >= n) return;
+    const int tb = find_threshold_bin(p.hist + (long long)seg * kHistBins, k, s_tmp);
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.thr_bin[seg] = tb;
+    const float* cls = seg_cls(p, b, l);
+    uint64_t* cand = p.cand + ((long long)b * p.pyr.total + p.pyr.lv[l].offset);
+    const int end = min(start + kChunk, n);
+    const int end_round = start + ((end - start + 255) / 256) * 256;   // keep warps converged for warp_alloc
+    for (int i = start + threadIdx.x; i < end_round; i += blockDim.x) {
+        bool take = false;
+        uint32_t key = 0;
+        if (i < end) {
+            key = f2key(load_logit(cls, n, i, p.score_mode, p.cls_ch));
+            take = (int)(key >> (32 - kHistBits)) >= tb;
+        }
+        const int slot = warp_alloc(take, &p.cand_count[seg]);
+        if (take) cand[slot] = make_comp(key, (uint32_t)i);
+    }
+}
+
+// ---------------------------------------------------------------- k_select
+// One block per segment.  Shared memory: kSortCap u64 sort buffer.
+__global__ void __launch_bounds__(kSelThreads) k_select(RpnLaunch p) {
+    extern __shared__ uint64_t s_buf[];
+    __shared__ uint32_t s_h[256];
+    __shared__ int s_cnt, s_cnt2, s_digit, s_base;
+    __shared__ int s_warp[kSelThreads / 32];
+    const int seg = blockIdx.x, b = seg / p.L, l = seg - b * p.L;
+    const b2d_level& lv = p.pyr.lv[l];
+    const int n = p.n[l], k = p.kcap[l];
+    const float* cls = seg_cls(p, b, l);
+    const bool identity = (k >= n) && !p.do_nms;          // AnchorHead path without top-k: keep index order
+    int total = 0;
+    if (k >= n) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            s_buf[i] = identity ? make_comp(0xffffffffu, (uint32_t)i)
+                                : make_comp(f2key(load_logit(cls, n, i, p.score_mode, p.cls_ch)), (uint32_t)i);
+        total = n;
+    } else {
+        uint64_t* list = p.cand + ((long long)b * p.pyr.total + lv.offset);
+        uint64_t* list2 = p.cand2 + ((long long)b * p.pyr.total + lv.offset);
+        int m = p.cand_count[seg];
+        if (m <= kSortCap) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) s_buf[i] = list[i];
+            total = m;
+        } else {
+            // radix narrowing (only reached on heavily tied / degenerate score maps)
+            if (threadIdx.x == 0) s_cnt = 0;
+            __syncthreads();
+            const int tb = p.thr_bin[seg];
+            // pass 0: the 12-bit bin
+            if (threadIdx.x == 0) s_cnt2 = 0;
+            __syncthreads();
+            for (int i0 = 0; i0 < m; i0 += blockDim.x) {
+                const int i = i0 + threadIdx.x;
+                uint64_t c = 0; int d = -1;
+                if (i < m) { c = list[i]; d = (int)(c >> (64 - kHistBits)); }
+                const int s1 = warp_alloc(d > tb, &s_cnt);
+                if (d > tb) s_buf[s1] = c;
+                const int s2 = warp_alloc(d == tb, &s_cnt2);
+                if (d == tb) list2[s2] = c;
+            }
+            __syncthreads();
+            int sel = s_cnt;
+            m = s_cnt2;
+            uint64_t* src = list2; uint64_t* dst = list;
+            int shift = 64 - kHistBits - 8;
+            while (sel + m > kSortCap) {
+                const int bits = shift >= 0 ? 8 : 8 + shift;   // last pass may be narrower
+                const int sh = shift >= 0 ? shift : 0;
+                const uint32_t dm = (1u << bits) - 1u;
+                if (threadIdx.x < 256) s_h[threadIdx.x] = 0;
+                __syncthreads();
+                for (int i = threadIdx.x; i < m; i += blockDim.x) atomicAdd(&s_h[(uint32_t)(src[i] >> sh) & dm], 1u);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const int need = k - sel;
+                    int run = 0, d = (int)dm;
+                    for (; d >= 0; --d) { run += (int)s_h[d]; if (run >= need) break; }
+                    s_digit = d < 0 ? 0 : d;
+                    s_cnt = sel; s_cnt2 = 0;
+                }
+                __syncthreads();
+                const int dg = s_digit;
+                for (int i0 = 0; i0 < m; i0 += blockDim.x) {
+                    const int i = i0 + threadIdx.x;
+                    uint64_t c = 0; int d = -1;
+                    if (i < m) { c = src[i]; d = (int)((uint32_t)(c >> sh) & dm); }
+                    const int s1 = warp_alloc(d > dg, &s_cnt);
+                    if (d > dg) s_buf[s1] = c;
+                    const int s2 = warp_alloc(d == dg, &s_cnt2);
+                    if (d == dg) dst[s2] = c;
+                }
+                __syncthreads();
+                sel = s_cnt; m = s_cnt2;
+                uint64_t* t = src; src = dst; dst = t;
+                if (shift <= 0) break;
+                shift -= 8;
+            }
+            for (int i = threadIdx.x; i < m; i += blockDim.x) s_buf[sel + i] = src[i];
+            total = sel + m;
+        }
+    }
+    int p2 = 1;
+    while (p2 < total) p2 <<= 1;
+    for (int i = total + threadIdx.x; i < p2; i += blockDim.x) s_buf[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc(s_buf, p2);
+    const int kk = min(k, total);
+
+    // decode + clip + min-size filter, order preserving
+    const float* reg = p.raw ? nullptr : seg_reg(p, b, l);
+    const float img_h = p.raw ? 0.0f : p.img_hw[2 * b], img_w = p.raw ? 0.0f : p.img_hw[2 * b + 1];
+    const long long so = (long long)b * p.sel_per_img + p.sel_off[l];
+    float4* sel_box = p.sel_box + so;
+    uint32_t* sel_key = p.sel_key + so;
+    int* sel_idx = p.sel_idx + so;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int r0 = 0; r0 < kk; r0 += blockDim.x) {
+        const int r = r0 + threadIdx.x;
+        bool keep = false;
+        Box o{0, 0, 0, 0};
+        uint32_t key = 0, idx = 0;
+        if (r < kk) {
+            const uint64_t c = s_buf[r];
+            idx = comp_idx(c);
+            key = identity ? f2key(load_logit(cls, n, (int)idx, p.score_mode, p.cls_ch)) : comp_key(c);
+            keep = true;
+            if (!p.raw) {
+                const Box a = anchor_flat(lv, (int)idx);
+                o = decode_box(a, reg[idx], reg[n + idx], reg[2 * n + idx], reg[3 * n + idx], p.ms, true, img_h, img_w);
+            }
+            if (!p.raw && p.min_size > 0.0f)
+                keep = ((o.x2 - o.x1) + 1.0f >= p.min_size) && ((o.y2 - o.y1) + 1.0f >= p.min_size);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane_id() == 0) s_warp[threadIdx.x >> 5] = __popc(m);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += s_warp[w];
+        if (keep) {
+            const int pos = before + __popc(m & ((1u << lane_id()) - 1u));
+            sel_box[pos] = make_float4(o.x1, o.y1, o.x2, o.y2);
+            sel_key[pos] = key;
+            sel_idx[pos] = (int)idx;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < kSelThreads / 32; ++w) t += s_warp[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) p.sel_count[seg] = s_base;
+}
+
+// ---------------------------------------------------------------- k_merge
+// One block per image: gather the per-level NMS survivors (or, without NMS, the
+// decoded selections), apply the global top-max_num, write [4, out_ld] + scores.
+__global__ void __launch_bounds__(kSelThreads) k_merge(RpnLaunch p, float* __restrict__ props,
+                                                       float* __restrict__ scores, int* __restrict__ count,
+                                                       int* __restrict__ prov) {
+    extern __shared__ uint64_t s_buf[];
+    __shared__ int s_off[kMaxLevels + 1];
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int l = 0; l < p.L; ++l) {
+            s_off[l] = run;
+            int c = p.do_nms ? p.keep_count[b * p.L + l] : p.sel_count[b * p.L + l];
+            if (p.post_nms > 0 && c > p.post_nms) c = p.post_nms;
+            run += c;
+        }
+        s_off[p.L] = run;
+    }
+    __syncthreads();
+    const int total = s_off[p.L];
+    const bool topk = (p.max_num > 0) && (total > p.max_num);
+    const int nout = topk ? p.max_num : total;
+    // element t of the level-major concatenation -> (level, position in that level's sel arrays)
+    auto locate = [&](int t, int& l, int& pos) {
+        l = 0;
+        for (int q = 1; q < p.L; ++q) if (t >= s_off[q]) l = q;
+        const int r = t - s_off[l];
+        pos = p.do_nms ? p.keep_pos[(long long)b * p.sel_per_img + p.sel_off[l] + r] : r;
+    };
+    if (topk) {
+        int p2 = 1;
+        while (p2 < total) p2 <<= 1;
+        for (int t = threadIdx.x; t < p2; t += blockDim.x) {
+            uint64_t c = 0ull;
+            if (t < total) {
+                int l, pos; locate(t, l, pos);
+                c = make_comp(p.sel_key[(long long)b * p.sel_per_img + p.sel_off[l] + pos], (uint32_t)t);
+            }
+            s_buf[t] = c;
+        }
+        __syncthreads();
+        bitonic_sort_desc(s_buf, p2);
+    }
+    float* pb = props + (long long)b * 4 * p.out_ld;
+    for (int r = threadIdx.x; r < p.out_ld; r += blockDim.x) {
+        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+        float sc = 0.0f;
+        int pv = -1;
+        if (r < nout) {
+            const int t = topk ? (int)comp_idx(s_buf[r]) : r;
+            int l, pos; locate(t, l, pos);
+            const long long o = (long long)b * p.sel_per_img + p.sel_off[l] + pos;
+            bx = p.sel_box[o];
+            sc = 1.0f / (1.0f + expf(-key2f(p.sel_key[o])));
+            pv = (int)(p.pyr.lv[l].offset + p.sel_idx[o]);
+        }
+        pb[r] = bx.x; pb[p.out_ld + r] = bx.y; pb[2 * p.out_ld + r] = bx.z; pb[3 * p.out_ld + r] = bx.w;
+        scores[(long long)b * p.out_ld + r] = sc;
+        if (prov) prov[(long long)b * p.out_ld + r] = pv;
+    }
+    if (threadIdx.x == 0) count[b] = nout;
+}
+
+// ---------------------------------------------------------------- generic segmented top-k
+__global__ void __launch_bounds__(kSelThreads) k_topk_small(int* __restrict__ idx, int* __restrict__ out_count,
+                                                            const float* __restrict__ values, long long ld,
+                                                            const int* __restrict__ counts, long long n, int k) {
+    extern __shared__ uint64_t s_buf[];
+    const int s = blockIdx.x;
+    const int m = counts ? counts[s] : (int)n;
+    int p2 = 1;
+    while (p2 < m) p2 <<= 1;
+    for (int i = threadIdx.x; i < p2; i += blockDim.x)
+        s_buf[i] = i < m ? make_comp(f2key(values[(long long)s * ld + i]), (uint32_t)i) : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(s_buf, p2);
+    const int kk = min(k, m);
+    for (int r = threadIdx.x; r < k; r += blockDim.x) idx[(long long)s * k + r] = r < kk ? (int)comp_idx(s_buf[r]) : -1;
+    if (threadIdx.x == 0) out_count[s] = kk;
+}
+
+}  // namespace b2d
+
+using namespace b2d;
+
+namespace b2d {
+
+// Workspace carving shared by the size query and the launcher.
+bool rpn_plan(RpnLaunch& p, const b2d_pyramid* pyr, int B, const b2d_rpn_cfg* cfg, char* base, size_t* bytes) {
+    memset(&p, 0, sizeof(p));
+    p.pyr = *pyr;
+    p.B = B; p.L = pyr->num_levels;
+    p.pre_nms = cfg->pre_nms; p.post_nms = cfg->post_nms; p.max_num = cfg->max_num;
+    p.score_mode = cfg->score_mode; p.cls_ch = cfg->num_cls_channels > 0 ? cfg->num_cls_channels : 1;
+    p.nms_thr = cfg->nms_thr_f; p.min_size = cfg->min_size; p.do_nms = cfg->do_nms;
+    for (int i = 0; i < 4; ++i) { p.ms[i] = cfg->means[i]; p.ms[4 + i] = cfg->stds[i]; }
+    long long off = 0;
+    int wmax = 0;
+    int out_sum = 0;
+    for (int l = 0; l < p.L; ++l) {
+        const b2d_level& lv = pyr->lv[l];
+        const long long n = (long long)lv.A * lv.H * lv.W;
+        if (n >= (1ll << 31)) return false;
+        p.n[l] = (int)n;
+        p.kcap[l] = (cfg->pre_nms > 0 && cfg->pre_nms < n) ? cfg->pre_nms : (int)n;
+        if (p.kcap[l] > kSortCap) return false;
+        p.sel_off[l] = off;
+        off += p.kcap[l];
+        const int w = (p.kcap[l] + 63) / 64;
+        wmax = w > wmax ? w : wmax;
+        p.mask_off[l] = 0;
+        out_sum += (cfg->post_nms > 0 && cfg->post_nms < p.kcap[l]) ? cfg->post_nms : p.kcap[l];
+    }
+    p.sel_per_img = off;
+    p.out_ld = cfg->max_num > 0 ? cfg->max_num : out_sum;
+    if (cfg->max_num > 0 && out_sum > kSortCap) return false;
+    // mask: per segment kcap * ceil(kcap/64) words
+    long long moff = 0;
+    for (int l = 0; l < p.L; ++l) { p.mask_off[l] = moff; moff += (long long)p.kcap[l] * ((p.kcap[l] + 63) / 64); }
+    p.mask_per_img = moff;
+    const int S = B * p.L;
+    size_t o = 0;
+    auto carve = [&](size_t sz) { size_t r = o; o += (sz + 255) & ~(size_t)255; return base ? base + r : (char*)nullptr; };
+    p.hist = (uint32_t*)carve((size_t)S * kHistBins * 4);
+    p.cand_count = (int*)carve((size_t)S * 4);
+    p.sel_count = (int*)carve((size_t)S * 4);
+    p.keep_count = (int*)carve((size_t)S * 4);
+    p.thr_bin = (int*)carve((size_t)S * 4);
+    p.zero_bytes = o;                                   // everything above is zeroed per call
+    p.cand = (uint64_t*)carve((size_t)B * pyr->total * 8);
+    p.cand2 = (uint64_t*)carve((size_t)B * pyr->total * 8);
+    p.sel_box = (float4*)carve((size_t)B * p.sel_per_img * 16);
+    p.sel_key = (uint32_t*)carve((size_t)B * p.sel_per_img * 4);
+    p.sel_idx = (int*)carve((size_t)B * p.sel_per_img * 4);
+    p.keep_pos = (int*)carve((size_t)B * p.sel_per_img * 4);
+    p.mask = (uint64_t*)carve(cfg->do_nms ? (size_t)B * p.mask_per_img * 8 : 0);
+    *bytes = o;
+    return true;
+}
+
+}  // namespace b2d
+
+extern "C" {
+
+size_t b2d_rpn_proposals_workspace_bytes(const b2d_pyramid* pyr_host, int B, const b2d_rpn_cfg* cfg_host) {
+    if (!pyr_host || !cfg_host || B < 1) return 0;
+    RpnLaunch p;
+    size_t bytes = 0;
+    if (!rpn_plan(p, pyr_host, B, cfg_host, nullptr, &bytes)) return 0;
+    return bytes;
+}
+
+int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const void* const* cls_ptrs_host,
+                      const void* const* reg_ptrs_host, const b2d_pyramid* pyr_host, const float* img_hw, int B,
+                      const b2d_rpn_cfg* cfg_host, void* workspace, size_t ws_bytes, void* stream) {
+    B2D_REQUIRE(props && scores && count && cls_ptrs_host && reg_ptrs_host && pyr_host && img_hw && cfg_host,
+                "rpn_proposals: null pointer");
+    B2D_REQUIRE(B >= 1 && pyr_host->num_levels >= 1 && pyr_host->num_levels <= B2D_MAX_LEVELS,
+                "rpn_proposals: bad B / levels");
+    RpnLaunch p;
+    size_t need = 0;
+    B2D_REQUIRE(rpn_plan(p, pyr_host, B, cfg_host, (char*)workspace, &need),
+                "rpn_proposals: a level needs a pre-NMS top-k <= 16384 (and the post-NMS concat must fit 16384)");
+    B2D_REQUIRE(workspace && ws_bytes >= need, "rpn_proposals: workspace too small");
+    for (int l = 0; l < p.L; ++l) { p.cls[l] = (const float*)cls_ptrs_host[l]; p.reg[l] = (const float*)reg_ptrs_host[l]; }
+    p.img_hw = img_hw;
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
+        cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
+        attr_set = true;
+    }
+    cudaMemsetAsync(workspace, 0, p.zero_bytes, st);
+    const int S = B * p.L;
+    int max_chunks = 1;
+    bool any_select = false;
+    for (int l = 0; l < p.L; ++l) {
+        if (p.kcap[l] < p.n[l]) { any_select = true; max_chunks = max(max_chunks, cdiv(p.n[l], kChunk)); }
+    }
+    if (any_select) {
+        dim3 grid(max_chunks, S);
+        k_hist<<<grid, 256, 0, st>>>(p);
+        k_compact<<<grid, 256, 0, st>>>(p);
+    }
+    k_select<<<S, kSelThreads, kSortCap * 8, st>>>(p);
+    if (p.do_nms) {
+        int rc = rpn_nms_launch(p, st);
+        if (rc != B2D_OK) return rc;
+    }
+    k_merge<<<B, kSelThreads, kSortCap * 8, st>>>(p, props, scores, count, prov);
+    return check_launch("rpn_proposals");
+}
+
+static void topk_cfg(long long n, int k, b2d_pyramid& pyr, b2d_rpn_cfg& cfg) {
+    memset(&pyr, 0, sizeof(pyr));
+    memset(&cfg, 0, sizeof(cfg));
+    pyr.num_levels = 1; pyr.total = n;
+    pyr.lv[0].H = 1; pyr.lv[0].W = (int)n; pyr.lv[0].A = 1; pyr.lv[0].stride = 1.0f;
+    cfg.pre_nms = k; cfg.post_nms = 0; cfg.max_num = 0; cfg.score_mode = 0; cfg.num_cls_channels = 1;
+    cfg.do_nms = 0;
+    for (int i = 0; i < 4; ++i) cfg.stds[i] = 1.0f;
+}
+
+size_t b2d_topk_workspace_bytes(long long n_max, int S, int k) {
+    if (n_max <= kSortCap) return 256;
+    if (k > kSortCap || n_max >= (1ll << 31)) return 0;
+    b2d_pyramid pyr; b2d_rpn_cfg cfg;
+    topk_cfg(n_max, k, pyr, cfg);
+    RpnLaunch p;
+    size_t bytes = 0;
+    if (!rpn_plan(p, &pyr, S, &cfg, nullptr, &bytes)) return 0;
+    return bytes;
+}
+
+namespace b2d {
+__global__ void __launch_bounds__(256) k_topk_emit(RpnLaunch p, int* __restrict__ idx, int* __restrict__ out_count, int k) {
+    const int s = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = p.sel_count[s];
+    if (r < k) idx[(long long)s * k + r] = r < c ? p.sel_idx[(long long)s * p.sel_per_img + r] : -1;
+    if (r == 0) out_count[s] = c;
+}
+}  // namespace b2d
+
+int b2d_topk(int* idx, int* out_count, const float* values, long long ld, const int* counts, long long n, int S,
+             int k, void* workspace, size_t ws_bytes, void* stream) {
+    B2D_REQUIRE(idx && out_count && values && S >= 1 && k >= 1, "topk: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= kSortCap) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_topk_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
+            attr_set = true;
+        }
+        k_topk_small<<<S, kSelThreads, kSortCap * 8, st>>>(idx, out_count, values, ld, counts, n, k);
+        return check_launch("topk");
+    }
+    // pyramid-sized inputs: radix histogram + compaction + exact narrowing (the K3 machinery)
+    B2D_REQUIRE(!counts && ld == n, "topk: n > 16384 needs dense equal-length segments");
+    B2D_REQUIRE(k <= kSortCap, "topk: k must be <= 16384");
+    b2d_pyramid pyr; b2d_rpn_cfg cfg;
+    topk_cfg(n, k, pyr, cfg);
+    RpnLaunch p;
+    size_t need = 0;
+    B2D_REQUIRE(rpn_plan(p, &pyr, S, &cfg, (char*)workspace, &need), "topk: unsupported size");
+    B2D_REQUIRE(workspace && ws_bytes >= need, "topk: workspace too small");
+    p.cls[0] = values; p.reg[0] = nullptr; p.img_hw = nullptr; p.raw = 1;
+    static bool attr2 = false;
+    if (!attr2) {
+        cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
+        attr2 = true;
+    }
+    cudaMemsetAsync(workspace, 0, p.zero_bytes, st);
+    dim3 grid(cdiv(n, kChunk), S);
+    k_hist<<<grid, 256, 0, st>>>(p);
+    k_compact<<<grid, 256, 0, st>>>(p);
+    k_select<<<S, kSelThreads, kSortCap * 8, st>>>(p);
+    dim3 g2(cdiv(k, 256), S);
+    k_topk_emit<<<g2, 256, 0, st>>>(p, idx, out_count, k);
+    return check_launch("topk");
+}
+
+}  // extern "C"

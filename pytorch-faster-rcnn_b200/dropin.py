@@ -1,0 +1,78 @@
+"""install(): rebind the reference's hot-path names to the B200 kernels without editing
+a single reference file: module attributes of lib.anchor / lib.bbox /
+lib.region / lib.utils, the names the head modules imported with `from .. import x`,
+`torchvision.ops.nms` as seen by lib.heads.rpn_head / lib.region / lib.utils, and the
+lib.builder.MODULES registry entries."""
+import sys
+import types
+
+_saved = []
+
+
+def _set(obj, name, value):
+    if hasattr(obj, name) or isinstance(obj, dict):
+        old = obj[name] if isinstance(obj, dict) else getattr(obj, name)
+        _saved.append((obj, name, old))
+        if isinstance(obj, dict):
+            obj[name] = value
+        else:
+            setattr(obj, name, value)
+
+
+def install(lib=None):
+    """lib: the reference's imported `lib` package (default: sys.modules['lib'])."""
+    from . import anchor, bbox, region, utils
+    lib = lib or sys.modules.get("lib")
+    if lib is None:
+        raise RuntimeError("import the reference package `lib` before calling install()")
+    mods = {n: sys.modules.get("lib." + n) for n in
+            ("anchor", "bbox", "region", "utils", "builder", "heads.anchor_head", "heads.rpn_head",
+             "heads.bbox_head", "heads.fcos_head", "heads.retina_head", "heads.rcnn_head",
+             "detectors.cascade_rcnn")}
+    util_names = ["calc_iou", "elem_iou", "bbox2param", "param2bbox", "batched_param2bbox", "clamp_bbox",
+                  "batched_nms", "multiclass_nms"]
+    if mods["utils"]:
+        for n in util_names:
+            _set(mods["utils"], n, getattr(utils, n))
+        # lib.utils calls tv.ops.nms: give it a module-like shim whose .ops.nms is ours
+        tvshim = types.SimpleNamespace(ops=types.SimpleNamespace(nms=utils.nms), transforms=mods["utils"].tv.transforms)
+        _set(mods["utils"], "tv", tvshim)
+    region_names = ["inside_grid_mask", "inside_anchor_mask", "MaxIoUAssigner", "RandomSampler",
+                    "IoUBalancedNegSampler", "ProposalCreator", "ScalableRoIPool", "ScalableRoIAlign",
+                    "BasicRoIExtractor", "SingleRoIExtractor"]
+    if mods["region"]:
+        for n in region_names:
+            _set(mods["region"], n, getattr(region, n))
+    if mods["anchor"]:
+        _set(mods["anchor"], "AnchorCreator", anchor.AnchorCreator)
+        _set(mods["anchor"], "anchor_target", anchor.anchor_target)
+    if mods["bbox"]:
+        _set(mods["bbox"], "bbox_target", bbox.bbox_target)
+    # names bound with `from .. import x` inside the heads
+    ah = mods["heads.anchor_head"]
+    if ah:
+        _set(ah, "AnchorCreator", anchor.AnchorCreator)
+        _set(ah, "anchor_target", anchor.anchor_target)
+        _set(ah, "inside_grid_mask", region.inside_grid_mask)
+        _set(ah, "inside_anchor_mask", region.inside_anchor_mask)
+    if mods["heads.bbox_head"]:
+        _set(mods["heads.bbox_head"], "bbox_target", bbox.bbox_target)
+    if mods["heads.rpn_head"]:
+        _set(mods["heads.rpn_head"], "tvops", types.SimpleNamespace(nms=utils.nms))
+    if mods["heads.fcos_head"] and hasattr(mods["heads.fcos_head"], "AnchorCreator"):
+        _set(mods["heads.fcos_head"], "AnchorCreator", anchor.AnchorCreator)
+    if mods["builder"]:
+        reg = mods["builder"].MODULES
+        for n in ("MaxIoUAssigner", "RandomSampler", "IoUBalancedNegSampler", "BasicRoIExtractor",
+                  "SingleRoIExtractor", "RoIAlign", "RoIPool", "ScalableRoIPool", "ScalableRoIAlign"):
+            _set(reg, n, getattr(region, n))
+    return lib
+
+
+def uninstall():
+    while _saved:
+        obj, name, old = _saved.pop()
+        if isinstance(obj, dict):
+            obj[name] = old
+        else:
+            setattr(obj, name, old)

@@ -1,0 +1,188 @@
+"""Batched (all images, all levels, one launch per stage) form of the hot path --
+SURVEY 8(f) rank 1: what RPNHead.predict_bboxes_from_output, AnchorHead.loss's target
+part, BBoxHead.bbox_targets and BasicRoIExtractor.forward compute per image in Python
+loops (lib/heads/anchor_head.py:152-199,268-289; lib/heads/rpn_head.py:68-120;
+lib/heads/bbox_head.py:47-52; lib/region.py:301-306) runs here as ~20 kernel launches
+per batch with no host synchronisation, no allocation and no [N,K] temporaries, so a
+whole step can be captured in a CUDA graph.
+
+Every stage is also reachable through the reference-signature functions in
+anchor.py / bbox.py / region.py / utils.py; this module only batches them.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _C
+
+
+def _ptrs(tensors):
+    arr = (_C.c_void_p * _C.MAX_LEVELS)()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+class AnchorPyramid(object):
+    """Closed-form anchors of an anchor head (lib/heads/anchor_head.py:33-36): per level
+    stride == base size, shared scales/ratios; nothing is materialised."""
+
+    def __init__(self, strides, grids, scales=(8,), ratios=(0.5, 1.0, 2.0), center_lt=False):
+        self.strides, self.grids = list(strides), [tuple(int(v) for v in g) for g in grids]
+        levels = []
+        for s, g in zip(self.strides, self.grids):
+            ws = [np.float32(s * sc * np.sqrt(ar)) for sc in scales for ar in ratios]   # lib/anchor.py:92-99
+            hs = [np.float32(s * sc / np.sqrt(ar)) for sc in scales for ar in ratios]
+            levels.append(dict(stride=s, H=g[0], W=g[1], ws=ws, hs=hs, center_lt=center_lt))
+        self.num_anchors = len(scales) * len(ratios)
+        self.c = _C.make_pyramid(levels)
+        self.total = int(self.c.total)
+        self.level_sizes = [self.num_anchors * g[0] * g[1] for g in self.grids]
+
+
+class RpnProposals(object):
+    """K3 + K4 over a batch: (cls_outs, reg_outs) -> props [B,4,P], scores [B,P], count [B]."""
+
+    def __init__(self, pyramid, B, cfg, means, stds, device, score_mode=0, cls_channels=1, do_nms=True,
+                 scale_factor=1.0):
+        self.pyr, self.B = pyramid, B
+        get = (lambda k, d=0: cfg.get(k, d)) if hasattr(cfg, "get") else (lambda k, d=0: getattr(cfg, k, d))
+        c = _C.RpnCfg()
+        c.pre_nms, c.post_nms, c.max_num = int(get("pre_nms")), int(get("post_nms")), int(get("max_num"))
+        c.score_mode, c.num_cls_channels, c.do_nms = int(score_mode), int(cls_channels), int(bool(do_nms))
+        c.nms_thr_f = _C.floor_f32(float(get("nms_iou", 0.7)))
+        c.min_size = float(np.float32(scale_factor * get("min_bbox_size", 0)))
+        for i in range(4):
+            c.means[i], c.stds[i] = float(means[i]), float(stds[i])
+        self.cfg = c
+        nbytes = _C.lib().b2d_rpn_proposals_workspace_bytes(ctypes.byref(self.pyr.c), B, ctypes.byref(c))
+        if nbytes == 0:
+            raise _C.B200DetError("rpn_proposals: unsupported configuration (a level needs a pre-NMS top-k <= 16384)")
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        post = [(c.post_nms if 0 < c.post_nms < k else k) for k in
+                [(c.pre_nms if 0 < c.pre_nms < n else n) for n in pyramid.level_sizes]]
+        self.P = c.max_num if c.max_num > 0 else sum(post)
+        self.props = torch.zeros((B, 4, self.P), dtype=torch.float32, device=device)
+        self.scores = torch.zeros((B, self.P), dtype=torch.float32, device=device)
+        self.count = torch.zeros(B, dtype=torch.int32, device=device)
+        self.prov = torch.zeros((B, self.P), dtype=torch.int32, device=device)
+        self.launches = 7 if do_nms else 5   # memset, hist, compact, select, (mask, scan), merge
+
+    def __call__(self, cls_outs, reg_outs, img_hw):
+        _C.call("b2d_rpn_proposals", _C.ptr(self.props), _C.ptr(self.scores), _C.ptr(self.count), _C.ptr(self.prov),
+                _ptrs(cls_outs), _ptrs(reg_outs), ctypes.byref(self.pyr.c), _C.ptr(img_hw), self.B,
+                ctypes.byref(self.cfg), _C.ptr(self.ws), self.ws.numel(), _C.stream())
+        return self.props, self.scores, self.count
+
+
+class BatchedTargets(object):
+    """K2 + sampler + K8 over a batch, for anchors (pyramid mode) or proposals (+ GT prepend)."""
+
+    def __init__(self, B, n_boxes, gt_ld, assigner, sampler, means, stds, device, pyramid=None, border=0.0,
+                 prepend_gt=False, seed=0):
+        self.B, self.N, self.gt_ld, self.pyr = B, int(n_boxes), int(gt_ld), pyramid
+        self.pos_iou, self.neg_iou, self.min_pos = (np.float32(assigner[k]) for k in ("pos_iou", "neg_iou", "min_pos_iou"))
+        self.max_num, self.pos_num = int(sampler["max_num"]), int(sampler["pos_num"])
+        self.border, self.prepend, self.seed = float(border), int(bool(prepend_gt)), int(seed)
+        self.out_ld = self.N + (self.gt_ld if prepend_gt else 0)
+        i32, f32, i64 = torch.int32, torch.float32, torch.int64
+        self.labels = torch.empty((B, self.out_ld), dtype=i64, device=device)
+        self.iou = torch.empty((B, self.out_ld), dtype=f32, device=device)
+        self.census = torch.zeros((B, 4), dtype=i32, device=device)
+        self.pos_list = torch.empty((B, self.out_ld), dtype=i32, device=device)
+        self.colmax = torch.empty((B, self.gt_ld), dtype=i32, device=device)
+        self.chosen = torch.empty((B, self.max_num), dtype=i32, device=device)
+        self.n_chosen = torch.zeros(B, dtype=i32, device=device)
+        self.tar_box = torch.zeros((B, 4, self.max_num), dtype=f32, device=device)
+        self.tar_gt = torch.zeros((B, 4, self.max_num), dtype=f32, device=device)
+        self.tar_param = torch.zeros((B, 4, self.max_num), dtype=f32, device=device)
+        self.tar_label = torch.zeros((B, self.max_num), dtype=i64, device=device)
+        self.tar_is_gt = torch.zeros((B, self.max_num), dtype=i64, device=device)
+        self.means, self.stds = _C.host_f4(means, [0, 0, 0, 0]), _C.host_f4(stds, [1, 1, 1, 1])
+        self.step = 0
+        self.launches = 6   # fill, memset, colmax, label, sample, encode
+
+    def __call__(self, gt, gt_count, gt_label=None, boxes=None, box_count=None, img_hw=None):
+        pyr = ctypes.byref(self.pyr.c) if boxes is None else None
+        box_ld = boxes.shape[-1] if boxes is not None else 0
+        _C.call("b2d_assign_max_iou", _C.ptr(self.labels), _C.ptr(self.iou), self.out_ld, _C.ptr(boxes), box_ld,
+                _C.ptr(box_count), self.N, pyr, _C.ptr(img_hw), self.border, _C.ptr(gt), self.gt_ld, _C.ptr(gt_count),
+                self.B, float(self.pos_iou), float(self.neg_iou), float(self.min_pos), self.prepend,
+                _C.ptr(self.census), _C.ptr(self.pos_list), self.out_ld, _C.ptr(self.colmax), self.colmax.numel() * 4,
+                _C.stream())
+        self.step += 1
+        cnt, cnt_add = (box_count, gt_count) if (self.prepend and box_count is not None) else \
+            ((None, gt_count) if self.prepend else (box_count, None))
+        n = self.N if cnt is None else 0
+        _C.call("b2d_sample_labels", _C.ptr(self.chosen), _C.ptr(self.n_chosen), _C.ptr(self.labels), self.out_ld,
+                _C.ptr(cnt), _C.ptr(cnt_add), n, _C.ptr(self.census), _C.ptr(self.pos_list), self.out_ld, self.B,
+                self.max_num, self.pos_num, (self.seed * 1000003 + self.step) & 0xFFFFFFFFFFFFFFFF, _C.stream())
+        _C.call("b2d_encode_targets", _C.ptr(self.tar_box), _C.ptr(self.tar_gt), _C.ptr(self.tar_param),
+                _C.ptr(self.tar_label), _C.ptr(self.tar_is_gt), _C.ptr(self.chosen), _C.ptr(self.n_chosen),
+                self.max_num, _C.ptr(self.labels), self.out_ld, _C.ptr(boxes), box_ld, pyr, _C.ptr(gt), self.gt_ld,
+                _C.ptr(gt_count), _C.ptr(gt_label), self.prepend, self.means, self.stds, self.B, _C.stream())
+        return self
+
+
+class BatchedRoIAlign(object):
+    """K5 over a batch: rois [B,4,ld] + counts -> [B*ld, C, PH, PW] (image-major rows)."""
+
+    def __init__(self, B, ld, feat_shapes, strides, device, out_size=(7, 7), sampling_ratio=2, finest_scale=56,
+                 layout=1):
+        cfg = _C.RoiCfg()
+        cfg.num_levels, cfg.C = len(strides), int(feat_shapes[0][0])
+        cfg.PH, cfg.PW, cfg.sampling_ratio, cfg.aligned = int(out_size[0]), int(out_size[1]), int(sampling_ratio), 0
+        cfg.layout, cfg.finest_scale = int(layout), float(finest_scale)
+        for l, (s, shp) in enumerate(zip(strides, feat_shapes)):
+            cfg.H[l], cfg.W[l], cfg.spatial_scale[l] = int(shp[1]), int(shp[2]), 1.0 / float(s)
+        self.cfg, self.B, self.ld = cfg, B, ld
+        self.out = torch.zeros((B * ld, cfg.C, cfg.PH, cfg.PW), dtype=torch.float32, device=device)
+        self.launches = 1
+
+    def __call__(self, feats, rois, counts):
+        _C.call("b2d_roi_align_fwd_batched", _C.ptr(self.out), _ptrs(feats), _C.ptr(rois), self.ld, _C.ptr(counts),
+                self.B, ctypes.byref(self.cfg), _C.stream())
+        return self.out
+
+
+class TrainHotPath(object):
+    """faster_rcnn_r50_fpn train path (BASELINE config 2): RPN proposals (K3+K4), RPN
+    anchor targets (K2, sampler, K8, head-output gather), RoI targets on the proposals
+    (K2 + GT prepend, sampler, K8) and FPN RoIAlign of the sampled RoIs (K5).
+    Mirrors CascadeRCNN.forward_train lines 106-131 (lib/detectors/cascade_rcnn.py)
+    minus convolutions and losses."""
+
+    def __init__(self, B, grids, device, strides=(4, 8, 16, 32, 64), gt_ld=64, feat_channels=256,
+                 rpn_proposal=None, rpn_assigner=None, rpn_sampler=None, rcnn_assigner=None, rcnn_sampler=None,
+                 rpn_stds=(1.0, 1.0, 1.0, 1.0), rcnn_stds=(0.1, 0.1, 0.2, 0.2), allowed_border=0, layout=1, seed=0):
+        z4 = (0.0, 0.0, 0.0, 0.0)
+        rpn_proposal = rpn_proposal or dict(pre_nms=2000, post_nms=2000, max_num=2000, nms_iou=0.7, min_bbox_size=0)
+        rpn_assigner = rpn_assigner or dict(pos_iou=0.7, neg_iou=0.3, min_pos_iou=0.3)
+        rpn_sampler = rpn_sampler or dict(max_num=256, pos_num=128)
+        rcnn_assigner = rcnn_assigner or dict(pos_iou=0.5, neg_iou=0.5, min_pos_iou=0.5)
+        rcnn_sampler = rcnn_sampler or dict(max_num=512, pos_num=128)
+        self.B, self.device = B, device
+        self.pyr = AnchorPyramid(strides, grids)
+        self.proposals = RpnProposals(self.pyr, B, rpn_proposal, z4, rpn_stds, device)
+        self.rpn_targets = BatchedTargets(B, self.pyr.total, gt_ld, rpn_assigner, rpn_sampler, z4, rpn_stds, device,
+                                          pyramid=self.pyr, border=allowed_border, seed=seed)
+        self.roi_targets = BatchedTargets(B, self.proposals.P, gt_ld, rcnn_assigner, rcnn_sampler, z4, rcnn_stds,
+                                          device, prepend_gt=True, seed=seed + 1)
+        roi_strides = list(strides[:4])
+        shapes = [(feat_channels, g[0], g[1]) for g in grids[:4]]
+        self.roi_align = BatchedRoIAlign(B, rcnn_sampler["max_num"], shapes, roi_strides, device, layout=layout)
+        m = rpn_sampler["max_num"]
+        self.tar_cls = torch.zeros((B, 1, m), dtype=torch.float32, device=device)
+        self.tar_reg = torch.zeros((B, 4, m), dtype=torch.float32, device=device)
+        self.launches = self.proposals.launches + self.rpn_targets.launches + 1 + self.roi_targets.launches + 1
+
+    def step(self, cls_outs, reg_outs, feats, gt, gt_count, gt_label, img_hw):
+        props, scores, count = self.proposals(cls_outs, reg_outs, img_hw)
+        rt = self.rpn_targets(gt, gt_count, None, img_hw=img_hw)
+        _C.call("b2d_gather_head_outputs", _C.ptr(self.tar_cls), _C.ptr(self.tar_reg), _ptrs(cls_outs), _ptrs(reg_outs),
+                ctypes.byref(self.pyr.c), 1, _C.ptr(rt.chosen), _C.ptr(rt.n_chosen), rt.max_num, self.B, _C.stream())
+        bt = self.roi_targets(gt, gt_count, gt_label, boxes=props, box_count=count)
+        roi_feats = self.roi_align(feats, bt.tar_box, bt.n_chosen)
+        return dict(props=props, scores=scores, prop_count=count, rpn=rt, rpn_tar_cls=self.tar_cls,
+                    rpn_tar_reg=self.tar_reg, rcnn=bt, roi_feats=roi_feats)

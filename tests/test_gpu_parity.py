@@ -1,0 +1,437 @@
+"""Parity of the CUDA path (through the package -> ctypes -> C-ABI of libb200det.so)
+against (1) golden vectors produced by the unmodified reference and (2) the CPU oracle
+on seeded inputs.  Bit-exact for labels / indices / IoU / NMS / RoIAlign; 1e-5 relative
+(north_star) where expf/logf are involved.  GPU only."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import fold0, load_golden
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import b200det
+    from b200det import anchor as banchor, bbox as bbbox, region as bregion, utils as butils, fused, workload
+    DEV = torch.device("cuda:0")
+
+
+def T(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+# ------------------------------------------------------------------ K1 / a2
+def test_anchor_grid_bit_exact():
+    g = load_golden("anchors")
+    for i, m in enumerate(g["meta"]):
+        m = json.loads(str(m))
+        ac = banchor.AnchorCreator(base=m["stride"], scales=m["scales"], aspect_ratios=m["ratios"],
+                                   center_lt=m["center_lt"], device=DEV)
+        a = N(ac(m["stride"], tuple(m["grid"])))
+        assert np.array_equal(bits(a), bits(g["a%d" % i])), m
+        assert np.array_equal(N(ac.anchor_ws), g["ws%d" % i])
+    import hashlib
+    grids = [(200, 336), (100, 168), (50, 84), (25, 42), (13, 21)]
+    for l, (s, gr) in enumerate(zip([4, 8, 16, 32, 64], grids)):
+        a = N(banchor.AnchorCreator(base=s, scales=[8], device=DEV)(s, gr))
+        sha = np.frombuffer(hashlib.sha1(a.tobytes()).digest(), dtype=np.uint8)
+        assert np.array_equal(sha, g["full_sha%d" % l])
+
+
+def test_inside_masks():
+    g = load_golden("anchors")
+    a = banchor.AnchorCreator(base=64, scales=[8], device=DEV)(64, (13, 21)).view(4, -1)
+    assert np.array_equal(N(bregion.inside_anchor_mask(a, (800, 1333), 0)), g["mask_img_b0"])
+    assert np.array_equal(N(bregion.inside_anchor_mask(a, (800, 1333), 16)), g["mask_img_b16"])
+    assert N(bregion.inside_anchor_mask(a, (800, 1333), -1)).all()
+    assert np.array_equal(N(bregion.inside_grid_mask(3, (800, 1333), (13, 21), 64, DEV)), g["mask_grid"])
+    assert np.array_equal(N(bregion.inside_grid_mask(3, (500, 700), (13, 21), 64, DEV)), g["mask_grid_small"])
+
+
+# ------------------------------------------------------------------ a3 / K2
+def test_calc_iou_bit_exact():
+    g = load_golden("iou_assign")
+    iou = N(butils.calc_iou(T(g["boxes"]), T(g["gt"])))
+    assert np.array_equal(bits(iou), bits(g["iou"]))          # including -0.0
+    assert np.array_equal(N(butils.calc_iou(T(g["lit"]), T(g["lit"]))), g["lit_iou"])
+    assert np.array_equal(N(butils.elem_iou(T(g["boxes"][:, :8].copy()), T(g["gt"]))), g["elem_iou"])
+
+
+def test_assigner_bit_exact_vs_reference():
+    g = load_golden("iou_assign")
+    for i, c in enumerate(g["cfgs"]):
+        lab, iou = bregion.MaxIoUAssigner(*c)(T(g["boxes"]), T(g["gt"]))
+        assert np.array_equal(N(lab), g["labels%d" % i]), i
+        assert np.array_equal(bits(N(iou)), bits(g["miou%d" % i])), i
+    for i, mp in enumerate([0.0, 0.3]):
+        lab, iou = bregion.MaxIoUAssigner(0.5, 0.4, mp)(T(g["ex_boxes"]), T(g["ex_gt"]))
+        assert np.array_equal(N(lab), g["ex_labels%d" % i])
+        assert np.array_equal(fold0(N(iou)), fold0(g["ex_miou%d" % i]))
+    with pytest.raises(ValueError):
+        bregion.MaxIoUAssigner(0.7, 0.3, 0.3)(T(g["boxes"]), torch.zeros((4, 0), device=DEV))
+
+
+@pytest.mark.parametrize("K", [1, 3, 64, 700])
+def test_assigner_vs_oracle_many_gt(K):
+    rng = np.random.default_rng(K)
+    gt, _ = workload.synth_gt(rng, K, 800, 1333)
+    cx, cy = rng.uniform(0, 1333, 5000), rng.uniform(0, 800, 5000)
+    w, h = rng.uniform(8, 400, 5000), rng.uniform(8, 400, 5000)
+    boxes = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2]).astype(np.float32)
+    boxes[:, :K] = gt                                            # exact hits
+    for cfg in [(0.7, 0.3, 0.3), (0.5, 0.4, 0.0)]:
+        lab, iou = bregion.MaxIoUAssigner(*cfg)(T(boxes), T(gt))
+        olab, oiou = oracle.assign_max_iou(boxes, gt, *cfg)
+        assert np.array_equal(N(lab), olab)
+        assert np.array_equal(bits(N(iou)), bits(oiou))
+
+
+def test_assigner_full_size_fused_pyramid_config2():
+    """268 569 in-register anchors x 8 GT (BASELINE config 2) == reference labels."""
+    g = load_golden("assign_full")
+    grids = [(200, 336), (100, 168), (50, 84), (25, 42), (13, 21)]
+    pyr = fused.AnchorPyramid((4, 8, 16, 32, 64), grids)
+    mask = np.unpackbits(g["mask_packed"])[: int(g["n"])].astype(bool)
+    gt = torch.zeros((2, 4, 8), device=DEV)
+    gt[:] = T(g["gt"])
+    gcount = torch.full((2,), 8, dtype=torch.int32, device=DEV)
+    img_hw = torch.tensor([[800.0, 1333.0]] * 2, device=DEV)
+    for i, c in enumerate(g["cfgs"]):
+        bt = fused.BatchedTargets(2, pyr.total, 8, dict(pos_iou=c[0], neg_iou=c[1], min_pos_iou=c[2]),
+                                  dict(max_num=256, pos_num=128), [0, 0, 0, 0], [1, 1, 1, 1], DEV, pyramid=pyr,
+                                  border=0.0 if i == 0 else 0.0)
+        bt(gt, gcount, None, img_hw=img_hw)
+        for b in range(2):
+            lab = N(bt.labels[b])
+            assert (lab[~mask] == -1).all()
+            assert np.array_equal(lab[mask], g["labels%d" % i].astype(np.int64))
+            iou = N(bt.iou[b])[mask]
+            ref = np.zeros_like(iou)
+            ref[g["iou_nz_idx%d" % i]] = g["iou_nz_val%d" % i]
+            assert np.array_equal(fold0(iou), ref)
+            cen = N(bt.census[b])
+            assert cen[0] == (lab > 0).sum() and cen[1] == (lab == 0).sum()
+
+
+# ------------------------------------------------------------------ K8
+def test_deltas_vs_reference():
+    g = load_golden("deltas")
+    st, z = [0.1, 0.1, 0.2, 0.2], [0, 0, 0, 0]
+    base, bbox, param = T(g["base"]), T(g["bbox"]), T(g["param"])
+    np.testing.assert_allclose(N(butils.bbox2param(base, bbox)), g["enc_plain"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(N(butils.bbox2param(base, bbox, z, st)), g["enc_norm"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(N(butils.param2bbox(base, param)), g["dec_plain"], rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(N(butils.param2bbox(base, param, z, st, (800, 1333))), g["dec_norm_clamp"],
+                               rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(N(butils.param2bbox(base, param, [0.1, -0.1, 0.05, 0.0], [0.05, 0.05, 0.1, 0.1],
+                                                   (800, 1333, 3))), g["dec_clamp3"], rtol=1e-5, atol=1e-3)
+    rt = butils.param2bbox(base, butils.bbox2param(base, bbox))
+    np.testing.assert_allclose(N(rt), g["roundtrip"], rtol=1e-5, atol=1e-3)
+    bd = butils.batched_param2bbox(T(g["base"][:, :64].copy()), T(g["bparam"]), z, st, (800, 1333))
+    np.testing.assert_allclose(N(bd), g["bdec"], rtol=1e-5, atol=1e-3)
+    assert np.array_equal(N(butils.clamp_bbox(T(g["bbox"] - 100), (600, 1000))), g["clamp"])
+
+
+# ------------------------------------------------------------------ K4
+def test_nms_bit_exact_vs_torchvision():
+    g = load_golden("nms")
+    for thr in (0.7, 0.5, 0.3):
+        assert np.array_equal(N(butils.nms(T(g["b0"]), T(g["s0"]), thr)), g["keep0_%d" % int(thr * 10)])
+    for thr in (0.3, 0.7, 0.5, 0.0):
+        assert np.array_equal(N(butils.nms(T(g["b1"]), T(g["s1"]), thr)), g["keep1_%d" % int(thr * 10)]), thr
+    assert butils.nms(torch.zeros((0, 4), device=DEV), torch.zeros(0, device=DEV), 0.5).numel() == 0
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 2000, 6000])
+def test_nms_vs_oracle_sizes_and_idempotence(n):
+    rng = np.random.default_rng(n)
+    ctr = rng.uniform(0, 1000, (2, max(n // 30, 1)))
+    idx = rng.integers(0, ctr.shape[1], n)
+    c = ctr[:, idx] + rng.normal(0, 8, (2, n))
+    wh = rng.uniform(20, 200, (2, n))
+    b = np.concatenate([c - wh / 2, c + wh / 2]).T.astype(np.float32).copy()
+    s = rng.permutation(n).astype(np.float32)
+    for thr in (0.7, 0.5):
+        keep = N(butils.nms(T(b), T(s), thr))
+        assert np.array_equal(keep, oracle.nms(b, s, thr))
+        again = N(butils.nms(T(b[keep]), T(s[keep]), thr))       # NMS of its own output keeps everything
+        assert np.array_equal(again, np.arange(keep.size))
+
+
+def test_batched_and_multiclass_nms_vs_reference():
+    g = load_golden("nms")
+    kb, ks, kl = butils.batched_nms(T(g["bn_bbox"]), T(g["bn_score"][:, 0].copy()), T(g["bn_label"]), 0.5)
+    assert np.array_equal(N(kb), g["bn_kb"]) and np.array_equal(N(ks), g["bn_ks"]) and np.array_equal(N(kl), g["bn_kl"])
+    C = g["bn_score"].shape[1]
+    for mode in ("official", "strict"):
+        kb, ks, kl = butils.multiclass_nms(T(g["bn_bbox"]), T(g["bn_score"]), list(range(1, C)), 0.5, 0.05, 100, mode=mode)
+        assert np.array_equal(N(kb), g["mc_%s_b" % mode])
+        assert np.array_equal(N(ks), g["mc_%s_s" % mode]) and np.array_equal(N(kl), g["mc_%s_l" % mode])
+    kb, ks, kl = butils.multiclass_nms(T(g["mc_bbc"]), T(g["bn_score"]), list(range(1, C)), 0.5, 0.05, 50,
+                                       score_factor=T(g["mc_fac"]))
+    assert np.array_equal(N(kb), g["mc_pc_b"]) and np.array_equal(N(kl), g["mc_pc_l"])
+    np.testing.assert_allclose(N(ks), g["mc_pc_s"], rtol=1e-6)
+    kb, ks, kl = butils.multiclass_nms(T(g["mc_bbc"]), T(g["bn_score"]), list(range(1, C)), 0.5, 0.05, 50, mode="strict")
+    assert np.array_equal(N(kb), g["mc_pcs_b"]) and np.array_equal(N(kl), g["mc_pcs_l"])
+
+
+# ------------------------------------------------------------------ K3 (+K4)
+def _rpn_run(g, cfg, B=2):
+    grids = [(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)]
+    pyr = fused.AnchorPyramid((4, 8, 16, 32, 64), grids)
+    rp = fused.RpnProposals(pyr, B, cfg, [0, 0, 0, 0], [1, 1, 1, 1], DEV)
+    cls = [T(np.stack([g["cls%d" % l]] * B)) for l in range(5)]
+    reg = [T(np.stack([g["reg%d" % l]] * B)) for l in range(5)]
+    img_hw = torch.tensor([[float(g["img_shape"][0]), float(g["img_shape"][1])]] * B, device=DEV)
+    props, scores, count = rp(cls, reg, img_hw)
+    torch.cuda.synchronize()
+    return N(props), N(scores), N(count), N(rp.prov)
+
+
+def test_rpn_proposals_vs_reference():
+    g = load_golden("rpn")
+    for i, c in enumerate(g["cfgs"]):
+        c = json.loads(str(c))
+        props, scores, count, prov = _rpn_run(g, c)
+        ref_b, ref_s = g["props%d" % i], g["scores%d" % i]
+        for b in range(2):
+            n = int(count[b])
+            assert n == ref_b.shape[1], (i, n, ref_b.shape)
+            np.testing.assert_allclose(scores[b, :n], ref_s, rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(props[b, :, :n], ref_b, rtol=1e-5, atol=1e-3)
+
+
+def test_rpn_proposals_selection_bit_exact_vs_oracle():
+    g = load_golden("rpn")
+    grids = [(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)]
+    anc = [oracle.anchor_grid(s, gr, scales=[8]).reshape(4, -1) for s, gr in zip([4, 8, 16, 32, 64], grids)]
+    offs = np.cumsum([0] + [a.shape[1] for a in anc])
+    lg = [g["cls%d" % l].reshape(-1) for l in range(5)]
+    dl = [g["reg%d" % l].reshape(4, -1) for l in range(5)]
+    for i, c in enumerate(g["cfgs"]):
+        c = json.loads(str(c))
+        _, _, count, prov = _rpn_run(g, c, B=1)
+        _, _, lv, ix = oracle.rpn_proposals(lg, dl, anc, c, [0, 0, 0, 0], [1, 1, 1, 1], tuple(g["img_shape"][:2]))
+        assert np.array_equal(prov[0, :count[0]], offs[lv] + ix), i
+
+
+def test_topk_large_and_ties():
+    rng = np.random.default_rng(7)
+    v = rng.standard_normal(201600).astype(np.float32)
+    for k in (1, 2000, 12000):
+        assert np.array_equal(N(bregion.topk_desc(T(v), k)), oracle.topk_desc(v, k))
+    tied = np.zeros(50000, np.float32)                            # all equal -> lowest indices, in order
+    assert np.array_equal(N(bregion.topk_desc(T(tied), 3000)), np.arange(3000))
+    few = rng.integers(0, 5, 40000).astype(np.float32)            # heavy ties across the radix bins
+    assert np.array_equal(N(bregion.topk_desc(T(few), 9000)), oracle.topk_desc(few, 9000))
+    small = rng.standard_normal(1000).astype(np.float32)
+    assert np.array_equal(N(bregion.topk_desc(T(small), 2000)), oracle.topk_desc(small, 1000))
+
+
+def test_proposal_creator_legacy():
+    g = load_golden("rpn")
+    pb, ps = bregion.ProposalCreator(200, 50, 0.7, 4)(T(g["pc_cls"]), T(g["pc_reg"]), T(g["pc_anchor"]), (160, 213))
+    np.testing.assert_allclose(N(ps), g["pc_scores"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(pb), g["pc_props"], rtol=1e-5, atol=1e-3)
+
+
+# ------------------------------------------------------------------ K5 / K6 / K7
+def _roi_feats(g, channels_last):
+    fs = [T(g["feat%d" % l]) for l in range(4)]
+    if channels_last:
+        fs = [f.contiguous(memory_format=torch.channels_last) for f in fs]
+    return fs
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_roi_extractor_vs_reference(channels_last):
+    g = load_golden("roi")
+    ext = bregion.BasicRoIExtractor([dict(type="RoIAlign", spatial_scale=1 / s, sampling_ratio=2) for s in (4, 8, 16, 32)],
+                                    output_size=(7, 7))
+    fs = [f.requires_grad_(True) for f in _roi_feats(g, channels_last)]
+    rois = T(g["rois"])
+    assert np.array_equal(N(ext.map_rois_to_levels(rois, 4)), g["lvls"])
+    assert np.array_equal(N(ext.map_rois_to_levels(T(g["lm_boxes"]), 4)), g["lm_lvls"])
+    out = ext(fs, [rois])[0]
+    np.testing.assert_allclose(N(out), g["out"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(bits(N(out)), bits(g["out"])), "RoIAlign is expected to be bit-identical to the CPU reference"
+    (out * T(g["gout"])).sum().backward()
+    for l in range(4):
+        np.testing.assert_allclose(N(fs[l].grad), g["gfeat%d" % l], rtol=1e-4, atol=1e-5)
+
+
+def test_roi_align_variants_vs_torchvision():
+    g = load_golden("roi")
+    f1 = T(g["feat1"])
+    r5 = torch.cat([torch.zeros((96, 1), device=DEV), T(g["rois"]).t()], 1)
+    np.testing.assert_allclose(N(bregion.roi_align(f1, r5, (7, 7), 1 / 8, 0, False)), g["ra_adapt"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(N(bregion.roi_align(f1, r5, (5, 3), 1 / 8, 2, True)), g["ra_aligned"], rtol=1e-5, atol=1e-6)
+    fs = _roi_feats(g, False)
+    sre = bregion.SingleRoIExtractor("RoIAlign", 7, [4, 8, 16, 32])
+    np.testing.assert_allclose(N(sre(fs, [T(g["rois"])])[0]), g["single_out"], rtol=1e-5, atol=1e-6)
+    sra = bregion.ScalableRoIAlign(scale=1.5, output_size=(7, 7), spatial_scale=1 / 8, sampling_ratio=2)
+    np.testing.assert_allclose(N(sra(f1, r5)), g["scalable_out"], rtol=1e-5, atol=1e-6)
+
+
+def test_roi_align_bf16_nhwc_close():
+    g = load_golden("roi")
+    fs = [f.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for f in _roi_feats(g, False)]
+    out = bregion.roi_align_levels(fs, T(g["rois"]), None, [1 / 4, 1 / 8, 1 / 16, 1 / 32])
+    ref = oracle.roi_extract([N(f[0].float()) for f in fs], g["rois"])
+    np.testing.assert_allclose(N(out), ref, rtol=1e-5, atol=1e-6)      # same bf16-rounded inputs, fp32 math
+
+
+def test_roi_pool_vs_torchvision():
+    g = load_golden("roi")
+    ext = bregion.BasicRoIExtractor([dict(type="RoIPool", spatial_scale=1 / 16, sampling_ratio=2)], output_size=(7, 7))
+    f = T(g["feat2"]).requires_grad_(True)
+    out = ext([f], [T(g["rois"])])[0]
+    assert np.array_equal(N(out), g["pool_out"])
+    (out * T(g["gout"])).sum().backward()
+    np.testing.assert_allclose(N(f.grad), g["pool_gfeat"], rtol=1e-5, atol=1e-6)
+
+
+def test_roi_align_multi_image_batch_and_determinism():
+    rng = np.random.default_rng(3)
+    B, C = 3, 32
+    grids = [(40, 56), (20, 28), (10, 14), (5, 7)]
+    feats = [rng.standard_normal((B, C) + gsz).astype(np.float32) for gsz in grids]
+    rois = [np.sort(rng.uniform(0, 160, (2, 2, 40)), axis=1).reshape(4, 40)[[0, 2, 1, 3]].astype(np.float32) for _ in range(B)]
+    ext = bregion.BasicRoIExtractor([dict(type="RoIAlign", spatial_scale=1 / s, sampling_ratio=2) for s in (4, 8, 16, 32)])
+    fs = [T(f).contiguous(memory_format=torch.channels_last).requires_grad_(True) for f in feats]
+    outs = ext(fs, [T(r) for r in rois])
+    for b in range(B):
+        ref = oracle.roi_extract([f[b] for f in feats], rois[b])
+        assert np.array_equal(bits(N(outs[b])), bits(ref))
+    go = rng.standard_normal((B * 40, C, 7, 7)).astype(np.float32)
+    (torch.cat(outs) * T(go)).sum().backward()
+    g1 = [N(f.grad).copy() for f in fs]
+    lv = [oracle.level_map(r) for r in rois]
+    for l, s in enumerate((4, 8, 16, 32)):
+        for b in range(B):
+            m = lv[b] == l
+            ref = oracle.roi_align_bwd(go[b * 40:(b + 1) * 40][m], (C,) + grids[l], np.ascontiguousarray(rois[b][:, m]), 1.0 / s)
+            np.testing.assert_allclose(g1[l][b], ref, rtol=1e-4, atol=1e-5)
+    for f in fs:
+        f.grad = None
+    (torch.cat(ext(fs, [T(r) for r in rois])) * T(go)).sum().backward()
+    for l in range(4):
+        assert np.array_equal(bits(N(fs[l].grad)), bits(g1[l])), "backward must be run-to-run deterministic"
+
+
+# ------------------------------------------------------------------ a5 / a6 / a13
+def test_targets_numpy_rng_mode_vs_reference():
+    g = load_golden("targets")
+    grids = [(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)]
+    H, W = 160, 213
+    acs = [banchor.AnchorCreator(base=s, scales=[8], device=DEV) for s in (4, 8, 16, 32, 64)]
+    anchors = torch.cat([ac(s, gr).view(4, -1) for ac, s, gr in zip(acs, (4, 8, 16, 32, 64), grids)], 1)
+    in_mask = bregion.inside_anchor_mask(anchors, (H, W), 0) & torch.cat(
+        [bregion.inside_grid_mask(3, (H, W), gr, s, DEV) for gr, s in zip(grids, (4, 8, 16, 32, 64))]).bool()
+    cls = torch.cat([T(g["cls%d" % l][0]).view(1, -1) for l in range(5)], 1)
+    reg = torch.cat([T(g["reg%d" % l][0]).view(4, -1) for l in range(5)], 1)
+    np.random.seed(2019)
+    r = banchor.anchor_target(cls, reg, 1, anchors[:, in_mask], in_mask, T(g["gt"]), None,
+                              dict(type="MaxIoUAssigner", pos_iou=0.7, neg_iou=0.3, min_pos_iou=0.3),
+                              bregion.RandomSampler(64, 32, rng="numpy"), [0, 0, 0, 0], [1, 1, 1, 1])
+    assert np.array_equal(N(r[0]), g["at_cls"]) and np.array_equal(N(r[1]), g["at_reg"])
+    assert np.array_equal(N(r[2]), g["at_lab"])
+    np.testing.assert_allclose(N(r[5]), g["at_par"], rtol=1e-5, atol=1e-6)
+    allm = torch.ones_like(in_mask)
+    grid_only = torch.cat([bregion.inside_grid_mask(3, (H, W), gr, s, DEV) for gr, s in zip(grids, (4, 8, 16, 32, 64))]).bool()
+    r2 = banchor.anchor_target(cls, reg, 1, anchors[:, grid_only & allm], grid_only, T(g["gt"]), T(g["gl"]),
+                               dict(type="MaxIoUAssigner", pos_iou=0.5, neg_iou=0.4, min_pos_iou=0.0), None,
+                               [0, 0, 0, 0], [1, 1, 1, 1])
+    assert np.array_equal(N(r2[2]), g["at2_lab"]) and np.array_equal(N(r2[0]), g["at2_cls"])
+    np.testing.assert_allclose(N(r2[5]), g["at2_par"], rtol=1e-5, atol=1e-6)
+    np.random.seed(2019)
+    r3 = bbbox.bbox_target(T(g["props"]), T(g["gt"]), T(g["gl"]),
+                           dict(type="MaxIoUAssigner", pos_iou=0.5, neg_iou=0.5, min_pos_iou=0.5),
+                           bregion.RandomSampler(128, 32, rng="numpy"), (0., 0., 0., 0.), (0.1, 0.1, 0.2, 0.2))
+    assert np.array_equal(N(r3[0]), g["bt_props"]) and np.array_equal(N(r3[1]), g["bt_bbox"])
+    assert np.array_equal(N(r3[2]), g["bt_label"]) and np.array_equal(N(r3[4]), g["bt_isgt"])
+    np.testing.assert_allclose(N(r3[3]), g["bt_param"], rtol=1e-5, atol=1e-5)
+    np.random.seed(2019)
+    assert np.array_equal(N(bregion.RandomSampler(256, 64, rng="numpy")(T(g["rs_in"]))), g["rs_out"])
+    np.random.seed(2019)
+    assert np.array_equal(N(bregion.IoUBalancedNegSampler(256, 64)(T(g["rs_in"]), T(g["ib_iou"]), None, None)), g["ib_out"])
+
+
+@pytest.mark.parametrize("n,max_num,pos_num", [(3000, 256, 64), (3000, 256, 2000), (100, 256, 128), (20000, 512, 128)])
+def test_device_sampler_matches_its_spec_and_properties(n, max_num, pos_num):
+    from oracle import sampler_spec
+    rng = np.random.default_rng(n + max_num)
+    labels = rng.choice([-1, 0, 0, 0, 1, 2, 3], n).astype(np.int64)
+    pos_num = min(pos_num, max_num)
+    s = bregion.RandomSampler(max_num, pos_num, rng="device", seed=5)
+    out = N(s(T(labels)))
+    chosen = np.nonzero(out >= 0)[0]
+    spec = sampler_spec.sample(labels, max_num, pos_num, (5 * 1000003 + 1) & ((1 << 64) - 1))
+    assert np.array_equal(chosen, spec)
+    assert np.array_equal(out[chosen], labels[chosen]) and (labels[chosen] >= 0).all()
+    npos, nneg = (labels > 0).sum(), (labels == 0).sum()
+    kp = min(npos, pos_num)
+    assert (out > 0).sum() == kp and (out == 0).sum() == min(max_num - kp, nneg)
+    out2 = N(bregion.RandomSampler(max_num, pos_num, rng="device", seed=5)(T(labels)))
+    assert np.array_equal(out, out2)
+
+
+# ------------------------------------------------------------------ fused train path vs oracle
+def test_fused_train_path_small_vs_oracle():
+    import __graft_entry__
+    __graft_entry__.smoke()
+
+
+def test_fused_train_path_full_size_properties():
+    """BASELINE config 2 sizes (B=2 here): size-independent properties + stage-wise oracle checks."""
+    B, K = 2, 8
+    w = workload.config2(B=B, K=K, channels=32)
+    hp = fused.TrainHotPath(B, w["grids"], DEV, gt_ld=K, feat_channels=32)
+    cls, reg = [T(c) for c in w["cls"]], [T(r) for r in w["reg"]]
+    feats = [T(f).contiguous(memory_format=torch.channels_last) for f in w["feats"]]
+    gt, gl = T(w["gt"]), T(w["gt_label"])
+    gcount = torch.full((B,), K, dtype=torch.int32, device=DEV)
+    img_hw = torch.tensor([[800.0, 1333.0]] * B, device=DEV)
+    out = hp.step(cls, reg, feats, gt, gcount, gl, img_hw)
+    torch.cuda.synchronize()
+    for b in range(B):
+        n = int(out["prop_count"][b])
+        assert n == 2000
+        sc = N(out["scores"][b, :n])
+        assert (np.diff(sc) <= 0).all()                              # global top-k is score-descending
+        pb = N(out["props"][b, :, :n])
+        assert (pb[0] >= 0).all() and (pb[2] <= 1332).all() and (pb[1] >= 0).all() and (pb[3] <= 799).all()
+        # RPN targets: counts and label/param consistency
+        rt = out["rpn"]
+        m = int(rt.n_chosen[b])
+        ch = N(rt.chosen[b, :m])
+        assert m == 256 and (np.diff(ch) > 0).all()
+        lab = N(rt.labels[b])
+        assert (lab[ch] >= 0).all() and (lab[ch] > 0).sum() <= 128
+        assert np.array_equal(N(rt.tar_label[b, :m]), (lab[ch] > 0).astype(np.int64))
+        enc = oracle.bbox2param(N(rt.tar_box[b, :, :m]), N(rt.tar_gt[b, :, :m]))
+        np.testing.assert_allclose(N(rt.tar_param[b, :, :m]), enc, rtol=1e-5, atol=1e-6)
+        flat_cls = np.concatenate([c[b].reshape(-1) for c in w["cls"]])
+        assert np.array_equal(N(out["rpn_tar_cls"][b, 0, :m]), flat_cls[ch])
+        # RoI targets: assignment of the GPU's own proposals == oracle; GT rows first
+        bt = out["rcnn"]
+        olab, oiou = oracle.assign_max_iou(pb, w["gt"][b], 0.5, 0.5, 0.5)
+        assert np.array_equal(N(bt.labels[b, K:K + n]), olab)
+        assert np.array_equal(N(bt.labels[b, :K]), np.arange(1, K + 1))
+        mm = int(bt.n_chosen[b])
+        assert mm == 512 and N(bt.tar_is_gt[b, :mm]).sum() <= K
+        rois = N(bt.tar_box[b, :, :mm])
+        ref = oracle.roi_extract([f[b] for f in w["feats"]], rois)
+        assert np.array_equal(bits(N(out["roi_feats"][b * 512:b * 512 + mm])), bits(ref))
