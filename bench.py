@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of RPN proposal + target assignment + RoIAlign, R50-FPN at
+800x1333 (BASELINE.json metric, config faster_rcnn_r50_fpn, train path).
+
+  python bench.py --gpus N --steps K --warmup W              # B200 kernels
+  python bench.py --impl reference --gpus N --steps K ...    # CPU reference arm (oracle port)
+
+One step = one pass of the hot path over a batch of 8 images per GPU (weak scaling):
+proposals (K3+K4) -> RPN anchor targets (K2, sampler, K8, head gather) -> RoI targets
+(K2 + GT prepend, sampler, K8) -> FPN RoIAlign of the 512 sampled RoIs/image (K5).
+Inputs are synthetic, 755 MB per step and GPU, i.e. larger than the
+126 MB L2, so no explicit flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+IMGS_PER_GPU = 8
+K_GT = 8
+METRIC = "images/sec of RPN proposal+assign+RoIAlign, R50-FPN 800x1333"
+WORKLOAD = "faster_rcnn_r50_fpn train path: batch 8/GPU at 800x1333 (pad 800x1344), 268569 anchors x 8 GT, " \
+           "2000 proposals/img, 256 RPN + 512 RCNN samples, RoIAlign 7x7x256 on 512 RoIs/img"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+        self.q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def touched_cell_bytes(rois_b4n, counts, grids, strides, C, finest=56.0):
+    """Bytes of distinct feature cells the bilinear taps of these RoIs touch (per-image union),
+    the input term of the RoIAlign algorithmic traffic, fp32."""
+    total = 0
+    for b in range(rois_b4n.shape[0]):
+        r = rois_b4n[b][:, :counts[b]].astype(np.float32)
+        s = np.sqrt((r[2] - r[0] + 1) * (r[3] - r[1] + 1))
+        lv = np.clip(np.floor(np.log2(s / finest + 1e-6)), 0, 3).astype(int)
+        for l in range(4):
+            H, W = grids[l]
+            m = np.zeros((H, W), bool)
+            rr = r[:, lv == l] / strides[l]
+            if rr.shape[1] == 0:
+                continue
+            x0, y0 = rr[0], rr[1]
+            rw, rh = np.maximum(rr[2] - x0, 1), np.maximum(rr[3] - y0, 1)
+            k = (np.arange(14) + 0.5) / 14.0
+            xs = np.clip(x0[:, None] + rw[:, None] * k[None], 0, W - 1)     # [n,14]
+            ys = np.clip(y0[:, None] + rh[:, None] * k[None], 0, H - 1)
+            xl, yl = np.floor(xs).astype(int), np.floor(ys).astype(int)
+            xh, yh = np.minimum(xl + 1, W - 1), np.minimum(yl + 1, H - 1)
+            for yy in (yl, yh):
+                for xx in (xl, xh):
+                    m[yy[:, :, None], xx[:, None, :]] = True
+            total += int(m.sum()) * C * 4
+    return total
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's CPU implementation of the path, timed on the host cores: the oracle
+    port (the Python reference itself does not travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from oracle import pipeline as opipe
+    from b200det import workload  # host-side input generator only
+    oracle.set_num_threads(os.cpu_count())
+    cores = oracle.num_threads()
+    w = workload.config2(B=1, K=K_GT)
+    path = opipe.ImagePath(w["grids"], w["strides"], w["img_shape"])
+    imgs = 1
+    args_img = ([c[0] for c in w["cls"]], [r[0] for r in w["reg"]], [f[0] for f in w["feats"]], w["gt"][0], w["gt_label"][0])
+    for _ in range(max(args.warmup, 1)):
+        path.run(*args_img)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        path.run(*args_img, seed=i)
+    dt = time.perf_counter() - t0
+    val = imgs * args.steps / dt
+    sample = "1 image per step (of the 8-image batch), %d steps; C port of the reference path with OpenMP" % args.steps
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# --------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import b200det
+    from b200det import _C, fused, workload
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _C.lib()
+    B = IMGS_PER_GPU
+    w = workload.config2(B=B, K=K_GT, seed=workload.SEED + rank)
+    grids, strides = w["grids"], w["strides"]
+    host = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_cls, h_reg, h_feat = [host(c) for c in w["cls"]], [host(r) for r in w["reg"]], [host(f) for f in w["feats"]]
+    h_gt, h_gl = host(w["gt"]), host(w["gt_label"])
+    cls, reg = [t.to(dev) for t in h_cls], [t.to(dev) for t in h_reg]
+    feats_nchw = [t.to(dev) for t in h_feat]
+    feats = [f.contiguous(memory_format=torch.channels_last) for f in feats_nchw]     # B200-native layout (NHWC)
+    gt, gl = h_gt.to(dev), h_gl.to(dev)
+    gcount = torch.full((B,), K_GT, dtype=torch.int32, device=dev)
+    img_hw = torch.tensor([[float(w["img_shape"][0]), float(w["img_shape"][1])]] * B, device=dev)
+    hp = fused.TrainHotPath(B, grids, dev, gt_ld=K_GT, feat_channels=256, layout=1)
+    hp_e2e = fused.TrainHotPath(B, grids, dev, gt_ld=K_GT, feat_channels=256, layout=0)  # NCHW, as the reference hands it over
+
+    def step():
+        return hp.step(cls, reg, feats, gt, gcount, gl, img_hw)
+
+    # warm-up (also sets the kernel attributes before graph capture)
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    torch.cuda.synchronize()
+    graph = None
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                out = step()
+        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        if graph is not None:
+            graph.replay()
+        else:
+            step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # ---- per-stage device times (eager, CUDA events on the launching stream)
+    stages = ["proposals", "rpn_targets", "roi_targets", "roi_align"]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    for it in range(args.steps):
+        ev = evs[it]
+        ev[0].record()
+        props, scores, count = hp.proposals(cls, reg, img_hw)
+        ev[1].record()
+        rt = hp.rpn_targets(gt, gcount, None, img_hw=img_hw)
+        _C.call("b2d_gather_head_outputs", _C.ptr(hp.tar_cls), _C.ptr(hp.tar_reg), fused._ptrs(cls), fused._ptrs(reg),
+                __import__("ctypes").byref(hp.pyr.c), 1, _C.ptr(rt.chosen), _C.ptr(rt.n_chosen), rt.max_num, B, _C.stream())
+        ev[2].record()
+        bt = hp.roi_targets(gt, gcount, gl, boxes=props, box_count=count)
+        ev[3].record()
+        hp.roi_align(feats, bt.tar_box, bt.n_chosen)
+        ev[4].record()
+    torch.cuda.synchronize()
+    stage_ms = {s: float(np.mean([evs[it][i].elapsed_time(evs[it][i + 1]) for it in range(args.steps)]))
+                for i, s in enumerate(stages)}
+    # ---- end-to-end through the public API with HOST buffers (NCHW fp32, reference layout)
+    d_cls, d_reg = [torch.empty_like(t) for t in cls], [torch.empty_like(t) for t in reg]
+    d_feat = [torch.empty_like(t) for t in feats_nchw]
+    d_gt, d_gl = torch.empty_like(gt), torch.empty_like(gl)
+    o = hp_e2e
+    h_out = dict(props=torch.empty((B, 4, o.proposals.P)).pin_memory(), scores=torch.empty((B, o.proposals.P)).pin_memory(),
+                 count=torch.empty(B, dtype=torch.int32).pin_memory(),
+                 rpn_lab=torch.empty((B, 256), dtype=torch.int64).pin_memory(), rpn_par=torch.empty((B, 4, 256)).pin_memory(),
+                 roi_lab=torch.empty((B, 512), dtype=torch.int64).pin_memory(), roi_par=torch.empty((B, 4, 512)).pin_memory(),
+                 roi_sum=torch.empty(1).pin_memory())
+    h2d = sum(t.numel() * t.element_size() for t in h_cls + h_reg + h_feat + [h_gt, h_gl])
+    d2h = sum(t.numel() * t.element_size() for t in h_out.values())
+
+    def e2e_step():
+        for d, h in zip(d_cls + d_reg + d_feat + [d_gt, d_gl], h_cls + h_reg + h_feat + [h_gt, h_gl]):
+            d.copy_(h, non_blocking=True)
+        r = o.step(d_cls, d_reg, d_feat, d_gt, gcount, d_gl, img_hw)
+        h_out["props"].copy_(r["props"], non_blocking=True); h_out["scores"].copy_(r["scores"], non_blocking=True)
+        h_out["count"].copy_(r["prop_count"], non_blocking=True)
+        h_out["rpn_lab"].copy_(r["rpn"].tar_label, non_blocking=True); h_out["rpn_par"].copy_(r["rpn"].tar_param, non_blocking=True)
+        h_out["roi_lab"].copy_(r["rcnn"].tar_label, non_blocking=True); h_out["roi_par"].copy_(r["rcnn"].tar_param, non_blocking=True)
+        h_out["roi_sum"].copy_(r["roi_feats"][0, 0, 0, :1], non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    n_e2e = max(3, min(args.steps, 10))
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(n_e2e):
+        e2e_step()
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1) / n_e2e
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    # ---- reduce over ranks (max time)
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    total_imgs = B * world
+    value = total_imgs * args.steps / (ms / 1e3)
+    e2e_val = total_imgs / (e2e_ms / 1e3)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        bt = out["rcnn"]
+        counts = bt.n_chosen.cpu().numpy()
+        rois = bt.tar_box.cpu().numpy()
+        C = 256
+        in_bytes = touched_cell_bytes(rois, counts, grids[:4], strides[:4], C)
+        out_bytes = int(counts.sum()) * C * 49 * 4
+        roi_bytes = in_bytes + out_bytes + int(counts.sum()) * 16
+        dom = max(stage_ms, key=stage_ms.get)
+        # per-step algorithmic bytes of every stage, batch of 8
+        n_anchor = hp.pyr.total
+        stage_bytes = {
+            "proposals": B * (n_anchor * 4 + (4 * 2000 + 819) * 16 + 2000 * 20),
+            "rpn_targets": B * (n_anchor * 12 + 256 * 36),
+            "roi_targets": B * (2008 * 12 + 2000 * 16 + 512 * 44),
+            "roi_align": roi_bytes,
+        }
+        ach = stage_bytes[dom] / (stage_ms[dom] / 1e3) / 1e9
+        path_bytes = sum(stage_bytes.values())
+        roofline = {"bound": "hbm", "kernel": {"roi_align": "k_roi_align_nhwc<float>", "proposals": "k_hist..k_merge (K3+K4)",
+                                               "rpn_targets": "k_assign_colmax/label (K2)", "roi_targets": "k_assign (K2)"}[dom],
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": stage_bytes[dom],
+                    "stage_ms": stage_ms, "stage_algorithmic_bytes": stage_bytes,
+                    "path_frac": (path_bytes / ((ms / args.steps) / 1e3) / 1e9) / peak}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            import oracle
+            from oracle import pipeline as opipe
+            oracle.set_num_threads(os.cpu_count())
+            path = opipe.ImagePath(grids, strides, w["img_shape"])
+            a = ([c[0] for c in w["cls"]], [r[0] for r in w["reg"]], [f[0] for f in w["feats"]], w["gt"][0], w["gt_label"][0])
+            path.run(*a)
+            t0, n = time.perf_counter(), 0
+            while n < 3 or (time.perf_counter() - t0 < 10 and n < 40):
+                path.run(*a, seed=n)
+                n += 1
+            dt = time.perf_counter() - t0
+            cpu = {"value": n / dt, "unit": "images/s", "cores": oracle.num_threads(), "kind": "port",
+                   "sample": "image 0 of the batch, %d repetitions (%.1f s); C port of the reference path, OpenMP" % (n, dt)}
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "global_batch": total_imgs, "parallelism": "per-image partition, dp%d" % world,
+                                            "features": "fp32 NHWC (channels_last) resident in HBM", "cuda_graph": graph is not None,
+                                            "l2": "inputs per step (755 MB/GPU) exceed the 126 MB L2; no flush needed"},
+            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "layout": "host fp32 NCHW (reference layout) -> H2D -> NCHW kernels"},
+            "gpu_launches": hp.launches * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
