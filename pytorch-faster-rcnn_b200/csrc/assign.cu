@@ -34,7 +34,7 @@ __device__ __forceinline__ void grid_limits(const b2d_level& lv, float img_h, fl
 
 // Fetch box i of image b (explicit or generated); returns false if it is masked out.
 __device__ __forceinline__ bool load_box(const AssignArgs& p, const b2d_pyramid& pyr, int b, long long i,
-                                         long long n_b, Box& bx) {
+                                         long long n_b, Box& bx, const int* __restrict__ s_lim) {
     if (i >= n_b) return false;
     if (!p.use_pyr) {
         const float* src = p.boxes + (long long)b * 4 * p.box_ld;
@@ -52,9 +52,7 @@ __device__ __forceinline__ bool load_box(const AssignArgs& p, const b2d_pyramid&
     const int y = r / lv.W, x = r - y * lv.W;
     bx = anchor_at(lv, a, y, x);
     const float img_h = p.img_hw[2 * b], img_w = p.img_hw[2 * b + 1];
-    int in_h, in_w;
-    grid_limits(lv, img_h, img_w, in_h, in_w);
-    bool ok = (y < in_h) && (x < in_w);
+    bool ok = (y < s_lim[2 * l]) && (x < s_lim[2 * l + 1]);
     if (p.border >= 0.0f)
         ok = ok && bx.x1 >= -p.border && bx.y1 >= -p.border && bx.x2 < img_w + p.border && bx.y2 < img_h + p.border;
     return ok;
@@ -70,6 +68,10 @@ __global__ void __launch_bounds__(256) k_assign_colmax(AssignArgs p, b2d_pyramid
     const long long n_b = p.box_count ? (long long)p.box_count[b] : p.N;
     const float* g = p.gt + (long long)b * 4 * p.gt_ld;
     const uint32_t kNegInf = f2key(-INFINITY);
+    __shared__ int s_lim[2 * kMaxLevels];
+    if (p.use_pyr && threadIdx.x < pyr.num_levels)     // fp64 once per (block, level), not per box
+        grid_limits(pyr.lv[threadIdx.x], p.img_hw[2 * b], p.img_hw[2 * b + 1], s_lim[2 * threadIdx.x], s_lim[2 * threadIdx.x + 1]);
+    __syncthreads();
 
     Box bx[kBoxesPerThread];
     float ba[kBoxesPerThread];
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(256) k_assign_colmax(AssignArgs p, b2d_pyramid
     const long long base = ((long long)blockIdx.x * blockDim.x) * kBoxesPerThread + threadIdx.x;
 #pragma unroll
     for (int r = 0; r < kBoxesPerThread; ++r) {
-        ok[r] = load_box(p, pyr, b, base + (long long)r * blockDim.x, n_b, bx[r]);
+        ok[r] = load_box(p, pyr, b, base + (long long)r * blockDim.x, n_b, bx[r], s_lim);
         ba[r] = ok[r] ? area_plus1(bx[r]) : 0.0f;
     }
     for (int j0 = 0; j0 < K; j0 += kGtChunk) {
@@ -125,6 +127,10 @@ __global__ void __launch_bounds__(256) k_assign_label(AssignArgs p, b2d_pyramid 
     const float* g = p.gt + (long long)b * 4 * p.gt_ld;
     const int lead = p.prepend_gt ? K : 0;
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __shared__ int s_lim[2 * kMaxLevels];
+    if (p.use_pyr && threadIdx.x < pyr.num_levels)
+        grid_limits(pyr.lv[threadIdx.x], p.img_hw[2 * b], p.img_hw[2 * b + 1], s_lim[2 * threadIdx.x], s_lim[2 * threadIdx.x + 1]);
+    __syncthreads();
 
     Box bx[kBoxesPerThread];
     float ba[kBoxesPerThread], best[kBoxesPerThread], veq[kBoxesPerThread];
@@ -133,7 +139,7 @@ __global__ void __launch_bounds__(256) k_assign_label(AssignArgs p, b2d_pyramid 
     const long long base = ((long long)blockIdx.x * blockDim.x) * kBoxesPerThread + threadIdx.x;
 #pragma unroll
     for (int r = 0; r < kBoxesPerThread; ++r) {
-        ok[r] = load_box(p, pyr, b, base + (long long)r * blockDim.x, n_b, bx[r]);
+        ok[r] = load_box(p, pyr, b, base + (long long)r * blockDim.x, n_b, bx[r], s_lim);
         ba[r] = ok[r] ? area_plus1(bx[r]) : 0.0f;
         best[r] = 0.0f; veq[r] = 0.0f; arg[r] = 0; eq[r] = -1;
     }

@@ -29,25 +29,38 @@ struct NmsSegs {
     const float4* boxes;                // score-sorted boxes
     const int* counts;                  // int[S]
     uint64_t* mask;
-    float thr;
+    float thr, thr_lo, thr_hi;          // thr_lo/hi: decisive bounds that avoid the divide (see suppresses)
 };
 
-__device__ __forceinline__ bool suppresses(const float4& a, float aa, const float4& b, float ab, float thr) {
+// (double)iou > thr with iou = inter / ((aa + ab) - inter), evaluated exactly like the
+// reference.  The IEEE divide is only executed inside the narrow band |iou/thr - 1| <
+// 2^-18 where the cheap products cannot decide; outside it the sign of
+// inter - thr*u already determines fl(inter/u) > thr (margin >> half an ulp).
+__device__ __forceinline__ bool suppresses(const float4& a, float aa, const float4& b, float ab, float thr,
+                                           float thr_lo, float thr_hi) {
     const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
     const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
     const float w = fmaxf(0.0f, xx2 - xx1), h = fmaxf(0.0f, yy2 - yy1);
     const float inter = w * h;
     if (inter == 0.0f && thr >= 0.0f) return false;      // 0/u is 0 or NaN: never > thr
-    const float ovr = inter / ((aa + ab) - inter);
-    return ovr > thr;
+    const float u = (aa + ab) - inter;
+    if (thr > 0.0f && u > 0.0f && u < 3.0e38f) {
+        if (inter > thr_hi * u) return true;
+        if (inter < thr_lo * u) return false;
+    }
+    return inter / u > thr;
 }
 
+// Tile (rb, cb), cb >= rb, of the 64x64-blocked suppression matrix.  Off-diagonal tiles
+// hold bit j of row i iff box i suppresses box j (j > i always).  DIAGONAL tiles hold the
+// full symmetric relation (bit j set iff i != j and IoU(i,j) > thr): the scan needs, for a
+// box j, the set of *earlier* boxes that suppress it, which by symmetry of the IoU
+// arithmetic is (word_j & lower_bits(j)).
 __global__ void __launch_bounds__(64) k_nms_mask(NmsSegs s, int wmax) {
     __shared__ float4 s_row[64];
     const int seg = blockIdx.y;
     const int l = seg % s.L, b = seg / s.L;
     const int n = s.counts[seg];
-    // decode the upper-triangular tile index
     int t = blockIdx.x, rb = 0;
     while (t >= wmax - rb) { t -= wmax - rb; ++rb; }
     const int cb = rb + t;
@@ -69,8 +82,8 @@ __global__ void __launch_bounds__(64) k_nms_mask(NmsSegs s, int wmax) {
         const int i = r0 + w * 32 + rr;
         const float4 rbx = s_row[w * 32 + rr];
         const float ra = (rbx.z - rbx.x) * (rbx.w - rbx.y);
-        const bool p0 = (j0 < n) && (j0 > i) && suppresses(rbx, ra, cb0, a0, s.thr);
-        const bool p1 = (j1 < n) && (j1 > i) && suppresses(rbx, ra, cb1, a1, s.thr);
+        const bool p0 = (j0 < n) && (j0 != i) && suppresses(rbx, ra, cb0, a0, s.thr, s.thr_lo, s.thr_hi);
+        const bool p1 = (j1 < n) && (j1 != i) && suppresses(rbx, ra, cb1, a1, s.thr, s.thr_lo, s.thr_hi);
         const unsigned lo = __ballot_sync(0xffffffffu, p0), hi = __ballot_sync(0xffffffffu, p1);
         if (lane == rr) myword = ((uint64_t)hi << 32) | lo;
     }
@@ -78,12 +91,23 @@ __global__ void __launch_bounds__(64) k_nms_mask(NmsSegs s, int wmax) {
     if (lane < rows) mask[(long long)row * wp + cb] = myword;
 }
 
-// mode 0: write positions into keep_pos (RPN pipeline); mode 1: write int64 original indices.
-__global__ void __launch_bounds__(256) k_nms_scan(NmsSegs s, int max_keep, int* __restrict__ keep_pos,
-                                                  int* __restrict__ keep_count, int64_t* __restrict__ keep64,
-                                                  const int* __restrict__ sorted_idx, long long keep_ld) {
+// One block (256 threads) per segment.  Per 64-box chunk c:
+//   resolve  warp 0 finds the kept boxes of the chunk as the unique fixed point of
+//            kept_j = alive_j & !(any kept i < j suppresses j), iterated with two ballots
+//            per round (bit j is final after all lower bits are; typically 2-5 rounds)
+//   update   thread w ORs the rows of the kept boxes into its word w > c of the removed-set
+// STAGE (W <= 32, the RPN case): the 64 x W words of chunk c+1 are prefetched into
+// registers by all 256 threads while chunk c is processed, then parked in shared memory, so
+// no global-memory latency sits on the serial chain.  Latency-bound by design.
+constexpr int kScanThreads = 256;
+
+template <bool STAGE>
+__global__ void __launch_bounds__(kScanThreads) k_nms_scan(NmsSegs s, int max_keep, int* __restrict__ keep_pos,
+                                                           int* __restrict__ keep_count, int64_t* __restrict__ keep64,
+                                                           const int* __restrict__ sorted_idx, long long keep_ld) {
     __shared__ uint64_t s_removed[kSortCap / 64];
     __shared__ uint64_t s_keepw[kSortCap / 64];
+    __shared__ uint64_t s_rows[STAGE ? 2 * 64 * 32 : 1];
     __shared__ uint64_t s_keep;
     const int seg = blockIdx.x;
     const int l = seg % s.L, b = seg / s.L;
@@ -97,27 +121,46 @@ __global__ void __launch_bounds__(256) k_nms_scan(NmsSegs s, int max_keep, int* 
         if (w == W - 1 && (n & 63)) r = ~0ull << (n & 63);   // rows past n are "removed"
         s_removed[w] = r; s_keepw[w] = 0;
     }
+    // staging geometry: thread t owns row (t >> 2) of the chunk and words [(t & 3) * 8, +8)
+    const int srow = threadIdx.x >> 2, sw0 = (threadIdx.x & 3) * 8;
+    uint64_t pre[8];
+    auto prefetch = [&](int c) {
+        const int row = c * 64 + srow;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int w = sw0 + q;
+            pre[q] = (row < n && w > c && w < W) ? mask[(long long)row * wp + w] : 0ull;
+        }
+    };
+    auto park = [&](int c) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s_rows[((c & 1) * 64 + srow) * 32 + sw0 + q] = pre[q];
+    };
+    uint64_t nd0 = 0, nd1 = 0;                       // diagonal words of the next chunk (warp 0)
+    auto load_diag = [&](int c) {
+        const int row0 = c * 64 + lane, row1 = row0 + 32;
+        nd0 = (c < W && row0 < n) ? mask[(long long)row0 * wp + c] : 0ull;
+        nd1 = (c < W && row1 < n) ? mask[(long long)row1 * wp + c] : 0ull;
+    };
+    if (STAGE) { prefetch(0); park(0); }
+    if (threadIdx.x < 32) load_diag(0);
     __syncthreads();
     int kept_total = 0;
     for (int c = 0; c < W; ++c) {
+        if (STAGE && c + 1 < W) prefetch(c + 1);
         if (threadIdx.x < 32) {
-            const int row0 = c * 64 + lane, row1 = row0 + 32;
-            const uint64_t d0 = row0 < n ? mask[(long long)row0 * wp + c] : 0ull;
-            const uint64_t d1 = row1 < n ? mask[(long long)row1 * wp + c] : 0ull;
-            uint64_t cur = s_removed[c], keep = 0;
-#pragma unroll
-            for (int bit = 0; bit < 32; ++bit) {
-                const uint64_t word = __shfl_sync(0xffffffffu, d0, bit);
-                const uint64_t alive = ((cur >> bit) & 1ull) ^ 1ull;
-                keep |= alive << bit;
-                cur |= word & (0ull - alive);
-            }
-#pragma unroll
-            for (int bit = 0; bit < 32; ++bit) {
-                const uint64_t word = __shfl_sync(0xffffffffu, d1, bit);
-                const uint64_t alive = ((cur >> (bit + 32)) & 1ull) ^ 1ull;
-                keep |= alive << (bit + 32);
-                cur |= word & (0ull - alive);
+            const uint64_t low0 = nd0 & ((1ull << lane) - 1ull);
+            const uint64_t low1 = nd1 & ((1ull << (lane + 32)) - 1ull);
+            load_diag(c + 1);                          // in flight during the fixed-point rounds
+            const uint64_t alive = ~s_removed[c];
+            const bool al0 = (alive >> lane) & 1ull, al1 = (alive >> (lane + 32)) & 1ull;
+            uint64_t keep = alive;
+            for (int round = 0; round < 65; ++round) {
+                const bool k0 = al0 && ((low0 & keep) == 0ull), k1 = al1 && ((low1 & keep) == 0ull);
+                const uint64_t nk = (uint64_t)__ballot_sync(0xffffffffu, k0) |
+                                    ((uint64_t)__ballot_sync(0xffffffffu, k1) << 32);
+                if (nk == keep) break;
+                keep = nk;
             }
             if (max_keep > 0 && kept_total + __popcll(keep) > max_keep) {
                 int room = max_keep - kept_total;        // keep only the first `room` set bits
@@ -134,13 +177,29 @@ __global__ void __launch_bounds__(256) k_nms_scan(NmsSegs s, int max_keep, int* 
         if (!done) {
             for (int w = c + 1 + threadIdx.x; w < W; w += blockDim.x) {
                 uint64_t acc = s_removed[w], rest = keep;
-                while (rest) {
-                    const int bit = __ffsll((long long)rest) - 1;
-                    rest &= rest - 1;
-                    acc |= mask[(long long)(c * 64 + bit) * wp + w];
+                if (STAGE) {
+                    while (rest) {
+                        const int bit = __ffsll((long long)rest) - 1;
+                        rest &= rest - 1;
+                        acc |= s_rows[((c & 1) * 64 + bit) * 32 + w];
+                    }
+                } else {
+                    while (rest) {                       // batches of 4 independent loads
+                        uint64_t v[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (rest) {
+                                const int bit = __ffsll((long long)rest) - 1;
+                                rest &= rest - 1;
+                                v[q] = mask[(long long)(c * 64 + bit) * wp + w];
+                            }
+                        }
+                        acc |= (v[0] | v[1]) | (v[2] | v[3]);
+                    }
                 }
                 s_removed[w] = acc;
             }
+            if (STAGE && c + 1 < W) park(c + 1);
         }
         __syncthreads();
         if (done) break;
@@ -160,6 +219,20 @@ __global__ void __launch_bounds__(256) k_nms_scan(NmsSegs s, int max_keep, int* 
         }
     }
     if (threadIdx.x == 0) keep_count[seg] = kept_total;
+}
+
+static void set_thr(NmsSegs& s, float thr) {
+    s.thr = thr;
+    s.thr_hi = thr * (1.0f + 1.0f / 262144.0f);
+    s.thr_lo = thr * (1.0f - 1.0f / 262144.0f);
+}
+
+static void launch_scan(const NmsSegs& s, int S, int wmax, int max_keep, int* keep_pos, int* keep_count, int64_t* keep64,
+                        const int* sorted_idx, long long keep_ld, cudaStream_t st) {
+    if (wmax <= 32)
+        k_nms_scan<true><<<S, kScanThreads, 0, st>>>(s, max_keep, keep_pos, keep_count, keep64, sorted_idx, keep_ld);
+    else
+        k_nms_scan<false><<<S, kScanThreads, 0, st>>>(s, max_keep, keep_pos, keep_count, keep64, sorted_idx, keep_ld);
 }
 
 // generic entry: sort (score desc, index asc) and gather boxes into score order
@@ -200,12 +273,12 @@ int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st) {
         s.wp[l] = (p.kcap[l] + 63) / 64;
         wmax = max(wmax, s.wp[l]);
     }
-    s.boxes = p.sel_box; s.counts = p.sel_count; s.mask = p.mask; s.thr = p.nms_thr;
+    s.boxes = p.sel_box; s.counts = p.sel_count; s.mask = p.mask;
+    set_thr(s, p.nms_thr);
     const int S = p.B * p.L;
     dim3 grid(wmax * (wmax + 1) / 2, S);
     k_nms_mask<<<grid, 64, 0, st>>>(s, wmax);
-    const int threads = min(256, max(32, ((wmax + 31) / 32) * 32));
-    k_nms_scan<<<S, threads, 0, st>>>(s, p.post_nms, p.keep_pos, p.keep_count, nullptr, nullptr, 0);
+    launch_scan(s, S, wmax, p.post_nms, p.keep_pos, p.keep_count, nullptr, nullptr, 0, st);
     return check_launch("rpn_nms");
 }
 
@@ -250,12 +323,12 @@ int b2d_nms(int64_t* keep, int* keep_count, const float* boxes, const float* sco
     NmsSegs s;
     memset(&s, 0, sizeof(s));
     s.L = 1; s.box_per_img = n_ld; s.mask_per_img = (long long)n_ld * wp; s.wp[0] = wp;
-    s.boxes = sorted_box; s.counts = cnt; s.mask = mask; s.thr = thr_f;
+    s.boxes = sorted_box; s.counts = cnt; s.mask = mask;
+    set_thr(s, thr_f);
     const int wmax = (int)((n + 63) / 64);
     dim3 grid(wmax * (wmax + 1) / 2, S);
     k_nms_mask<<<grid, 64, 0, st>>>(s, wmax);
-    const int threads = min(256, max(32, ((wmax + 31) / 32) * 32));
-    k_nms_scan<<<S, threads, 0, st>>>(s, max_keep, nullptr, keep_count, keep, sorted_idx, n_ld);
+    launch_scan(s, S, wmax, max_keep, nullptr, keep_count, keep, sorted_idx, n_ld, st);
     return check_launch("nms");
 }
 

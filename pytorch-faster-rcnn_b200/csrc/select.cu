@@ -59,24 +59,26 @@ __global__ void __launch_bounds__(256) k_hist(RpnLaunch p) {
 }
 
 // Find the largest bin t with sum_{bin >= t} hist[bin] >= k.  blockDim.x == 256.
-__device__ int find_threshold_bin(const uint32_t* __restrict__ gh, int k, uint32_t* s_tmp /*256*/) {
+__device__ int find_threshold_bin(const uint32_t* __restrict__ gh, int k, uint32_t* s_tmp /*>= 8*/) {
     constexpr int per = kHistBins / 256;
     uint32_t loc[per];
     uint32_t sum = 0;
 #pragma unroll
     for (int q = 0; q < per; ++q) { loc[q] = gh[threadIdx.x * per + q]; sum += loc[q]; }
-    s_tmp[threadIdx.x] = sum;
-    __syncthreads();
-    // suffix sums over 256 partials (small: serial by warp 0 lanes over 8 each + shuffle would also do)
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int t = 255; t >= 0; --t) { const uint32_t v = s_tmp[t]; s_tmp[t] = run; run += v; }
+    // suffix scan over the 256 partial sums: shuffles inside a warp, 8 warp totals through smem
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t v = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_down_sync(0xffffffffu, v, o);
+        if (lane + o < 32) v += t;
     }
-    __syncthreads();
-    const uint32_t above = s_tmp[threadIdx.x];            // count in bins owned by higher threads
     __shared__ int s_bin;
+    if (lane == 0) s_tmp[warp] = v;
     if (threadIdx.x == 0) s_bin = 0;
     __syncthreads();
+    uint32_t above = v - sum;                              // bins owned by higher lanes of this warp
+    for (int w = warp + 1; w < 8; ++w) above += s_tmp[w];  // ... and by higher warps
     if (above < (uint32_t)k && above + sum >= (uint32_t)k) {
         uint32_t run = above;
         for (int q = per - 1; q >= 0; --q) {
@@ -89,8 +91,14 @@ __device__ int find_threshold_bin(const uint32_t* __restrict__ gh, int k, uint32
 }
 
 // ---------------------------------------------------------------- k_compact
+// Candidates (bin >= threshold bin) are staged in shared memory per 2048-element round and
+// leave with ONE global atomic per round and a coalesced copy (order is irrelevant: the
+// candidates are sorted afterwards).
 __global__ void __launch_bounds__(256) k_compact(RpnLaunch p) {
-    __shared__ uint32_t s_tmp[256];
+    constexpr int kRound = 2048;
+    __shared__ uint32_t s_tmp[8];
+    __shared__ uint64_t s_stage[kRound];
+    __shared__ int s_n, s_base;
     const int seg = blockIdx.y, b = seg / p.L, l = seg - b * p.L;
     const int n = p.n[l], k = p.kcap[l];
     if (k >= n) return;
@@ -101,16 +109,22 @@ __global__ void __launch_bounds__(256) k_compact(RpnLaunch p) {
     const float* cls = seg_cls(p, b, l);
     uint64_t* cand = p.cand + ((long long)b * p.pyr.total + p.pyr.lv[l].offset);
     const int end = min(start + kChunk, n);
-    const int end_round = start + ((end - start + 255) / 256) * 256;   // keep warps converged for warp_alloc
-    for (int i = start + threadIdx.x; i < end_round; i += blockDim.x) {
-        bool take = false;
-        uint32_t key = 0;
-        if (i < end) {
-            key = f2key(load_logit(cls, n, i, p.score_mode, p.cls_ch));
-            take = (int)(key >> (32 - kHistBits)) >= tb;
+    for (int r0 = start; r0 < end; r0 += kRound) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kRound / 256; ++q) {
+            const int i = r0 + q * 256 + threadIdx.x;
+            if (i < end) {
+                const uint32_t key = f2key(load_logit(cls, n, i, p.score_mode, p.cls_ch));
+                if ((int)(key >> (32 - kHistBits)) >= tb) s_stage[atomicAdd(&s_n, 1)] = make_comp(key, (uint32_t)i);
+            }
         }
-        const int slot = warp_alloc(take, &p.cand_count[seg]);
-        if (take) cand[slot] = make_comp(key, (uint32_t)i);
+        __syncthreads();
+        const int m = s_n;
+        if (threadIdx.x == 0 && m > 0) s_base = atomicAdd(&p.cand_count[seg], m);
+        __syncthreads();
+        for (int t = threadIdx.x; t < m; t += blockDim.x) cand[s_base + t] = s_stage[t];
     }
 }
 
@@ -282,7 +296,41 @@ __global__ void __launch_bounds__(kSelThreads) k_merge(RpnLaunch p, float* __res
         const int r = t - s_off[l];
         pos = p.do_nms ? p.keep_pos[(long long)b * p.sel_per_img + p.sel_off[l] + r] : r;
     };
-    if (topk) {
+    // Every level list is already key-descending (NMS keeps score order; the selection is
+    // sorted), so the global order is a 5-way merge: the rank of an element is its position
+    // in its own level plus, per other level, the number of elements that precede it
+    // (binary search; ties go to the earlier concat position).  No sort, two barriers.
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(s_buf);
+    int* s_rank2t = reinterpret_cast<int*>(s_key + total);
+    bool sorted_lists = true;
+    for (int l = 0; l < p.L; ++l) if (p.kcap[l] >= p.n[l] && !p.do_nms) sorted_lists = false;
+    if (topk && sorted_lists) {
+        for (int t = threadIdx.x; t < total; t += blockDim.x) {
+            int l, pos; locate(t, l, pos);
+            s_key[t] = p.sel_key[(long long)b * p.sel_per_img + p.sel_off[l] + pos];
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < total; t += blockDim.x) {
+            int l = 0;
+            for (int q = 1; q < p.L; ++q) if (t >= s_off[q]) l = q;
+            const uint32_t key = s_key[t];
+            int rank = t - s_off[l];
+            for (int q = 0; q < p.L; ++q) {
+                if (q == l) continue;
+                // count elements of level q with key' > key (q > l) or key' >= key (q < l)
+                int lo = s_off[q], hi = s_off[q + 1];
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const uint32_t km = s_key[mid];
+                    const bool before = (q < l) ? (km >= key) : (km > key);
+                    if (before) lo = mid + 1; else hi = mid;
+                }
+                rank += lo - s_off[q];
+            }
+            if (rank < nout) s_rank2t[rank] = t;
+        }
+        __syncthreads();
+    } else if (topk) {
         int p2 = 1;
         while (p2 < total) p2 <<= 1;
         for (int t = threadIdx.x; t < p2; t += blockDim.x) {
@@ -302,7 +350,7 @@ __global__ void __launch_bounds__(kSelThreads) k_merge(RpnLaunch p, float* __res
         float sc = 0.0f;
         int pv = -1;
         if (r < nout) {
-            const int t = topk ? (int)comp_idx(s_buf[r]) : r;
+            const int t = !topk ? r : (sorted_lists ? s_rank2t[r] : (int)comp_idx(s_buf[r]));
             int l, pos; locate(t, l, pos);
             const long long o = (long long)b * p.sel_per_img + p.sel_off[l] + pos;
             bx = p.sel_box[o];
