@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_assign_colmax(AssignArgs p, b2d_pyramid
     const int K = p.gt_count[b];
     const long long n_b = p.box_count ? (long long)p.box_count[b] : p.N;
     const float* g = p.gt + (long long)b * 4 * p.gt_ld;
-    const uint32_t kNegInf = f2key(-INFINITY);
+    const uint32_t kNegInf = f2key(-INFINITY), kZero = f2key(0.0f);
     __shared__ int s_lim[2 * kMaxLevels];
     if (p.use_pyr && threadIdx.x < pyr.num_levels)     // fp64 once per (block, level), not per box
         grid_limits(pyr.lv[threadIdx.x], p.img_hw[2 * b], p.img_hw[2 * b + 1], s_lim[2 * threadIdx.x], s_lim[2 * threadIdx.x + 1]);
@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(256) k_assign_colmax(AssignArgs p, b2d_pyramid
         ok[r] = load_box(p, pyr, b, base + (long long)r * blockDim.x, n_b, bx[r], s_lim);
         ba[r] = ok[r] ? area_plus1(bx[r]) : 0.0f;
     }
+    bool any_ok = false;
+#pragma unroll
+    for (int r = 0; r < kBoxesPerThread; ++r) any_ok |= ok[r];
+    any_ok = __any_sync(0xffffffffu, any_ok);          // warp-uniform
     for (int j0 = 0; j0 < K; j0 += kGtChunk) {
         const int kc = min(kGtChunk, K - j0);
         __syncthreads();
@@ -93,17 +97,23 @@ __global__ void __launch_bounds__(256) k_assign_colmax(AssignArgs p, b2d_pyramid
         for (int j = 0; j < kc; ++j) {
             const Box t = s_gt[j];
             const float ta = s_ga[j];
-            uint32_t m = kNegInf;
+            uint32_t m = any_ok ? kZero : kNegInf;      // every valid box contributes at least +-0
 #pragma unroll
             for (int r = 0; r < kBoxesPerThread; ++r) {
-                if (ok[r]) {
+                if (!ok[r]) continue;
+                // a miss with positive areas is +-0 (see iou_plus1): only hits need arithmetic
+                const bool hit = fmaxf(bx[r].x1, t.x1) < fminf(bx[r].x2, t.x2) && fmaxf(bx[r].y1, t.y1) < fminf(bx[r].y2, t.y2);
+                if (hit || !(ba[r] > 0.0f && ta > 0.0f)) {
                     const float v = iou_plus1(bx[r], ba[r], t, ta) + 0.0f;  // -0 -> +0
                     m = max(m, f2key(v));
                 }
             }
-            // one REDUX per warp per GT; skip the shared atomic when the warp only saw zeros
-            m = __reduce_max_sync(0xffffffffu, m);
-            if (lane_id() == 0 && m > s_max[j]) atomicMax(&s_max[j], m);
+            if (__any_sync(0xffffffffu, m > kZero) || j0 + j == 0 || !any_ok) {
+                m = __reduce_max_sync(0xffffffffu, m);
+                if (lane_id() == 0 && m > s_max[j]) atomicMax(&s_max[j], m);
+            } else if (lane_id() == 0 && s_max[j] < kZero) {
+                atomicMax(&s_max[j], kZero);
+            }
         }
         __syncthreads();
         for (int j = threadIdx.x; j < kc; j += blockDim.x)
@@ -156,9 +166,14 @@ __global__ void __launch_bounds__(256) k_assign_label(AssignArgs p, b2d_pyramid 
             const Box t = s_gt[j];
             const float ta = s_ga[j], cm = s_cm[j];
             const bool cm_ok = cm >= p.min_pos_iou;
+            // a miss is +-0: it can only matter as the initial arg-max (GT 0) or when this GT's
+            // column max is itself 0 and qualifies (min_pos_iou <= 0) -- both warp-uniform
+            const bool need_all = (j0 + j) == 0 || (cm_ok && cm == 0.0f) || !(ta > 0.0f);
 #pragma unroll
             for (int r = 0; r < kBoxesPerThread; ++r) {
                 if (!ok[r]) continue;
+                const bool hit = fmaxf(bx[r].x1, t.x1) < fminf(bx[r].x2, t.x2) && fmaxf(bx[r].y1, t.y1) < fminf(bx[r].y2, t.y2);
+                if (!(hit || need_all || !(ba[r] > 0.0f))) continue;
                 const float v = iou_plus1(bx[r], ba[r], t, ta);
                 if ((j0 + j) == 0 || v > best[r]) { best[r] = v; arg[r] = j0 + j; }       // first max wins
                 if (eq[r] < 0 && cm_ok && v == cm) { eq[r] = j0 + j; veq[r] = v; }        // lowest GT wins

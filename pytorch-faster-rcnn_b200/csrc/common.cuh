@@ -133,20 +133,85 @@ __host__ __device__ __forceinline__ uint32_t mix_key(uint64_t seed, uint64_t i) 
     return (uint32_t)(z >> 32);
 }
 
-// In-shared-memory bitonic sort of n (power of two) u64 values, DESCENDING.
-__device__ __forceinline__ void bitonic_sort_desc(uint64_t* s, int n) {
+// ---- block-wide bitonic sort of u64 keys, DESCENDING ---------------------------------
+// n = E * blockDim.x keys live in s[0..n).  Each thread keeps E consecutive keys in
+// registers: strides < E are compare-exchanges inside the thread, strides < 32*E are warp
+// shuffles, and only strides >= 32*E go through shared memory (conflict-free [e][thread]
+// layout) -- 15 shared-memory exchanges instead of 78 barrier-separated passes for n = 4096.
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m);
+    const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+template <int E>
+__device__ __forceinline__ void block_sort_desc_E(uint64_t* s) {
+    const int t = threadIdx.x, T = blockDim.x;
+    const int n = E * T;
+    uint64_t v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = s[t * E + e];
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
-                // element pair (i, i^j) with i having bit j clear
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int p = i | j;
-                const uint64_t a = s[i], b = s[p];
-                const bool desc = ((i & k) == 0);
-                if ((a < b) == desc) { s[i] = b; s[p] = a; }
+            if (j >= 32 * E) {
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; ++e) s[e * T + t] = v[e];
+                __syncthreads();
+                const int pt = t ^ (j / E);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int x = t * E + e;
+                    const uint64_t o = s[e * T + pt];
+                    const bool want_max = (((x & j) == 0) == ((x & k) == 0));
+                    v[e] = want_max ? (v[e] > o ? v[e] : o) : (v[e] < o ? v[e] : o);
+                }
+            } else if (j >= E) {
+                const int m = j / E;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int x = t * E + e;
+                    const uint64_t o = shfl_xor_u64(v[e], m);
+                    const bool want_max = (((x & j) == 0) == ((x & k) == 0));
+                    v[e] = want_max ? (v[e] > o ? v[e] : o) : (v[e] < o ? v[e] : o);
+                }
+            } else {
+#pragma unroll
+                for (int jj = E / 2; jj > 0; jj >>= 1) {
+                    if (jj != j) continue;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        if (e & jj) continue;
+                        const int x = t * E + e;
+                        const bool desc = ((x & k) == 0);
+                        const uint64_t a = v[e], b = v[e | jj];
+                        if ((a < b) == desc) { v[e] = b; v[e | jj] = a; }
+                    }
+                }
             }
-            __syncthreads();
         }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e) s[t * E + e] = v[e];
+    __syncthreads();
+}
+
+// Sort s[0..n) descending; n must be a power of two, entries [n, max(n, blockDim)) must be
+// writable (they are zero-filled here).  blockDim.x must be 1024.
+__device__ __forceinline__ void bitonic_sort_desc(uint64_t* s, int n) {
+    const int T = blockDim.x;
+    if (n < T) {
+        for (int i = n + threadIdx.x; i < T; i += T) s[i] = 0ull;
+        n = T;
+    }
+    __syncthreads();
+    switch (n / T) {
+        case 1: block_sort_desc_E<1>(s); break;
+        case 2: block_sort_desc_E<2>(s); break;
+        case 4: block_sort_desc_E<4>(s); break;
+        case 8: block_sort_desc_E<8>(s); break;
+        default: block_sort_desc_E<16>(s); break;
     }
 }
 

@@ -101,13 +101,20 @@ __global__ void __launch_bounds__(64) k_nms_mask(NmsSegs s, int wmax) {
 // no global-memory latency sits on the serial chain.  Latency-bound by design.
 constexpr int kScanThreads = 256;
 
+struct ScanOut {
+    // RPN pipeline: survivors are compacted (score order) from the sel_* arrays into kept_*
+    const uint32_t* src_key; const int* src_idx; float4* dst_box; uint32_t* dst_key; int* dst_idx;
+    // generic entry: int64 original indices
+    int64_t* keep64; const int* sorted_idx; long long keep_ld;
+    int* keep_count;
+};
+
 template <bool STAGE>
-__global__ void __launch_bounds__(kScanThreads) k_nms_scan(NmsSegs s, int max_keep, int* __restrict__ keep_pos,
-                                                           int* __restrict__ keep_count, int64_t* __restrict__ keep64,
-                                                           const int* __restrict__ sorted_idx, long long keep_ld) {
+__global__ void __launch_bounds__(kScanThreads) k_nms_scan(NmsSegs s, int max_keep, ScanOut o) {
     __shared__ uint64_t s_removed[kSortCap / 64];
     __shared__ uint64_t s_keepw[kSortCap / 64];
     __shared__ uint64_t s_rows[STAGE ? 2 * 64 * 32 : 1];
+    __shared__ int s_prefix[kSortCap / 64];
     __shared__ uint64_t s_keep;
     const int seg = blockIdx.x;
     const int l = seg % s.L, b = seg / s.L;
@@ -175,15 +182,20 @@ __global__ void __launch_bounds__(kScanThreads) k_nms_scan(NmsSegs s, int max_ke
         kept_total += __popcll(keep);
         const bool done = (max_keep > 0 && kept_total >= max_keep);
         if (!done) {
-            for (int w = c + 1 + threadIdx.x; w < W; w += blockDim.x) {
-                uint64_t acc = s_removed[w], rest = keep;
-                if (STAGE) {
-                    while (rest) {
-                        const int bit = __ffsll((long long)rest) - 1;
-                        rest &= rest - 1;
-                        acc |= s_rows[((c & 1) * 64 + bit) * 32 + w];
-                    }
-                } else {
+            if (STAGE) {
+                // warp g ORs the kept rows 8g..8g+7 of the chunk, lane = word: conflict-free LDS
+                const int w = lane, g = threadIdx.x >> 5;
+                if (w > c && w < W) {
+                    uint64_t acc = 0ull;
+                    const uint64_t* rows = s_rows + ((c & 1) * 64 + g * 8) * 32 + w;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if ((keep >> (g * 8 + q)) & 1ull) acc |= rows[q * 32];
+                    if (acc) atomicOr(reinterpret_cast<unsigned long long*>(&s_removed[w]), (unsigned long long)acc);
+                }
+            } else {
+                for (int w = c + 1 + threadIdx.x; w < W; w += blockDim.x) {
+                    uint64_t acc = s_removed[w], rest = keep;
                     while (rest) {                       // batches of 4 independent loads
                         uint64_t v[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
@@ -196,29 +208,35 @@ __global__ void __launch_bounds__(kScanThreads) k_nms_scan(NmsSegs s, int max_ke
                         }
                         acc |= (v[0] | v[1]) | (v[2] | v[3]);
                     }
+                    s_removed[w] = acc;
                 }
-                s_removed[w] = acc;
             }
             if (STAGE && c + 1 < W) park(c + 1);
         }
         __syncthreads();
         if (done) break;
     }
-    // ordered write-out
-    for (int w = threadIdx.x; w < W; w += blockDim.x) {
-        int pos = 0;
-        for (int q = 0; q < w; ++q) pos += __popcll(s_keepw[q]);
-        uint64_t rest = s_keepw[w];
-        while (rest) {
-            const int bit = __ffsll((long long)rest) - 1;
-            rest &= rest - 1;
-            const int r = w * 64 + bit;
-            if (keep64) keep64[(long long)seg * keep_ld + pos] = (int64_t)sorted_idx[(long long)seg * keep_ld + r];
-            else keep_pos[(long long)b * s.box_per_img + s.box_off[l] + pos] = r;
-            ++pos;
+    // ordered write-out: position = kept boxes before this one (prefix over words + popc)
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int w = 0; w < W; ++w) { s_prefix[w] = run; run += __popcll(s_keepw[w]); }
+    }
+    __syncthreads();
+    const long long base = (long long)b * s.box_per_img + s.box_off[l];
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        const int w = r >> 6, bit = r & 63;
+        const uint64_t kw = s_keepw[w];
+        if (!((kw >> bit) & 1ull)) continue;
+        const int pos = s_prefix[w] + __popcll(kw & ((1ull << bit) - 1ull));
+        if (o.keep64) {
+            o.keep64[(long long)seg * o.keep_ld + pos] = (int64_t)o.sorted_idx[(long long)seg * o.keep_ld + r];
+        } else {
+            o.dst_box[base + pos] = s.boxes[base + r];
+            o.dst_key[base + pos] = o.src_key[base + r];
+            o.dst_idx[base + pos] = o.src_idx[base + r];
         }
     }
-    if (threadIdx.x == 0) keep_count[seg] = kept_total;
+    if (threadIdx.x == 0) o.keep_count[seg] = kept_total;
 }
 
 static void set_thr(NmsSegs& s, float thr) {
@@ -227,12 +245,9 @@ static void set_thr(NmsSegs& s, float thr) {
     s.thr_lo = thr * (1.0f - 1.0f / 262144.0f);
 }
 
-static void launch_scan(const NmsSegs& s, int S, int wmax, int max_keep, int* keep_pos, int* keep_count, int64_t* keep64,
-                        const int* sorted_idx, long long keep_ld, cudaStream_t st) {
-    if (wmax <= 32)
-        k_nms_scan<true><<<S, kScanThreads, 0, st>>>(s, max_keep, keep_pos, keep_count, keep64, sorted_idx, keep_ld);
-    else
-        k_nms_scan<false><<<S, kScanThreads, 0, st>>>(s, max_keep, keep_pos, keep_count, keep64, sorted_idx, keep_ld);
+static void launch_scan(const NmsSegs& s, int S, int wmax, int max_keep, const ScanOut& o, cudaStream_t st) {
+    if (wmax <= 32) k_nms_scan<true><<<S, kScanThreads, 0, st>>>(s, max_keep, o);
+    else k_nms_scan<false><<<S, kScanThreads, 0, st>>>(s, max_keep, o);
 }
 
 // generic entry: sort (score desc, index asc) and gather boxes into score order
@@ -278,7 +293,11 @@ int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st) {
     const int S = p.B * p.L;
     dim3 grid(wmax * (wmax + 1) / 2, S);
     k_nms_mask<<<grid, 64, 0, st>>>(s, wmax);
-    launch_scan(s, S, wmax, p.post_nms, p.keep_pos, p.keep_count, nullptr, nullptr, 0, st);
+    ScanOut o;
+    memset(&o, 0, sizeof(o));
+    o.src_key = p.sel_key; o.src_idx = p.sel_idx; o.dst_box = p.kept_box; o.dst_key = p.kept_key; o.dst_idx = p.kept_idx;
+    o.keep_count = p.keep_count;
+    launch_scan(s, S, wmax, p.post_nms, o, st);
     return check_launch("rpn_nms");
 }
 
@@ -328,7 +347,10 @@ int b2d_nms(int64_t* keep, int* keep_count, const float* boxes, const float* sco
     const int wmax = (int)((n + 63) / 64);
     dim3 grid(wmax * (wmax + 1) / 2, S);
     k_nms_mask<<<grid, 64, 0, st>>>(s, wmax);
-    launch_scan(s, S, wmax, max_keep, nullptr, keep_count, keep, sorted_idx, n_ld, st);
+    ScanOut o;
+    memset(&o, 0, sizeof(o));
+    o.keep64 = keep; o.sorted_idx = sorted_idx; o.keep_ld = n_ld; o.keep_count = keep_count;
+    launch_scan(s, S, wmax, max_keep, o, st);
     return check_launch("nms");
 }
 

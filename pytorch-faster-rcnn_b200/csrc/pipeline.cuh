@@ -27,7 +27,8 @@ struct RpnLaunch {
     uint32_t* hist; int* cand_count; int* sel_count; int* keep_count; int* thr_bin;
     size_t zero_bytes;
     uint64_t* cand; uint64_t* cand2;
-    float4* sel_box; uint32_t* sel_key; int* sel_idx; int* keep_pos;
+    float4* sel_box; uint32_t* sel_key; int* sel_idx;
+    float4* kept_box; uint32_t* kept_key; int* kept_idx;   // NMS survivors, compacted in score order
     uint64_t* mask;
 };
 

@@ -96,7 +96,6 @@ __device__ __forceinline__ RoiGeom roi_geom(float x1, float y1, float x2, float 
     return g;
 }
 
-constexpr int kMaxAxis = 64;     // PH*sampling_ratio and PW*sampling_ratio limit of the fast kernel
 constexpr int kCTile = 256;      // channels per shared-memory tile
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -108,10 +107,17 @@ __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
     return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
 
+// Per-sample descriptor staged in shared memory: element offsets of the 4 taps (relative
+// to the image's feature base, channel 0) and their bilinear weights.  Invalid samples
+// (outside (-1, size)) get zero weights, exactly like torchvision's pre-calc table.
+struct __align__(16) Tap4 { int o1, o2, o3, o4; float w1, w2, w3, w4; };
+
+constexpr int kMaxSamples = 256;   // PH*PW*sr*sr limit of the fast kernel (7*7*2*2 = 196)
+
 template <typename FT>
 __global__ void __launch_bounds__(256) k_roi_align_nhwc(RoiArgs a, float* __restrict__ out) {
     extern __shared__ float s_tile[];                      // [bins][kCTile + 4]
-    __shared__ AxisTap s_y[kMaxAxis], s_x[kMaxAxis];
+    __shared__ Tap4 s_tap[kMaxSamples];
     const long long r = blockIdx.x;
     const b2d_roi_cfg& c = a.cfg;
     float x1, y1, x2, y2;
@@ -120,43 +126,50 @@ __global__ void __launch_bounds__(256) k_roi_align_nhwc(RoiArgs a, float* __rest
     int lvl;
     if (a.levels) lvl = a.levels[r];
     else lvl = c.num_levels > 1 ? roi_level(x1, y1, x2, y2, c.finest_scale, c.num_levels) : 0;
-    const int H = c.H[lvl], W = c.W[lvl];
+    const int H = c.H[lvl], W = c.W[lvl], C = c.C;
     const RoiGeom g = roi_geom(x1, y1, x2, y2, c.spatial_scale[lvl], c.PH, c.PW, c.sampling_ratio, c.aligned);
-    const int ny = c.PH * g.gy, nx = c.PW * g.gx;
-    if ((int)threadIdx.x < ny) s_y[threadIdx.x] = axis_tap(g.sy, g.bh, threadIdx.x / g.gy, threadIdx.x % g.gy, g.gy, H);
-    if ((int)threadIdx.x >= 64 && (int)threadIdx.x - 64 < nx) {
-        const int t = threadIdx.x - 64;
-        s_x[t] = axis_tap(g.sx, g.bw, t / g.gx, t % g.gx, g.gx, W);
+    const int spb = g.gy * g.gx;                           // samples per bin
+    const int bins = c.PH * c.PW;
+    {   // sample t = ((ph*PW + pw)*gy + iy)*gx + ix  (torchvision's pre-calc order)
+        const int t = threadIdx.x;
+        if (t < bins * spb) {
+            const int ix = t % g.gx, iy = (t / g.gx) % g.gy;
+            const int bin = t / spb, ph = bin / c.PW, pw = bin - ph * c.PW;
+            const AxisTap ty = axis_tap(g.sy, g.bh, ph, iy, g.gy, H);
+            const AxisTap tx = axis_tap(g.sx, g.bw, pw, ix, g.gx, W);
+            Tap4 q;
+            if (ty.valid && tx.valid) {
+                q.o1 = (ty.lo * W + tx.lo) * C; q.o2 = (ty.lo * W + tx.hi) * C;
+                q.o3 = (ty.hi * W + tx.lo) * C; q.o4 = (ty.hi * W + tx.hi) * C;
+                q.w1 = ty.h * tx.h; q.w2 = ty.h * tx.l; q.w3 = ty.l * tx.h; q.w4 = ty.l * tx.l;
+            } else {
+                q.o1 = q.o2 = q.o3 = q.o4 = 0; q.w1 = q.w2 = q.w3 = q.w4 = 0.0f;
+            }
+            s_tap[t] = q;
+        }
     }
     __syncthreads();
-    const int C = c.C;
     const FT* feat = reinterpret_cast<const FT*>(a.feat[lvl]) + (long long)img * H * W * C;
-    const int bins = c.PH * c.PW;
     const int pitch = kCTile + 4;
-    const float cnt = (float)max(g.gy * g.gx, 1);
+    const float cnt = (float)max(spb, 1);
     const int cq = threadIdx.x & 63, grp = threadIdx.x >> 6;
     float* o = out + r * (long long)C * bins;
     for (int c0 = 0; c0 < C; c0 += kCTile) {
         const int ch = c0 + cq * 4;
         if (ch < C) {
+            const FT* fc = feat + ch;
             for (int bin = grp; bin < bins; bin += 4) {
-                const int ph = bin / c.PW, pw = bin - ph * c.PW;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int iy = 0; iy < g.gy; ++iy) {
-                    const AxisTap ty = s_y[ph * g.gy + iy];
-                    for (int ix = 0; ix < g.gx; ++ix) {
-                        const AxisTap tx = s_x[pw * g.gx + ix];
-                        if (!(ty.valid && tx.valid)) continue;
-                        const FT* r0 = feat + ((long long)ty.lo * W) * C + ch;
-                        const FT* r1 = feat + ((long long)ty.hi * W) * C + ch;
-                        const float4 v1 = ld4(r0 + (long long)tx.lo * C), v2 = ld4(r0 + (long long)tx.hi * C);
-                        const float4 v3 = ld4(r1 + (long long)tx.lo * C), v4 = ld4(r1 + (long long)tx.hi * C);
-                        const float w1 = ty.h * tx.h, w2 = ty.h * tx.l, w3 = ty.l * tx.h, w4 = ty.l * tx.l;
-                        acc.x += ((w1 * v1.x + w2 * v2.x) + w3 * v3.x) + w4 * v4.x;
-                        acc.y += ((w1 * v1.y + w2 * v2.y) + w3 * v3.y) + w4 * v4.y;
-                        acc.z += ((w1 * v1.z + w2 * v2.z) + w3 * v3.z) + w4 * v4.z;
-                        acc.w += ((w1 * v1.w + w2 * v2.w) + w3 * v3.w) + w4 * v4.w;
-                    }
+                const Tap4* tp = s_tap + bin * spb;
+#pragma unroll 4
+                for (int sidx = 0; sidx < spb; ++sidx) {
+                    const int4 of = *reinterpret_cast<const int4*>(&tp[sidx].o1);
+                    const float4 w = *reinterpret_cast<const float4*>(&tp[sidx].w1);
+                    const float4 v1 = ld4(fc + of.x), v2 = ld4(fc + of.y), v3 = ld4(fc + of.z), v4 = ld4(fc + of.w);
+                    acc.x += ((w.x * v1.x + w.y * v2.x) + w.z * v3.x) + w.w * v4.x;
+                    acc.y += ((w.x * v1.y + w.y * v2.y) + w.z * v3.y) + w.w * v4.y;
+                    acc.z += ((w.x * v1.z + w.y * v2.z) + w.z * v3.z) + w.w * v4.z;
+                    acc.w += ((w.x * v1.w + w.y * v2.w) + w.z * v3.w) + w.w * v4.w;
                 }
                 acc.x /= cnt; acc.y /= cnt; acc.z /= cnt; acc.w /= cnt;
                 *reinterpret_cast<float4*>(&s_tile[bin * pitch + cq * 4]) = acc;
@@ -256,8 +269,9 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
     a.batched_ld = batched_ld; a.counts = counts;
     cudaStream_t st = (cudaStream_t)stream;
     const int bins = c.PH * c.PW;
-    const bool fast = c.layout >= 1 && c.sampling_ratio > 0 && c.PH * c.sampling_ratio <= kMaxAxis &&
-                      c.PW * c.sampling_ratio <= kMaxAxis && (c.C % 4) == 0 && bins * (kCTile + 4) * 4 <= 200 * 1024;
+    const bool fast = c.layout >= 1 && c.sampling_ratio > 0 &&
+                      bins * c.sampling_ratio * c.sampling_ratio <= kMaxSamples && (c.C % 4) == 0 &&
+                      bins * (kCTile + 4) * 4 <= 200 * 1024;
     if (fast) {
         const size_t smem = (size_t)bins * (kCTile + 4) * 4;
         static size_t attr_f32 = 0, attr_bf16 = 0;

@@ -48,9 +48,16 @@ __global__ void __launch_bounds__(256) k_hist(RpnLaunch p) {
     __syncthreads();
     const float* cls = seg_cls(p, b, l);
     const int end = min(start + kChunk, n);
-    for (int i = start + threadIdx.x; i < end; i += blockDim.x) {
-        const uint32_t key = f2key(load_logit(cls, n, i, p.score_mode, p.cls_ch));
-        atomicAdd(&s_h[key >> (32 - kHistBits)], 1u);
+    for (int r0 = start; r0 < end; r0 += 8 * 256) {
+        float v[8];                                       // 8 independent loads in flight per thread
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = r0 + q * 256 + threadIdx.x;
+            v[q] = i < end ? load_logit(cls, n, i, p.score_mode, p.cls_ch) : 0.0f;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (r0 + q * 256 + (int)threadIdx.x < end) atomicAdd(&s_h[f2key(v[q]) >> (32 - kHistBits)], 1u);
     }
     __syncthreads();
     uint32_t* gh = p.hist + (long long)seg * kHistBins;
@@ -112,13 +119,17 @@ __global__ void __launch_bounds__(256) k_compact(RpnLaunch p) {
     for (int r0 = start; r0 < end; r0 += kRound) {
         if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
+        float v[kRound / 256];
 #pragma unroll
         for (int q = 0; q < kRound / 256; ++q) {
             const int i = r0 + q * 256 + threadIdx.x;
-            if (i < end) {
-                const uint32_t key = f2key(load_logit(cls, n, i, p.score_mode, p.cls_ch));
-                if ((int)(key >> (32 - kHistBits)) >= tb) s_stage[atomicAdd(&s_n, 1)] = make_comp(key, (uint32_t)i);
-            }
+            v[q] = i < end ? load_logit(cls, n, i, p.score_mode, p.cls_ch) : 0.0f;
+        }
+#pragma unroll
+        for (int q = 0; q < kRound / 256; ++q) {
+            const int i = r0 + q * 256 + threadIdx.x;
+            const uint32_t key = f2key(v[q]);
+            if (i < end && (int)(key >> (32 - kHistBits)) >= tb) s_stage[atomicAdd(&s_n, 1)] = make_comp(key, (uint32_t)i);
         }
         __syncthreads();
         const int m = s_n;
@@ -289,12 +300,14 @@ __global__ void __launch_bounds__(kSelThreads) k_merge(RpnLaunch p, float* __res
     const int total = s_off[p.L];
     const bool topk = (p.max_num > 0) && (total > p.max_num);
     const int nout = topk ? p.max_num : total;
-    // element t of the level-major concatenation -> (level, position in that level's sel arrays)
+    const float4* m_box = p.do_nms ? p.kept_box : p.sel_box;
+    const uint32_t* m_key = p.do_nms ? p.kept_key : p.sel_key;
+    const int* m_idx = p.do_nms ? p.kept_idx : p.sel_idx;
+    // element t of the level-major concatenation -> (level, position in that level's arrays)
     auto locate = [&](int t, int& l, int& pos) {
         l = 0;
         for (int q = 1; q < p.L; ++q) if (t >= s_off[q]) l = q;
-        const int r = t - s_off[l];
-        pos = p.do_nms ? p.keep_pos[(long long)b * p.sel_per_img + p.sel_off[l] + r] : r;
+        pos = t - s_off[l];
     };
     // Every level list is already key-descending (NMS keeps score order; the selection is
     // sorted), so the global order is a 5-way merge: the rank of an element is its position
@@ -307,7 +320,7 @@ __global__ void __launch_bounds__(kSelThreads) k_merge(RpnLaunch p, float* __res
     if (topk && sorted_lists) {
         for (int t = threadIdx.x; t < total; t += blockDim.x) {
             int l, pos; locate(t, l, pos);
-            s_key[t] = p.sel_key[(long long)b * p.sel_per_img + p.sel_off[l] + pos];
+            s_key[t] = m_key[(long long)b * p.sel_per_img + p.sel_off[l] + pos];
         }
         __syncthreads();
         for (int t = threadIdx.x; t < total; t += blockDim.x) {
@@ -315,18 +328,27 @@ __global__ void __launch_bounds__(kSelThreads) k_merge(RpnLaunch p, float* __res
             for (int q = 1; q < p.L; ++q) if (t >= s_off[q]) l = q;
             const uint32_t key = s_key[t];
             int rank = t - s_off[l];
-            for (int q = 0; q < p.L; ++q) {
-                if (q == l) continue;
-                // count elements of level q with key' > key (q > l) or key' >= key (q < l)
-                int lo = s_off[q], hi = s_off[q + 1];
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    const uint32_t km = s_key[mid];
-                    const bool before = (q < l) ? (km >= key) : (km > key);
-                    if (before) lo = mid + 1; else hi = mid;
-                }
-                rank += lo - s_off[q];
+            // independent binary searches over the other levels, stepped together for ILP
+            int lo[kMaxLevels], hi[kMaxLevels];
+#pragma unroll
+            for (int q = 0; q < kMaxLevels; ++q) {
+                const bool on = q < p.L && q != l;
+                lo[q] = on ? s_off[q] : 0; hi[q] = on ? s_off[q + 1] : 0;
             }
+            for (int step = 0; step < 15; ++step) {      // 2^14 = kSortCap elements at most
+#pragma unroll
+                for (int q = 0; q < kMaxLevels; ++q) {
+                    if (lo[q] < hi[q]) {
+                        const int mid = (lo[q] + hi[q]) >> 1;
+                        const uint32_t km = s_key[mid];
+                        const bool before = (q < l) ? (km >= key) : (km > key);
+                        if (before) lo[q] = mid + 1; else hi[q] = mid;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kMaxLevels; ++q)
+                if (q < p.L && q != l) rank += lo[q] - s_off[q];
             if (rank < nout) s_rank2t[rank] = t;
         }
         __syncthreads();
@@ -337,7 +359,7 @@ __global__ void __launch_bounds__(kSelThreads) k_merge(RpnLaunch p, float* __res
             uint64_t c = 0ull;
             if (t < total) {
                 int l, pos; locate(t, l, pos);
-                c = make_comp(p.sel_key[(long long)b * p.sel_per_img + p.sel_off[l] + pos], (uint32_t)t);
+                c = make_comp(m_key[(long long)b * p.sel_per_img + p.sel_off[l] + pos], (uint32_t)t);
             }
             s_buf[t] = c;
         }
@@ -353,9 +375,9 @@ __global__ void __launch_bounds__(kSelThreads) k_merge(RpnLaunch p, float* __res
             const int t = !topk ? r : (sorted_lists ? s_rank2t[r] : (int)comp_idx(s_buf[r]));
             int l, pos; locate(t, l, pos);
             const long long o = (long long)b * p.sel_per_img + p.sel_off[l] + pos;
-            bx = p.sel_box[o];
-            sc = 1.0f / (1.0f + expf(-key2f(p.sel_key[o])));
-            pv = (int)(p.pyr.lv[l].offset + p.sel_idx[o]);
+            bx = m_box[o];
+            sc = 1.0f / (1.0f + expf(-key2f(m_key[o])));
+            pv = (int)(p.pyr.lv[l].offset + m_idx[o]);
         }
         pb[r] = bx.x; pb[p.out_ld + r] = bx.y; pb[2 * p.out_ld + r] = bx.z; pb[3 * p.out_ld + r] = bx.w;
         scores[(long long)b * p.out_ld + r] = sc;
@@ -435,7 +457,10 @@ bool rpn_plan(RpnLaunch& p, const b2d_pyramid* pyr, int B, const b2d_rpn_cfg* cf
     p.sel_box = (float4*)carve((size_t)B * p.sel_per_img * 16);
     p.sel_key = (uint32_t*)carve((size_t)B * p.sel_per_img * 4);
     p.sel_idx = (int*)carve((size_t)B * p.sel_per_img * 4);
-    p.keep_pos = (int*)carve((size_t)B * p.sel_per_img * 4);
+    const size_t kept = cfg->do_nms ? (size_t)B * p.sel_per_img : 0;
+    p.kept_box = (float4*)carve(kept * 16);
+    p.kept_key = (uint32_t*)carve(kept * 4);
+    p.kept_idx = (int*)carve(kept * 4);
     p.mask = (uint64_t*)carve(cfg->do_nms ? (size_t)B * p.mask_per_img * 8 : 0);
     *bytes = o;
     return true;
