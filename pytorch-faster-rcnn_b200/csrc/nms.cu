@@ -2,18 +2,25 @@
 // (stable descending score order, areas without +1, suppress iff (double)iou > thr;
 // reference call sites lib/heads/rpn_head.py:103, lib/region.py:207, lib/utils.py:220).
 //
-//   k_nms_sort  (generic entry only) per-segment bitonic sort of (score, index)
-//   k_nms_mask  64x64 tiles of the upper triangle: column boxes live in registers,
-//               row boxes are staged in shared memory and broadcast, the 64-bit
-//               suppression word of a row is assembled with two __ballot_sync
-//   k_nms_scan  one block per segment: 64-box chunks; the intra-chunk dependency is
-//               resolved by warp 0 from the diagonal words (register/shuffle only),
-//               then every thread ORs the kept rows into its own word of the
-//               removed-set.  Latency-bound by design.
+//   k_nms_sort       (generic entry only) per-segment bitonic sort of (score, index)
+//   k_nms_mask_sym   n <= 2048: 64x64 tiles of the upper triangle; column boxes live in
+//                    registers, row boxes are staged in shared memory and broadcast.  A tile
+//                    yields BOTH orientations of the (bitwise symmetric) relation: the row
+//                    words by __ballot_sync and the column words by lane-local accumulation,
+//                    so afterwards row j of the matrix holds every box that overlaps box j.
+//                    Only NON-ZERO words are stored, and a per-row bitmap `nz` says which.
+//   k_nms_scan_fp    n <= 2048: one block per segment.  Greedy NMS is the unique fixed point of
+//                    kept_j = !(exists i < j: kept_i and M_ij); a thread per row iterates that
+//                    map from kept = all (Jacobi), which converges after (longest suppression
+//                    chain + 1) sweeps of a few hundred cycles each -- instead of n dependent
+//                    steps.  A row keeps its (few) non-zero words in registers.
+//   k_nms_mask_dense / k_nms_scan_seq   16384 >= n > 2048: dense upper-triangle words and the
+//                    sequential 64-box-chunk scan (latency-bound; generic entry only).
 //
-// The fp32 threshold passed in is the largest float <= the caller's double
-// threshold, which makes `iou > thr_f` identical to torchvision's CPU comparison
-// `(double)iou > thr` for every float iou.
+// The fp32 threshold passed in is the largest float <= the caller's double threshold, which
+// makes `iou > thr_f` identical to torchvision's CPU comparison `(double)iou > thr` for every
+// float iou.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -29,77 +36,97 @@ struct NmsSegs {
     const float4* boxes;                // score-sorted boxes
     const int* counts;                  // int[S]
     uint64_t* mask;
+    uint32_t* nz;                       // sym path: per row, bit w set iff word w of the row is non-zero (laid out like boxes)
     float thr, thr_lo, thr_hi;          // thr_lo/hi: decisive bounds that avoid the divide (see suppresses)
 };
 
 // (double)iou > thr with iou = inter / ((aa + ab) - inter), evaluated exactly like the
 // reference.  The IEEE divide is only executed inside the narrow band |iou/thr - 1| <
-// 2^-18 where the cheap products cannot decide; outside it the sign of
-// inter - thr*u already determines fl(inter/u) > thr (margin >> half an ulp).
+// 2^-18 where the cheap products cannot decide (or for NaN/inf inputs and thr <= 0, where the
+// host makes the bounds +-inf): outside it the sign of inter - thr*u already determines
+// fl(inter/u) > thr (margin >> half an ulp).
 __device__ __forceinline__ bool suppresses(const float4& a, float aa, const float4& b, float ab, float thr,
                                            float thr_lo, float thr_hi) {
     const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
     const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
     const float w = fmaxf(0.0f, xx2 - xx1), h = fmaxf(0.0f, yy2 - yy1);
     const float inter = w * h;
-    if (inter == 0.0f && thr >= 0.0f) return false;      // 0/u is 0 or NaN: never > thr
     const float u = (aa + ab) - inter;
-    if (thr > 0.0f && u > 0.0f && u < 3.0e38f) {
-        if (inter > thr_hi * u) return true;
-        if (inter < thr_lo * u) return false;
-    }
+    const bool yes = inter > thr_hi * u, no = inter < thr_lo * u;
+    if (yes || no) return yes;
     return inter / u > thr;
 }
 
-// Tile (rb, cb), cb >= rb, of the 64x64-blocked suppression matrix.  Off-diagonal tiles
-// hold bit j of row i iff box i suppresses box j (j > i always).  DIAGONAL tiles hold the
-// full symmetric relation (bit j set iff i != j and IoU(i,j) > thr): the scan needs, for a
-// box j, the set of *earlier* boxes that suppress it, which by symmetry of the IoU
-// arithmetic is (word_j & lower_bits(j)).
-__global__ void __launch_bounds__(64) k_nms_mask(NmsSegs s, int wmax) {
+// Padding box for rows/columns past n: far away from anything finite a caller passes, with a
+// finite positive area, so a real-vs-pad pair takes the cheap "no" exit.
+__device__ __forceinline__ float4 pad_box() { return make_float4(-2.0e18f, -2.0e18f, -1.0e18f, -1.0e18f); }
+__device__ __forceinline__ float area_of(const float4& b) { return (b.z - b.x) * (b.w - b.y); }
+
+__device__ __forceinline__ void tile_of(int t, int wmax, int& rb, int& cb) {
+    rb = 0;
+    while (t >= wmax - rb) { t -= wmax - rb; ++rb; }
+    cb = rb + t;
+}
+
+// ---- symmetric, sparse-output mask (n <= 2048) ------------------------------------------------
+__global__ void __launch_bounds__(64) k_nms_mask_sym(NmsSegs s, int wmax) {
     __shared__ float4 s_row[64];
+    __shared__ float s_ra[64];
+    __shared__ uint32_t s_cw[2][64];
     const int seg = blockIdx.y;
     const int l = seg % s.L, b = seg / s.L;
     const int n = s.counts[seg];
-    int t = blockIdx.x, rb = 0;
-    while (t >= wmax - rb) { t -= wmax - rb; ++rb; }
-    const int cb = rb + t;
+    int rb, cb;
+    tile_of(blockIdx.x, wmax, rb, cb);
     const int r0 = rb * 64, c0 = cb * 64;
     if (r0 >= n || c0 >= n) return;
-    const float4* boxes = s.boxes + (long long)b * s.box_per_img + s.box_off[l];
+    const long long base = (long long)b * s.box_per_img + s.box_off[l];
+    const float4* boxes = s.boxes + base;
+    uint32_t* nz = s.nz + base;
     uint64_t* mask = s.mask + (long long)b * s.mask_per_img + s.mask_off[l];
     const int wp = s.wp[l];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    s_row[threadIdx.x] = (r0 + (int)threadIdx.x < n) ? boxes[r0 + threadIdx.x] : zero;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const float4 pad = pad_box();
+    {
+        const float4 rbx = (r0 + tid < n) ? boxes[r0 + tid] : pad;
+        s_row[tid] = rbx; s_ra[tid] = area_of(rbx);
+    }
     const int j0 = c0 + lane, j1 = c0 + 32 + lane;
-    const float4 cb0 = j0 < n ? boxes[j0] : zero, cb1 = j1 < n ? boxes[j1] : zero;
-    const float a0 = (cb0.z - cb0.x) * (cb0.w - cb0.y), a1 = (cb1.z - cb1.x) * (cb1.w - cb1.y);
+    const float4 cb0 = j0 < n ? boxes[j0] : pad, cb1 = j1 < n ? boxes[j1] : pad;
+    const float a0 = area_of(cb0), a1 = area_of(cb1);
     __syncthreads();
     uint64_t myword = 0;
-    const int rows = min(32, n - (r0 + w * 32));
-    for (int rr = 0; rr < rows; ++rr) {
-        const int i = r0 + w * 32 + rr;
-        const float4 rbx = s_row[w * 32 + rr];
-        const float ra = (rbx.z - rbx.x) * (rbx.w - rbx.y);
-        const bool p0 = (j0 < n) && (j0 != i) && suppresses(rbx, ra, cb0, a0, s.thr, s.thr_lo, s.thr_hi);
-        const bool p1 = (j1 < n) && (j1 != i) && suppresses(rbx, ra, cb1, a1, s.thr, s.thr_lo, s.thr_hi);
+    uint32_t cw0 = 0, cw1 = 0;
+    const float4* rowp = s_row + w * 32;
+    const float* rap = s_ra + w * 32;
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr) {
+        const float4 rbx = rowp[rr];
+        const float ra = rap[rr];
+        const bool p0 = suppresses(rbx, ra, cb0, a0, s.thr, s.thr_lo, s.thr_hi);
+        const bool p1 = suppresses(rbx, ra, cb1, a1, s.thr, s.thr_lo, s.thr_hi);
         const unsigned lo = __ballot_sync(0xffffffffu, p0), hi = __ballot_sync(0xffffffffu, p1);
         if (lane == rr) myword = ((uint64_t)hi << 32) | lo;
+        cw0 |= p0 ? (1u << rr) : 0u;
+        cw1 |= p1 ? (1u << rr) : 0u;
     }
+    if (rb == cb) myword &= ~(1ull << (w * 32 + lane));      // a box does not suppress itself
     const int row = r0 + w * 32 + lane;
-    if (lane < rows) mask[(long long)row * wp + cb] = myword;
+    if (row < n && myword) {
+        mask[(long long)row * wp + cb] = myword;
+        atomicOr(&nz[row], 1u << cb);
+    }
+    if (rb != cb) {                                          // transposed words: rows of block cb, word rb
+        s_cw[w][lane] = cw0; s_cw[w][32 + lane] = cw1;
+        __syncthreads();
+        const uint64_t cw = (uint64_t)s_cw[0][tid] | ((uint64_t)s_cw[1][tid] << 32);
+        const int j = c0 + tid;
+        if (j < n && cw) {
+            mask[(long long)j * wp + rb] = cw;
+            atomicOr(&nz[j], 1u << rb);
+        }
+    }
 }
-
-// One block (256 threads) per segment.  Per 64-box chunk c:
-//   resolve  warp 0 finds the kept boxes of the chunk as the unique fixed point of
-//            kept_j = alive_j & !(any kept i < j suppresses j), iterated with two ballots
-//            per round (bit j is final after all lower bits are; typically 2-5 rounds)
-//   update   thread w ORs the rows of the kept boxes into its word w > c of the removed-set
-// STAGE (W <= 32, the RPN case): the 64 x W words of chunk c+1 are prefetched into
-// registers by all 256 threads while chunk c is processed, then parked in shared memory, so
-// no global-memory latency sits on the serial chain.  Latency-bound by design.
-constexpr int kScanThreads = 256;
 
 struct ScanOut {
     // RPN pipeline: survivors are compacted (score order) from the sel_* arrays into kept_*
@@ -109,11 +136,163 @@ struct ScanOut {
     int* keep_count;
 };
 
-template <bool STAGE>
-__global__ void __launch_bounds__(kScanThreads) k_nms_scan(NmsSegs s, int max_keep, ScanOut o) {
+__device__ __forceinline__ void emit_kept(const NmsSegs& s, const ScanOut& o, int seg, long long base, int r, int pos) {
+    if (o.keep64) {
+        o.keep64[(long long)seg * o.keep_ld + pos] = (int64_t)o.sorted_idx[(long long)seg * o.keep_ld + r];
+    } else {
+        o.dst_box[base + pos] = s.boxes[base + r];
+        o.dst_key[base + pos] = o.src_key[base + r];
+        o.dst_idx[base + pos] = o.src_idx[base + r];
+    }
+}
+
+// ---- fixed-point scan (n <= 2048) ---------------------------------------------------------------
+constexpr int kFpThreads = 1024;
+constexpr int kFpRows = 2;                           // rows per thread: 2048 boxes
+constexpr int kFpEntries = 6;                        // non-zero words of a row kept in registers
+
+__global__ void __launch_bounds__(kFpThreads) k_nms_scan_fp(NmsSegs s, int max_keep, ScanOut o) {
+    __shared__ uint32_t s_k[2][64];                  // kept bits, ping-pong (2048 bits each)
+    __shared__ int s_prefix[65];
+    const int seg = blockIdx.x;
+    const int l = seg % s.L, b = seg / s.L;
+    const int n = s.counts[seg];
+    const long long base = (long long)b * s.box_per_img + s.box_off[l];
+    const uint64_t* mask = s.mask + (long long)b * s.mask_per_img + s.mask_off[l];
+    const uint32_t* nz = s.nz + base;
+    const int wp = s.wp[l];
+    const int tid = threadIdx.x, lane = tid & 31;
+    // ---- my rows: the words (earlier boxes only) that can suppress them
+    uint64_t eb[kFpRows][kFpEntries];
+    uint32_t ew[kFpRows], over[kFpRows];
+#pragma unroll
+    for (int q = 0; q < kFpRows; ++q) {
+        const int row = tid + q * kFpThreads;
+        uint32_t m = 0;
+        if (row < n) {
+            const int dw = row >> 6;
+            m = nz[row] & (dw == 31 ? 0xffffffffu : ((2u << dw) - 1u));
+        }
+        ew[q] = 0;
+#pragma unroll
+        for (int e = 0; e < kFpEntries; ++e) {
+            uint64_t word = 0ull;
+            if (m) {
+                const int w = __ffs(m) - 1;
+                m &= m - 1;
+                word = mask[(long long)row * wp + w];
+                if (w == (row >> 6)) word &= (1ull << (row & 63)) - 1ull;
+                ew[q] |= (uint32_t)w << (5 * e);
+            }
+            eb[q][e] = word;
+        }
+        over[q] = m;                                 // rare: more than kFpEntries candidate words
+    }
+    if (tid < 64) {
+        const int lo = tid * 32;
+        s_k[0][tid] = n >= lo + 32 ? 0xffffffffu : (n > lo ? ((1u << (n - lo)) - 1u) : 0u);
+    }
+    __syncthreads();
+    int it = 0;
+    for (;; ++it) {
+        const uint32_t* cur = s_k[it & 1];
+        uint32_t* nxt = s_k[(it & 1) ^ 1];
+        bool changed = false;
+#pragma unroll
+        for (int q = 0; q < kFpRows; ++q) {
+            const int row = tid + q * kFpThreads;
+            bool sup = false;
+#pragma unroll
+            for (int e = 0; e < kFpEntries; ++e) {
+                if (eb[q][e]) {
+                    const int w = (ew[q] >> (5 * e)) & 31;
+                    const uint64_t k = (uint64_t)cur[2 * w] | ((uint64_t)cur[2 * w + 1] << 32);
+                    sup |= (k & eb[q][e]) != 0ull;
+                }
+            }
+            uint32_t m = over[q];
+            while (m && !sup) {
+                const int w = __ffs(m) - 1;
+                m &= m - 1;
+                uint64_t word = mask[(long long)row * wp + w];
+                if (w == (row >> 6)) word &= (1ull << (row & 63)) - 1ull;
+                const uint64_t k = (uint64_t)cur[2 * w] | ((uint64_t)cur[2 * w + 1] << 32);
+                sup |= (k & word) != 0ull;
+            }
+            const bool nk = (row < n) && !sup;
+            const uint32_t bits = __ballot_sync(0xffffffffu, nk);
+            const uint32_t old = cur[row >> 5];
+            if (lane == 0) nxt[row >> 5] = bits;
+            changed |= (bits != old);
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    const uint32_t* fin = s_k[(it & 1) ^ 1];
+    if (tid == 0) {
+        int run = 0;
+        for (int w = 0; w < 64; ++w) { s_prefix[w] = run; run += __popc(fin[w]); }
+        s_prefix[64] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kFpRows; ++q) {
+        const int row = tid + q * kFpThreads;
+        const uint32_t kw = fin[row >> 5];
+        if (row < n && ((kw >> lane) & 1u)) {
+            const int pos = s_prefix[row >> 5] + __popc(kw & ((1u << lane) - 1u));
+            if (max_keep <= 0 || pos < max_keep) emit_kept(s, o, seg, base, row, pos);
+        }
+    }
+    if (tid == 0) o.keep_count[seg] = (max_keep > 0 && s_prefix[64] > max_keep) ? max_keep : s_prefix[64];
+}
+
+// ---- dense upper-triangle mask + sequential scan (2048 < n <= 16384; generic entry) ------------
+// Off-diagonal tiles hold bit j of row i iff box i suppresses box j (j > i always); DIAGONAL
+// tiles hold the full symmetric relation, so (word_j & lower_bits(j)) is the set of earlier
+// boxes of the same chunk that suppress j.
+__global__ void __launch_bounds__(64) k_nms_mask_dense(NmsSegs s, int wmax) {
+    __shared__ float4 s_row[64];
+    const int seg = blockIdx.y;
+    const int l = seg % s.L, b = seg / s.L;
+    const int n = s.counts[seg];
+    int rb, cb;
+    tile_of(blockIdx.x, wmax, rb, cb);
+    const int r0 = rb * 64, c0 = cb * 64;
+    if (r0 >= n || c0 >= n) return;
+    const float4* boxes = s.boxes + (long long)b * s.box_per_img + s.box_off[l];
+    uint64_t* mask = s.mask + (long long)b * s.mask_per_img + s.mask_off[l];
+    const int wp = s.wp[l];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float4 pad = pad_box();
+    s_row[threadIdx.x] = (r0 + (int)threadIdx.x < n) ? boxes[r0 + threadIdx.x] : pad;
+    const int j0 = c0 + lane, j1 = c0 + 32 + lane;
+    const float4 cb0 = j0 < n ? boxes[j0] : pad, cb1 = j1 < n ? boxes[j1] : pad;
+    const float a0 = area_of(cb0), a1 = area_of(cb1);
+    __syncthreads();
+    uint64_t myword = 0;
+    const int rows = min(32, n - (r0 + w * 32));
+    for (int rr = 0; rr < rows; ++rr) {
+        const int i = r0 + w * 32 + rr;
+        const float4 rbx = s_row[w * 32 + rr];
+        const float ra = area_of(rbx);
+        const bool p0 = (j0 < n) && (j0 != i) && suppresses(rbx, ra, cb0, a0, s.thr, s.thr_lo, s.thr_hi);
+        const bool p1 = (j1 < n) && (j1 != i) && suppresses(rbx, ra, cb1, a1, s.thr, s.thr_lo, s.thr_hi);
+        const unsigned lo = __ballot_sync(0xffffffffu, p0), hi = __ballot_sync(0xffffffffu, p1);
+        if (lane == rr) myword = ((uint64_t)hi << 32) | lo;
+    }
+    const int row = r0 + w * 32 + lane;
+    if (lane < rows) mask[(long long)row * wp + cb] = myword;
+}
+
+// One block (256 threads) per segment.  Per 64-box chunk c: warp 0 finds the kept boxes of the
+// chunk as the fixed point of kept_j = alive_j & !(any kept i < j suppresses j) from the
+// diagonal word (two ballots per round), then every thread ORs the rows of the kept boxes into
+// its words w > c of the removed-set.
+constexpr int kScanThreads = 256;
+
+__global__ void __launch_bounds__(kScanThreads) k_nms_scan_seq(NmsSegs s, int max_keep, ScanOut o) {
     __shared__ uint64_t s_removed[kSortCap / 64];
     __shared__ uint64_t s_keepw[kSortCap / 64];
-    __shared__ uint64_t s_rows[STAGE ? 2 * 64 * 32 : 1];
     __shared__ int s_prefix[kSortCap / 64];
     __shared__ uint64_t s_keep;
     const int seg = blockIdx.x;
@@ -128,33 +307,16 @@ __global__ void __launch_bounds__(kScanThreads) k_nms_scan(NmsSegs s, int max_ke
         if (w == W - 1 && (n & 63)) r = ~0ull << (n & 63);   // rows past n are "removed"
         s_removed[w] = r; s_keepw[w] = 0;
     }
-    // staging geometry: thread t owns row (t >> 2) of the chunk and words [(t & 3) * 8, +8)
-    const int srow = threadIdx.x >> 2, sw0 = (threadIdx.x & 3) * 8;
-    uint64_t pre[8];
-    auto prefetch = [&](int c) {
-        const int row = c * 64 + srow;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int w = sw0 + q;
-            pre[q] = (row < n && w > c && w < W) ? mask[(long long)row * wp + w] : 0ull;
-        }
-    };
-    auto park = [&](int c) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) s_rows[((c & 1) * 64 + srow) * 32 + sw0 + q] = pre[q];
-    };
     uint64_t nd0 = 0, nd1 = 0;                       // diagonal words of the next chunk (warp 0)
     auto load_diag = [&](int c) {
         const int row0 = c * 64 + lane, row1 = row0 + 32;
         nd0 = (c < W && row0 < n) ? mask[(long long)row0 * wp + c] : 0ull;
         nd1 = (c < W && row1 < n) ? mask[(long long)row1 * wp + c] : 0ull;
     };
-    if (STAGE) { prefetch(0); park(0); }
     if (threadIdx.x < 32) load_diag(0);
     __syncthreads();
     int kept_total = 0;
     for (int c = 0; c < W; ++c) {
-        if (STAGE && c + 1 < W) prefetch(c + 1);
         if (threadIdx.x < 32) {
             const uint64_t low0 = nd0 & ((1ull << lane) - 1ull);
             const uint64_t low1 = nd1 & ((1ull << (lane + 32)) - 1ull);
@@ -182,36 +344,22 @@ __global__ void __launch_bounds__(kScanThreads) k_nms_scan(NmsSegs s, int max_ke
         kept_total += __popcll(keep);
         const bool done = (max_keep > 0 && kept_total >= max_keep);
         if (!done) {
-            if (STAGE) {
-                // warp g ORs the kept rows 8g..8g+7 of the chunk, lane = word: conflict-free LDS
-                const int w = lane, g = threadIdx.x >> 5;
-                if (w > c && w < W) {
-                    uint64_t acc = 0ull;
-                    const uint64_t* rows = s_rows + ((c & 1) * 64 + g * 8) * 32 + w;
+            for (int w = c + 1 + threadIdx.x; w < W; w += blockDim.x) {
+                uint64_t acc = s_removed[w], rest = keep;
+                while (rest) {                       // batches of 4 independent loads
+                    uint64_t v[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if ((keep >> (g * 8 + q)) & 1ull) acc |= rows[q * 32];
-                    if (acc) atomicOr(reinterpret_cast<unsigned long long*>(&s_removed[w]), (unsigned long long)acc);
-                }
-            } else {
-                for (int w = c + 1 + threadIdx.x; w < W; w += blockDim.x) {
-                    uint64_t acc = s_removed[w], rest = keep;
-                    while (rest) {                       // batches of 4 independent loads
-                        uint64_t v[4] = {0ull, 0ull, 0ull, 0ull};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (rest) {
-                                const int bit = __ffsll((long long)rest) - 1;
-                                rest &= rest - 1;
-                                v[q] = mask[(long long)(c * 64 + bit) * wp + w];
-                            }
+                    for (int q = 0; q < 4; ++q) {
+                        if (rest) {
+                            const int bit = __ffsll((long long)rest) - 1;
+                            rest &= rest - 1;
+                            v[q] = mask[(long long)(c * 64 + bit) * wp + w];
                         }
-                        acc |= (v[0] | v[1]) | (v[2] | v[3]);
                     }
-                    s_removed[w] = acc;
+                    acc |= (v[0] | v[1]) | (v[2] | v[3]);
                 }
+                s_removed[w] = acc;
             }
-            if (STAGE && c + 1 < W) park(c + 1);
         }
         __syncthreads();
         if (done) break;
@@ -227,27 +375,33 @@ __global__ void __launch_bounds__(kScanThreads) k_nms_scan(NmsSegs s, int max_ke
         const int w = r >> 6, bit = r & 63;
         const uint64_t kw = s_keepw[w];
         if (!((kw >> bit) & 1ull)) continue;
-        const int pos = s_prefix[w] + __popcll(kw & ((1ull << bit) - 1ull));
-        if (o.keep64) {
-            o.keep64[(long long)seg * o.keep_ld + pos] = (int64_t)o.sorted_idx[(long long)seg * o.keep_ld + r];
-        } else {
-            o.dst_box[base + pos] = s.boxes[base + r];
-            o.dst_key[base + pos] = o.src_key[base + r];
-            o.dst_idx[base + pos] = o.src_idx[base + r];
-        }
+        emit_kept(s, o, seg, base, r, s_prefix[w] + __popcll(kw & ((1ull << bit) - 1ull)));
     }
     if (threadIdx.x == 0) o.keep_count[seg] = kept_total;
 }
 
 static void set_thr(NmsSegs& s, float thr) {
     s.thr = thr;
-    s.thr_hi = thr * (1.0f + 1.0f / 262144.0f);
-    s.thr_lo = thr * (1.0f - 1.0f / 262144.0f);
+    if (thr > 0.0f && thr < 3.0e38f) {
+        s.thr_hi = thr * (1.0f + 1.0f / 262144.0f);
+        s.thr_lo = thr * (1.0f - 1.0f / 262144.0f);
+    } else {                                         // thr <= 0 / inf / NaN: always take the exact divide
+        s.thr_hi = INFINITY;
+        s.thr_lo = -INFINITY;
+    }
 }
 
-static void launch_scan(const NmsSegs& s, int S, int wmax, int max_keep, const ScanOut& o, cudaStream_t st) {
-    if (wmax <= 32) k_nms_scan<true><<<S, kScanThreads, 0, st>>>(s, max_keep, o);
-    else k_nms_scan<false><<<S, kScanThreads, 0, st>>>(s, max_keep, o);
+// mask + scan of S segments of at most n_max boxes; s.nz must be zeroed by the caller (sym path)
+static void launch_mask_scan(const NmsSegs& s, int S, int n_max, int max_keep, const ScanOut& o, cudaStream_t st) {
+    const int wmax = (n_max + 63) / 64 > 0 ? (n_max + 63) / 64 : 1;
+    dim3 grid(wmax * (wmax + 1) / 2, S);
+    if (n_max <= kFpThreads * kFpRows) {
+        k_nms_mask_sym<<<grid, 64, 0, st>>>(s, wmax);
+        k_nms_scan_fp<<<S, kFpThreads, 0, st>>>(s, max_keep, o);
+    } else {
+        k_nms_mask_dense<<<grid, 64, 0, st>>>(s, wmax);
+        k_nms_scan_seq<<<S, kScanThreads, 0, st>>>(s, max_keep, o);
+    }
 }
 
 // generic entry: sort (score desc, index asc) and gather boxes into score order
@@ -288,16 +442,17 @@ int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st) {
         s.wp[l] = (p.kcap[l] + 63) / 64;
         wmax = max(wmax, s.wp[l]);
     }
-    s.boxes = p.sel_box; s.counts = p.sel_count; s.mask = p.mask;
+    s.boxes = p.sel_box; s.counts = p.sel_count; s.mask = p.mask; s.nz = p.nz;   // nz zeroed with the workspace head
     set_thr(s, p.nms_thr);
     const int S = p.B * p.L;
-    dim3 grid(wmax * (wmax + 1) / 2, S);
-    k_nms_mask<<<grid, 64, 0, st>>>(s, wmax);
+    int n_max = 1;
+    for (int l = 0; l < p.L; ++l) n_max = max(n_max, p.kcap[l]);
+    (void)wmax;
     ScanOut o;
     memset(&o, 0, sizeof(o));
     o.src_key = p.sel_key; o.src_idx = p.sel_idx; o.dst_box = p.kept_box; o.dst_key = p.kept_key; o.dst_idx = p.kept_idx;
     o.keep_count = p.keep_count;
-    launch_scan(s, S, wmax, p.post_nms, o, st);
+    launch_mask_scan(s, S, n_max, p.post_nms, o, st);
     return check_launch("rpn_nms");
 }
 
@@ -312,7 +467,8 @@ size_t b2d_nms_workspace_bytes(long long n_max, int S) {
     const size_t n = (size_t)(n_max > 0 ? n_max : 1);
     const size_t wp = (n + 63) / 64;
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    return al((size_t)S * n * 16) + al((size_t)S * n * 4) + al((size_t)S * n * wp * 8) + al((size_t)S * 4);
+    return al((size_t)S * n * 16) + al((size_t)S * n * 4) + al((size_t)S * n * wp * 8) + al((size_t)S * 4) +
+           al((size_t)S * n * 4);
 }
 
 int b2d_nms(int64_t* keep, int* keep_count, const float* boxes, const float* scores, long long n_ld,
@@ -329,7 +485,8 @@ int b2d_nms(int64_t* keep, int* keep_count, const float* boxes, const float* sco
     float4* sorted_box = (float4*)base; base += al((size_t)S * n_ld * 16);
     int* sorted_idx = (int*)base; base += al((size_t)S * n_ld * 4);
     uint64_t* mask = (uint64_t*)base; base += al((size_t)S * n_ld * wp * 8);
-    int* cnt = (int*)base;
+    int* cnt = (int*)base; base += al((size_t)S * 4);
+    uint32_t* nz = (uint32_t*)base;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_nms_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
@@ -342,15 +499,13 @@ int b2d_nms(int64_t* keep, int* keep_count, const float* boxes, const float* sco
     NmsSegs s;
     memset(&s, 0, sizeof(s));
     s.L = 1; s.box_per_img = n_ld; s.mask_per_img = (long long)n_ld * wp; s.wp[0] = wp;
-    s.boxes = sorted_box; s.counts = cnt; s.mask = mask;
+    s.boxes = sorted_box; s.counts = cnt; s.mask = mask; s.nz = nz;
     set_thr(s, thr_f);
-    const int wmax = (int)((n + 63) / 64);
-    dim3 grid(wmax * (wmax + 1) / 2, S);
-    k_nms_mask<<<grid, 64, 0, st>>>(s, wmax);
+    if (n <= kFpThreads * kFpRows) cudaMemsetAsync(nz, 0, (size_t)S * n_ld * 4, st);
     ScanOut o;
     memset(&o, 0, sizeof(o));
     o.keep64 = keep; o.sorted_idx = sorted_idx; o.keep_ld = n_ld; o.keep_count = keep_count;
-    launch_scan(s, S, wmax, max_keep, o, st);
+    launch_mask_scan(s, S, (int)n, max_keep, o, st);
     return check_launch("nms");
 }
 

@@ -25,6 +25,7 @@ struct RpnLaunch {
     float nms_thr, min_size, ms[8];
     // workspace
     uint32_t* hist; int* cand_count; int* sel_count; int* keep_count; int* thr_bin;
+    uint32_t* nz;                       // NMS: per selected box, bitmap of its non-zero mask words (nms.cu)
     size_t zero_bytes;
     uint64_t* cand; uint64_t* cand2;
     float4* sel_box; uint32_t* sel_key; int* sel_idx;

@@ -386,6 +386,82 @@ __global__ void __launch_bounds__(kSelThreads) k_merge(RpnLaunch p, float* __res
     if (threadIdx.x == 0) count[b] = nout;
 }
 
+
+// ---------------------------------------------------------------- k_merge_rank
+// Multi-block form of the merge for the common case (every per-level list is key-descending):
+// one thread per surviving element computes its global rank by binary searches over the other
+// levels' key lists in global memory (L2-resident) and scatters box/score/provenance straight
+// to its output slot.  Replaces a single 1024-thread block per image (69 us, ncu r1d).
+__global__ void __launch_bounds__(256) k_merge_rank(RpnLaunch p, float* __restrict__ props,
+                                                    float* __restrict__ scores, int* __restrict__ count,
+                                                    int* __restrict__ prov) {
+    __shared__ int s_off[kMaxLevels + 1];
+    const int b = blockIdx.y;
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int l = 0; l < p.L; ++l) {
+            s_off[l] = run;
+            int c = p.do_nms ? p.keep_count[b * p.L + l] : p.sel_count[b * p.L + l];
+            if (p.post_nms > 0 && c > p.post_nms) c = p.post_nms;
+            run += c;
+        }
+        s_off[p.L] = run;
+    }
+    __syncthreads();
+    const int total = s_off[p.L];
+    const bool topk = (p.max_num > 0) && (total > p.max_num);
+    const int nout = topk ? p.max_num : total;
+    const float4* m_box = (p.do_nms ? p.kept_box : p.sel_box) + (long long)b * p.sel_per_img;
+    const uint32_t* m_key = (p.do_nms ? p.kept_key : p.sel_key) + (long long)b * p.sel_per_img;
+    const int* m_idx = (p.do_nms ? p.kept_idx : p.sel_idx) + (long long)b * p.sel_per_img;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    float* pb = props + (long long)b * 4 * p.out_ld;
+    if (t == 0) count[b] = nout;
+    if (t >= nout && t < p.out_ld) {                     // padding slots
+        pb[t] = 0.f; pb[p.out_ld + t] = 0.f; pb[2 * p.out_ld + t] = 0.f; pb[3 * p.out_ld + t] = 0.f;
+        scores[(long long)b * p.out_ld + t] = 0.f;
+        if (prov) prov[(long long)b * p.out_ld + t] = -1;
+    }
+    if (t >= total) return;
+    int l = 0;
+    for (int q = 1; q < p.L; ++q) if (t >= s_off[q]) l = q;
+    const int pos = t - s_off[l];
+    const long long o = p.sel_off[l] + pos;
+    const uint32_t key = m_key[o];
+    int rank = t;
+    if (topk) {
+        rank = pos;
+        int lo[kMaxLevels], hi[kMaxLevels];
+#pragma unroll
+        for (int q = 0; q < kMaxLevels; ++q) {
+            const bool on = q < p.L && q != l;
+            lo[q] = 0; hi[q] = on ? s_off[q + 1] - s_off[q] : 0;
+        }
+        for (int step = 0; step < 15; ++step) {          // 2^14 = kSortCap elements at most
+            bool any = false;
+#pragma unroll
+            for (int q = 0; q < kMaxLevels; ++q) {
+                if (lo[q] < hi[q]) {
+                    const int mid = (lo[q] + hi[q]) >> 1;
+                    const uint32_t km = m_key[p.sel_off[q] + mid];
+                    const bool before = (q < l) ? (km >= key) : (km > key);
+                    if (before) lo[q] = mid + 1; else hi[q] = mid;
+                    any = true;
+                }
+            }
+            if (!any) break;
+        }
+#pragma unroll
+        for (int q = 0; q < kMaxLevels; ++q) rank += lo[q];
+    }
+    if (rank < nout) {
+        const float4 bx = m_box[o];
+        pb[rank] = bx.x; pb[p.out_ld + rank] = bx.y; pb[2 * p.out_ld + rank] = bx.z; pb[3 * p.out_ld + rank] = bx.w;
+        scores[(long long)b * p.out_ld + rank] = 1.0f / (1.0f + expf(-key2f(key)));
+        if (prov) prov[(long long)b * p.out_ld + rank] = (int)(p.pyr.lv[l].offset + m_idx[o]);
+    }
+}
+
 // ---------------------------------------------------------------- generic segmented top-k
 __global__ void __launch_bounds__(kSelThreads) k_topk_small(int* __restrict__ idx, int* __restrict__ out_count,
                                                             const float* __restrict__ values, long long ld,
@@ -451,6 +527,7 @@ bool rpn_plan(RpnLaunch& p, const b2d_pyramid* pyr, int B, const b2d_rpn_cfg* cf
     p.sel_count = (int*)carve((size_t)S * 4);
     p.keep_count = (int*)carve((size_t)S * 4);
     p.thr_bin = (int*)carve((size_t)S * 4);
+    p.nz = (uint32_t*)carve(cfg->do_nms ? (size_t)B * p.sel_per_img * 4 : 0);
     p.zero_bytes = o;                                   // everything above is zeroed per call
     p.cand = (uint64_t*)carve((size_t)B * pyr->total * 8);
     p.cand2 = (uint64_t*)carve((size_t)B * pyr->total * 8);
@@ -516,7 +593,18 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
         int rc = rpn_nms_launch(p, st);
         if (rc != B2D_OK) return rc;
     }
-    k_merge<<<B, kSelThreads, kSortCap * 8, st>>>(p, props, scores, count, prov);
+    bool sorted_lists = true;                            // see k_merge: unsorted only without NMS and without top-k
+    int cat = 0;
+    for (int l = 0; l < p.L; ++l) {
+        if (p.kcap[l] >= p.n[l] && !p.do_nms) sorted_lists = false;
+        cat += (p.post_nms > 0 && p.post_nms < p.kcap[l]) ? p.post_nms : p.kcap[l];
+    }
+    if (sorted_lists) {
+        dim3 g(cdiv(max(cat, p.out_ld), 256), B);
+        k_merge_rank<<<g, 256, 0, st>>>(p, props, scores, count, prov);
+    } else {
+        k_merge<<<B, kSelThreads, kSortCap * 8, st>>>(p, props, scores, count, prov);
+    }
     return check_launch("rpn_proposals");
 }
 

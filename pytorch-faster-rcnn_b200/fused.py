@@ -24,6 +24,21 @@ def _ptrs(tensors):
     return arr
 
 
+def _batch_view(obj, b0, b1, rows_per_image=None):
+    """Shallow copy of a batched stage object restricted to images [b0, b1): every tensor
+    attribute is re-sliced along dim 0 (views, no copies), so a sub-batch can run on its own
+    stream while the full-batch object keeps owning the memory."""
+    import copy
+    v = copy.copy(obj)
+    rows_per_image = rows_per_image or {}
+    for k, t in list(vars(obj).items()):
+        if isinstance(t, torch.Tensor) and t.dim() >= 1 and k != "ws":
+            r = rows_per_image.get(k, 1)
+            v.__dict__[k] = t[b0 * r:b1 * r]
+    v.B, v.b0 = b1 - b0, getattr(obj, "b0", 0) + b0
+    return v
+
+
 class AnchorPyramid(object):
     """Closed-form anchors of an anchor head (lib/heads/anchor_head.py:33-36): per level
     stride == base size, shared scales/ratios; nothing is materialised."""
@@ -69,6 +84,12 @@ class RpnProposals(object):
         self.prov = torch.zeros((B, self.P), dtype=torch.int32, device=device)
         self.launches = 7 if do_nms else 5   # memset, hist, compact, select, (mask, scan), merge
 
+    def slice(self, b0, b1):
+        v = _batch_view(self, b0, b1)
+        nbytes = _C.lib().b2d_rpn_proposals_workspace_bytes(ctypes.byref(self.pyr.c), v.B, ctypes.byref(self.cfg))
+        v.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.ws.device)
+        return v
+
     def __call__(self, cls_outs, reg_outs, img_hw):
         _C.call("b2d_rpn_proposals", _C.ptr(self.props), _C.ptr(self.scores), _C.ptr(self.count), _C.ptr(self.prov),
                 _ptrs(cls_outs), _ptrs(reg_outs), ctypes.byref(self.pyr.c), _C.ptr(img_hw), self.B,
@@ -101,7 +122,11 @@ class BatchedTargets(object):
         self.tar_is_gt = torch.zeros((B, self.max_num), dtype=i64, device=device)
         self.means, self.stds = _C.host_f4(means, [0, 0, 0, 0]), _C.host_f4(stds, [1, 1, 1, 1])
         self.step = 0
+        self.b0 = 0
         self.launches = 6   # fill, memset, colmax, label, sample, encode
+
+    def slice(self, b0, b1):
+        return _batch_view(self, b0, b1)
 
     def __call__(self, gt, gt_count, gt_label=None, boxes=None, box_count=None, img_hw=None):
         pyr = ctypes.byref(self.pyr.c) if boxes is None else None
@@ -117,7 +142,8 @@ class BatchedTargets(object):
         n = self.N if cnt is None else 0
         _C.call("b2d_sample_labels", _C.ptr(self.chosen), _C.ptr(self.n_chosen), _C.ptr(self.labels), self.out_ld,
                 _C.ptr(cnt), _C.ptr(cnt_add), n, _C.ptr(self.census), _C.ptr(self.pos_list), self.out_ld, self.B,
-                self.max_num, self.pos_num, (self.seed * 1000003 + self.step) & 0xFFFFFFFFFFFFFFFF, _C.stream())
+                self.max_num, self.pos_num,
+                (self.seed * 1000003 + self.step + 0x632BE59BD9B4E019 * self.b0) & 0xFFFFFFFFFFFFFFFF, _C.stream())
         _C.call("b2d_encode_targets", _C.ptr(self.tar_box), _C.ptr(self.tar_gt), _C.ptr(self.tar_param),
                 _C.ptr(self.tar_label), _C.ptr(self.tar_is_gt), _C.ptr(self.chosen), _C.ptr(self.n_chosen),
                 self.max_num, _C.ptr(self.labels), self.out_ld, _C.ptr(boxes), box_ld, pyr, _C.ptr(gt), self.gt_ld,
@@ -140,6 +166,9 @@ class BatchedRoIAlign(object):
         self.out = torch.zeros((B * ld, cfg.C, cfg.PH, cfg.PW), dtype=torch.float32, device=device)
         self.launches = 1
 
+    def slice(self, b0, b1):
+        return _batch_view(self, b0, b1, rows_per_image={"out": self.ld})
+
     def __call__(self, feats, rois, counts):
         _C.call("b2d_roi_align_fwd_batched", _C.ptr(self.out), _ptrs(feats), _C.ptr(rois), self.ld, _C.ptr(counts),
                 self.B, ctypes.byref(self.cfg), _C.stream())
@@ -155,7 +184,8 @@ class TrainHotPath(object):
 
     def __init__(self, B, grids, device, strides=(4, 8, 16, 32, 64), gt_ld=64, feat_channels=256,
                  rpn_proposal=None, rpn_assigner=None, rpn_sampler=None, rcnn_assigner=None, rcnn_sampler=None,
-                 rpn_stds=(1.0, 1.0, 1.0, 1.0), rcnn_stds=(0.1, 0.1, 0.2, 0.2), allowed_border=0, layout=1, seed=0):
+                 rpn_stds=(1.0, 1.0, 1.0, 1.0), rcnn_stds=(0.1, 0.1, 0.2, 0.2), allowed_border=0, layout=1, seed=0,
+                 groups=1, overlap=False):
         z4 = (0.0, 0.0, 0.0, 0.0)
         rpn_proposal = rpn_proposal or dict(pre_nms=2000, post_nms=2000, max_num=2000, nms_iou=0.7, min_bbox_size=0)
         rpn_assigner = rpn_assigner or dict(pos_iou=0.7, neg_iou=0.3, min_pos_iou=0.3)
@@ -175,14 +205,58 @@ class TrainHotPath(object):
         m = rpn_sampler["max_num"]
         self.tar_cls = torch.zeros((B, 1, m), dtype=torch.float32, device=device)
         self.tar_reg = torch.zeros((B, 4, m), dtype=torch.float32, device=device)
-        self.launches = self.proposals.launches + self.rpn_targets.launches + 1 + self.roi_targets.launches + 1
+        # Stream plan.  The proposal chain (top-k -> NMS scan -> merge) is a sequence of small,
+        # latency-bound grids, the RPN-target and RoIAlign kernels are throughput-bound, and the
+        # images are independent, so the batch is cut into `groups` sub-batches whose chains
+        # (proposals -> RoI targets -> RoIAlign) run on their own streams next to the RPN-target
+        # chain: latency-bound kernels of one group fill the SMs the others leave idle.  Under
+        # CUDA-graph capture the fork/join below becomes parallel graph branches.
+        groups = max(1, min(int(groups), B))
+        while B % groups:
+            groups -= 1
+        self.groups = groups
+        self.subs = []
+        if groups > 1 or overlap:
+            per = B // groups
+            for g in range(groups):
+                b0, b1 = g * per, (g + 1) * per
+                self.subs.append((b0, b1, self.proposals.slice(b0, b1) if groups > 1 else self.proposals,
+                                  self.roi_targets.slice(b0, b1) if groups > 1 else self.roi_targets,
+                                  self.roi_align.slice(b0, b1) if groups > 1 else self.roi_align,
+                                  torch.cuda.Stream(device=device, priority=-1),     # latency-bound chain
+                                  torch.cuda.Stream(device=device, priority=0)))     # RoIAlign (throughput)
+            self.s_rpn = torch.cuda.Stream(device=device, priority=0)
+        per_group = self.proposals.launches + self.roi_targets.launches + 1
+        self.launches = per_group * groups + self.rpn_targets.launches + 1
 
-    def step(self, cls_outs, reg_outs, feats, gt, gt_count, gt_label, img_hw):
-        props, scores, count = self.proposals(cls_outs, reg_outs, img_hw)
+    def _rpn_target_chain(self, cls_outs, reg_outs, gt, gt_count, img_hw):
         rt = self.rpn_targets(gt, gt_count, None, img_hw=img_hw)
         _C.call("b2d_gather_head_outputs", _C.ptr(self.tar_cls), _C.ptr(self.tar_reg), _ptrs(cls_outs), _ptrs(reg_outs),
                 ctypes.byref(self.pyr.c), 1, _C.ptr(rt.chosen), _C.ptr(rt.n_chosen), rt.max_num, self.B, _C.stream())
-        bt = self.roi_targets(gt, gt_count, gt_label, boxes=props, box_count=count)
-        roi_feats = self.roi_align(feats, bt.tar_box, bt.n_chosen)
-        return dict(props=props, scores=scores, prop_count=count, rpn=rt, rpn_tar_cls=self.tar_cls,
-                    rpn_tar_reg=self.tar_reg, rcnn=bt, roi_feats=roi_feats)
+        return rt
+
+    def step(self, cls_outs, reg_outs, feats, gt, gt_count, gt_label, img_hw):
+        if not self.subs:
+            props, scores, count = self.proposals(cls_outs, reg_outs, img_hw)
+            rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
+            bt = self.roi_targets(gt, gt_count, gt_label, boxes=props, box_count=count)
+            self.roi_align(feats, bt.tar_box, bt.n_chosen)
+        else:
+            cur = torch.cuda.current_stream()
+            for (b0, b1, prop, tgt, ra, st, st_lo) in self.subs:
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    p, _, c = prop([t[b0:b1] for t in cls_outs], [t[b0:b1] for t in reg_outs], img_hw[b0:b1])
+                    t2 = tgt(gt[b0:b1], gt_count[b0:b1], gt_label[b0:b1], boxes=p, box_count=c)
+                st_lo.wait_stream(st)
+                with torch.cuda.stream(st_lo):
+                    ra([f[b0:b1] for f in feats], t2.tar_box, t2.n_chosen)
+            self.s_rpn.wait_stream(cur)
+            with torch.cuda.stream(self.s_rpn):
+                rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
+            for sub in self.subs:
+                cur.wait_stream(sub[-1])
+            cur.wait_stream(self.s_rpn)
+        return dict(props=self.proposals.props, scores=self.proposals.scores, prop_count=self.proposals.count,
+                    rpn=self.rpn_targets, rpn_tar_cls=self.tar_cls, rpn_tar_reg=self.tar_reg, rcnn=self.roi_targets,
+                    roi_feats=self.roi_align.out)
