@@ -40,6 +40,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's dominant kernel, from the
+    committed ncu --set full capture (profiles/traffic.json, written by scripts/profile_summary.py)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(stage)
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
@@ -159,8 +168,7 @@ def run_b200(args):
     gt, gl = h_gt.to(dev), h_gl.to(dev)
     gcount = torch.full((B,), K_GT, dtype=torch.int32, device=dev)
     img_hw = torch.tensor([[float(w["img_shape"][0]), float(w["img_shape"][1])]] * B, device=dev)
-    hp = fused.TrainHotPath(B, grids, dev, gt_ld=K_GT, feat_channels=256, layout=1)
-    hp_e2e = fused.TrainHotPath(B, grids, dev, gt_ld=K_GT, feat_channels=256, layout=0)  # NCHW, as the reference hands it over
+    hp = fused.TrainHotPath(B, grids, dev, gt_ld=K_GT, feat_channels=256, layout=1, overlap=True)
 
     def step():
         return hp.step(cls, reg, feats, gt, gcount, gl, img_hw)
@@ -220,31 +228,16 @@ def run_b200(args):
     torch.cuda.synchronize()
     stage_ms = {s: float(np.mean([evs[it][i].elapsed_time(evs[it][i + 1]) for it in range(args.steps)]))
                 for i, s in enumerate(stages)}
-    # ---- end-to-end through the public API with HOST buffers (NCHW fp32, reference layout)
-    d_cls, d_reg = [torch.empty_like(t) for t in cls], [torch.empty_like(t) for t in reg]
-    d_feat = [torch.empty_like(t) for t in feats_nchw]
-    d_gt, d_gl = torch.empty_like(gt), torch.empty_like(gl)
-    o = hp_e2e
-    h_out = dict(props=torch.empty((B, 4, o.proposals.P)).pin_memory(), scores=torch.empty((B, o.proposals.P)).pin_memory(),
-                 count=torch.empty(B, dtype=torch.int32).pin_memory(),
-                 rpn_lab=torch.empty((B, 256), dtype=torch.int64).pin_memory(), rpn_par=torch.empty((B, 4, 256)).pin_memory(),
-                 roi_lab=torch.empty((B, 512), dtype=torch.int64).pin_memory(), roi_par=torch.empty((B, 4, 512)).pin_memory(),
-                 roi_sum=torch.empty(1).pin_memory())
-    h2d = sum(t.numel() * t.element_size() for t in h_cls + h_reg + h_feat + [h_gt, h_gl])
-    d2h = sum(t.numel() * t.element_size() for t in h_out.values())
-
+    # ---- end-to-end through the public API with HOST buffers (fp32 NCHW, the reference layout):
+    # TrainHotPath.step_from_host = pinned host inputs -> H2D -> NCHW->NHWC -> hot path -> D2H of the results
     def e2e_step():
-        for d, h in zip(d_cls + d_reg + d_feat + [d_gt, d_gl], h_cls + h_reg + h_feat + [h_gt, h_gl]):
-            d.copy_(h, non_blocking=True)
-        r = o.step(d_cls, d_reg, d_feat, d_gt, gcount, d_gl, img_hw)
-        h_out["props"].copy_(r["props"], non_blocking=True); h_out["scores"].copy_(r["scores"], non_blocking=True)
-        h_out["count"].copy_(r["prop_count"], non_blocking=True)
-        h_out["rpn_lab"].copy_(r["rpn"].tar_label, non_blocking=True); h_out["rpn_par"].copy_(r["rpn"].tar_param, non_blocking=True)
-        h_out["roi_lab"].copy_(r["rcnn"].tar_label, non_blocking=True); h_out["roi_par"].copy_(r["rcnn"].tar_param, non_blocking=True)
-        h_out["roi_sum"].copy_(r["roi_feats"][0, 0, 0, :1], non_blocking=True)
+        return hp.step_from_host(h_cls, h_reg, h_feat, h_gt, h_gl, gcount, img_hw)
 
     for _ in range(3):
-        e2e_step()
+        h_out = e2e_step()
+    torch.cuda.synchronize()
+    h2d = sum(t.numel() * t.element_size() for t in h_cls + h_reg + h_feat + [h_gt, h_gl])
+    d2h = sum(t.numel() * t.element_size() for t in h_out.values())
     n_e2e = max(3, min(args.steps, 10))
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -285,9 +278,9 @@ def run_b200(args):
         }
         ach = stage_bytes[dom] / (stage_ms[dom] / 1e3) / 1e9
         path_bytes = sum(stage_bytes.values())
-        roofline = {"bound": "hbm", "kernel": {"roi_align": "k_roi_align_nhwc<float>", "proposals": "k_hist..k_merge (K3+K4)",
+        roofline = {"bound": "hbm", "kernel": {"roi_align": "k_roi_align_win<float>", "proposals": "k_hist..k_merge (K3+K4)",
                                                "rpn_targets": "k_assign_colmax/label (K2)", "roi_targets": "k_assign (K2)"}[dom],
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic(dom),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": stage_bytes[dom],
                     "stage_ms": stage_ms, "stage_algorithmic_bytes": stage_bytes,
                     "path_frac": (path_bytes / ((ms / args.steps) / 1e3) / 1e9) / peak}
@@ -313,7 +306,7 @@ def run_b200(args):
                                             "features": "fp32 NHWC (channels_last) resident in HBM", "cuda_graph": graph is not None,
                                             "l2": "inputs per step (755 MB/GPU) exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "layout": "host fp32 NCHW (reference layout) -> H2D -> NCHW kernels"},
+                    "ms_per_step": e2e_ms, "layout": "pinned host fp32 NCHW (reference layout) -> H2D (copy stream) -> NCHW->NHWC -> hot path -> D2H of proposals/targets"},
             "gpu_launches": hp.launches * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}))
     if world > 1:
         dist.destroy_process_group()

@@ -190,6 +190,9 @@ B2D_API size_t b2d_roi_align_bwd_workspace_bytes(long long R, int B, const b2d_r
 B2D_API int b2d_roi_align_bwd(void* const* grad_feat_ptrs_host, const float* grad_out, const float* rois,
                       long long roi_ld, const int* roi_img, const int* levels, long long R, int B,
                       const b2d_roi_cfg* cfg_host, void* workspace, size_t ws_bytes, void* stream);
+/* fp32 NCHW [B,C,H,W] -> NHWC [B,H,W,C]: reference-layout FPN features (lib/necks.py:69-90)
+ * to the channels-last layout the vectorised RoIAlign kernels read. */
+B2D_API int b2d_nchw_to_nhwc(float* dst, const float* src, int B, int C, int H, int W, void* stream);
 B2D_API int b2d_roi_levels(int* levels, const float* rois, long long roi_ld, long long R, float finest_scale,
                    int num_levels, void* stream);
 

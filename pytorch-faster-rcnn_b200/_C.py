@@ -71,6 +71,7 @@ _SIGS = {
     "b2d_roi_align_fwd": [_P, _P, _P, c_ll, _P, _P, c_ll, _P, _P],
     "b2d_roi_align_bwd": [_P, _P, _P, c_ll, _P, _P, c_ll, c_int, _P, _P, c_size_t, _P],
     "b2d_roi_levels": [_P, _P, c_ll, c_ll, c_float, c_int, _P],
+    "b2d_nchw_to_nhwc": [_P, _P, c_int, c_int, c_int, c_int, _P],
     "b2d_roi_pool_fwd": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_ll, _P, c_ll, c_float, c_int, c_int, _P],
     "b2d_roi_pool_bwd": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_ll, _P, c_ll, c_float, c_int, c_int, _P,
                          c_size_t, _P],

@@ -32,6 +32,7 @@ struct RoiArgs {
     long long R;
     long long batched_ld;          // > 0: rois are image-major [B][4][ld], counts per image
     const int* counts;
+    int pf_dist;                   // window kernel: L2-prefetch the RoI pf_dist CTAs ahead (0 = off)
 };
 
 // slot r -> (image, coordinates); false if the slot is past the image's count
@@ -299,6 +300,184 @@ __global__ void __launch_bounds__(256, MINB) k_roi_align_nhwc4(RoiArgs a, float*
     }
 }
 
+
+// ---- window kernel: the batched-load kernel with the duplicate taps of a bin removed ------------
+// The 2x2 samples of a bin touch the cells {lo0, hi0, lo1, hi1} per axis.  With a sample
+// spacing below two cells (RoI narrower than ~28 cells, i.e. every RoI the FPN level map
+// sends to a level) lo1 - lo0 is 0, 1 or 2 and the taps fall into a (PY+2) x (PX+2) window of
+// distinct cells, so a bin needs 4..16 loads instead of 16 (387 instead of 784 per RoI on the
+// config-2 workload: the kernel was bound by L1 wavefronts, ncu prof_roi4).  The pattern
+// (PY, PX) is uniform over the two warps that share a bin, every sample still reads "its"
+// four cells from the window registers and is summed in torchvision's order, so the result
+// stays bit-identical to the reference.
+struct __align__(16) BinTab {
+    int ry[4];          // byte offsets of the window rows   (rows PY, PY+1 belong to sample iy = 1)
+    int cx[4];          // byte offsets of the window columns
+    float w[16];        // w1..w4 of the samples (iy, ix) = (0,0), (0,1), (1,0), (1,1)
+    int pat, _p0, _p1, _p2;
+};
+
+template <typename FT, int PY, int PX>
+__device__ __forceinline__ float4 bin_eval(const char* fb, const BinTab* t) {
+    const int4 ry = *reinterpret_cast<const int4*>(t->ry);
+    const int4 cx = *reinterpret_cast<const int4*>(t->cx);
+    const int ryv[4] = {ry.x, ry.y, ry.z, ry.w}, cxv[4] = {cx.x, cx.y, cx.z, cx.w};
+    float4 v[4][4];
+#pragma unroll
+    for (int r = 0; r < PY + 2; ++r) {
+        const char* rp = fb + ryv[r];
+#pragma unroll
+        for (int c = 0; c < PX + 2; ++c) v[r][c] = ld4b<FT>(rp + cxv[c]);
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy) {
+#pragma unroll
+        for (int ix = 0; ix < 2; ++ix) {
+            const int r0 = iy ? PY : 0, c0 = ix ? PX : 0;
+            const float4 w = *reinterpret_cast<const float4*>(&t->w[(iy * 2 + ix) * 4]);
+            const float4 v1 = v[r0][c0], v2 = v[r0][c0 + 1], v3 = v[r0 + 1][c0], v4 = v[r0 + 1][c0 + 1];
+            acc.x += ((w.x * v1.x + w.y * v2.x) + w.z * v3.x) + w.w * v4.x;
+            acc.y += ((w.x * v1.y + w.y * v2.y) + w.z * v3.y) + w.w * v4.y;
+            acc.z += ((w.x * v1.z + w.y * v2.z) + w.z * v3.z) + w.w * v4.z;
+            acc.w += ((w.x * v1.w + w.y * v2.w) + w.z * v3.w) + w.w * v4.w;
+        }
+    }
+    return acc;
+}
+
+template <typename FT>
+__global__ void __launch_bounds__(256, 2) k_roi_align_win(RoiArgs a, float* __restrict__ out) {
+    extern __shared__ float s_tile[];                      // [kCTile][bins] (+ bin table behind it)
+    const long long r = blockIdx.x;
+    const b2d_roi_cfg& c = a.cfg;
+    float x1, y1, x2, y2;
+    int img;
+    if (!roi_fetch(a, r, img, x1, y1, x2, y2)) return;
+    int lvl;
+    if (a.levels) lvl = a.levels[r];
+    else lvl = c.num_levels > 1 ? roi_level(x1, y1, x2, y2, c.finest_scale, c.num_levels) : 0;
+    const int H = c.H[lvl], W = c.W[lvl], C = c.C;
+    const int bins = c.PH * c.PW;
+    BinTab* s_tab = reinterpret_cast<BinTab*>(s_tile + kCTile * bins);
+    const RoiGeom g = roi_geom(x1, y1, x2, y2, c.spatial_scale[lvl], c.PH, c.PW, 2, c.aligned);
+    // L2 prefetch for the RoI that runs `pf_dist` CTAs later: one bulk prefetch per feature row of
+    // its tap rectangle (rows are contiguous in NHWC).  Costs no registers, and turns the DRAM
+    // round trips of that CTA's gathers into L2 hits.
+    if (a.pf_dist > 0 && threadIdx.x >= 64 && threadIdx.x < 128) {
+        const long long r2 = r + a.pf_dist;
+        float px1, py1, px2, py2;
+        int img2;
+        if (r2 < a.R && roi_fetch(a, r2, img2, px1, py1, px2, py2)) {
+            const int lvl2 = a.levels ? a.levels[r2]
+                                      : (c.num_levels > 1 ? roi_level(px1, py1, px2, py2, c.finest_scale, c.num_levels) : 0);
+            const int H2 = c.H[lvl2], W2 = c.W[lvl2];
+            const RoiGeom g2 = roi_geom(px1, py1, px2, py2, c.spatial_scale[lvl2], c.PH, c.PW, 2, c.aligned);
+            const AxisTap ya = axis_tap(g2.sy, g2.bh, 0, 0, 2, H2), yb = axis_tap(g2.sy, g2.bh, c.PH - 1, 1, 2, H2);
+            const AxisTap xa = axis_tap(g2.sx, g2.bw, 0, 0, 2, W2), xb = axis_tap(g2.sx, g2.bw, c.PW - 1, 1, 2, W2);
+            const int ylo = min(ya.lo, yb.lo), yhi = max(ya.hi, yb.hi);
+            const int xlo = min(xa.lo, xb.lo), xhi = max(xa.hi, xb.hi);
+            const FT* f2 = reinterpret_cast<const FT*>(a.feat[lvl2]) + (long long)img2 * H2 * W2 * C;
+            const unsigned bytes = (unsigned)(xhi - xlo + 1) * C * (unsigned)sizeof(FT);
+            for (int y = ylo + (int)threadIdx.x - 64; y <= yhi; y += 64) {
+                const FT* ptr = f2 + ((long long)y * W2 + xlo) * C;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+            }
+        }
+    }
+    if ((int)threadIdx.x < bins) {
+        const int bin = threadIdx.x, ph = bin / c.PW, pw = bin - ph * c.PW;
+        const AxisTap ty0 = axis_tap(g.sy, g.bh, ph, 0, 2, H), ty1 = axis_tap(g.sy, g.bh, ph, 1, 2, H);
+        const AxisTap tx0 = axis_tap(g.sx, g.bw, pw, 0, 2, W), tx1 = axis_tap(g.sx, g.bw, pw, 1, 2, W);
+        const int es = (int)sizeof(FT);
+        BinTab t;
+        // window rows: PY in {0,1}: lo0 + {0..PY+1} clamped like the taps; PY = 2: {lo0, hi0, lo1, hi1}
+        const int dy = ty1.lo - ty0.lo, dx = tx1.lo - tx0.lo;
+        const int py = (dy >= 0 && dy < 2) ? dy : 2, px = (dx >= 0 && dx < 2) ? dx : 2;   // 2 = explicit {lo0,hi0,lo1,hi1}
+        int yy[4], xx[4];
+        if (py < 2) { for (int k = 0; k < 4; ++k) yy[k] = min(ty0.lo + k, H - 1); }
+        else { yy[0] = ty0.lo; yy[1] = ty0.hi; yy[2] = ty1.lo; yy[3] = ty1.hi; }
+        if (px < 2) { for (int k = 0; k < 4; ++k) xx[k] = min(tx0.lo + k, W - 1); }
+        else { xx[0] = tx0.lo; xx[1] = tx0.hi; xx[2] = tx1.lo; xx[3] = tx1.hi; }
+        for (int k = 0; k < 4; ++k) { t.ry[k] = yy[k] * W * C * es; t.cx[k] = xx[k] * C * es; }
+        const AxisTap* tys[2] = {&ty0, &ty1};
+        const AxisTap* txs[2] = {&tx0, &tx1};
+        for (int iy = 0; iy < 2; ++iy)
+            for (int ix = 0; ix < 2; ++ix) {
+                const AxisTap& ty = *tys[iy];
+                const AxisTap& tx = *txs[ix];
+                float* w = &t.w[(iy * 2 + ix) * 4];
+                if (ty.valid && tx.valid) { w[0] = ty.h * tx.h; w[1] = ty.h * tx.l; w[2] = ty.l * tx.h; w[3] = ty.l * tx.l; }
+                else { w[0] = w[1] = w[2] = w[3] = 0.0f; }
+            }
+        t.pat = py * 3 + px; t._p0 = t._p1 = t._p2 = 0;
+        s_tab[bin] = t;
+    }
+    __syncthreads();
+    const FT* feat = reinterpret_cast<const FT*>(a.feat[lvl]) + (long long)img * H * W * C;
+    const int cq = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    float* o = out + r * (long long)C * bins;
+    for (int c0 = 0; c0 < C; c0 += kCTile) {
+        const int ch = c0 + cq * 4;
+        if (ch < C) {
+            const char* fb = reinterpret_cast<const char*>(feat + ch);
+            for (int bin = grp; bin < bins; bin += 4) {
+                const BinTab* t = s_tab + bin;
+                float4 acc;
+                switch (t->pat) {                          // uniform over the two warps of a bin
+                    case 0: acc = bin_eval<FT, 0, 0>(fb, t); break;
+                    case 1: acc = bin_eval<FT, 0, 1>(fb, t); break;
+                    case 2: acc = bin_eval<FT, 0, 2>(fb, t); break;
+                    case 3: acc = bin_eval<FT, 1, 0>(fb, t); break;
+                    case 4: acc = bin_eval<FT, 1, 1>(fb, t); break;
+                    case 5: acc = bin_eval<FT, 1, 2>(fb, t); break;
+                    case 6: acc = bin_eval<FT, 2, 0>(fb, t); break;
+                    case 7: acc = bin_eval<FT, 2, 1>(fb, t); break;
+                    default: acc = bin_eval<FT, 2, 2>(fb, t); break;
+                }
+                float* st = s_tile + (cq * 4) * bins + bin;    // x / 4 == x * 0.25 exactly
+                st[0] = acc.x * 0.25f; st[bins] = acc.y * 0.25f; st[2 * bins] = acc.z * 0.25f; st[3 * bins] = acc.w * 0.25f;
+            }
+        }
+        __syncthreads();
+        const int ctile = min(kCTile, C - c0);
+        const int total = ctile * bins;                    // multiple of 4 (C % 4 == 0)
+        float4* dst = reinterpret_cast<float4*>(o + (long long)c0 * bins);
+        const float4* src = reinterpret_cast<const float4*>(s_tile);
+        for (int q = threadIdx.x; q < total / 4; q += blockDim.x) dst[q] = src[q];
+        __syncthreads();
+    }
+}
+
+
+// ---- NCHW -> NHWC (fp32): lets reference-layout features (lib/necks.py FPN output) use the
+// channel-vectorised kernels above.  64(hw) x 32(c) tiles through padded shared memory; reads
+// are 256 B runs along hw, writes 128 B runs along c.
+__global__ void __launch_bounds__(256) k_nchw_to_nhwc(float* __restrict__ dst, const float* __restrict__ src, int C,
+                                                      long long HW) {
+    __shared__ float tile[32][65];
+    const long long b = blockIdx.z;
+    const float* s = src + b * C * HW;
+    float* d = dst + b * C * HW;
+    const long long hw0 = (long long)blockIdx.x * 64;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;       // 64 x 4
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = c0 + ty + 4 * k;
+        const long long hw = hw0 + tx;
+        if (c < C && hw < HW) tile[ty + 4 * k][tx] = s[(long long)c * HW + hw];
+    }
+    __syncthreads();
+    const int cx = threadIdx.x & 31, hy = threadIdx.x >> 5;       // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const long long hw = hw0 + hy + 8 * k;
+        const int c = c0 + cx;
+        if (c < C && hw < HW) d[hw * C + c] = tile[cx][hy + 8 * k];
+    }
+}
+
 // generic: one thread per output element (r, c, ph, pw); layout 0 = NCHW fp32, 1 = NHWC fp32
 __global__ void __launch_bounds__(256) k_roi_align_any(RoiArgs a, float* __restrict__ out) {
     const b2d_roi_cfg& c = a.cfg;
@@ -373,7 +552,7 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
     // 2x2 samples per bin (every reference config): batched-load kernel
     const bool fast4 = fast && c.sampling_ratio == 2 && bins * 4 <= 256 &&
                        (((long long)c.C * bins) % 4) == 0 && (c.C <= kCTile || ((long long)kCTile * bins) % 4 == 0);
-    int variant = 4;
+    int variant = 5;
     { const char* e = getenv("B2D_ROI_VARIANT"); if (e) variant = atoi(e); }   // dev knob
     if (fast4 && variant != 0) {
         const size_t smem = (size_t)kCTile * bins * 4 + (size_t)bins * 4 * sizeof(TapB);
@@ -381,7 +560,17 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             kern<<<(unsigned)R, 256, smem, st>>>(a, out);
         };
-        if (c.layout == 1) {
+        if (variant == 5) {
+            { const char* e = getenv("B2D_ROI_PF"); a.pf_dist = e ? atoi(e) : 0; }   // dev knob: measured slower (r1)
+            const size_t smem5 = (size_t)kCTile * bins * 4 + (size_t)bins * sizeof(BinTab);
+            if (c.layout == 1) {
+                cudaFuncSetAttribute(k_roi_align_win<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
+                k_roi_align_win<float><<<(unsigned)R, 256, smem5, st>>>(a, out);
+            } else {
+                cudaFuncSetAttribute(k_roi_align_win<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
+                k_roi_align_win<__nv_bfloat16><<<(unsigned)R, 256, smem5, st>>>(a, out);
+            }
+        } else if (c.layout == 1) {
             if (variant == 2) launch(k_roi_align_nhwc4<float, 2, 3>);
             else if (variant == 3) launch(k_roi_align_nhwc4<float, 2, 2>);
             else if (variant == 1) launch(k_roi_align_nhwc4<float, 1, 3>);
@@ -418,6 +607,15 @@ int b2d_roi_align_fwd_batched(float* out, const void* const* feat_ptrs_host, con
     B2D_REQUIRE(counts && ld >= 1 && B >= 1, "roi_align_fwd_batched: bad args");
     return roi_align_launch(out, feat_ptrs_host, rois, ld, nullptr, nullptr, (long long)B * ld, ld, counts, cfg_host,
                             stream);
+}
+
+int b2d_nchw_to_nhwc(float* dst, const float* src, int B, int C, int H, int W, void* stream) {
+    B2D_REQUIRE(dst && src && B >= 1 && C >= 1 && H >= 1 && W >= 1, "nchw_to_nhwc: bad args");
+    const long long HW = (long long)H * W;
+    B2D_REQUIRE(cdiv(C, 32) <= 65535 && B <= 65535, "nchw_to_nhwc: C or B too large");
+    dim3 grid(cdiv(HW, 64), cdiv(C, 32), B);
+    k_nchw_to_nhwc<<<grid, 256, 0, (cudaStream_t)stream>>>(dst, src, C, HW);
+    return check_launch("nchw_to_nhwc");
 }
 
 }  // extern "C"

@@ -82,7 +82,7 @@ class RpnProposals(object):
         self.scores = torch.zeros((B, self.P), dtype=torch.float32, device=device)
         self.count = torch.zeros(B, dtype=torch.int32, device=device)
         self.prov = torch.zeros((B, self.P), dtype=torch.int32, device=device)
-        self.launches = 7 if do_nms else 5   # memset, hist, compact, select, (mask, scan), merge
+        self.launches = 6 if do_nms else 4   # kernels: hist, compact, select, (mask, scan), merge  (+1 memset node)
 
     def slice(self, b0, b1):
         v = _batch_view(self, b0, b1)
@@ -123,7 +123,7 @@ class BatchedTargets(object):
         self.means, self.stds = _C.host_f4(means, [0, 0, 0, 0]), _C.host_f4(stds, [1, 1, 1, 1])
         self.step = 0
         self.b0 = 0
-        self.launches = 6   # fill, memset, colmax, label, sample, encode
+        self.launches = 5   # kernels: fill, colmax, label, sample, encode  (+1 memset node)
 
     def slice(self, b0, b1):
         return _batch_view(self, b0, b1)
@@ -235,8 +235,13 @@ class TrainHotPath(object):
                 ctypes.byref(self.pyr.c), 1, _C.ptr(rt.chosen), _C.ptr(rt.n_chosen), rt.max_num, self.B, _C.stream())
         return rt
 
-    def step(self, cls_outs, reg_outs, feats, gt, gt_count, gt_label, img_hw):
+    def step(self, cls_outs, reg_outs, feats, gt, gt_count, gt_label, img_hw, feats_ready=None):
+        """One pass of the hot path over the batch (device-resident inputs).  `feats_ready`: optional
+        CUDA event after which `feats` may be read (lets the proposal / target chains start while
+        the feature maps are still arriving, see step_from_host)."""
         if not self.subs:
+            if feats_ready is not None:
+                torch.cuda.current_stream().wait_event(feats_ready)
             props, scores, count = self.proposals(cls_outs, reg_outs, img_hw)
             rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
             bt = self.roi_targets(gt, gt_count, gt_label, boxes=props, box_count=count)
@@ -249,6 +254,8 @@ class TrainHotPath(object):
                     p, _, c = prop([t[b0:b1] for t in cls_outs], [t[b0:b1] for t in reg_outs], img_hw[b0:b1])
                     t2 = tgt(gt[b0:b1], gt_count[b0:b1], gt_label[b0:b1], boxes=p, box_count=c)
                 st_lo.wait_stream(st)
+                if feats_ready is not None:
+                    st_lo.wait_event(feats_ready)
                 with torch.cuda.stream(st_lo):
                     ra([f[b0:b1] for f in feats], t2.tar_box, t2.n_chosen)
             self.s_rpn.wait_stream(cur)
@@ -260,3 +267,74 @@ class TrainHotPath(object):
         return dict(props=self.proposals.props, scores=self.proposals.scores, prop_count=self.proposals.count,
                     rpn=self.rpn_targets, rpn_tar_cls=self.tar_cls, rpn_tar_reg=self.tar_reg, rcnn=self.roi_targets,
                     roi_feats=self.roi_align.out)
+
+    # ------------------------------------------------------------------ host-buffer entry
+    def step_from_host(self, h_cls, h_reg, h_feats, h_gt, h_gt_label, gt_count, img_hw, h_out=None,
+                       with_roi_feats=False):
+        """End-to-end form of step(): inputs are pinned HOST tensors in the reference's layout
+        (head maps [B,A*C,H,W] / [B,4A,H,W], FPN features fp32 NCHW [B,C,H,W], GT [B,4,K] and
+        labels [B,K]); results land in pinned host tensors (`h_out`, allocated on first use).
+        The H2D copies run on a copy stream in the order GT, head maps, features (largest level
+        first); the proposal and target chains start as soon as the head maps have landed, each
+        feature level is transposed to NHWC (b2d_nchw_to_nhwc) while the next one is still in
+        flight, and only RoIAlign waits for the features.  gt_count / img_hw are device tensors.
+        The RoI features (the input of the next GPU stage, 205 MB at config 2) stay on the device
+        unless with_roi_feats is set; a one-element probe of them is always read back."""
+        dev, B = self.device, self.B
+        if not hasattr(self, "_stage"):
+            st = dict(cls=[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in h_cls],
+                      reg=[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in h_reg],
+                      feat=[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in h_feats],
+                      nhwc=[torch.empty(t.shape, dtype=t.dtype, device=dev).contiguous(memory_format=torch.channels_last)
+                            for t in h_feats],
+                      gt=torch.empty(h_gt.shape, dtype=h_gt.dtype, device=dev),
+                      gl=torch.empty(h_gt_label.shape, dtype=h_gt_label.dtype, device=dev),
+                      s_copy=torch.cuda.Stream(device=dev), s_xpose=torch.cuda.Stream(device=dev, priority=0),
+                      ev_heads=torch.cuda.Event(), ev_feat=[torch.cuda.Event() for _ in h_feats],
+                      ev_ready=torch.cuda.Event())
+            self._stage = st
+        st = self._stage
+        if h_out is None:
+            if not hasattr(self, "_h_out"):
+                pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                rt, bt = self.rpn_targets, self.roi_targets
+                self._h_out = dict(props=pin(self.proposals.props), scores=pin(self.proposals.scores),
+                                   prop_count=pin(self.proposals.count), rpn_label=pin(rt.tar_label),
+                                   rpn_param=pin(rt.tar_param), rpn_tar_cls=pin(self.tar_cls), rpn_tar_reg=pin(self.tar_reg),
+                                   roi_label=pin(bt.tar_label), roi_param=pin(bt.tar_param), roi_count=pin(bt.n_chosen),
+                                   roi_probe=torch.empty(1).pin_memory())
+                if with_roi_feats:
+                    self._h_out["roi_feats"] = pin(self.roi_align.out)
+            h_out = self._h_out
+        cur = torch.cuda.current_stream()
+        sc, sx = st["s_copy"], st["s_xpose"]
+        sc.wait_stream(cur)
+        sx.wait_stream(cur)
+        with torch.cuda.stream(sc):
+            st["gt"].copy_(h_gt, non_blocking=True)
+            st["gl"].copy_(h_gt_label, non_blocking=True)
+            for d, h in zip(st["cls"] + st["reg"], list(h_cls) + list(h_reg)):
+                d.copy_(h, non_blocking=True)
+            st["ev_heads"].record(sc)
+            for l in sorted(range(len(h_feats)), key=lambda i: -h_feats[i].numel()):
+                st["feat"][l].copy_(h_feats[l], non_blocking=True)
+                st["ev_feat"][l].record(sc)
+        with torch.cuda.stream(sx):
+            for l in sorted(range(len(h_feats)), key=lambda i: -h_feats[i].numel()):
+                sx.wait_event(st["ev_feat"][l])
+                f = st["feat"][l]
+                _C.call("b2d_nchw_to_nhwc", _C.ptr(st["nhwc"][l]), _C.ptr(f), f.shape[0], f.shape[1], f.shape[2],
+                        f.shape[3], _C.stream())
+            st["ev_ready"].record(sx)
+        cur.wait_event(st["ev_heads"])
+        out = self.step(st["cls"], st["reg"], st["nhwc"], st["gt"], gt_count, st["gl"], img_hw, feats_ready=st["ev_ready"])
+        pairs = [("props", out["props"]), ("scores", out["scores"]), ("prop_count", out["prop_count"]),
+                 ("rpn_label", out["rpn"].tar_label), ("rpn_param", out["rpn"].tar_param),
+                 ("rpn_tar_cls", out["rpn_tar_cls"]), ("rpn_tar_reg", out["rpn_tar_reg"]),
+                 ("roi_label", out["rcnn"].tar_label), ("roi_param", out["rcnn"].tar_param),
+                 ("roi_count", out["rcnn"].n_chosen), ("roi_feats", out["roi_feats"]),
+                 ("roi_probe", out["roi_feats"][0, 0, 0, :1])]
+        for k, t in pairs:
+            if k in h_out:
+                h_out[k].copy_(t, non_blocking=True)
+        return h_out

@@ -34,12 +34,30 @@ def main():
     if "roi" in which:
         ref = None
         for v in os.environ.get("VARIANTS", "0,4,3,2,1").split(","):
+            if ":" in v:
+                v, pf = v.split(":"); os.environ["B2D_ROI_PF"] = pf
             os.environ["B2D_ROI_VARIANT"] = v
             hp.roi_align.out.zero_()
             us = timeit(lambda: hp.roi_align(feats, bt.tar_box, bt.n_chosen))
             o = hp.roi_align.out.clone()
             if ref is None: ref = o
-            print("roi_align variant %s: %.1f us  bitexact_vs_first=%s" % (v, us, bool(torch.equal(o, ref))))
+            print("roi_align variant %s pf=%s: %.1f us  bitexact_vs_first=%s" % (v, os.environ.get("B2D_ROI_PF"), us, bool(torch.equal(o, ref))))
+    if "roil2" in which:
+        # same RoIs, but every image reads the features of image 0 -> after warm-up all taps are L2 hits
+        import ctypes
+        m = int(bt.n_chosen[0])
+        rois1 = bt.tar_box[0, :, :m].contiguous()
+        rois = rois1.repeat(1, 8).contiguous()
+        R = rois.shape[1]
+        outb = torch.empty((R, 256, 7, 7), device=dev)
+        cfg = hp.roi_align.cfg
+        for v in os.environ.get("VARIANTS", "4,5").split(","):
+            if ":" in v:
+                v, pf = v.split(":"); os.environ["B2D_ROI_PF"] = pf
+            os.environ["B2D_ROI_VARIANT"] = v
+            fn = lambda: _C.call("b2d_roi_align_fwd", _C.ptr(outb), fused._ptrs(feats), _C.ptr(rois), R, None, None, R,
+                                 ctypes.byref(cfg), _C.stream())
+            print("L2-resident roi_align variant %s: %.1f us for %d rois" % (v, timeit(fn), R))
     if "stages" in which:
         print("proposals %.1f us" % timeit(lambda: hp.proposals(cls, reg, img_hw)))
         print("rpn_targets %.1f us" % timeit(lambda: hp.rpn_targets(gt, gcount, None, img_hw=img_hw)))
