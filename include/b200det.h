@@ -205,6 +205,37 @@ B2D_API int b2d_roi_pool_bwd(float* grad_feat, const float* grad_out, const int*
                      const float* rois, long long roi_ld, const int* roi_img, long long R, float spatial_scale,
                      int PH, int PW, void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- a17: BBoxHead.refine_bboxes_single_image (lib/heads/bbox_head.py:100-120), batched.
+ * props [B][4][ld] with counts int32[B] (NULL => n); label int64 [B][ld]; reg_out [B][ld][4*C]
+ * row-major with channel = coord*C + class (C = 1 when class-agnostic, label may then be NULL);
+ * is_gt int64 [B][ld] or NULL.  out [B][4][ld] receives the non-GT columns in order, decoded with
+ * means/stds and (clamp != 0) clamped to img_hw[b]; out_count int32[B]. */
+B2D_API int b2d_refine_bboxes(float* out, int* out_count, const float* props, long long ld, const int* counts,
+                      long long n, const int64_t* label, const float* reg_out, int C, const int64_t* is_gt,
+                      const float* means_host, const float* stds_host, int clamp, const float* img_hw, int B,
+                      void* stream);
+
+/* ---- a18 / K9: ATSS target assignment (FCOSHead.single_image_targets_atss,
+ * lib/heads/fcos_head.py:283-368 with topk_by_center :106-116 read as integer division).
+ * pyr: one anchor per cell (ws = hs = stride * atss scale).  Outputs are level-major over the
+ * pyr->total cells of an image: cls_tar int64 [B][total], reg_tar fp32 [B][total][4] (ltrb),
+ * ctr_tar fp32 [B][total].  Distance ties are broken by the lowest cell index. */
+B2D_API size_t b2d_atss_workspace_bytes(const b2d_pyramid* pyr_host, int B);
+B2D_API int b2d_atss_assign(int64_t* cls_tar, float* reg_tar, float* ctr_tar, const b2d_pyramid* pyr_host,
+                    const float* gt, int gt_ld, const int* gt_count, const int64_t* gt_label, const float* img_hw,
+                    int B, int topk, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a19: FCOS decode (FCOSHead.predict_single_image, lib/heads/fcos_head.py:578-604 +
+ * ltrb2bbox :63-75): per cell ltrb*std+mean -> xyxy, clamp to img_hw[b], strict min-size test.
+ * cls_ptrs_host[l] -> [B, C, H, W] logits, reg_ptrs_host[l] -> [B, 4, H, W], ctr_ptrs_host
+ * (NULL or [l] -> [B, 1, H, W]).  boxes [B][4][total], score [B][C][total] = sigmoid(cls),
+ * ctr_score [B][total] = sigmoid(ctr), key [B][total] = max_c score (* ctr_score), -inf where the
+ * size test fails (the per-level top-k of :605-613 runs on key). */
+B2D_API int b2d_fcos_decode(float* boxes, float* key, float* score, float* ctr_score, const void* const* cls_ptrs_host,
+                    const void* const* reg_ptrs_host, const void* const* ctr_ptrs_host, const b2d_pyramid* pyr_host,
+                    int cls_channels, float reg_mean, float reg_std, float min_size, const float* img_hw, int B,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,9 @@ _SIGS = {
     "b2d_roi_align_bwd": [_P, _P, _P, c_ll, _P, _P, c_ll, c_int, _P, _P, c_size_t, _P],
     "b2d_roi_levels": [_P, _P, c_ll, c_ll, c_float, c_int, _P],
     "b2d_nchw_to_nhwc": [_P, _P, c_int, c_int, c_int, c_int, _P],
+    "b2d_refine_bboxes": [_P, _P, _P, c_ll, _P, c_ll, _P, _P, c_int, _P, _P, _P, c_int, _P, c_int, _P],
+    "b2d_atss_assign": [_P, _P, _P, _P, _P, c_int, _P, _P, _P, c_int, c_int, _P, c_size_t, _P],
+    "b2d_fcos_decode": [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_float, c_float, c_float, _P, c_int, _P],
     "b2d_roi_pool_fwd": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_ll, _P, c_ll, c_float, c_int, c_int, _P],
     "b2d_roi_pool_bwd": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_ll, _P, c_ll, c_float, c_int, c_int, _P,
                          c_size_t, _P],
@@ -81,6 +84,7 @@ _SIZE_FNS = {
     "b2d_topk_workspace_bytes": [c_ll, c_int, c_int],
     "b2d_nms_workspace_bytes": [c_ll, c_int],
     "b2d_roi_align_bwd_workspace_bytes": [c_ll, c_int, _P],
+    "b2d_atss_workspace_bytes": [_P, c_int],
 }
 EXPORTS = sorted(list(_SIGS) + list(_SIZE_FNS) + ["b2d_last_error_string", "b2d_version"])
 

@@ -53,7 +53,9 @@ __device__ __forceinline__ bool suppresses(const float4& a, float aa, const floa
     const float inter = w * h;
     const float u = (aa + ab) - inter;
     const bool yes = inter > thr_hi * u, no = inter < thr_lo * u;
-    if (yes || no) return yes;
+    // the product test is only decisive for a finite positive union (malformed boxes with
+    // x2 < x1 give u <= 0; the reference then compares the signed / NaN quotient)
+    if ((yes || no) && u > 0.0f && u < 3.0e38f) return yes;
     return inter / u > thr;
 }
 

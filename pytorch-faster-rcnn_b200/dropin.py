@@ -21,7 +21,7 @@ def _set(obj, name, value):
 
 def install(lib=None):
     """lib: the reference's imported `lib` package (default: sys.modules['lib'])."""
-    from . import anchor, bbox, region, utils
+    from . import anchor, bbox, heads, region, utils
     lib = lib or sys.modules.get("lib")
     if lib is None:
         raise RuntimeError("import the reference package `lib` before calling install()")
@@ -61,6 +61,20 @@ def install(lib=None):
         _set(mods["heads.rpn_head"], "tvops", types.SimpleNamespace(nms=utils.nms))
     if mods["heads.fcos_head"] and hasattr(mods["heads.fcos_head"], "AnchorCreator"):
         _set(mods["heads.fcos_head"], "AnchorCreator", anchor.AnchorCreator)
+    # head methods that are part of the path: rebind on the classes
+    bh, fh = mods["heads.bbox_head"], mods["heads.fcos_head"]
+    if bh and hasattr(bh, "BBoxHead"):
+        _set(bh.BBoxHead, "refine_bboxes_single_image", heads.refine_bboxes_single_image)
+    if fh and hasattr(fh, "FCOSHead"):
+        _set(fh.FCOSHead, "single_image_targets_atss", heads.single_image_targets_atss)
+        ref_predict = fh.FCOSHead.predict_single_image
+
+        def _predict(self, cls_outs, reg_outs, ctr_outs, img_meta, test_cfg):
+            if getattr(self, "use_dfl", False):          # DFL decode stays with the reference
+                return ref_predict(self, cls_outs, reg_outs, ctr_outs, img_meta, test_cfg)
+            return heads.predict_single_image(self, cls_outs, reg_outs, ctr_outs, img_meta, test_cfg)
+
+        _set(fh.FCOSHead, "predict_single_image", _predict)
     if mods["builder"]:
         reg = mods["builder"].MODULES
         for n in ("MaxIoUAssigner", "RandomSampler", "IoUBalancedNegSampler", "BasicRoIExtractor",

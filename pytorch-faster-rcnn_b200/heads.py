@@ -1,0 +1,149 @@
+"""Head-side glue of the hot path, same call signatures as the
+reference methods they replace so dropin.install() can rebind them:
+
+  refine_bboxes_single_image   BBoxHead.refine_bboxes_single_image   lib/heads/bbox_head.py:100-120
+  single_image_targets_atss    FCOSHead.single_image_targets_atss    lib/heads/fcos_head.py:283-368
+  fcos_predict_single_image    FCOSHead.predict_single_image         lib/heads/fcos_head.py:570-631
+
+The arithmetic runs in csrc/heads.cu (b2d_refine_bboxes, b2d_atss_assign, b2d_fcos_decode)
+plus the K3 top-k and K4 NMS; torch is only used for views, concatenation and indexing."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _C, region, utils
+
+
+def _ptrs(tensors):
+    arr = (_C.c_void_p * _C.MAX_LEVELS)()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def _img_hw(img_size, device, B=1):
+    return torch.tensor([[float(img_size[0]), float(img_size[1])]] * B, dtype=torch.float32, device=device)
+
+
+# ------------------------------------------------------------------ a17
+def refine_bboxes(props, label, reg_out, is_gt=None, img_shape=None, target_means=None, target_stds=None,
+                  reg_class_agnostic=False, num_classes=21):
+    """props [4,s], label int64[s], reg_out [s, 4] or [s, 4*num_classes] -> refined [4, s - #gt]."""
+    _C.require_cuda(props, reg_out)
+    s = int(props.shape[1])
+    C = 1 if reg_class_agnostic else int(num_classes)
+    if s == 0:
+        return props.new_zeros((4, 0))
+    assert reg_out.shape[0] == s and reg_out.shape[1] == 4 * C
+    pr, rg = _C.f32c(props), _C.f32c(reg_out)
+    lab = label.to(torch.int64).contiguous() if label is not None else None
+    gt = is_gt.to(torch.int64).contiguous() if is_gt is not None else None
+    out = torch.empty((4, s), dtype=torch.float32, device=props.device)
+    cnt = torch.empty(1, dtype=torch.int32, device=props.device)
+    clamp = img_shape is not None
+    hw = _img_hw(img_shape[:2], props.device) if clamp else None
+    _C.call("b2d_refine_bboxes", _C.ptr(out), _C.ptr(cnt), _C.ptr(pr), s, None, s, _C.ptr(lab), _C.ptr(rg), C,
+            _C.ptr(gt), _C.host_f4(target_means, [0, 0, 0, 0]), _C.host_f4(target_stds, [1, 1, 1, 1]), int(clamp),
+            _C.ptr(hw), 1, _C.stream())
+    n_out = s if gt is None else int(cnt.item())
+    return out[:, :n_out]
+
+
+def refine_bboxes_single_image(self, props, label, reg_out, is_gt=None, img_meta=None):
+    """Method form (bound onto the reference's BBoxHead by dropin.install)."""
+    assert props.shape[1] == reg_out.shape[0]
+    return refine_bboxes(props, label, reg_out, is_gt, img_meta['img_shape'] if img_meta is not None else None,
+                         self.target_means, self.target_stds, self.reg_class_agnostic, self.num_classes)
+
+
+# ------------------------------------------------------------------ a18 (K9)
+def _point_pyramid(grids, strides, scale):
+    levels = [dict(stride=s, H=int(g[0]), W=int(g[1]), ws=[np.float32(s * scale * np.sqrt(1.0))],
+                   hs=[np.float32(s * scale / np.sqrt(1.0))], center_lt=False) for s, g in zip(strides, grids)]
+    return _C.make_pyramid(levels)
+
+
+def atss_assign(grids, strides, gt, gt_count, gt_label, img_hw, topk=9, scale=8):
+    """Batched ATSS: gt [B,4,K], gt_count int32[B], gt_label int64[B,K], img_hw fp32[B,2] ->
+    (cls int64 [B,total], reg fp32 [B,total,4], ctr fp32 [B,total]), cells level-major."""
+    _C.require_cuda(gt)
+    pyr = _point_pyramid(grids, strides, scale)
+    B, dev = int(gt.shape[0]), gt.device
+    total = int(pyr.total)
+    cls = torch.empty((B, total), dtype=torch.int64, device=dev)
+    reg = torch.empty((B, total, 4), dtype=torch.float32, device=dev)
+    ctr = torch.empty((B, total), dtype=torch.float32, device=dev)
+    wsb = _C.lib().b2d_atss_workspace_bytes(ctypes.byref(pyr), B)
+    ws = utils._workspace(wsb, dev, "atss")
+    _C.call("b2d_atss_assign", _C.ptr(cls), _C.ptr(reg), _C.ptr(ctr), ctypes.byref(pyr), _C.ptr(_C.f32c(gt)),
+            int(gt.shape[2]), _C.ptr(gt_count), _C.ptr(gt_label.to(torch.int64).contiguous()), _C.ptr(img_hw), B, int(topk),
+            _C.ptr(ws), ws.numel(), _C.stream())
+    return cls, reg, ctr
+
+
+def single_image_targets_atss(self, cls_outs, reg_outs, ctr_outs, lvl_anchors, gt_bboxes, gt_labels, img_meta,
+                              train_cfg):
+    """Method form of FCOSHead.single_image_targets_atss: per-level lists of [H,W,1] int64,
+    [H,W,4] fp32, [H,W,1] fp32.  The level anchors are implied by (stride, atss_cfg.scale)."""
+    grids = [tuple(int(v) for v in x.shape[-2:]) for x in cls_outs]
+    dev = cls_outs[0].device
+    K = int(gt_bboxes.shape[1])
+    gt = _C.f32c(gt_bboxes).view(1, 4, K)
+    cnt = torch.tensor([K], dtype=torch.int32, device=dev)
+    cls, reg, ctr = atss_assign(grids, self.strides, gt, cnt, gt_labels.view(1, K), _img_hw(img_meta['img_shape'][:2], dev),
+                                self.atss_cfg.topk, self.atss_cfg.scale)
+    cls_t, reg_t, ctr_t, off = [], [], [], 0
+    for (h, w) in grids:
+        n = h * w
+        cls_t.append(cls[0, off:off + n].view(h, w, 1))
+        reg_t.append(reg[0, off:off + n].view(h, w, 4))
+        ctr_t.append(ctr[0, off:off + n].view(h, w, 1))
+        off += n
+    return cls_t, reg_t, ctr_t
+
+
+# ------------------------------------------------------------------ a19
+def fcos_predict_single_image(cls_outs, reg_outs, ctr_outs, strides, img_meta, test_cfg, reg_mean=0.0, reg_std=300.0,
+                              use_centerness=True):
+    """cls_outs[l] [C,H,W] logits, reg_outs[l] [4,H,W] ltrb (before *std+mean), ctr_outs[l] [1,H,W]
+    -> (bbox [4,k], score [k], label int64 [k], 1-based) like FCOSHead.predict_single_image."""
+    get = (lambda k, d=None: test_cfg.get(k, d)) if hasattr(test_cfg, "get") else (lambda k, d=None: getattr(test_cfg, k, d))
+    dev = cls_outs[0].device
+    _C.require_cuda(*cls_outs)
+    grids = [tuple(int(v) for v in x.shape[-2:]) for x in cls_outs]
+    C = int(cls_outs[0].shape[0])
+    pyr = _point_pyramid(grids, strides, 8)
+    total = int(pyr.total)
+    boxes = torch.empty((1, 4, total), dtype=torch.float32, device=dev)
+    key = torch.empty((1, total), dtype=torch.float32, device=dev)
+    score = torch.empty((1, C, total), dtype=torch.float32, device=dev)
+    ctrs = torch.empty((1, total), dtype=torch.float32, device=dev) if use_centerness else None
+    cl, rg = [_C.f32c(x) for x in cls_outs], [_C.f32c(x) for x in reg_outs]
+    ct = [_C.f32c(x) for x in ctr_outs] if use_centerness else None
+    min_size = float(np.float32(img_meta['scale_factor'] * get('min_bbox_size', 0)))
+    _C.call("b2d_fcos_decode", _C.ptr(boxes), _C.ptr(key), _C.ptr(score), _C.ptr(ctrs), _ptrs(cl), _ptrs(rg),
+            _ptrs(ct) if ct is not None else None, ctypes.byref(pyr), C, float(reg_mean), float(reg_std), min_size,
+            _C.ptr(_img_hw(img_meta['img_shape'][:2], dev)), 1, _C.stream())
+    pre_nms = int(get('pre_nms', 0))
+    sel, off = [], 0
+    for (h, w) in grids:                                  # per-level filter + top-k (lib/heads/fcos_head.py:602-613)
+        n = h * w
+        k_l = key[0, off:off + n]
+        valid = torch.nonzero(k_l > float("-inf")).view(-1)
+        if pre_nms > 0 and pre_nms < int(valid.numel()):
+            valid = region.topk_desc(k_l, pre_nms)        # -inf keys can never enter: #valid > pre_nms
+        sel.append(valid + off)
+        off += n
+    sel = torch.cat(sel)
+    mlvl_bbox, mlvl_score = boxes[0][:, sel], score[0][:, sel]
+    mlvl_ctr = ctrs[0][sel] if use_centerness else None
+    kb, ks, kl = utils.multiclass_nms(mlvl_bbox.t(), mlvl_score.t(), list(range(0, C)), get('nms_iou'), get('min_score'),
+                                      get('max_per_img'), mlvl_ctr, mode=get('nms_type', 'official'))
+    return kb.t(), ks, kl + 1
+
+
+def predict_single_image(self, cls_outs, reg_outs, ctr_outs, img_meta, test_cfg):
+    """Method form of FCOSHead.predict_single_image (DFL heads keep the reference path)."""
+    return fcos_predict_single_image(cls_outs, reg_outs, ctr_outs, self.strides, img_meta, test_cfg, self.reg_mean,
+                                     self.reg_std, self.use_centerness)

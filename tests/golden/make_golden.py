@@ -350,10 +350,93 @@ def g_targets():
     save("targets", **out)
 
 
+# --------------------------------------------------------------------------
+def _patched_fcos_module():
+    """lib.heads.fcos_head with the reference's known bug worked around, documented in SURVEY 8(c):
+    topk_by_center line 115 `k_inds / w` is true division on torch >= 1.5 (float indices ->
+    IndexError at :342); the oracle is the same function with `//`.  The function source is
+    re-executed from the reference file with that one token changed; nothing is copied."""
+    import inspect
+    import lib.heads.fcos_head as fh
+    if getattr(fh, "_b2d_patched", False):
+        return fh
+    fh._b2d_patched = True
+    src = inspect.getsource(fh.topk_by_center)
+    assert "k_inds / w" in src
+    exec(compile(src.replace("k_inds / w", "k_inds // w"), "<topk_by_center //>", "exec"), fh.__dict__)
+    return fh
+
+
+def g_atss():
+    import types
+    fh = _patched_fcos_module()
+    rng = np.random.default_rng(SEED + 11)
+    strides = [8, 16, 32, 64, 128]
+    out = {}
+    for tag, img_shape, pad, K in (("s", (500, 597, 3), (512, 640), 6), ("f", (800, 1333, 3), (800, 1344), 16)):
+        grids = [(-(-pad[0] // s), -(-pad[1] // s)) for s in strides]
+        gt, gl = synth_gt(rng, K, img_shape[0], img_shape[1])
+        creators = [ranchor.AnchorCreator(base=s, scales=[8], aspect_ratios=[1.0]) for s in strides]
+        lvl_anchors = tuple(creators[i](strides[i], grids[i]).squeeze() for i in range(5))
+        me = types.SimpleNamespace(strides=strides, atss_cfg=ref_shim.AttrDict(topk=9, scale=8))
+        dummy = [torch.zeros((20,) + g) for g in grids]
+        with torch.no_grad():
+            cls_t, reg_t, ctr_t = fh.FCOSHead.single_image_targets_atss(
+                me, dummy, dummy, dummy, lvl_anchors, T(gt), T(gl), dict(img_shape=img_shape), None)
+        out.update({"gt_" + tag: gt, "gl_" + tag: gl, "img_" + tag: np.array(img_shape), "grids_" + tag: np.array(grids),
+                    "cls_" + tag: torch.cat([c.reshape(-1) for c in cls_t]),
+                    "reg_" + tag: torch.cat([r.reshape(-1, 4) for r in reg_t]),
+                    "ctr_" + tag: torch.cat([c.reshape(-1) for c in ctr_t])})
+        print("atss", tag, "positives", int((out["cls_" + tag] > 0).sum()))
+    save("atss", **out)
+
+
+def g_heads():
+    """a17 cascade refine (lib/heads/bbox_head.py:100-120) and a19 FCOS predict (lib/heads/fcos_head.py:570-631)."""
+    import types
+    import lib.heads.bbox_head as bh
+    fh = _patched_fcos_module()
+    rng = np.random.default_rng(SEED + 12)
+    out = {}
+    # ---- refine_bboxes_single_image: 21 classes, per-class deltas, first 5 columns are GT
+    s, C = 200, 21
+    props = rand_boxes(rng, s, 400, 600, 8, 200)
+    label = rng.integers(0, C, s).astype(np.int64)
+    reg_out = rng.normal(0, 1, (s, 4 * C)).astype(np.float32)
+    is_gt = np.zeros(s, np.int64); is_gt[:5] = 1; is_gt[37] = 1
+    me = types.SimpleNamespace(reg_class_agnostic=False, num_classes=C, target_means=[0.0, 0.0, 0.0, 0.0],
+                               target_stds=[0.05, 0.05, 0.1, 0.1])
+    with torch.no_grad():
+        ref = bh.BBoxHead.refine_bboxes_single_image(me, T(props), T(label), T(reg_out), T(is_gt), dict(img_shape=(400, 600, 3)))
+        me2 = types.SimpleNamespace(reg_class_agnostic=True, num_classes=C, target_means=[0.0, 0.0, 0.0, 0.0],
+                                    target_stds=[0.1, 0.1, 0.2, 0.2])
+        ref2 = bh.BBoxHead.refine_bboxes_single_image(me2, T(props), T(label), T(reg_out[:, :4].copy()), None, None)
+    out.update(rf_props=props, rf_label=label, rf_reg=reg_out, rf_is_gt=is_gt, rf_out=ref, rf_out_agnostic=ref2)
+    # ---- FCOS predict_single_image (centerness, strict multiclass NMS)
+    strides = [8, 16, 32, 64, 128]
+    img_shape, pad = (250, 317, 3), (256, 320)
+    grids = [(-(-pad[0] // st) , -(-pad[1] // st)) for st in strides]
+    cls = [rng.normal(-2, 2, (20,) + g).astype(np.float32) for g in grids]
+    reg = [np.abs(rng.normal(0.15, 0.1, (4,) + g)).astype(np.float32) for g in grids]
+    ctr = [rng.normal(0, 1, (1,) + g).astype(np.float32) for g in grids]
+    me = types.SimpleNamespace(use_centerness=True, use_dfl=False, strides=strides, reg_std=300, reg_mean=0, cls_channels=20)
+    for i, cfg in enumerate([dict(pre_nms=1000, min_bbox_size=0, min_score=0.05, nms_iou=0.6, nms_type="strict", max_per_img=100),
+                             dict(pre_nms=50, min_bbox_size=40, min_score=0.3, nms_iou=0.5, nms_type="official", max_per_img=60)]):
+        with torch.no_grad():
+            b, sc, lab = fh.FCOSHead.predict_single_image(me, [T(x) for x in cls], [T(x.copy()) for x in reg], [T(x) for x in ctr],
+                                                          dict(img_shape=img_shape, scale_factor=1.0), ref_shim.AttrDict(cfg))
+        out.update({"fc_bbox%d" % i: b, "fc_score%d" % i: sc, "fc_label%d" % i: lab})
+        print("fcos predict", i, "detections", int(sc.numel()))
+    for l in range(5):
+        out["fc_cls%d" % l], out["fc_reg%d" % l], out["fc_ctr%d" % l] = cls[l], reg[l], ctr[l]
+    out["fc_img"] = np.array(img_shape)
+    save("heads", **out)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     gens = dict(anchors=g_anchors, iou_assign=g_iou_assign, deltas=g_deltas, nms=g_nms, rpn=g_rpn, roi=g_roi,
-                targets=g_targets)
+                targets=g_targets, atss=g_atss, heads=g_heads)
     for k, fn in gens.items():
         if not only or k in only:
             fn()

@@ -1,0 +1,193 @@
+"""GPU parity of the head-side rows and of BASELINE configs 3-5:
+cascade refine / 3-stage targets, RetinaNet dense assignment + per-level top-k NMS, ATSS.
+Compared with golden vectors from the unmodified reference and with the CPU oracle."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import b200det
+    from b200det import heads as bheads, region as bregion, utils as butils, fused, workload
+    DEV = torch.device("cuda:0")
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------ a17
+def test_refine_bboxes_vs_reference():
+    g = load_golden("heads")
+    me = types.SimpleNamespace(reg_class_agnostic=False, num_classes=21, target_means=[0.0] * 4,
+                               target_stds=[0.05, 0.05, 0.1, 0.1])
+    out = bheads.refine_bboxes_single_image(me, T(g["rf_props"]), T(g["rf_label"]), T(g["rf_reg"]), T(g["rf_is_gt"]),
+                                            dict(img_shape=(400, 600, 3)))
+    assert out.shape == g["rf_out"].shape
+    np.testing.assert_allclose(N(out), g["rf_out"], rtol=1e-5, atol=1e-3)       # expf: 1e-5 relative (north_star)
+    me2 = types.SimpleNamespace(reg_class_agnostic=True, num_classes=21, target_means=[0.0] * 4, target_stds=[0.1, 0.1, 0.2, 0.2])
+    out2 = bheads.refine_bboxes_single_image(me2, T(g["rf_props"]), T(g["rf_label"]), T(g["rf_reg"][:, :4].copy()), None, None)
+    np.testing.assert_allclose(N(out2), g["rf_out_agnostic"], rtol=1e-5, atol=1e-3)
+    # ragged / degenerate: everything is GT -> empty result
+    all_gt = bheads.refine_bboxes(T(g["rf_props"]), T(g["rf_label"]), T(g["rf_reg"]), torch.ones(200, dtype=torch.int64, device=DEV),
+                                  (400, 600), None, None, False, 21)
+    assert all_gt.shape == (4, 0)
+
+
+# ------------------------------------------------------------------ a18 / config 5
+@pytest.mark.parametrize("tag", ["s", "f"])
+def test_atss_targets_vs_reference(tag):
+    g = load_golden("atss")
+    grids = [tuple(int(v) for v in x) for x in g["grids_" + tag]]
+    me = types.SimpleNamespace(strides=[8, 16, 32, 64, 128], atss_cfg=types.SimpleNamespace(topk=9, scale=8))
+    dummy = [torch.zeros((20,) + gr, device=DEV) for gr in grids]
+    cls_t, reg_t, ctr_t = bheads.single_image_targets_atss(me, dummy, dummy, dummy, None, T(g["gt_" + tag]), T(g["gl_" + tag]),
+                                                           dict(img_shape=tuple(int(v) for v in g["img_" + tag])), None)
+    assert [tuple(c.shape) for c in cls_t] == [gr + (1,) for gr in grids]
+    cls = np.concatenate([N(c).reshape(-1) for c in cls_t])
+    reg = np.concatenate([N(r).reshape(-1, 4) for r in reg_t])
+    ctr = np.concatenate([N(c).reshape(-1) for c in ctr_t])
+    assert np.array_equal(cls, g["cls_" + tag])                                  # labels: bit-exact
+    assert np.array_equal(reg, g["reg_" + tag])                                  # ltrb: exact fp32 differences
+    np.testing.assert_allclose(ctr, g["ctr_" + tag], rtol=1e-5, atol=1e-6)
+    assert (cls > 0).sum() > 0
+
+
+def test_atss_batched_vs_oracle_ragged():
+    """config 5 size (22 400 points), ragged GT counts incl. a single GT, K up to 64."""
+    rng = np.random.default_rng(7)
+    strides, pad, img = [8, 16, 32, 64, 128], (800, 1344), (800, 1333)
+    grids = [(-(-pad[0] // s), -(-pad[1] // s)) for s in strides]
+    counts = [1, 16, 64, 5]
+    B, ld = len(counts), 64
+    gt = np.zeros((B, 4, ld), np.float32)
+    gl = np.zeros((B, ld), np.int64)
+    for b, k in enumerate(counts):
+        bb, ll = workload.synth_gt(rng, k, *img)
+        gt[b, :, :k], gl[b, :k] = bb, ll
+    cls, reg, ctr = bheads.atss_assign(grids, strides, T(gt), torch.tensor(counts, dtype=torch.int32, device=DEV), T(gl),
+                                       torch.tensor([[800.0, 1333.0]] * B, device=DEV))
+    for b, k in enumerate(counts):
+        oc, orr, octr = oracle.atss_assign(grids, strides, gt[b, :, :k], gl[b, :k], img)
+        assert np.array_equal(N(cls[b]), oc), b
+        assert np.array_equal(N(reg[b]), orr), b
+        np.testing.assert_allclose(N(ctr[b]), octr, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ a19
+@pytest.mark.parametrize("i,cfg", [(0, dict(pre_nms=1000, min_bbox_size=0, min_score=0.05, nms_iou=0.6, nms_type="strict", max_per_img=100)),
+                                   (1, dict(pre_nms=50, min_bbox_size=40, min_score=0.3, nms_iou=0.5, nms_type="official", max_per_img=60))])
+def test_fcos_predict_vs_reference(i, cfg):
+    g = load_golden("heads")
+    cls = [T(g["fc_cls%d" % l]) for l in range(5)]
+    reg = [T(g["fc_reg%d" % l]) for l in range(5)]
+    ctr = [T(g["fc_ctr%d" % l]) for l in range(5)]
+    b, s, lab = bheads.fcos_predict_single_image(cls, reg, ctr, [8, 16, 32, 64, 128],
+                                                 dict(img_shape=tuple(int(v) for v in g["fc_img"]), scale_factor=1.0), cfg,
+                                                 reg_mean=0, reg_std=300, use_centerness=True)
+    assert np.array_equal(N(lab), g["fc_label%d" % i])
+    np.testing.assert_allclose(N(s), g["fc_score%d" % i], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(b), g["fc_bbox%d" % i], rtol=1e-5, atol=1e-3)
+
+
+# ------------------------------------------------------------------ config 4: RetinaNet
+def test_retinanet_dense_assign_full_size_vs_oracle():
+    """201 600 anchors (A=9, strides 8-128, scales 4*2^{0,1/3,2/3}) x K GT, pos .5 / neg .4 / min_pos 0,
+    allowed_border -1, no sampler (configs/retinanet_r50_fpn.py:34-43)."""
+    rng = np.random.default_rng(11)
+    strides, pad, img = [8, 16, 32, 64, 128], (800, 1344), (800, 1333)
+    grids = [(-(-pad[0] // s), -(-pad[1] // s)) for s in strides]
+    scales = [4 * 2 ** (k / 3) for k in range(3)]
+    pyr = fused.AnchorPyramid(strides, grids, scales=scales, ratios=(0.5, 1.0, 2.0))
+    assert pyr.total == 201600
+    B, K = 2, 16
+    gts = [workload.synth_gt(rng, K, *img)[0] for _ in range(B)]
+    gt = np.stack(gts)
+    bt = fused.BatchedTargets(B, pyr.total, K, dict(pos_iou=0.5, neg_iou=0.4, min_pos_iou=0.0), dict(max_num=256, pos_num=128),
+                              None, None, DEV, pyramid=pyr, border=-1.0)
+    import ctypes
+    from b200det import _C
+    img_hw = torch.tensor([[800.0, 1333.0]] * B, device=DEV)
+    gcount = torch.full((B,), K, dtype=torch.int32, device=DEV)
+    _C.call("b2d_assign_max_iou", _C.ptr(bt.labels), _C.ptr(bt.iou), bt.out_ld, None, 0, None, bt.N, ctypes.byref(pyr.c),
+            _C.ptr(img_hw), -1.0, _C.ptr(T(gt)), K, _C.ptr(gcount), B, 0.5, 0.4, 0.0, 0, _C.ptr(bt.census), _C.ptr(bt.pos_list),
+            bt.out_ld, _C.ptr(bt.colmax), bt.colmax.numel() * 4, _C.stream())
+    anc = np.concatenate([oracle.anchor_grid(s, g, scales=scales).reshape(4, -1) for s, g in zip(strides, grids)], 1)
+    mask = np.concatenate([oracle.valid_mask(oracle.anchor_grid(s, g, scales=scales), img, g, s, -1) for s, g in zip(strides, grids)])
+    for b in range(B):
+        lab, iou = oracle.assign_max_iou(np.ascontiguousarray(anc[:, mask]), gt[b], 0.5, 0.4, 0.0)
+        full = np.full(anc.shape[1], -1, np.int64)
+        full[mask] = lab
+        assert np.array_equal(N(bt.labels[b]), full), b
+        cen = N(bt.census[b])
+        assert cen[0] == (full > 0).sum() and cen[1] == (full == 0).sum()
+
+
+def test_retinanet_per_level_topk_batched_nms_vs_oracle():
+    """test path of config 4: per-level top-1000 on max-over-classes score, decode, then class-aware NMS."""
+    rng = np.random.default_rng(12)
+    n, C = 3000, 20
+    boxes = np.sort(rng.uniform(0, 800, (n, 2, 2)), axis=1).reshape(n, 4)[:, [0, 2, 1, 3]].astype(np.float32)
+    score = rng.uniform(0, 1, n).astype(np.float32)
+    label = rng.integers(0, C, n).astype(np.int64)
+    kb, ks, kl = butils.batched_nms(T(boxes), T(score), T(label), 0.5)
+    keep = oracle.batched_nms(boxes, score, label, 0.5)
+    assert np.array_equal(N(kl), label[keep]) and np.array_equal(N(ks), score[keep]) and np.array_equal(N(kb), boxes[keep])
+    idx = bregion.topk_desc(T(score), 1000)
+    assert np.array_equal(N(idx), np.argsort(-score, kind="stable")[:1000])
+
+
+# ------------------------------------------------------------------ config 3: cascade
+def test_cascade_three_stage_targets_refine_roialign_fwd_bwd():
+    """3 x (bbox_target -> RoIAlign fwd -> synthetic reg_out -> refine) + RoIAlign bwd, thresholds .5/.6/.7 and
+    stage stds of configs/cascade_rcnn_r50_fpn.py; every stage is checked against the oracle on the GPU's own inputs."""
+    from b200det import bbox as bbbox
+    rng = np.random.default_rng(13)
+    img, C = (320, 416), 16
+    strides = (4, 8, 16, 32)
+    grids = [(-(-img[0] // s), -(-img[1] // s)) for s in strides]
+    feats_np = [rng.standard_normal((1, C) + g).astype(np.float32) for g in grids]
+    feats = [T(f).requires_grad_(True) for f in feats_np]
+    gt, gl = workload.synth_gt(rng, 5, *img)
+    cx, cy = rng.uniform(0, img[1], 300), rng.uniform(0, img[0], 300)
+    w, h = rng.uniform(16, 200, 300), rng.uniform(16, 200, 300)
+    props = np.stack([np.clip(cx - w / 2, 0, img[1] - 1), np.clip(cy - h / 2, 0, img[0] - 1),
+                      np.clip(cx + w / 2, 0, img[1] - 1), np.clip(cy + h / 2, 0, img[0] - 1)]).astype(np.float32)
+    props = T(props)
+    ext = bregion.BasicRoIExtractor([dict(type="RoIAlign", spatial_scale=1 / s, sampling_ratio=2) for s in strides], output_size=(7, 7))
+    stage_stds = [(0.1, 0.1, 0.2, 0.2), (0.05, 0.05, 0.1, 0.1), (0.033, 0.033, 0.067, 0.067)]
+    total = 0
+    for st, (thr, stds) in enumerate(zip((0.5, 0.6, 0.7), stage_stds)):
+        assigner = bregion.MaxIoUAssigner(thr, thr, thr)
+        sampler = bregion.RandomSampler(128, 32, rng="numpy")
+        np.random.seed(100 + st)
+        tar_props, tar_bbox, tar_label, tar_param, tar_is_gt = bbbox.bbox_target(props, T(gt), T(gl), assigner, sampler, [0.0] * 4, list(stds))
+        # stage-wise oracle: assignment of these proposals
+        olab, _ = oracle.assign_max_iou(N(props), gt, thr, thr, thr)
+        lab_gpu, _ = assigner(props, T(gt))
+        assert np.array_equal(N(lab_gpu), olab)
+        enc = oracle.bbox2param(N(tar_props), N(tar_bbox), [0.0] * 4, list(stds))
+        np.testing.assert_allclose(N(tar_param), enc, rtol=1e-5, atol=1e-5)
+        out = ext(feats, [tar_props])[0]
+        ref = oracle.roi_extract([f[0] for f in feats_np], N(tar_props))
+        np.testing.assert_allclose(N(out), ref, rtol=1e-5, atol=1e-6)
+        total = total + (out * out).sum()
+        reg_out = T(rng.standard_normal((tar_props.shape[1], 4)).astype(np.float32))
+        refined = bheads.refine_bboxes(tar_props, tar_label, reg_out, tar_is_gt, img + (3,), [0.0] * 4, list(stds), True, 21)
+        keep = N(tar_is_gt) == 0
+        dec = oracle.param2bbox(N(tar_props)[:, keep], N(reg_out).T[:, keep], [0.0] * 4, list(stds), img)
+        np.testing.assert_allclose(N(refined), dec, rtol=1e-5, atol=1e-3)
+        props = refined
+    total.backward()
+    assert all(f.grad is not None and torch.isfinite(f.grad).all() for f in feats)
+    assert sum(float(f.grad.abs().sum()) for f in feats) > 0

@@ -163,3 +163,15 @@ def test_rpn_proposals():
         assert b.shape == g["props%d" % i].shape, (i, b.shape)
         np.testing.assert_allclose(s, g["scores%d" % i], rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(b, g["props%d" % i], rtol=1e-5, atol=1e-3)
+
+
+def test_atss_oracle_vs_reference():
+    """a18: FCOSHead.single_image_targets_atss (with the `//` fix, SURVEY 8(c)) -- labels and ltrb bit-exact,
+    centerness within 1e-6 (sqrt/divide of the vectorised torch kernel)."""
+    g = load_golden("atss")
+    for tag in "sf":
+        grids = [tuple(int(v) for v in x) for x in g["grids_" + tag]]
+        cls, reg, ctr = oracle.atss_assign(grids, [8, 16, 32, 64, 128], g["gt_" + tag], g["gl_" + tag], g["img_" + tag][:2])
+        assert np.array_equal(cls, g["cls_" + tag])
+        assert np.array_equal(reg, g["reg_" + tag])
+        np.testing.assert_allclose(ctr, g["ctr_" + tag], rtol=1e-5, atol=1e-6)
