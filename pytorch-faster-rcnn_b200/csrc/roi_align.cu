@@ -8,10 +8,12 @@
 // the sample count) with FMA contraction disabled, so results are bit-identical to
 // the reference on CPU, far inside the 1e-5 north_star tolerance.
 //
-//   k_roi_align_nhwc  one CTA per RoI, lanes across channels: every bilinear tap is
-//                     a coalesced 128-bit load of 4 consecutive channels (a warp
-//                     reads 512 contiguous bytes); the [C,7,7] result is transposed
-//                     through shared memory and leaves as contiguous 128-bit stores.
+//   k_roi_align_win   NHWC, 2x2 samples per bin (every reference config): one CTA per (RoI,
+//                     128-channel tile), lanes across channels; the distinct tap cells of a
+//                     bin are loaded once as coalesced 128-bit channel quads, all loads of a
+//                     bin in flight together; the [C,7,7] result is staged in shared memory
+//                     in its HBM layout and leaves as contiguous 128-bit stores.
+//   k_roi_align_nhwc  NHWC, any fixed sampling ratio: per-sample tap descriptors in smem.
 //   k_roi_align_any   generic fallback (NCHW input, adaptive sampling, odd shapes):
 //                     one thread per output element, pw fastest.
 // HBM roofline: 50 176 B/RoI of output + the touched feature cells.
@@ -204,110 +206,23 @@ __global__ void __launch_bounds__(256) k_roi_align_nhwc(RoiArgs a, float* __rest
 }
 
 
-// ---- fast path: PH*PW*sr*sr <= 256 samples, sr*sr == 4, one 256-channel tile per pass ----
-// The previous formulation let ptxas interleave the 4 tap loads of a sample with their use
-// (2 loads in flight per thread => latency-bound at 0.29 of the HBM roofline, ncu r1d).  Here
-// a thread first ISSUES the 4*NS*... 128-bit loads of NS samples (NS*4 independent LDG.128 in
-// flight per thread), then consumes them in torchvision's summation order, so the arithmetic
-// (and the result) is unchanged.  Tap offsets are pre-multiplied to BYTES relative to the
-// thread's own channel pointer (one 64-bit add per tap), the [C][bins] result tile is laid
-// out in shared memory exactly as it lies in HBM (write-out = straight 128-bit copy), and
-// the sample mean is a multiply by the exact reciprocal 1/4.
-struct __align__(16) TapB { int o1, o2, o3, o4; float w1, w2, w3, w4; };
-
 template <typename FT>
 __device__ __forceinline__ float4 ld4b(const char* p) { return ld4(reinterpret_cast<const FT*>(p)); }
 
-// MINB (min resident CTAs/SM) is what makes ptxas keep the NS*4 loads batched: with the
-// default bound it targets 64 registers and sinks every load next to its use.
-template <typename FT, int NS, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_roi_align_nhwc4(RoiArgs a, float* __restrict__ out) {
-    extern __shared__ float s_tile[];                      // [kCTile][bins] (+ tap table behind it)
-    const long long r = blockIdx.x;
-    const b2d_roi_cfg& c = a.cfg;
-    float x1, y1, x2, y2;
-    int img;
-    if (!roi_fetch(a, r, img, x1, y1, x2, y2)) return;
-    int lvl;
-    if (a.levels) lvl = a.levels[r];
-    else lvl = c.num_levels > 1 ? roi_level(x1, y1, x2, y2, c.finest_scale, c.num_levels) : 0;
-    const int H = c.H[lvl], W = c.W[lvl], C = c.C;
-    const int bins = c.PH * c.PW;
-    TapB* s_tap = reinterpret_cast<TapB*>(s_tile + kCTile * bins);
-    const RoiGeom g = roi_geom(x1, y1, x2, y2, c.spatial_scale[lvl], c.PH, c.PW, c.sampling_ratio, c.aligned);
-    {   // sample t = ((ph*PW + pw)*2 + iy)*2 + ix  (torchvision's pre-calc order)
-        const int t = threadIdx.x;
-        if (t < bins * 4) {
-            const int ix = t & 1, iy = (t >> 1) & 1;
-            const int bin = t >> 2, ph = bin / c.PW, pw = bin - ph * c.PW;
-            const AxisTap ty = axis_tap(g.sy, g.bh, ph, iy, 2, H);
-            const AxisTap tx = axis_tap(g.sx, g.bw, pw, ix, 2, W);
-            TapB q;
-            const int es = (int)sizeof(FT);
-            if (ty.valid && tx.valid) {
-                q.o1 = (ty.lo * W + tx.lo) * C * es; q.o2 = (ty.lo * W + tx.hi) * C * es;
-                q.o3 = (ty.hi * W + tx.lo) * C * es; q.o4 = (ty.hi * W + tx.hi) * C * es;
-                q.w1 = ty.h * tx.h; q.w2 = ty.h * tx.l; q.w3 = ty.l * tx.h; q.w4 = ty.l * tx.l;
-            } else {
-                q.o1 = q.o2 = q.o3 = q.o4 = 0; q.w1 = q.w2 = q.w3 = q.w4 = 0.0f;
-            }
-            s_tap[t] = q;
-        }
-    }
-    __syncthreads();
-    const FT* feat = reinterpret_cast<const FT*>(a.feat[lvl]) + (long long)img * H * W * C;
-    const int cq = threadIdx.x & 63, grp = threadIdx.x >> 6;
-    float* o = out + r * (long long)C * bins;
-    for (int c0 = 0; c0 < C; c0 += kCTile) {
-        const int ch = c0 + cq * 4;
-        if (ch < C) {
-            const char* fb = reinterpret_cast<const char*>(feat + ch);
-            for (int bin = grp; bin < bins; bin += 4) {
-                const TapB* tp = s_tap + bin * 4;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int s0 = 0; s0 < 4; s0 += NS) {
-                    int4 of[NS];
-                    float4 v[NS][4];
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) of[s] = *reinterpret_cast<const int4*>(&tp[s0 + s].o1);
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) {
-                        v[s][0] = ld4b<FT>(fb + of[s].x); v[s][1] = ld4b<FT>(fb + of[s].y);
-                        v[s][2] = ld4b<FT>(fb + of[s].z); v[s][3] = ld4b<FT>(fb + of[s].w);
-                    }
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) {
-                        const float4 w = *reinterpret_cast<const float4*>(&tp[s0 + s].w1);
-                        acc.x += ((w.x * v[s][0].x + w.y * v[s][1].x) + w.z * v[s][2].x) + w.w * v[s][3].x;
-                        acc.y += ((w.x * v[s][0].y + w.y * v[s][1].y) + w.z * v[s][2].y) + w.w * v[s][3].y;
-                        acc.z += ((w.x * v[s][0].z + w.y * v[s][1].z) + w.z * v[s][2].z) + w.w * v[s][3].z;
-                        acc.w += ((w.x * v[s][0].w + w.y * v[s][1].w) + w.z * v[s][2].w) + w.w * v[s][3].w;
-                    }
-                }
-                // x / 4 == x * 0.25 exactly (power of two)
-                float* st = s_tile + (cq * 4) * bins + bin;
-                st[0] = acc.x * 0.25f; st[bins] = acc.y * 0.25f; st[2 * bins] = acc.z * 0.25f; st[3 * bins] = acc.w * 0.25f;
-            }
-        }
-        __syncthreads();
-        const int ctile = min(kCTile, C - c0);
-        const int total = ctile * bins;                    // multiple of 4 (C % 4 == 0)
-        float4* dst = reinterpret_cast<float4*>(o + (long long)c0 * bins);
-        const float4* src = reinterpret_cast<const float4*>(s_tile);
-        for (int q = threadIdx.x; q < total / 4; q += blockDim.x) dst[q] = src[q];
-        __syncthreads();
-    }
-}
-
-
-// ---- window kernel: the batched-load kernel with the duplicate taps of a bin removed ------------
+// ---- window kernel (2x2 samples per bin: every reference config) --------------------------------
+// Design notes from the ncu captures of round 1 (profiles/):
+//  * ptxas, left to its default occupancy target, sinks every tap load next to its use (2 loads
+//    in flight per thread, 0.29 of the HBM roofline).  __launch_bounds__(NT, MINB) with a
+//    register budget of ~80 makes it issue the whole window of a bin back-to-back.
+//  * With the loads batched the kernel was bound by L1 wavefronts (784 128-bit taps per RoI per
+//    4 channels), hence the tap de-duplication below; after that by the number of resident
+//    warps (L1-miss latency x concurrency), hence 128-thread CTAs over 128 channels, 6 per SM.
 // The 2x2 samples of a bin touch the cells {lo0, hi0, lo1, hi1} per axis.  With a sample
 // spacing below two cells (RoI narrower than ~28 cells, i.e. every RoI the FPN level map
 // sends to a level) lo1 - lo0 is 0, 1 or 2 and the taps fall into a (PY+2) x (PX+2) window of
 // distinct cells, so a bin needs 4..16 loads instead of 16 (387 instead of 784 per RoI on the
 // config-2 workload: the kernel was bound by L1 wavefronts, ncu prof_roi4).  The pattern
-// (PY, PX) is uniform over the two warps that share a bin, every sample still reads "its"
+// (PY, PX) is uniform over the warps that share a bin, every sample still reads "its"
 // four cells from the window registers and is summed in torchvision's order, so the result
 // stays bit-identical to the reference.
 struct __align__(16) BinTab {
@@ -346,9 +261,11 @@ __device__ __forceinline__ float4 bin_eval(const char* fb, const BinTab* t) {
     return acc;
 }
 
-template <typename FT>
-__global__ void __launch_bounds__(256, 2) k_roi_align_win(RoiArgs a, float* __restrict__ out) {
-    extern __shared__ float s_tile[];                      // [kCTile][bins] (+ bin table behind it)
+// NT threads per CTA, CT channels per CTA (grid.y = C / CT tiles), MINB = min resident CTAs/SM
+// (the register bound that keeps the window loads batched, see the notes above).
+template <typename FT, int NT, int CT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_roi_align_win(RoiArgs a, float* __restrict__ out) {
+    extern __shared__ float s_tile[];                      // [CT][bins] (+ bin table behind it)
     const long long r = blockIdx.x;
     const b2d_roi_cfg& c = a.cfg;
     float x1, y1, x2, y2;
@@ -359,7 +276,7 @@ __global__ void __launch_bounds__(256, 2) k_roi_align_win(RoiArgs a, float* __re
     else lvl = c.num_levels > 1 ? roi_level(x1, y1, x2, y2, c.finest_scale, c.num_levels) : 0;
     const int H = c.H[lvl], W = c.W[lvl], C = c.C;
     const int bins = c.PH * c.PW;
-    BinTab* s_tab = reinterpret_cast<BinTab*>(s_tile + kCTile * bins);
+    BinTab* s_tab = reinterpret_cast<BinTab*>(s_tile + CT * bins);
     const RoiGeom g = roi_geom(x1, y1, x2, y2, c.spatial_scale[lvl], c.PH, c.PW, 2, c.aligned);
     // L2 prefetch for the RoI that runs `pf_dist` CTAs later: one bulk prefetch per feature row of
     // its tap rectangle (rows are contiguous in NHWC).  Costs no registers, and turns the DRAM
@@ -415,16 +332,18 @@ __global__ void __launch_bounds__(256, 2) k_roi_align_win(RoiArgs a, float* __re
     }
     __syncthreads();
     const FT* feat = reinterpret_cast<const FT*>(a.feat[lvl]) + (long long)img * H * W * C;
-    const int cq = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    constexpr int LG = CT / 4, NG = NT / LG;               // lanes per bin group, bin groups
+    const int cq = threadIdx.x % LG, grp = threadIdx.x / LG;
     float* o = out + r * (long long)C * bins;
-    for (int c0 = 0; c0 < C; c0 += kCTile) {
+    {
+        const int c0 = blockIdx.y * CT;
         const int ch = c0 + cq * 4;
         if (ch < C) {
             const char* fb = reinterpret_cast<const char*>(feat + ch);
-            for (int bin = grp; bin < bins; bin += 4) {
+            for (int bin = grp; bin < bins; bin += NG) {
                 const BinTab* t = s_tab + bin;
                 float4 acc;
-                switch (t->pat) {                          // uniform over the two warps of a bin
+                switch (t->pat) {                          // uniform over the warps of a bin
                     case 0: acc = bin_eval<FT, 0, 0>(fb, t); break;
                     case 1: acc = bin_eval<FT, 0, 1>(fb, t); break;
                     case 2: acc = bin_eval<FT, 0, 2>(fb, t); break;
@@ -440,15 +359,13 @@ __global__ void __launch_bounds__(256, 2) k_roi_align_win(RoiArgs a, float* __re
             }
         }
         __syncthreads();
-        const int ctile = min(kCTile, C - c0);
-        const int total = ctile * bins;                    // multiple of 4 (C % 4 == 0)
+        const int ctile = min(CT, C - c0);
+        const int total = ctile * bins;                    // multiple of 4 (checked by the launcher)
         float4* dst = reinterpret_cast<float4*>(o + (long long)c0 * bins);
         const float4* src = reinterpret_cast<const float4*>(s_tile);
-        for (int q = threadIdx.x; q < total / 4; q += blockDim.x) dst[q] = src[q];
-        __syncthreads();
+        for (int q = threadIdx.x; q < total / 4; q += NT) dst[q] = src[q];
     }
 }
-
 
 // ---- NCHW -> NHWC (fp32): lets reference-layout features (lib/necks.py FPN output) use the
 // channel-vectorised kernels above.  64(hw) x 32(c) tiles through padded shared memory; reads
@@ -549,35 +466,19 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
     const bool fast = c.layout >= 1 && c.sampling_ratio > 0 &&
                       bins * c.sampling_ratio * c.sampling_ratio <= kMaxSamples && (c.C % 4) == 0 &&
                       bins * (kCTile + 4) * 4 <= 200 * 1024;
-    // 2x2 samples per bin (every reference config): batched-load kernel
-    const bool fast4 = fast && c.sampling_ratio == 2 && bins * 4 <= 256 &&
-                       (((long long)c.C * bins) % 4) == 0 && (c.C <= kCTile || ((long long)kCTile * bins) % 4 == 0);
-    int variant = 5;
-    { const char* e = getenv("B2D_ROI_VARIANT"); if (e) variant = atoi(e); }   // dev knob
-    if (fast4 && variant != 0) {
-        const size_t smem = (size_t)kCTile * bins * 4 + (size_t)bins * 4 * sizeof(TapB);
-        auto launch = [&](auto kern) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kern<<<(unsigned)R, 256, smem, st>>>(a, out);
+    // 2x2 samples per bin (every reference config): window kernel, 128 channels per 128-thread CTA
+    const bool win = fast && c.sampling_ratio == 2 && bins <= 64 && (((long long)c.C * bins) % 4) == 0 &&
+                     ((128ll * bins) % 4) == 0;
+    if (win) {
+        { const char* e = getenv("B2D_ROI_PF"); a.pf_dist = e ? atoi(e) : 0; }   // dev knob (L2 prefetch: measured slower, r1)
+        auto launch5 = [&](auto kern, int nt, int ct) {
+            const size_t smem5 = (size_t)ct * bins * 4 + (size_t)bins * sizeof(BinTab);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
+            dim3 grid((unsigned)R, (unsigned)cdiv(c.C, ct));
+            kern<<<grid, nt, smem5, st>>>(a, out);
         };
-        if (variant == 5) {
-            { const char* e = getenv("B2D_ROI_PF"); a.pf_dist = e ? atoi(e) : 0; }   // dev knob: measured slower (r1)
-            const size_t smem5 = (size_t)kCTile * bins * 4 + (size_t)bins * sizeof(BinTab);
-            if (c.layout == 1) {
-                cudaFuncSetAttribute(k_roi_align_win<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
-                k_roi_align_win<float><<<(unsigned)R, 256, smem5, st>>>(a, out);
-            } else {
-                cudaFuncSetAttribute(k_roi_align_win<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
-                k_roi_align_win<__nv_bfloat16><<<(unsigned)R, 256, smem5, st>>>(a, out);
-            }
-        } else if (c.layout == 1) {
-            if (variant == 2) launch(k_roi_align_nhwc4<float, 2, 3>);
-            else if (variant == 3) launch(k_roi_align_nhwc4<float, 2, 2>);
-            else if (variant == 1) launch(k_roi_align_nhwc4<float, 1, 3>);
-            else launch(k_roi_align_nhwc4<float, 4, 2>);
-        } else {
-            if (variant == 2) launch(k_roi_align_nhwc4<__nv_bfloat16, 2, 3>); else launch(k_roi_align_nhwc4<__nv_bfloat16, 4, 2>);
-        }
+        if (c.layout == 1) launch5(k_roi_align_win<float, 128, 128, 6>, 128, 128);
+        else launch5(k_roi_align_win<__nv_bfloat16, 128, 128, 6>, 128, 128);
     } else if (fast) {
         const size_t smem = (size_t)bins * (kCTile + 4) * 4;
         static size_t attr_f32 = 0, attr_bf16 = 0;
