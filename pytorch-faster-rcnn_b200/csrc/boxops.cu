@@ -2,6 +2,7 @@
 // All HBM-write/read bound elementwise kernels: coalesced SoA rows, 128-bit
 // stores where the row pitch allows, grids sized to the work (tiny launches).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -19,6 +20,8 @@ void set_error(const char* msg) {
 }
 
 int check_launch(const char* what) {
+    static const bool debug_sync = getenv("B2D_DEBUG_SYNC") != nullptr;   // debugging aid: localise a faulting kernel
+    if (debug_sync) cudaDeviceSynchronize();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         char buf[512];

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(kSelThreads) k_nms_sort(float4* __restrict__ s
                                                           const float4* __restrict__ boxes,
                                                           const float* __restrict__ scores, long long n_ld,
                                                           const int* __restrict__ counts, long long n, int presorted) {
-    extern __shared__ uint64_t s_buf[];
+    extern __shared__ __align__(16) uint64_t s_buf[];
     const int s = blockIdx.x;
     const int m = counts ? counts[s] : (int)n;
     if (!presorted) {

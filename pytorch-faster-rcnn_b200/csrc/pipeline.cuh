@@ -22,9 +22,10 @@ struct RpnLaunch {
     long long mask_off[kMaxLevels], mask_per_img;
     int pre_nms, post_nms, max_num, score_mode, cls_ch, do_nms, out_ld;
     int raw;                            // 1: plain segmented top-k (no anchors / deltas / decode)
+    int dbg;                            // development knob (B2D_DBG)
     float nms_thr, min_size, ms[8];
     // workspace
-    uint32_t* hist; int* cand_count; int* sel_count; int* keep_count; int* thr_bin;
+    uint32_t* hist; int* cand_count; int* cand2_count; int* sel_count; int* keep_count; int* thr_bin;
     uint32_t* nz;                       // NMS: per selected box, bitmap of its non-zero mask words (nms.cu)
     size_t zero_bytes;
     uint64_t* cand; uint64_t* cand2;

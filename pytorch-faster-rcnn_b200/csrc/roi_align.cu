@@ -120,7 +120,7 @@ constexpr int kMaxSamples = 256;   // PH*PW*sr*sr limit of the fast kernel (7*7*
 
 template <typename FT>
 __global__ void __launch_bounds__(256) k_roi_align_nhwc(RoiArgs a, float* __restrict__ out) {
-    extern __shared__ float s_tile[];                      // [bins][kCTile + 4]
+    extern __shared__ __align__(16) float s_tile[];                      // [bins][kCTile + 4]
     __shared__ Tap4 s_tap[kMaxSamples];
     const long long r = blockIdx.x;
     const b2d_roi_cfg& c = a.cfg;
@@ -265,7 +265,7 @@ __device__ __forceinline__ float4 bin_eval(const char* fb, const BinTab* t) {
 // (the register bound that keeps the window loads batched, see the notes above).
 template <typename FT, int NT, int CT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_roi_align_win(RoiArgs a, float* __restrict__ out) {
-    extern __shared__ float s_tile[];                      // [CT][bins] (+ bin table behind it)
+    extern __shared__ __align__(16) float s_tile[];                      // [CT][bins] (+ bin table behind it)
     const long long r = blockIdx.x;
     const b2d_roi_cfg& c = a.cfg;
     float x1, y1, x2, y2;

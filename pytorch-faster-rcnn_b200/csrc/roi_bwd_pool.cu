@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) k_roi_pool_bwd(float* __restrict__ grad, 
                                                       const float* __restrict__ rois, long long ld,
                                                       const int* __restrict__ roi_img, long long R, float scale,
                                                       int PH, int PW) {
-    extern __shared__ int s_roi[];             // per RoI: sh, sw, rh, rw, img  (chunks of 256)
+    extern __shared__ __align__(16) int s_roi[];             // per RoI: sh, sw, rh, rw, img  (chunks of 256)
     const long long total = (long long)B * C * H * W;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < total;

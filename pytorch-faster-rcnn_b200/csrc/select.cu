@@ -10,6 +10,7 @@
 // Selection and ordering use the *logit* (sigmoid is monotone), ties broken by the
 // lowest index; torch.topk's tie order is unspecified, so this is the
 // documented contract and parity is asserted on tie-free inputs.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -98,14 +99,15 @@ __device__ int find_threshold_bin(const uint32_t* __restrict__ gh, int k, uint32
 }
 
 // ---------------------------------------------------------------- k_compact
-// Candidates (bin >= threshold bin) are staged in shared memory per 2048-element round and
-// leave with ONE global atomic per round and a coalesced copy (order is irrelevant: the
-// candidates are sorted afterwards).
+// Candidates are staged in shared memory per 2048-element round and leave with ONE global
+// atomic per list and round and a coalesced copy (order is irrelevant: they are sorted
+// afterwards).  Two lists per segment: `cand` = keys ABOVE the threshold bin (all of them are
+// selected, count < k), `cand2` = keys IN the threshold bin (only the best k - |cand| are).
 __global__ void __launch_bounds__(256) k_compact(RpnLaunch p) {
     constexpr int kRound = 2048;
     __shared__ uint32_t s_tmp[8];
-    __shared__ uint64_t s_stage[kRound];
-    __shared__ int s_n, s_base;
+    __shared__ uint64_t s_stage[kRound];                 // above-bin entries grow from 0, in-bin entries from the top
+    __shared__ int s_n, s_n2, s_base, s_base2;
     const int seg = blockIdx.y, b = seg / p.L, l = seg - b * p.L;
     const int n = p.n[l], k = p.kcap[l];
     if (k >= n) return;
@@ -115,9 +117,10 @@ __global__ void __launch_bounds__(256) k_compact(RpnLaunch p) {
     if (blockIdx.x == 0 && threadIdx.x == 0) p.thr_bin[seg] = tb;
     const float* cls = seg_cls(p, b, l);
     uint64_t* cand = p.cand + ((long long)b * p.pyr.total + p.pyr.lv[l].offset);
+    uint64_t* cand2 = p.cand2 + ((long long)b * p.pyr.total + p.pyr.lv[l].offset);
     const int end = min(start + kChunk, n);
     for (int r0 = start; r0 < end; r0 += kRound) {
-        if (threadIdx.x == 0) s_n = 0;
+        if (threadIdx.x == 0) { s_n = 0; s_n2 = 0; }
         __syncthreads();
         float v[kRound / 256];
 #pragma unroll
@@ -129,21 +132,111 @@ __global__ void __launch_bounds__(256) k_compact(RpnLaunch p) {
         for (int q = 0; q < kRound / 256; ++q) {
             const int i = r0 + q * 256 + threadIdx.x;
             const uint32_t key = f2key(v[q]);
-            if (i < end && (int)(key >> (32 - kHistBits)) >= tb) s_stage[atomicAdd(&s_n, 1)] = make_comp(key, (uint32_t)i);
+            const int bin = (int)(key >> (32 - kHistBits));
+            if (i < end && bin > tb) s_stage[atomicAdd(&s_n, 1)] = make_comp(key, (uint32_t)i);
+            else if (i < end && bin == tb) s_stage[kRound - 1 - atomicAdd(&s_n2, 1)] = make_comp(key, (uint32_t)i);
         }
         __syncthreads();
-        const int m = s_n;
+        const int m = s_n, m2 = s_n2;
         if (threadIdx.x == 0 && m > 0) s_base = atomicAdd(&p.cand_count[seg], m);
+        if (threadIdx.x == 32 && m2 > 0) s_base2 = atomicAdd(&p.cand2_count[seg], m2);
         __syncthreads();
         for (int t = threadIdx.x; t < m; t += blockDim.x) cand[s_base + t] = s_stage[t];
+        for (int t = threadIdx.x; t < m2; t += blockDim.x) cand2[s_base2 + t] = s_stage[kRound - 1 - t];
     }
+}
+
+// ---------------------------------------------------------------- block bucket sort
+// Descending sort of `total` distinct u64 composites (score key << 32 | ~index) held in
+// s_list[0..total), one 1024-thread block.  The candidates are split into <= 4096 buckets
+// that are linear in the monotone score key, bucket = (key_max - key) >> shift with the
+// smallest shift that fits the candidates' key range, so buckets hold a handful of elements
+// even in the dense part of the score distribution.  The sort is then: count per bucket,
+// prefix over the buckets, scatter, and a rank-by-counting INSIDE each bucket -- ~7 block
+// barriers instead of the 66-78 compare-exchange stages of a bitonic network.  Returns false
+// (s_list unchanged) when a bucket is too large for the quadratic in-bucket ranking (heavily
+// tied / degenerate score maps); the caller then falls back to the bitonic sort.
+constexpr int kBucketCap = kSortCap / 2;             // s_list and s_bkt share the sort buffer
+constexpr int kMaxBucket = 128;
+
+__device__ __noinline__ bool bucket_sort_desc(uint64_t* s_list, uint64_t* s_bkt, int total, uint32_t* s_off /*[kHistBins + 1]*/,
+                                 uint32_t* s_cur /*[kHistBins]*/, uint32_t* s_wsum /*[66]*/, int dbg = 0) {
+    const int t = threadIdx.x;
+    if (dbg == 1) return false;
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
+    for (int i = t; i < total; i += blockDim.x) {
+        const uint32_t key = (uint32_t)(s_list[i] >> 32);
+        kmin = min(kmin, key); kmax = max(kmax, key);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((t & 31) == 0) { s_wsum[t >> 5] = kmin; s_wsum[33 + (t >> 5)] = kmax; }
+    for (int i = t; i < kHistBins; i += blockDim.x) s_cur[i] = 0;
+    __syncthreads();
+    kmin = s_wsum[0]; kmax = s_wsum[33];
+    for (int w = 1; w < 32; ++w) { kmin = min(kmin, s_wsum[w]); kmax = max(kmax, s_wsum[33 + w]); }
+    int shift = 0;
+    while (((kmax - kmin) >> shift) >= (uint32_t)kHistBins) ++shift;
+    __syncthreads();                                  // s_wsum is reused below
+    if (dbg == 2) return false;
+    for (int i = t; i < total; i += blockDim.x) atomicAdd(&s_cur[(kmax - (uint32_t)(s_list[i] >> 32)) >> shift], 1u);
+    __syncthreads();
+    // exclusive prefix over the 4096 counts (4 per thread, 1024 threads)
+    uint32_t c[4], sum = 0, mx = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { c[q] = s_cur[4 * t + q]; sum += c[q]; mx = max(mx, c[q]); }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((t & 31) >= o) incl += v;
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((t & 31) == 31) s_wsum[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+        uint32_t w = s_wsum[t], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (t >= o) wi += v;
+        }
+        s_wsum[t] = wi - w;                           // exclusive warp offsets
+    }
+    const bool too_big = __syncthreads_or(mx > (uint32_t)kMaxBucket);
+    if (too_big || dbg == 3) return false;
+    uint32_t run = s_wsum[t >> 5] + incl - sum;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { s_off[4 * t + q] = run; s_cur[4 * t + q] = run; run += c[q]; }
+    if (t == blockDim.x - 1) s_off[kHistBins] = run;
+    __syncthreads();
+    for (int i = t; i < total; i += blockDim.x) {
+        const uint64_t v = s_list[i];
+        s_bkt[atomicAdd(&s_cur[(kmax - (uint32_t)(v >> 32)) >> shift], 1u)] = v;
+    }
+    __syncthreads();
+    if (dbg == 4) return false;
+    for (int i = t; i < total; i += blockDim.x) {
+        const uint64_t v = s_bkt[i];
+        const int rb = (int)((kmax - (uint32_t)(v >> 32)) >> shift);
+        const int o = (int)s_off[rb], e = (int)s_off[rb + 1];
+        int r = o;
+        for (int q = o; q < e; ++q) r += (s_bkt[q] > v) ? 1 : 0;
+        s_list[r] = v;
+    }
+    __syncthreads();
+    return true;
 }
 
 // ---------------------------------------------------------------- k_select
 // One block per segment.  Shared memory: kSortCap u64 sort buffer.
 __global__ void __launch_bounds__(kSelThreads) k_select(RpnLaunch p) {
-    extern __shared__ uint64_t s_buf[];
+    extern __shared__ __align__(16) uint64_t s_buf[];
     __shared__ uint32_t s_h[256];
+    __shared__ __align__(16) uint32_t s_off[kHistBins + 4], s_cur[kHistBins], s_wsum[80];
     __shared__ int s_cnt, s_cnt2, s_digit, s_base;
     __shared__ int s_warp[kSelThreads / 32];
     const int seg = blockIdx.x, b = seg / p.L, l = seg - b * p.L;
@@ -152,39 +245,55 @@ __global__ void __launch_bounds__(kSelThreads) k_select(RpnLaunch p) {
     const float* cls = seg_cls(p, b, l);
     const bool identity = (k >= n) && !p.do_nms;          // AnchorHead path without top-k: keep index order
     int total = 0;
+    bool presorted = false;                               // s_buf holds two sorted runs: [0, split_at) and [split_off, ...)
+    int split_at = 1 << 30, split_off = 0;
     if (k >= n) {
         for (int i = threadIdx.x; i < n; i += blockDim.x)
             s_buf[i] = identity ? make_comp(0xffffffffu, (uint32_t)i)
                                 : make_comp(f2key(load_logit(cls, n, i, p.score_mode, p.cls_ch)), (uint32_t)i);
         total = n;
+        if (!identity && n <= kBucketCap) {
+            __syncthreads();
+            presorted = bucket_sort_desc(s_buf, s_buf + kBucketCap, total, s_off, s_cur, s_wsum, p.dbg);
+        }
     } else {
-        uint64_t* list = p.cand + ((long long)b * p.pyr.total + lv.offset);
-        uint64_t* list2 = p.cand2 + ((long long)b * p.pyr.total + lv.offset);
-        int m = p.cand_count[seg];
-        if (m <= kSortCap) {
-            for (int i = threadIdx.x; i < m; i += blockDim.x) s_buf[i] = list[i];
-            total = m;
+        uint64_t* listA = p.cand + ((long long)b * p.pyr.total + lv.offset);
+        uint64_t* listB = p.cand2 + ((long long)b * p.pyr.total + lv.offset);
+        const int sA = p.cand_count[seg];                 // above the threshold bin: all selected (sA < k)
+        int m = p.cand2_count[seg];                       // in the threshold bin: best k - sA selected
+        int pA = kSelThreads, pB = kSelThreads;
+        while (pA < sA) pA <<= 1;
+        while (pB < m) pB <<= 1;
+        bool done = false;
+        if (sA + m <= kBucketCap) {
+            for (int i = threadIdx.x; i < sA; i += blockDim.x) s_buf[i] = listA[i];
+            for (int i = threadIdx.x; i < m; i += blockDim.x) s_buf[sA + i] = listB[i];
+            total = sA + m;
+            __syncthreads();
+            done = presorted = bucket_sort_desc(s_buf, s_buf + kBucketCap, total, s_off, s_cur, s_wsum, p.dbg);
+        }
+        if (done) {
+        } else if (sA + m <= kSortCap && (sA == 0 || m == 0 || pA + pB > kSortCap)) {
+            for (int i = threadIdx.x; i < sA; i += blockDim.x) s_buf[i] = listA[i];
+            for (int i = threadIdx.x; i < m; i += blockDim.x) s_buf[sA + i] = listB[i];
+            total = sA + m;
+        } else if (sA + m <= kSortCap) {
+            // Two sorted runs (pow2(sA) + pow2(m) elements) instead of one sort of pow2(sA + m)
+            // -- typically 2048 + 1024 instead of 4096 for k = 2000.
+            for (int i = threadIdx.x; i < pA; i += blockDim.x) s_buf[i] = i < sA ? listA[i] : 0ull;
+            for (int i = threadIdx.x; i < pB; i += blockDim.x) s_buf[pA + i] = i < m ? listB[i] : 0ull;
+            __syncthreads();
+            bitonic_sort_desc(s_buf, pA);
+            bitonic_sort_desc(s_buf + pA, pB);
+            split_at = sA; split_off = pA;
+            total = sA + m;
+            presorted = true;
         } else {
-            // radix narrowing (only reached on heavily tied / degenerate score maps)
-            if (threadIdx.x == 0) s_cnt = 0;
+            // radix narrowing of the threshold bin (only reached on heavily tied / degenerate score maps)
+            for (int i = threadIdx.x; i < sA; i += blockDim.x) s_buf[i] = listA[i];
             __syncthreads();
-            const int tb = p.thr_bin[seg];
-            // pass 0: the 12-bit bin
-            if (threadIdx.x == 0) s_cnt2 = 0;
-            __syncthreads();
-            for (int i0 = 0; i0 < m; i0 += blockDim.x) {
-                const int i = i0 + threadIdx.x;
-                uint64_t c = 0; int d = -1;
-                if (i < m) { c = list[i]; d = (int)(c >> (64 - kHistBits)); }
-                const int s1 = warp_alloc(d > tb, &s_cnt);
-                if (d > tb) s_buf[s1] = c;
-                const int s2 = warp_alloc(d == tb, &s_cnt2);
-                if (d == tb) list2[s2] = c;
-            }
-            __syncthreads();
-            int sel = s_cnt;
-            m = s_cnt2;
-            uint64_t* src = list2; uint64_t* dst = list;
+            int sel = sA;
+            uint64_t* src = listB; uint64_t* dst = listA;   // listA is free once copied
             int shift = 64 - kHistBits - 8;
             while (sel + m > kSortCap) {
                 const int bits = shift >= 0 ? 8 : 8 + shift;   // last pass may be narrower
@@ -222,11 +331,13 @@ __global__ void __launch_bounds__(kSelThreads) k_select(RpnLaunch p) {
             total = sel + m;
         }
     }
-    int p2 = 1;
-    while (p2 < total) p2 <<= 1;
-    for (int i = total + threadIdx.x; i < p2; i += blockDim.x) s_buf[i] = 0ull;
-    __syncthreads();
-    bitonic_sort_desc(s_buf, p2);
+    if (!presorted) {
+        int p2 = 1;
+        while (p2 < total) p2 <<= 1;
+        for (int i = total + threadIdx.x; i < p2; i += blockDim.x) s_buf[i] = 0ull;
+        __syncthreads();
+        bitonic_sort_desc(s_buf, p2);
+    }
     const int kk = min(k, total);
 
     // decode + clip + min-size filter, order preserving
@@ -244,7 +355,7 @@ __global__ void __launch_bounds__(kSelThreads) k_select(RpnLaunch p) {
         Box o{0, 0, 0, 0};
         uint32_t key = 0, idx = 0;
         if (r < kk) {
-            const uint64_t c = s_buf[r];
+            const uint64_t c = s_buf[r < split_at ? r : split_off + (r - split_at)];
             idx = comp_idx(c);
             key = identity ? f2key(load_logit(cls, n, (int)idx, p.score_mode, p.cls_ch)) : comp_key(c);
             keep = true;
@@ -283,7 +394,7 @@ __global__ void __launch_bounds__(kSelThreads) k_select(RpnLaunch p) {
 __global__ void __launch_bounds__(kSelThreads) k_merge(RpnLaunch p, float* __restrict__ props,
                                                        float* __restrict__ scores, int* __restrict__ count,
                                                        int* __restrict__ prov) {
-    extern __shared__ uint64_t s_buf[];
+    extern __shared__ __align__(16) uint64_t s_buf[];
     __shared__ int s_off[kMaxLevels + 1];
     const int b = blockIdx.x;
     if (threadIdx.x == 0) {
@@ -466,7 +577,7 @@ __global__ void __launch_bounds__(256) k_merge_rank(RpnLaunch p, float* __restri
 __global__ void __launch_bounds__(kSelThreads) k_topk_small(int* __restrict__ idx, int* __restrict__ out_count,
                                                             const float* __restrict__ values, long long ld,
                                                             const int* __restrict__ counts, long long n, int k) {
-    extern __shared__ uint64_t s_buf[];
+    extern __shared__ __align__(16) uint64_t s_buf[];
     const int s = blockIdx.x;
     const int m = counts ? counts[s] : (int)n;
     int p2 = 1;
@@ -524,6 +635,7 @@ bool rpn_plan(RpnLaunch& p, const b2d_pyramid* pyr, int B, const b2d_rpn_cfg* cf
     auto carve = [&](size_t sz) { size_t r = o; o += (sz + 255) & ~(size_t)255; return base ? base + r : (char*)nullptr; };
     p.hist = (uint32_t*)carve((size_t)S * kHistBins * 4);
     p.cand_count = (int*)carve((size_t)S * 4);
+    p.cand2_count = (int*)carve((size_t)S * 4);
     p.sel_count = (int*)carve((size_t)S * 4);
     p.keep_count = (int*)carve((size_t)S * 4);
     p.thr_bin = (int*)carve((size_t)S * 4);
@@ -569,6 +681,7 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
     B2D_REQUIRE(workspace && ws_bytes >= need, "rpn_proposals: workspace too small");
     for (int l = 0; l < p.L; ++l) { p.cls[l] = (const float*)cls_ptrs_host[l]; p.reg[l] = (const float*)reg_ptrs_host[l]; }
     p.img_hw = img_hw;
+    { const char* e = getenv("B2D_DBG"); p.dbg = e ? atoi(e) : 0; }
     cudaStream_t st = (cudaStream_t)stream;
     static bool attr_set = false;
     if (!attr_set) {
@@ -586,9 +699,12 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
     if (any_select) {
         dim3 grid(max_chunks, S);
         k_hist<<<grid, 256, 0, st>>>(p);
+        if (int rc = check_launch("rpn_proposals/k_hist")) return rc;
         k_compact<<<grid, 256, 0, st>>>(p);
+        if (int rc = check_launch("rpn_proposals/k_compact")) return rc;
     }
     k_select<<<S, kSelThreads, kSortCap * 8, st>>>(p);
+    if (int rc = check_launch("rpn_proposals/k_select")) return rc;
     if (p.do_nms) {
         int rc = rpn_nms_launch(p, st);
         if (rc != B2D_OK) return rc;

@@ -123,7 +123,8 @@ class BatchedTargets(object):
         self.means, self.stds = _C.host_f4(means, [0, 0, 0, 0]), _C.host_f4(stds, [1, 1, 1, 1])
         self.step = 0
         self.b0 = 0
-        self.launches = 5   # kernels: fill, colmax, label, sample, encode  (+1 memset node)
+        small = pyramid is None and self.N <= 4096 and self.gt_ld <= 512
+        self.launches = 3 if small else 5   # kernels: (assign_small | fill, colmax, label), sample, encode
 
     def slice(self, b0, b1):
         return _batch_view(self, b0, b1)
