@@ -6,6 +6,7 @@
 //
 // Roofline: HBM-bound on its 12 B/anchor output (int64 label + fp32 IoU) for the
 // handful of GTs of config 2; fp32-issue bound beyond K ~ 8.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -222,6 +223,213 @@ __global__ void __launch_bounds__(256) k_assign_label(AssignArgs p, b2d_pyramid 
     if (threadIdx.x < 2 && s_cnt[threadIdx.x]) atomicAdd(&census[4 * b + threadIdx.x], s_cnt[threadIdx.x]);
 }
 
+
+// ================= pyramid mode, structure-aware (K2 for anchor heads) ============================
+// Anchors are a closed form of (level, a, y, x), so the 94 % of (anchor, GT) pairs that cannot
+// intersect never have to be enumerated:
+//   k_colmax_rect   CTAs per (GT, level, a, row chunk, image): walk only the cell rectangle whose
+//                   anchors can intersect the GT and reduce the exact IoU maximum there (one
+//                   atomicMax per CTA).  A GT that no valid anchor intersects keeps "none";
+//                   k_label_rows reads that as +0 for valid anchors (a miss is +-0).
+//   k_label_rows    a thread owns 4 x-consecutive anchors of one (level, a, y) row -- one index
+//                   decomposition per thread instead of one per anchor --, rejects a GT for all 4
+//                   with two compares on the row's y-extent, and evaluates the IoU (one IEEE
+//                   divide) only for true hits.  128-bit label / IoU stores.
+// Both reproduce lib/region.py:75-107 exactly, including the signed zero of max_gt_iou (GT 0 is
+// always evaluated in full: it is the first arg-max when nothing overlaps).
+constexpr int kRowAnchors = 4;
+
+__device__ __forceinline__ bool anchor_valid(const AssignArgs& p, const Box& a, int y, int x, int in_h, int in_w,
+                                             float img_h, float img_w) {
+    bool ok = (y < in_h) && (x < in_w);
+    if (p.border >= 0.0f)
+        ok = ok && a.x1 >= -p.border && a.y1 >= -p.border && a.x2 < img_w + p.border && a.y2 < img_h + p.border;
+    return ok;
+}
+
+constexpr int kRectChunks = 4;                        // row-interleaved CTAs per (GT, level, a) rectangle
+
+// grid.x enumerates (GT j, level l, anchor a, row chunk rc); colmax holds monotone keys, 0 = "none yet"
+__global__ void __launch_bounds__(256) k_colmax_rect(AssignArgs p, b2d_pyramid pyr, uint32_t* __restrict__ colmax,
+                                                     int max_a) {
+    __shared__ uint32_t s_red[8];
+    const int b = blockIdx.y;
+    int w = blockIdx.x;
+    const int rc = w % kRectChunks; w /= kRectChunks;
+    const int a = w % max_a; w /= max_a;
+    const int l = w % pyr.num_levels;
+    const int j = w / pyr.num_levels;
+    if (j >= p.gt_count[b]) return;
+    const b2d_level& lv = pyr.lv[l];
+    if (a >= lv.A) return;
+    const float* g = p.gt + (long long)b * 4 * p.gt_ld;
+    const Box t{g[j], g[p.gt_ld + j], g[2 * p.gt_ld + j], g[3 * p.gt_ld + j]};
+    const float ta = area_plus1(t);
+    const float img_h = p.img_hw[2 * b], img_w = p.img_hw[2 * b + 1];
+    int in_h, in_w;
+    grid_limits(lv, img_h, img_w, in_h, in_w);
+    const float s = lv.stride;
+    // cells whose anchor can satisfy max(x1) < min(x2): centre in (g.x1 - w/2, g.x2 + w/2), widened by
+    // one cell on each side against rounding; the exact test is iou_plus1's.  A degenerate GT (area
+    // not > 0: even a miss may be NaN / inf) scans the whole level.
+    const float hw = lv.ws[a] / 2.0f, hh = lv.hs[a] / 2.0f, off = lv.center_lt ? 0.0f : s / 2.0f;
+    int x0 = 0, x1 = lv.W - 1, y0 = 0, y1 = lv.H - 1;
+    if (ta > 0.0f) {
+        x0 = max(0, (int)floorf((t.x1 - hw - off) / s) - 1);
+        x1 = min(lv.W - 1, (int)ceilf((t.x2 + hw - off) / s) + 1);
+        y0 = max(0, (int)floorf((t.y1 - hh - off) / s) - 1);
+        y1 = min(lv.H - 1, (int)ceilf((t.y2 + hh - off) / s) + 1);
+    }
+    const int rw = x1 - x0 + 1;
+    uint32_t m = 0u;
+    if (rw > 0) {
+        // thread -> (row within my chunk, x): rows y0 + rc, y0 + rc + kRectChunks, ...
+        const int tx = threadIdx.x % 64, ty = threadIdx.x / 64;           // 64 x 4 tile of the rectangle
+        for (int y = y0 + rc + ty * kRectChunks; y <= y1; y += 4 * kRectChunks) {
+            for (int x = x0 + tx; x <= x1; x += 64) {
+                const Box an = anchor_at(lv, a, y, x);
+                if (!anchor_valid(p, an, y, x, in_h, in_w, img_h, img_w)) continue;
+                m = max(m, f2key(iou_plus1(an, area_plus1(an), t, ta) + 0.0f));   // -0 -> +0
+            }
+        }
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane_id() == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 8; ++q) m = max(m, s_red[q]);
+        if (m) atomicMax(&colmax[(long long)b * p.gt_ld + j], m);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_label_rows(AssignArgs p, b2d_pyramid pyr, const uint32_t* __restrict__ colmax,
+                                                    int64_t* __restrict__ labels, float* __restrict__ out_iou,
+                                                    int* __restrict__ census, int* __restrict__ pos_list, int pos_cap) {
+    __shared__ Box s_gt[kGtChunk];
+    __shared__ float s_ga[kGtChunk];
+    __shared__ float s_cm[kGtChunk];
+    __shared__ unsigned char s_all[kGtChunk];        // GT must be evaluated for every anchor (see below)
+    __shared__ int s_cnt[2];
+    const int b = blockIdx.y;
+    const int K = p.gt_count[b];
+    const float* g = p.gt + (long long)b * 4 * p.gt_ld;
+    const float img_h = p.img_hw[2 * b], img_w = p.img_hw[2 * b + 1];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    // ---- my 4 anchors: flattened index i0 .. i0+3 of the level-major concatenation
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * kRowAnchors;
+    Box bx[kRowAnchors];
+    float ba[kRowAnchors], best[kRowAnchors], veq[kRowAnchors];
+    int arg[kRowAnchors], eq[kRowAnchors];
+    bool ok[kRowAnchors], live[kRowAnchors];
+    float ylo = INFINITY, yhi = -INFINITY;            // y-extent of my valid anchors (they share a row, mostly)
+    {
+        int l = -1, a = 0, y = 0, x = 0, in_h = 0, in_w = 0;
+        long long lend = -1;                          // first flattened index past the current level
+#pragma unroll
+        for (int q = 0; q < kRowAnchors; ++q) {
+            const long long i = i0 + q;
+            live[q] = i < pyr.total;
+            ok[q] = false;
+            bx[q] = Box{0.f, 0.f, 0.f, 0.f};
+            if (live[q]) {
+                if (i >= lend) {                      // first element, or the group crosses a level end
+                    l = 0;
+                    for (int r = 1; r < pyr.num_levels; ++r) if (i >= pyr.lv[r].offset) l = r;
+                    const b2d_level& nv = pyr.lv[l];
+                    const int li = (int)(i - nv.offset), hw = nv.H * nv.W;
+                    a = li / hw;
+                    const int r2 = li - a * hw;
+                    y = r2 / nv.W; x = r2 - y * nv.W;
+                    lend = nv.offset + (long long)nv.A * hw;
+                    grid_limits(nv, img_h, img_w, in_h, in_w);
+                }
+                const b2d_level& lv = pyr.lv[l];
+                bx[q] = anchor_at(lv, a, y, x);
+                ok[q] = anchor_valid(p, bx[q], y, x, in_h, in_w, img_h, img_w);
+                if (++x == lv.W) { x = 0; if (++y == lv.H) { y = 0; ++a; } }
+            }
+            ba[q] = ok[q] ? area_plus1(bx[q]) : 0.0f;
+            if (ok[q]) { ylo = fminf(ylo, bx[q].y1); yhi = fmaxf(yhi, bx[q].y2); }
+            best[q] = 0.0f; veq[q] = 0.0f; arg[q] = 0; eq[q] = -1;
+        }
+    }
+    for (int j0 = 0; j0 < K; j0 += kGtChunk) {
+        const int kc = min(kGtChunk, K - j0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < kc; j += blockDim.x) {
+            Box t{g[j0 + j], g[p.gt_ld + j0 + j], g[2 * p.gt_ld + j0 + j], g[3 * p.gt_ld + j0 + j]};
+            const float ta = area_plus1(t);
+            // column max over VALID anchors; an anchor that exists contributes at least a +-0
+            const uint32_t ck = colmax[(long long)b * p.gt_ld + j0 + j];
+            const float cm = ck ? fmaxf(key2f(ck), 0.0f) : 0.0f;
+            s_gt[j] = t; s_ga[j] = ta; s_cm[j] = cm;
+            // a miss is +-0: it only matters as the initial arg-max (GT 0), when this GT's column max is
+            // itself 0 and qualifies (min_pos_iou <= 0), or when the GT is degenerate (IoU may be NaN)
+            s_all[j] = ((j0 + j) == 0 || (cm >= p.min_pos_iou && cm == 0.0f) || !(ta > 0.0f)) ? 1 : 0;
+        }
+        __syncthreads();
+        for (int j = 0; j < kc; ++j) {
+            const Box t = s_gt[j];
+            const bool all = s_all[j] != 0;
+            if (!all && !(fmaxf(ylo, t.y1) < fminf(yhi, t.y2))) continue;      // no valid anchor of mine overlaps in y
+            const float ta = s_ga[j], cm = s_cm[j];
+            const bool cm_ok = cm >= p.min_pos_iou;
+#pragma unroll
+            for (int q = 0; q < kRowAnchors; ++q) {
+                if (!ok[q]) continue;
+                const bool hit = fmaxf(bx[q].x1, t.x1) < fminf(bx[q].x2, t.x2) && fmaxf(bx[q].y1, t.y1) < fminf(bx[q].y2, t.y2);
+                if (!(hit || all || !(ba[q] > 0.0f))) continue;
+                const float v = iou_plus1(bx[q], ba[q], t, ta);
+                if ((j0 + j) == 0 || v > best[q]) { best[q] = v; arg[q] = j0 + j; }       // first max wins
+                if (eq[q] < 0 && cm_ok && v == cm) { eq[q] = j0 + j; veq[q] = v; }        // lowest GT wins
+            }
+        }
+    }
+    int64_t* lab = labels + (long long)b * p.out_ld;
+    float* oiou = out_iou + (long long)b * p.out_ld;
+    int* plist = pos_list ? pos_list + (long long)b * pos_cap : nullptr;
+    int64_t ol[kRowAnchors];
+    float ov[kRowAnchors];
+#pragma unroll
+    for (int q = 0; q < kRowAnchors; ++q) {
+        ol[q] = -1; ov[q] = 0.0f;
+        if (ok[q]) {
+            int lb = -1;
+            if (best[q] < p.neg_iou) lb = 0;
+            if (best[q] >= p.pos_iou) lb = 1;
+            int a = arg[q];
+            ov[q] = best[q];
+            if (eq[q] >= 0) { lb = 1; a = eq[q]; ov[q] = veq[q]; }
+            ol[q] = (lb == 1) ? (int64_t)(a + 1) : (int64_t)lb;
+        }
+    }
+    const bool vec = live[kRowAnchors - 1] && ((reinterpret_cast<uintptr_t>(lab) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(oiou) & 15) == 0);     // i0 is a multiple of 4
+    if (vec) {
+        reinterpret_cast<longlong2*>(lab + i0)[0] = make_longlong2(ol[0], ol[1]);
+        reinterpret_cast<longlong2*>(lab + i0)[1] = make_longlong2(ol[2], ol[3]);
+        *reinterpret_cast<float4*>(oiou + i0) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < kRowAnchors; ++q)
+            if (live[q]) { lab[i0 + q] = ol[q]; oiou[i0 + q] = ov[q]; }
+    }
+#pragma unroll
+    for (int q = 0; q < kRowAnchors; ++q) {
+        const bool is_pos = live[q] && ol[q] > 0, is_neg = live[q] && ol[q] == 0;
+        const unsigned mp = __ballot_sync(0xffffffffu, is_pos), mn = __ballot_sync(0xffffffffu, is_neg);
+        if (lane_id() == 0) {
+            if (mp) atomicAdd(&s_cnt[0], __popc(mp));
+            if (mn) atomicAdd(&s_cnt[1], __popc(mn));
+        }
+        if (plist) {
+            const int slot = warp_alloc(is_pos, &census[4 * b + 2]);
+            if (is_pos && slot < pos_cap) plist[slot] = (int)(i0 + q);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 && s_cnt[threadIdx.x]) atomicAdd(&census[4 * b + threadIdx.x], s_cnt[threadIdx.x]);
+}
 
 // ---- small problems (explicit boxes, N <= 4096: the RoI-target assignment of 2000 proposals) ----
 // colmax + label + census in ONE launch, one CTA per image: the two-pass grid version costs two
@@ -616,6 +824,18 @@ int b2d_assign_max_iou(int64_t* labels, float* max_iou, long long out_ld, const 
     if (a.use_pyr) { pyr = *pyr_host; a.N = pyr.total; }
     if (!a.use_pyr && N <= kSmallThreads * kSmallBoxes && gt_ld <= kGtChunk) {
         k_assign_small<<<B, kSmallThreads, 0, st>>>(a, labels, max_iou, census, pos_list, pos_cap);
+        return check_launch("assign_max_iou");
+    }
+    if (a.use_pyr && !prepend_gt && !getenv("B2D_ASSIGN_OLD")) {
+        uint32_t* cmx = (uint32_t*)workspace;
+        cudaMemsetAsync(census, 0, sizeof(int) * 4 * B, st);
+        cudaMemsetAsync(cmx, 0, sizeof(uint32_t) * (size_t)B * gt_ld, st);
+        int max_a = 1;
+        for (int l = 0; l < pyr.num_levels; ++l) max_a = max(max_a, pyr.lv[l].A);
+        dim3 g1(gt_ld * pyr.num_levels * max_a * kRectChunks, B);
+        k_colmax_rect<<<g1, 256, 0, st>>>(a, pyr, cmx, max_a);
+        dim3 g2(cdiv(pyr.total, 256 * kRowAnchors), B);
+        k_label_rows<<<g2, 256, 0, st>>>(a, pyr, cmx, labels, max_iou, census, pos_list, pos_cap);
         return check_launch("assign_max_iou");
     }
     uint32_t* colmax = (uint32_t*)workspace;

@@ -59,6 +59,25 @@ __device__ __forceinline__ bool suppresses(const float4& a, float aa, const floa
     return inter / u > thr;
 }
 
+// Same decision when both boxes are well-formed (x2 >= x1, y2 >= y1, no NaN): then 0 <= inter <=
+// min(aa, ab), so u >= 0, and u = +inf / NaN / 0 all fall through to the exact quotient or give
+// the same answer as it (see suppresses) -- the two range tests on u are not needed.
+__device__ __forceinline__ bool suppresses_wf(const float4& a, float aa, const float4& b, float ab, float thr,
+                                              float thr_lo, float thr_hi) {
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.0f, xx2 - xx1), h = fmaxf(0.0f, yy2 - yy1);
+    const float inter = w * h;
+    const float u = (aa + ab) - inter;
+    const bool yes = inter > thr_hi * u, no = inter < thr_lo * u;
+    if (yes || no) return yes;
+    return inter / u > thr;
+}
+// (sides <= 1e18 keep thr * u far from fp32 overflow, where the product test would stop being decisive)
+__device__ __forceinline__ bool well_formed(const float4& b) {
+    return b.z >= b.x && b.w >= b.y && (b.z - b.x) <= 1.0e18f && (b.w - b.y) <= 1.0e18f;
+}
+
 // Padding box for rows/columns past n: far away from anything finite a caller passes, with a
 // finite positive area, so a real-vs-pad pair takes the cheap "no" exit.
 __device__ __forceinline__ float4 pad_box() { return make_float4(-2.0e18f, -2.0e18f, -1.0e18f, -1.0e18f); }
@@ -96,21 +115,36 @@ __global__ void __launch_bounds__(64) k_nms_mask_sym(NmsSegs s, int wmax) {
     const int j0 = c0 + lane, j1 = c0 + 32 + lane;
     const float4 cb0 = j0 < n ? boxes[j0] : pad, cb1 = j1 < n ? boxes[j1] : pad;
     const float a0 = area_of(cb0), a1 = area_of(cb1);
-    __syncthreads();
+    // all 128 boxes of the tile pair well-formed (the normal case) -> cheaper decision
+    const bool wf = __syncthreads_and(well_formed(s_row[tid]) && well_formed(cb0) && well_formed(cb1));
     uint64_t myword = 0;
     uint32_t cw0 = 0, cw1 = 0;
     const float4* rowp = s_row + w * 32;
     const float* rap = s_ra + w * 32;
-#pragma unroll 8
-    for (int rr = 0; rr < 32; ++rr) {
-        const float4 rbx = rowp[rr];
-        const float ra = rap[rr];
-        const bool p0 = suppresses(rbx, ra, cb0, a0, s.thr, s.thr_lo, s.thr_hi);
-        const bool p1 = suppresses(rbx, ra, cb1, a1, s.thr, s.thr_lo, s.thr_hi);
-        const unsigned lo = __ballot_sync(0xffffffffu, p0), hi = __ballot_sync(0xffffffffu, p1);
-        if (lane == rr) myword = ((uint64_t)hi << 32) | lo;
-        cw0 |= p0 ? (1u << rr) : 0u;
-        cw1 |= p1 ? (1u << rr) : 0u;
+    if (wf) {
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+            const float4 rbx = rowp[rr];
+            const float ra = rap[rr];
+            const bool p0 = suppresses_wf(rbx, ra, cb0, a0, s.thr, s.thr_lo, s.thr_hi);
+            const bool p1 = suppresses_wf(rbx, ra, cb1, a1, s.thr, s.thr_lo, s.thr_hi);
+            const unsigned lo = __ballot_sync(0xffffffffu, p0), hi = __ballot_sync(0xffffffffu, p1);
+            if (lane == rr) myword = ((uint64_t)hi << 32) | lo;
+            cw0 |= p0 ? (1u << rr) : 0u;
+            cw1 |= p1 ? (1u << rr) : 0u;
+        }
+    } else {
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+            const float4 rbx = rowp[rr];
+            const float ra = rap[rr];
+            const bool p0 = suppresses(rbx, ra, cb0, a0, s.thr, s.thr_lo, s.thr_hi);
+            const bool p1 = suppresses(rbx, ra, cb1, a1, s.thr, s.thr_lo, s.thr_hi);
+            const unsigned lo = __ballot_sync(0xffffffffu, p0), hi = __ballot_sync(0xffffffffu, p1);
+            if (lane == rr) myword = ((uint64_t)hi << 32) | lo;
+            cw0 |= p0 ? (1u << rr) : 0u;
+            cw1 |= p1 ? (1u << rr) : 0u;
+        }
     }
     if (rb == cb) myword &= ~(1ull << (w * 32 + lane));      // a box does not suppress itself
     const int row = r0 + w * 32 + lane;

@@ -232,30 +232,54 @@ struct __align__(16) BinTab {
     int pat, _p0, _p1, _p2;
 };
 
-template <typename FT, int PY, int PX>
-__device__ __forceinline__ float4 bin_eval(const char* fb, const BinTab* t) {
+// V consecutive channels of one cell as fp32 (V = 4: one 128-bit load of fp32 / 64-bit of bf16)
+template <int V> struct VecF { float f[V]; };
+
+template <typename FT, int V>
+__device__ __forceinline__ VecF<V> ldv(const char* p) {
+    VecF<V> o;
+    if constexpr (sizeof(FT) == 4 && V == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        o.f[0] = t.x; o.f[1] = t.y; o.f[2] = t.z; o.f[3] = t.w;
+    } else if constexpr (sizeof(FT) == 4 && V == 2) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        o.f[0] = t.x; o.f[1] = t.y;
+    } else if constexpr (sizeof(FT) == 2 && V == 4) {
+        const float4 t = ld4(reinterpret_cast<const __nv_bfloat16*>(p));
+        o.f[0] = t.x; o.f[1] = t.y; o.f[2] = t.z; o.f[3] = t.w;
+    } else {
+        const unsigned u = __ldg(reinterpret_cast<const unsigned*>(p));
+        const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+        o.f[0] = t.x; o.f[1] = t.y;
+    }
+    return o;
+}
+
+template <typename FT, int V, int PY, int PX>
+__device__ __forceinline__ VecF<V> bin_eval(const char* fb, const BinTab* t) {
     const int4 ry = *reinterpret_cast<const int4*>(t->ry);
     const int4 cx = *reinterpret_cast<const int4*>(t->cx);
     const int ryv[4] = {ry.x, ry.y, ry.z, ry.w}, cxv[4] = {cx.x, cx.y, cx.z, cx.w};
-    float4 v[4][4];
+    VecF<V> v[4][4];
 #pragma unroll
     for (int r = 0; r < PY + 2; ++r) {
         const char* rp = fb + ryv[r];
 #pragma unroll
-        for (int c = 0; c < PX + 2; ++c) v[r][c] = ld4b<FT>(rp + cxv[c]);
+        for (int c = 0; c < PX + 2; ++c) v[r][c] = ldv<FT, V>(rp + cxv[c]);
     }
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    VecF<V> acc;
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc.f[e] = 0.0f;
 #pragma unroll
     for (int iy = 0; iy < 2; ++iy) {
 #pragma unroll
         for (int ix = 0; ix < 2; ++ix) {
             const int r0 = iy ? PY : 0, c0 = ix ? PX : 0;
             const float4 w = *reinterpret_cast<const float4*>(&t->w[(iy * 2 + ix) * 4]);
-            const float4 v1 = v[r0][c0], v2 = v[r0][c0 + 1], v3 = v[r0 + 1][c0], v4 = v[r0 + 1][c0 + 1];
-            acc.x += ((w.x * v1.x + w.y * v2.x) + w.z * v3.x) + w.w * v4.x;
-            acc.y += ((w.x * v1.y + w.y * v2.y) + w.z * v3.y) + w.w * v4.y;
-            acc.z += ((w.x * v1.z + w.y * v2.z) + w.z * v3.z) + w.w * v4.z;
-            acc.w += ((w.x * v1.w + w.y * v2.w) + w.z * v3.w) + w.w * v4.w;
+#pragma unroll
+            for (int e = 0; e < V; ++e)      // torchvision's order: ((w1 v1 + w2 v2) + w3 v3) + w4 v4, summed over samples
+                acc.f[e] += ((w.x * v[r0][c0].f[e] + w.y * v[r0][c0 + 1].f[e]) + w.z * v[r0 + 1][c0].f[e]) +
+                            w.w * v[r0 + 1][c0 + 1].f[e];
         }
     }
     return acc;
@@ -263,7 +287,7 @@ __device__ __forceinline__ float4 bin_eval(const char* fb, const BinTab* t) {
 
 // NT threads per CTA, CT channels per CTA (grid.y = C / CT tiles), MINB = min resident CTAs/SM
 // (the register bound that keeps the window loads batched, see the notes above).
-template <typename FT, int NT, int CT, int MINB>
+template <typename FT, int NT, int CT, int MINB, int V>
 __global__ void __launch_bounds__(NT, MINB) k_roi_align_win(RoiArgs a, float* __restrict__ out) {
     extern __shared__ __align__(16) float s_tile[];                      // [CT][bins] (+ bin table behind it)
     const long long r = blockIdx.x;
@@ -332,30 +356,31 @@ __global__ void __launch_bounds__(NT, MINB) k_roi_align_win(RoiArgs a, float* __
     }
     __syncthreads();
     const FT* feat = reinterpret_cast<const FT*>(a.feat[lvl]) + (long long)img * H * W * C;
-    constexpr int LG = CT / 4, NG = NT / LG;               // lanes per bin group, bin groups
+    constexpr int LG = CT / V, NG = NT / LG;               // lanes per bin group, bin groups
     const int cq = threadIdx.x % LG, grp = threadIdx.x / LG;
     float* o = out + r * (long long)C * bins;
     {
         const int c0 = blockIdx.y * CT;
-        const int ch = c0 + cq * 4;
+        const int ch = c0 + cq * V;
         if (ch < C) {
             const char* fb = reinterpret_cast<const char*>(feat + ch);
             for (int bin = grp; bin < bins; bin += NG) {
                 const BinTab* t = s_tab + bin;
-                float4 acc;
+                VecF<V> acc;
                 switch (t->pat) {                          // uniform over the warps of a bin
-                    case 0: acc = bin_eval<FT, 0, 0>(fb, t); break;
-                    case 1: acc = bin_eval<FT, 0, 1>(fb, t); break;
-                    case 2: acc = bin_eval<FT, 0, 2>(fb, t); break;
-                    case 3: acc = bin_eval<FT, 1, 0>(fb, t); break;
-                    case 4: acc = bin_eval<FT, 1, 1>(fb, t); break;
-                    case 5: acc = bin_eval<FT, 1, 2>(fb, t); break;
-                    case 6: acc = bin_eval<FT, 2, 0>(fb, t); break;
-                    case 7: acc = bin_eval<FT, 2, 1>(fb, t); break;
-                    default: acc = bin_eval<FT, 2, 2>(fb, t); break;
+                    case 0: acc = bin_eval<FT, V, 0, 0>(fb, t); break;
+                    case 1: acc = bin_eval<FT, V, 0, 1>(fb, t); break;
+                    case 2: acc = bin_eval<FT, V, 0, 2>(fb, t); break;
+                    case 3: acc = bin_eval<FT, V, 1, 0>(fb, t); break;
+                    case 4: acc = bin_eval<FT, V, 1, 1>(fb, t); break;
+                    case 5: acc = bin_eval<FT, V, 1, 2>(fb, t); break;
+                    case 6: acc = bin_eval<FT, V, 2, 0>(fb, t); break;
+                    case 7: acc = bin_eval<FT, V, 2, 1>(fb, t); break;
+                    default: acc = bin_eval<FT, V, 2, 2>(fb, t); break;
                 }
-                float* st = s_tile + (cq * 4) * bins + bin;    // x / 4 == x * 0.25 exactly
-                st[0] = acc.x * 0.25f; st[bins] = acc.y * 0.25f; st[2 * bins] = acc.z * 0.25f; st[3 * bins] = acc.w * 0.25f;
+                float* st = s_tile + (cq * V) * bins + bin;    // x / 4 == x * 0.25 exactly
+#pragma unroll
+                for (int e = 0; e < V; ++e) st[e * bins] = acc.f[e] * 0.25f;
             }
         }
         __syncthreads();
@@ -477,8 +502,12 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
             dim3 grid((unsigned)R, (unsigned)cdiv(c.C, ct));
             kern<<<grid, nt, smem5, st>>>(a, out);
         };
-        if (c.layout == 1) launch5(k_roi_align_win<float, 128, 128, 6>, 128, 128);
-        else launch5(k_roi_align_win<__nv_bfloat16, 128, 128, 6>, 128, 128);
+        // 128 threads x 4 channels = 128 channels per CTA, 6 CTAs/SM: fastest of the measured
+        // (threads, channels/CTA, CTAs/SM, channels/thread) points -- (256,256,2,4) 200 us,
+        // (256,256,3,4) 169, (128,128,4,4) 169, (128,128,6,4) 159, (128,128,7,4) 186 (spills),
+        // (256,128,5,2) 175, (128,64,8,2) 186, (128,64,10,2) 173 (config 2, 4096 RoIs)
+        if (c.layout == 1) launch5(k_roi_align_win<float, 128, 128, 6, 4>, 128, 128);
+        else launch5(k_roi_align_win<__nv_bfloat16, 128, 128, 6, 4>, 128, 128);
     } else if (fast) {
         const size_t smem = (size_t)bins * (kCTile + 4) * 4;
         static size_t attr_f32 = 0, attr_bf16 = 0;

@@ -99,51 +99,59 @@ __device__ int find_threshold_bin(const uint32_t* __restrict__ gh, int k, uint32
 }
 
 // ---------------------------------------------------------------- k_compact
-// Candidates are staged in shared memory per 2048-element round and leave with ONE global
-// atomic per list and round and a coalesced copy (order is irrelevant: they are sorted
-// afterwards).  Two lists per segment: `cand` = keys ABOVE the threshold bin (all of them are
-// selected, count < k), `cand2` = keys IN the threshold bin (only the best k - |cand| are).
+// Two lists per segment: `cand` = keys ABOVE the threshold bin (all of them are selected,
+// count < k), `cand2` = keys IN the threshold bin (only the best k - |cand| are).  A block
+// stages its candidates (about 1 % of its 16384 elements) in shared memory while it streams
+// the chunk with 8 loads in flight per thread and NO barrier in the loop, then leaves with one
+// global atomic per list and a coalesced copy (order is irrelevant: they are sorted afterwards).
+// Stage overflow (dense candidates: degenerate score maps) appends straight to the global list.
 __global__ void __launch_bounds__(256) k_compact(RpnLaunch p) {
-    constexpr int kRound = 2048;
+    constexpr int kCapA = 1536, kCapB = 512;
     __shared__ uint32_t s_tmp[8];
-    __shared__ uint64_t s_stage[kRound];                 // above-bin entries grow from 0, in-bin entries from the top
+    __shared__ uint64_t s_stageA[kCapA], s_stageB[kCapB];
     __shared__ int s_n, s_n2, s_base, s_base2;
     const int seg = blockIdx.y, b = seg / p.L, l = seg - b * p.L;
     const int n = p.n[l], k = p.kcap[l];
     if (k >= n) return;
     const int start = blockIdx.x * kChunk;
     if (start >= n) return;
-    const int tb = find_threshold_bin(p.hist + (long long)seg * kHistBins, k, s_tmp);
+    if (threadIdx.x == 0) { s_n = 0; s_n2 = 0; }
+    const int tb = find_threshold_bin(p.hist + (long long)seg * kHistBins, k, s_tmp);   // has barriers
     if (blockIdx.x == 0 && threadIdx.x == 0) p.thr_bin[seg] = tb;
     const float* cls = seg_cls(p, b, l);
     uint64_t* cand = p.cand + ((long long)b * p.pyr.total + p.pyr.lv[l].offset);
     uint64_t* cand2 = p.cand2 + ((long long)b * p.pyr.total + p.pyr.lv[l].offset);
     const int end = min(start + kChunk, n);
-    for (int r0 = start; r0 < end; r0 += kRound) {
-        if (threadIdx.x == 0) { s_n = 0; s_n2 = 0; }
-        __syncthreads();
-        float v[kRound / 256];
+    for (int r0 = start; r0 < end; r0 += 8 * 256) {
+        float v[8];
 #pragma unroll
-        for (int q = 0; q < kRound / 256; ++q) {
+        for (int q = 0; q < 8; ++q) {
             const int i = r0 + q * 256 + threadIdx.x;
             v[q] = i < end ? load_logit(cls, n, i, p.score_mode, p.cls_ch) : 0.0f;
         }
 #pragma unroll
-        for (int q = 0; q < kRound / 256; ++q) {
+        for (int q = 0; q < 8; ++q) {
             const int i = r0 + q * 256 + threadIdx.x;
             const uint32_t key = f2key(v[q]);
             const int bin = (int)(key >> (32 - kHistBits));
-            if (i < end && bin > tb) s_stage[atomicAdd(&s_n, 1)] = make_comp(key, (uint32_t)i);
-            else if (i < end && bin == tb) s_stage[kRound - 1 - atomicAdd(&s_n2, 1)] = make_comp(key, (uint32_t)i);
+            if (i < end && bin > tb) {
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < kCapA) s_stageA[pos] = make_comp(key, (uint32_t)i);
+                else cand[atomicAdd(&p.cand_count[seg], 1)] = make_comp(key, (uint32_t)i);
+            } else if (i < end && bin == tb) {
+                const int pos = atomicAdd(&s_n2, 1);
+                if (pos < kCapB) s_stageB[pos] = make_comp(key, (uint32_t)i);
+                else cand2[atomicAdd(&p.cand2_count[seg], 1)] = make_comp(key, (uint32_t)i);
+            }
         }
-        __syncthreads();
-        const int m = s_n, m2 = s_n2;
-        if (threadIdx.x == 0 && m > 0) s_base = atomicAdd(&p.cand_count[seg], m);
-        if (threadIdx.x == 32 && m2 > 0) s_base2 = atomicAdd(&p.cand2_count[seg], m2);
-        __syncthreads();
-        for (int t = threadIdx.x; t < m; t += blockDim.x) cand[s_base + t] = s_stage[t];
-        for (int t = threadIdx.x; t < m2; t += blockDim.x) cand2[s_base2 + t] = s_stage[kRound - 1 - t];
     }
+    __syncthreads();
+    const int m = min(s_n, kCapA), m2 = min(s_n2, kCapB);
+    if (threadIdx.x == 0 && m > 0) s_base = atomicAdd(&p.cand_count[seg], m);
+    if (threadIdx.x == 32 && m2 > 0) s_base2 = atomicAdd(&p.cand2_count[seg], m2);
+    __syncthreads();
+    for (int t = threadIdx.x; t < m; t += blockDim.x) cand[s_base + t] = s_stageA[t];
+    for (int t = threadIdx.x; t < m2; t += blockDim.x) cand2[s_base2 + t] = s_stageB[t];
 }
 
 // ---------------------------------------------------------------- block bucket sort

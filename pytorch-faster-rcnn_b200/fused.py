@@ -124,7 +124,8 @@ class BatchedTargets(object):
         self.step = 0
         self.b0 = 0
         small = pyramid is None and self.N <= 4096 and self.gt_ld <= 512
-        self.launches = 3 if small else 5   # kernels: (assign_small | fill, colmax, label), sample, encode
+        # kernels: assign_small | (colmax_rect, label_rows) | (fill, colmax, label); then sample, encode
+        self.launches = 3 if small else (4 if pyramid is not None else 5)
 
     def slice(self, b0, b1):
         return _batch_view(self, b0, b1)
