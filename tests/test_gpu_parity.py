@@ -293,6 +293,51 @@ def test_roi_align_bf16_nhwc_close():
     np.testing.assert_allclose(N(out), ref, rtol=1e-5, atol=1e-6)      # same bf16-rounded inputs, fp32 math
 
 
+def _ring_case(seed, C, K, B=2):
+    """RoIs that exercise every branch of the TMA-ring kernel (csrc/roi_align_tma.cu): level-mapped sizes,
+    RoIs wider than the ring holds (generic in-kernel path), sub-cell RoIs, RoIs on / beyond the borders."""
+    rng = np.random.default_rng(seed)
+    grids = [(48, 80), (24, 40), (12, 20), (6, 10)]                       # 192 x 320 image, strides 4..32
+    feats = [rng.standard_normal((B, C) + gsz).astype(np.float32) for gsz in grids]
+    Wimg, Himg = 320.0, 192.0
+    w = np.exp(rng.uniform(np.log(2.0), np.log(400.0), K)); h = np.exp(rng.uniform(np.log(2.0), np.log(300.0), K))
+    cx = rng.uniform(-20, Wimg + 20, K); cy = rng.uniform(-20, Himg + 20, K)
+    rois = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2]).astype(np.float32)
+    rois[:, :8] = np.array([[0, 0, 319, 191], [-50, -50, 400, 300], [100, 80, 100.2, 80.1], [310, 185, 330, 200],
+                            [-300, -300, -200, -250], [0, 0, 170, 30], [5, 5, 60, 190], [318.5, 190.5, 319, 191]], np.float32).T
+    img = rng.integers(0, B, K).astype(np.int32)
+    return grids, feats, rois, img
+
+
+@pytest.mark.parametrize("C,K", [(256, 700), (128, 333)])
+def test_roi_align_tma_ring_bit_exact_vs_oracle(C, K):
+    grids, feats, rois, img = _ring_case(11, C, K)
+    fs = [T(f).contiguous(memory_format=torch.channels_last) for f in feats]
+    out = N(bregion.roi_align_levels(fs, T(rois), T(img), [1 / 4, 1 / 8, 1 / 16, 1 / 32]))
+    for b in range(feats[0].shape[0]):
+        m = img == b
+        ref = oracle.roi_extract([f[b] for f in feats], np.ascontiguousarray(rois[:, m]))
+        assert np.array_equal(bits(out[m]), bits(ref)), "ring kernel must be bit-identical to the oracle"
+    # single level, one image, aligned=True (bin sizes may be ~0 / negative -> generic path), 5x3 bins
+    r1 = np.ascontiguousarray(rois[:, img == 0])
+    o1 = N(bregion.roi_align_levels([fs[1][:1]], T(r1), None, [1 / 8], out_size=(5, 3), aligned=True))
+    ref1 = oracle.roi_align(feats[1][0], r1, 1 / 8, (5, 3), 2, True)
+    assert np.array_equal(bits(o1), bits(ref1))
+
+
+def test_roi_align_tma_ring_bf16_and_l1_path_agree(monkeypatch):
+    grids, feats, rois, img = _ring_case(12, 256, 500)
+    fs = [T(f).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for f in feats]
+    out = N(bregion.roi_align_levels(fs, T(rois), T(img), [1 / 4, 1 / 8, 1 / 16, 1 / 32]))
+    monkeypatch.setenv("B2D_ROI_TMA", "0")                                # L1-path kernel (k_roi_align_win)
+    out_l1 = N(bregion.roi_align_levels(fs, T(rois), T(img), [1 / 4, 1 / 8, 1 / 16, 1 / 32]))
+    assert np.array_equal(bits(out), bits(out_l1))
+    for b in range(2):
+        m = img == b
+        ref = oracle.roi_extract([N(f[b].float()) for f in fs], np.ascontiguousarray(rois[:, m]))
+        assert np.array_equal(bits(out[m]), bits(ref))
+
+
 def test_roi_pool_vs_torchvision():
     g = load_golden("roi")
     ext = bregion.BasicRoIExtractor([dict(type="RoIPool", spatial_scale=1 / 16, sampling_ratio=2)], output_size=(7, 7))
