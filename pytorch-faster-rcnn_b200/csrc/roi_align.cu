@@ -428,9 +428,10 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
     const bool win = fast && c.sampling_ratio == 2 && bins <= 64 && (((long long)c.C * bins) % 4) == 0 &&
                      ((128ll * bins) % 4) == 0;
     if (win) {
-        // TMA-ring kernel (roi_align_tma.cu) when the cell size suits its ring; B2D_ROI_TMA=0 forces the L1-path kernel
+        // TMA-ring kernel (roi_align_tma.cu): opt-in with B2D_ROI_TMA=1.  Bit-identical, but measured slower than
+        // the L1-path kernel below on config 2 (380 vs 159 us, round 1: issue-bound consumers).
         const char* e_tma = getenv("B2D_ROI_TMA");
-        const int use_tma = e_tma ? atoi(e_tma) : 1;
+        const int use_tma = e_tma ? atoi(e_tma) : 0;
         if (use_tma) {
             const int rc = roi_align_tma_try(a, out, st);
             if (rc != 1) return rc;

@@ -3,30 +3,36 @@
 //
 // Why: the L1-path kernel (roi_align.cu, k_roi_align_win) is bound by the L1-miss latency x
 // concurrency product of the LSU path, not by DRAM (profiles/, round 1): every byte in flight
-// costs registers.  Here a producer warp streams the feature cells a RoI touches into a
+// costs registers.  Here two producer warps stream the feature rows a RoI touches into a
 // shared-memory ring with bulk async copies (cp.async.bulk -> UBLKCP, completion counted on
 // mbarriers), so the bytes in flight per SM are bounded by shared memory, not by registers,
-// and the consumer warps only ever wait on shared memory.
+// and the 14 consumer warps only ever wait on shared memory.
 //
-//   work item  = (RoI, 128-channel tile); CTA b of the persistent grid takes items b, b+grid, ...
-//   ring       = kNS slots of kSlotBytes; a slot holds the 128-channel part of up to `cpc`
-//                consecutive cells of one feature row (one 512 B bulk copy per cell for fp32).
-//                Chunk g of the CTA's running chunk sequence lives in slot g mod kNS.
-//   full[slot] : armed by the producer with the chunk's byte count, completed by the copies.
-//   empty[slot]: one arrival per consumer warp when no later bin row reads the row.
+//   layout NHWC: the cells [x0, x1] of feature row y are ONE contiguous run of (x1-x0+1)*C*es
+//   bytes.  A row is cut into chunks of kSlotBytes (8 cells of 256 fp32 channels); every chunk
+//   is one bulk copy into ring slot (g mod kNS), g = running chunk number of this CTA.
+//   full[slot]  : armed by the producer with the chunk's byte count, completed by the copy.
+//   empty[slot] : one arrival per consumer warp when no later bin row reads the row.
+//   filled[slot]: use number of the last fill (guards the 1-bit phase parity: a producer lane
+//                 polls `empty` for use n only after fill n-1 has been issued).
 //   Only the DISTINCT rows {lo, hi} of the 2*PH sample rows are fetched, in ascending order; a
 //   bin row needs at most 4 of them at a time (<= 16 slots for cpr <= 4 chunks per row, i.e.
 //   RoIs up to 32 cells wide), the other slots are prefetch depth; wider RoIs take the generic
 //   in-kernel path.
-//   The producer warp is also the planner: it writes the per-bin tap table (ring offsets +
-//   bilinear weights) of the NEXT item while the consumers work on the current one
+//   Issue rate (scripts/tma_probe.cu, B200): one thread issues a bulk copy every ~430 ns when
+//   each copy has its own wait + expect_tx, ~55 ns when the lanes of a warp do the mbarrier
+//   work in SIMT and only the UBLKCPs serialise -> one lane per chunk, 16 chunks per round,
+//   rounds alternate between the two producer warps.
+//   Producer warp 0 is also the planner: it writes the per-bin tap table (ring offsets +
+//   bilinear weights) of the NEXT RoI while the consumers work on the current one
 //   (double-buffered, tab_full / tab_empty mbarriers).
 //
 // Arithmetic is that of k_roi_align_win (torchvision's order, no FMA): bit-identical results.
-// The [128][PH*PW] result tile is staged in shared memory in its HBM layout and leaves as ONE
+// The [C][PH*PW] result tile is staged in shared memory in its HBM layout and leaves as ONE
 // bulk store (cp.async.bulk.global.shared::cta).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "roi_common.cuh"
@@ -34,13 +40,14 @@
 namespace b2d {
 namespace {
 
-constexpr int kCT = 128;                      // channels per work item
-constexpr int kSlotBytes = 4096;              // 8 cells x 128 fp32 channels
-constexpr int kNS = 18;                       // ring slots (72 KB)
-constexpr int kConsWarps = 7;
+constexpr int kSlotBytes = 8192;              // 8 cells x 256 fp32 channels
+constexpr int kNS = 20;                       // ring slots (160 KB)
+constexpr int kConsWarps = 14;
 constexpr int kConsThreads = kConsWarps * 32;
-constexpr int kThreads = kConsThreads + 32;   // + producer / planner warp
-constexpr int kMaxCpr = 4;                    // chunks per row: 4 live rows x 4 <= kNS - 2
+constexpr int kProdWarps = 2;
+constexpr int kThreads = kConsThreads + 32 * kProdWarps;
+constexpr int kRound = 16;                    // chunks a producer warp polls at once (< kNS: distinct slots)
+constexpr int kMaxCpr = 4;                    // chunks per row: 4 live rows x 4 <= kNS
 constexpr int kMaxP = 8;                      // PH, PW <= 8
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,6 +66,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -108,7 +121,7 @@ struct __align__(16) TBin {
 
 struct Hdr {                // per item, written by the planner, double-buffered
     int valid, fits, cpr, nrows;
-    int gbase, _pad[3];    // running chunk number of the item's first chunk, mod 2 * kNS
+    int gbase, _pad[3];    // running chunk number of the RoI's first chunk, mod 2 * kNS
     int kmax[kMaxP];       // highest row index bin row ph reads
     int krel[kMaxP];       // rows below this index are dead once bin row ph is done
 };
@@ -158,7 +171,7 @@ __device__ __forceinline__ void bin_eval_s(const char* ring_ch, const TBin* t, f
 
 
 // Planner: bin table + header of one item, by the 32 lanes of the producer warp.
-__device__ __forceinline__ void plan_item(const RoiArgs& a, const Plan& p, int gbase, int cpc, int cellpart, TBin* tab,
+__device__ __forceinline__ void plan_item(const RoiArgs& a, const Plan& p, int gbase, int cpc, int cellb, TBin* tab,
                                           Hdr* hdr, int lane) {
     const b2d_roi_cfg& c = a.cfg;
     const int bins = c.PH * c.PW;
@@ -207,7 +220,7 @@ __device__ __forceinline__ void plan_item(const RoiArgs& a, const Plan& p, int g
             for (int cc = 0; cc < 4; ++cc) {
                 const int j = max(0, min(jc[cc], p.ncols - 1));            // (unused window columns stay in range)
                 const int g = (gbase + kr[rr] * p.cpr + j / cpc) % kNS;
-                t.off[rr * 4 + cc] = (uint32_t)(g * kSlotBytes + (j % cpc) * cellpart);
+                t.off[rr * 4 + cc] = (uint32_t)(g * kSlotBytes + (j % cpc) * cellb);
             }
         const AxisTap* tys[2] = {&ty0, &ty1};
         const AxisTap* txs[2] = {&tx0, &tx1};
@@ -230,26 +243,26 @@ __device__ __forceinline__ void plan_item(const RoiArgs& a, const Plan& p, int g
 }
 
 template <typename FT>
-__global__ void __launch_bounds__(kThreads, 2) k_roi_align_tma(RoiArgs a, float* __restrict__ out) {
+__global__ void __launch_bounds__(kThreads, 1) k_roi_align_tma(RoiArgs a, float* __restrict__ out) {
     extern __shared__ __align__(128) char smem[];
     const b2d_roi_cfg& c = a.cfg;
     const int C = c.C, bins = c.PH * c.PW;
     constexpr int es = (int)sizeof(FT);
-    constexpr int cellpart = kCT * es;                 // bytes of one cell's channel tile (one bulk copy)
-    constexpr int cpc = kSlotBytes / cellpart;         // cells per chunk
-    const int nct = C / kCT;                           // channel tiles per RoI
-    const long long items = a.R * nct;
+    const int cellb = C * es;                          // bytes per cell
+    const int cpc = kSlotBytes / cellb;                // cells per chunk
     char* ring = smem;
     float* s_tile = reinterpret_cast<float*>(smem + kNS * kSlotBytes);
-    TBin* s_tab = reinterpret_cast<TBin*>(reinterpret_cast<char*>(s_tile) + (size_t)kCT * bins * 4);   // [2][bins]
+    TBin* s_tab = reinterpret_cast<TBin*>(reinterpret_cast<char*>(s_tile) + (size_t)C * bins * 4);     // [2][bins]
     Hdr* s_hdr = reinterpret_cast<Hdr*>(s_tab + 2 * bins);                                             // [2]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_hdr + 2);        // full[kNS], empty[kNS], tab_full[2], tab_empty[2]
+    volatile int* s_filled = reinterpret_cast<volatile int*>(s_bar + 2 * kNS + 4);                     // [kNS]
+    int* s_rows = const_cast<int*>(s_filled) + kNS;                                                    // [kProdWarps][32]
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + kNS);
     const uint32_t tab_full = smem_u32(s_bar + 2 * kNS), tab_empty = smem_u32(s_bar + 2 * kNS + 2);
     const uint32_t ring_u32 = smem_u32(ring);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kNS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, kConsWarps); }
+        for (int s = 0; s < kNS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, kConsWarps); s_filled[s] = -1; }
         for (int s = 0; s < 2; ++s) { mbar_init(tab_full + 8 * s, 1); mbar_init(tab_empty + 8 * s, kConsWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -257,56 +270,75 @@ __global__ void __launch_bounds__(kThreads, 2) k_roi_align_tma(RoiArgs a, float*
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x >= kConsThreads) {
-        // ------------------------------------------------------------------ producer / planner warp
-        int g = 0;                                     // running chunk number mod 2 * kNS
+        // ------------------------------------------------------------------ producer warps (warp 0 also plans)
+        const int pwarp = (threadIdx.x - kConsThreads) >> 5;
+        int* rows = s_rows + pwarp * 32;
+        long long g = 0;                               // running chunk number of the CTA
         int it = 0;
-        for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-            const long long r = item / nct;
-            const int ct = (int)(item - r * nct);
+        for (long long r = blockIdx.x; r < a.R; r += gridDim.x, ++it) {
             const Plan p = make_plan(a, r, cpc);
-            const int tb = it & 1;
-            mbar_wait(tab_empty + 8 * tb, ((it >> 1) & 1) ^ 1);           // consumers are done with item it - 2
-            plan_item(a, p, g, cpc, cellpart, s_tab + tb * bins, s_hdr + tb, lane);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tab_full + 8 * tb);
+            if (pwarp == 0) {
+                const int tb = it & 1;
+                mbar_wait(tab_empty + 8 * tb, ((it >> 1) & 1) ^ 1);       // consumers are done with RoI it - 2
+                plan_item(a, p, (int)(g % (2 * kNS)), cpc, cellb, s_tab + tb * bins, s_hdr + tb, lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tab_full + 8 * tb);
+            }
             if (!p.valid || !p.fits) continue;
-            const char* fimg = reinterpret_cast<const char*>(a.feat[p.lvl]) + ((long long)p.img * p.H * p.W * C + ct * kCT) * es;
-            const long long cellb = (long long)C * es;
-            int last = -1;
-            for (int s = 0; s < 2 * c.PH; ++s) {
-                const AxisTap t = axis_tap(p.g.sy, p.g.bh, s >> 1, s & 1, 2, p.H);
+            // the distinct rows, ascending (same enumeration as plan_item)
+            int lo = 0, hi = 0;
+            if (lane < 2 * c.PH) {
+                const AxisTap t = axis_tap(p.g.sy, p.g.bh, lane >> 1, lane & 1, 2, p.H);
+                lo = t.lo; hi = t.hi;
+            }
+            int prev_hi = __shfl_up_sync(0xffffffffu, hi, 1);
+            if (lane == 0) prev_hi = -1;
+            const int new_lo = (lane < 2 * c.PH) && lo > prev_hi;
+            const int new_hi = (lane < 2 * c.PH) && hi > max(lo, prev_hi);
+            int incl = new_lo + new_hi;
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int y = hh ? t.hi : t.lo;
-                    if (y <= last) continue;
-                    last = y;
-                    const char* src = fimg + ((long long)y * p.W + p.x0) * cellb;
-                    if (lane < p.cpr) {                                   // lane q arms chunk q of the row
-                        const int gq = (g + lane) % (2 * kNS), slot = gq % kNS;
-                        const int cells = min(cpc, p.ncols - lane * cpc);
-                        mbar_wait(bar_empty + 8 * slot, (uint32_t)(gq / kNS) ^ 1);
-                        mbar_expect_tx(bar_full + 8 * slot, (uint32_t)(cells * cellpart));
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const int before = incl - (new_lo + new_hi);
+            if (new_lo) rows[before] = lo;
+            if (new_hi) rows[before + new_lo] = hi;
+            const int nrows = __shfl_sync(0xffffffffu, incl, 2 * c.PH - 1);
+            __syncwarp();
+            const int nchunks = nrows * p.cpr;
+            const char* fimg = reinterpret_cast<const char*>(a.feat[p.lvl]) + (long long)p.img * p.H * p.W * cellb;
+            for (int base = pwarp * kRound; base < nchunks; base += kRound * kProdWarps) {
+                const int j = base + lane;
+                bool pending = lane < kRound && j < nchunks;
+                const int k = pending ? j / p.cpr : 0, q = pending ? j - k * p.cpr : 0;
+                const long long gj = g + j;
+                const int slot = (int)(gj % kNS), use = (int)(gj / kNS);
+                const int cells = min(cpc, p.ncols - q * cpc);
+                const uint32_t bytes = (uint32_t)(cells * cellb);
+                const char* src = fimg + ((long long)rows[k] * p.W + p.x0 + q * cpc) * cellb;
+                while (__any_sync(0xffffffffu, pending)) {
+                    if (pending && s_filled[slot] == use - 1 && mbar_try(bar_empty + 8 * slot, (uint32_t)(use & 1) ^ 1)) {
+                        mbar_expect_tx(bar_full + 8 * slot, bytes);
+                        bulk_g2s(ring_u32 + slot * kSlotBytes, src, bytes, bar_full + 8 * slot);
+                        s_filled[slot] = use;
+                        pending = false;
                     }
-                    __syncwarp();
-                    for (int j = lane; j < p.ncols; j += 32) {            // one bulk copy per cell
-                        const int slot = (g + j / cpc) % kNS;
-                        bulk_g2s(ring_u32 + slot * kSlotBytes + (j % cpc) * cellpart, src + j * cellb, cellpart,
-                                 bar_full + 8 * slot);
-                    }
-                    g = (g + p.cpr) % (2 * kNS);
                 }
             }
+            __syncwarp();
+            g += nchunks;
         }
         return;
     }
 
     // ---------------------------------------------------------------------- consumers
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int passes = C / 128;
+    const int units = c.PW * passes;                   // (pw, 128-channel pass) per bin row
     bool store_pending = false;
     int it = 0;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-        const long long r = item / nct;
-        const int ct = (int)(item - r * nct);
+    for (long long r = blockIdx.x; r < a.R; r += gridDim.x, ++it) {
         const int tb = it & 1;
         const Hdr* hdr = s_hdr + tb;
         const TBin* tab = s_tab + tb * bins;
@@ -317,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_roi_align_tma(RoiArgs a, float*
             continue;
         }
         const bool fits = hdr->fits != 0;
-        float* o = out + (r * C + ct * kCT) * (long long)bins;
+        float* o = out + r * (long long)C * bins;
         if (fits) {
             const int cpr = hdr->cpr, gbase = hdr->gbase;
             int k_wait = 0, k_rel = 0;
@@ -335,10 +367,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_roi_align_tma(RoiArgs a, float*
                     if (tid == 0) bulk_wait_read0();
                     cons_sync();
                 }
-                for (int pw = warp; pw < c.PW; pw += kConsWarps) {
+                for (int u = warp; u < units; u += kConsWarps) {
+                    const int pw = u / passes, cp = u - pw * passes;
                     const int bin = ph * c.PW + pw;
                     const TBin* t = tab + bin;
-                    const char* rc = ring + lane * 4 * es;
+                    const char* rc = ring + (cp * 128 + lane * 4) * es;
                     float acc[4];
                     switch (t->pat) {                          // uniform over the warp
                         case 0: bin_eval_s<FT, 0, 0>(rc, t, acc); break;
@@ -351,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_roi_align_tma(RoiArgs a, float*
                         case 7: bin_eval_s<FT, 2, 1>(rc, t, acc); break;
                         default: bin_eval_s<FT, 2, 2>(rc, t, acc); break;
                     }
-                    float* st = s_tile + (lane * 4) * bins + bin;    // x / 4 == x * 0.25 exactly
+                    float* st = s_tile + (cp * 128 + lane * 4) * bins + bin;    // x / 4 == x * 0.25 exactly
 #pragma unroll
                     for (int e = 0; e < 4; ++e) st[e * bins] = acc[e] * 0.25f;
                 }
@@ -370,9 +403,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_roi_align_tma(RoiArgs a, float*
                 cons_sync();
             }
             const Plan p = make_plan(a, r, cpc);
-            const FT* feat = reinterpret_cast<const FT*>(a.feat[p.lvl]) + (long long)p.img * p.H * p.W * C + ct * kCT;
-            for (int t = tid; t < kCT * bins; t += kConsThreads) {
-                const int ch = t % kCT, bin = t / kCT, ph = bin / c.PW, pw = bin - ph * c.PW;
+            const FT* feat = reinterpret_cast<const FT*>(a.feat[p.lvl]) + (long long)p.img * p.H * p.W * C;
+            for (int t = tid; t < (a.pf_dist == -7 ? 0 : C * bins); t += kConsThreads) {      // (-7: dev knob, timing without this path)
+                const int ch = t % C, bin = t / C, ph = bin / c.PW, pw = bin - ph * c.PW;
                 float acc = 0.0f;
                 for (int iy = 0; iy < 2; ++iy) {
                     const AxisTap ty = axis_tap(p.g.sy, p.g.bh, ph, iy, 2, p.H);
@@ -390,11 +423,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_roi_align_tma(RoiArgs a, float*
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(tab_empty + 8 * tb);            // table / header of this item are free
+        if (lane == 0) mbar_arrive(tab_empty + 8 * tb);            // table / header of this RoI are free
         fence_async_smem();                                        // generic-proxy tile writes -> async-proxy read
         cons_sync();
         if (tid == 0) {
-            bulk_s2g(o, smem_u32(s_tile), (uint32_t)(kCT * bins * 4));
+            bulk_s2g(o, smem_u32(s_tile), (uint32_t)(C * bins * 4));
             bulk_commit();
         }
         store_pending = true;
@@ -409,28 +442,26 @@ int roi_align_tma_try(const RoiArgs& a, float* out, cudaStream_t st) {
     const int bins = c.PH * c.PW;
     const int es = c.layout == 2 ? 2 : 4;
     if (c.layout < 1 || c.sampling_ratio != 2 || c.PH > kMaxP || c.PW > kMaxP) return 1;
-    if (c.C % kCT != 0) return 1;
-    if (((long long)kCT * bins * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
+    if (c.C % 128 != 0 || c.C * es > 1024 || kSlotBytes % (c.C * es) != 0) return 1;
+    if (((long long)c.C * bins * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
     for (int l = 0; l < c.num_levels; ++l)
         if (reinterpret_cast<uintptr_t>(a.feat[l]) & 15) return 1;
-    const size_t smem = (size_t)kNS * kSlotBytes + (size_t)kCT * bins * 4 + 2 * (size_t)bins * sizeof(TBin) + 2 * sizeof(Hdr) +
-                        (2 * kNS + 4) * sizeof(uint64_t);
-    if (smem > 113 * 1024) return 1;                   // two CTAs per SM
-    (void)es;
+    const size_t smem = (size_t)kNS * kSlotBytes + (size_t)c.C * bins * 4 + 2 * (size_t)bins * sizeof(TBin) + 2 * sizeof(Hdr) +
+                        (2 * kNS + 4) * sizeof(uint64_t) + (kNS + 32 * kProdWarps) * sizeof(int);
+    if (smem > 227 * 1024) return 1;
     static int sms = 0;
     if (sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_roi_align_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        cudaFuncSetAttribute(k_roi_align_tma<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        cudaFuncSetAttribute(k_roi_align_tma<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(k_roi_align_tma<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_roi_align_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_roi_align_tma<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
-    const long long items = a.R * (c.C / kCT);
-    const unsigned grid = (unsigned)(items < 2ll * sms ? items : 2ll * sms);
-    if (c.layout == 1) k_roi_align_tma<float><<<grid, kThreads, smem, st>>>(a, out);
-    else k_roi_align_tma<__nv_bfloat16><<<grid, kThreads, smem, st>>>(a, out);
+    const unsigned grid = (unsigned)(a.R < sms ? a.R : sms);
+    RoiArgs b = a;
+    { const char* e = getenv("B2D_ROI_TMA_DEV"); b.pf_dist = e ? atoi(e) : 0; }
+    if (c.layout == 1) k_roi_align_tma<float><<<grid, kThreads, smem, st>>>(b, out);
+    else k_roi_align_tma<__nv_bfloat16><<<grid, kThreads, smem, st>>>(b, out);
     return check_launch("roi_align_fwd(tma)");
 }
 

@@ -44,7 +44,18 @@ def main():
             print("roi_align variant %s pf=%s: %.1f us  bitexact_vs_first=%s" % (v, os.environ.get("B2D_ROI_PF"), us, bool(torch.equal(o, ref))))
     if "tma" in which:
         ref = None
-        for v in ("0", "1"):
+        rb = bt.tar_box.cpu().numpy(); nb = bt.n_chosen.cpu().numpy()
+        wide = 0; tot = 0
+        for b in range(B):
+            r = rb[b][:, :nb[b]]
+            s_ = np.sqrt((r[2] - r[0] + 1) * (r[3] - r[1] + 1))
+            lv = np.clip(np.floor(np.log2(s_ / 56 + 1e-6)), 0, 3)
+            wc = (r[2] - r[0]) / (4 * 2 ** lv)
+            wide += int((wc > 29).sum()); tot += r.shape[1]
+        print("RoIs wider than 29 cells: %d of %d" % (wide, tot), flush=True)
+        for v in ("0", "1", "1:-7"):
+            if ":" in v:
+                v, d = v.split(":"); os.environ["B2D_ROI_TMA_DEV"] = d
             os.environ["B2D_ROI_TMA"] = v
             hp.roi_align.out.zero_()
             us = timeit(lambda: hp.roi_align(feats, bt.tar_box, bt.n_chosen))

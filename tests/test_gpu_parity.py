@@ -310,7 +310,8 @@ def _ring_case(seed, C, K, B=2):
 
 
 @pytest.mark.parametrize("C,K", [(256, 700), (128, 333)])
-def test_roi_align_tma_ring_bit_exact_vs_oracle(C, K):
+def test_roi_align_tma_ring_bit_exact_vs_oracle(C, K, monkeypatch):
+    monkeypatch.setenv("B2D_ROI_TMA", "1")                                # opt-in kernel
     grids, feats, rois, img = _ring_case(11, C, K)
     fs = [T(f).contiguous(memory_format=torch.channels_last) for f in feats]
     out = N(bregion.roi_align_levels(fs, T(rois), T(img), [1 / 4, 1 / 8, 1 / 16, 1 / 32]))
@@ -328,6 +329,7 @@ def test_roi_align_tma_ring_bit_exact_vs_oracle(C, K):
 def test_roi_align_tma_ring_bf16_and_l1_path_agree(monkeypatch):
     grids, feats, rois, img = _ring_case(12, 256, 500)
     fs = [T(f).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for f in feats]
+    monkeypatch.setenv("B2D_ROI_TMA", "1")
     out = N(bregion.roi_align_levels(fs, T(rois), T(img), [1 / 4, 1 / 8, 1 / 16, 1 / 32]))
     monkeypatch.setenv("B2D_ROI_TMA", "0")                                # L1-path kernel (k_roi_align_win)
     out_l1 = N(bregion.roi_align_levels(fs, T(rois), T(img), [1 / 4, 1 / 8, 1 / 16, 1 / 32]))
