@@ -121,6 +121,18 @@ B2D_API int b2d_encode_targets(float* tar_box, float* tar_gt, float* tar_param, 
                        const float* gt, int gt_ld, const int* gt_count, const int64_t* gt_label,
                        int prepend_gt, const float* means_host, const float* stds_host, int B, void* stream);
 
+/* ---- a13 in ONE launch: bbox_target (lib/bbox.py:6-82) for explicit boxes (N <= 4096,
+ * gt_ld <= 512, max_num <= 1024): b2d_assign_max_iou + b2d_sample_labels +
+ * b2d_encode_targets with identical outputs (same sampler specification and seed
+ * convention), one CTA per image.  Arguments as in those three entry points. */
+B2D_API int b2d_roi_targets_fused(int64_t* labels, float* max_iou, long long out_ld, const float* boxes, long long box_ld,
+                          const int* box_count, long long N, const float* gt, int gt_ld, const int* gt_count,
+                          const int64_t* gt_label, int B, float pos_iou, float neg_iou, float min_pos_iou,
+                          int prepend_gt, int* census, int* pos_list, int pos_cap, int* chosen, int* n_chosen,
+                          int max_num, int pos_num, unsigned long long seed, float* tar_box, float* tar_gt,
+                          float* tar_param, int64_t* tar_label, int64_t* tar_is_gt, const float* means_host,
+                          const float* stds_host, void* stream);
+
 /* gather of the head outputs at the sampled anchors (lib/anchor.py:49-56), batched:
  * cls_ptrs_host[l] -> [B, C, n_l], reg_ptrs_host[l] -> [B, 4, n_l] (the views of
  * lib/heads/anchor_head.py:82-83) -> tar_cls [B][C][max_num], tar_reg [B][4][max_num]. */

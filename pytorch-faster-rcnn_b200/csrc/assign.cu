@@ -437,13 +437,21 @@ __global__ void __launch_bounds__(256) k_label_rows(AssignArgs p, b2d_pyramid py
 constexpr int kSmallThreads = 1024;
 constexpr int kSmallBoxes = 4;
 
-__global__ void __launch_bounds__(kSmallThreads) k_assign_small(AssignArgs p, int64_t* __restrict__ labels,
-                                                                float* __restrict__ out_iou, int* __restrict__ census,
-                                                                int* __restrict__ pos_list, int pos_cap) {
-    __shared__ Box s_gt[kGtChunk];
-    __shared__ float s_ga[kGtChunk];
-    __shared__ uint32_t s_max[kGtChunk];
-    __shared__ int s_cnt[3];
+struct SmallSmem {
+    Box gt[kGtChunk];
+    float ga[kGtChunk];
+    uint32_t mx[kGtChunk];
+    int cnt[3];
+};
+
+// s_lab (optional, shared memory, >= lead + n_b entries): the labels as int32, for the fused kernel below
+__device__ __forceinline__ void assign_small_body(const AssignArgs& p, SmallSmem& sm, int64_t* __restrict__ labels,
+                                                  float* __restrict__ out_iou, int* __restrict__ census,
+                                                  int* __restrict__ pos_list, int pos_cap, int* s_lab) {
+    Box* s_gt = sm.gt;
+    float* s_ga = sm.ga;
+    uint32_t* s_max = sm.mx;
+    int* s_cnt = sm.cnt;
     const int b = blockIdx.x;
     const int K = p.gt_count[b];
     const int n_b = p.box_count ? p.box_count[b] : (int)p.N;
@@ -514,6 +522,7 @@ __global__ void __launch_bounds__(kSmallThreads) k_assign_small(AssignArgs p, in
             if (eq[r] >= 0) { l = 1; a = eq[r]; out_v = veq[r]; }
             out_l = (l == 1) ? (int64_t)(a + 1) : (int64_t)l;
             lab[lead + i] = out_l; oiou[lead + i] = out_v;
+            if (s_lab) s_lab[lead + i] = (int)out_l;
         }
         const bool is_pos = ok[r] && out_l > 0, is_neg = ok[r] && out_l == 0;
         const unsigned mp = __ballot_sync(0xffffffffu, is_pos), mn = __ballot_sync(0xffffffffu, is_neg);
@@ -530,6 +539,7 @@ __global__ void __launch_bounds__(kSmallThreads) k_assign_small(AssignArgs p, in
     if (p.prepend_gt) {                                   // prepended GT rows (lib/bbox.py:27-29): labels 1..K, IoU 1
         for (int j = threadIdx.x; j < K; j += blockDim.x) {
             lab[j] = j + 1; oiou[j] = 1.0f;
+            if (s_lab) s_lab[j] = j + 1;
             if (plist) { const int slot = atomicAdd(&s_cnt[2], 1); if (slot < pos_cap) plist[slot] = j; }
         }
         __syncthreads();
@@ -540,6 +550,14 @@ __global__ void __launch_bounds__(kSmallThreads) k_assign_small(AssignArgs p, in
         census[4 * b + 2] = s_cnt[2];
         census[4 * b + 3] = 0;
     }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSmallThreads) k_assign_small(AssignArgs p, int64_t* __restrict__ labels,
+                                                                float* __restrict__ out_iou, int* __restrict__ census,
+                                                                int* __restrict__ pos_list, int pos_cap) {
+    __shared__ SmallSmem sm;
+    assign_small_body(p, sm, labels, out_iou, census, pos_list, pos_cap, nullptr);
 }
 
 // ---- census of an arbitrary labels vector -------------------------------------
@@ -792,6 +810,193 @@ __global__ void __launch_bounds__(128) k_gather_head(GatherArgs p, b2d_pyramid p
         tar_reg[((long long)b * 4 + c) * p.max_num + t] = live ? p.reg[l][((long long)b * 4 + c) * n + li] : 0.0f;
 }
 
+// ---- bbox_target of one image in ONE launch (lib/bbox.py:6-82) -----------------------------------
+// assignment (assign_small_body) -> device-RNG sampler (the specification of k_sample,
+// oracle/sampler_spec.py: identical `chosen`) -> gather + encode (k_encode_targets), one CTA per
+// image, labels / flags in shared memory.  Replaces three dependent launches of 8 CTAs (13 + 17 +
+// 5 us + gaps on the critical path of config 2); the negative walk is one block scan per 4096
+// permutation steps and the ascending output order comes from a flag compaction, not a sort.
+constexpr int kFusedMaxN = kSmallThreads * kSmallBoxes + kGtChunk;     // candidates incl. prepended GT
+constexpr int kFusedPer = (kFusedMaxN + kSmallThreads - 1) / kSmallThreads;
+
+struct FusedArgs {
+    int* chosen; int* n_chosen; int max_num, pos_num;
+    unsigned long long seed;
+    const int64_t* gt_label;
+    float* tar_box; float* tar_gt; float* tar_param; int64_t* tar_label; int64_t* tar_is_gt;
+    float ms[8];
+};
+
+__global__ void __launch_bounds__(kSmallThreads) k_roi_targets_small(AssignArgs p, int64_t* __restrict__ labels,
+                                                                     float* __restrict__ out_iou,
+                                                                     int* __restrict__ census, int* __restrict__ pos_list,
+                                                                     int pos_cap, FusedArgs f) {
+    __shared__ SmallSmem sm;
+    __shared__ int s_lab[kFusedMaxN];
+    __shared__ unsigned char s_flag[kFusedMaxN];
+    __shared__ int s_chosen[kSmallThreads];
+    __shared__ int s_w[4][32];
+    __shared__ int s_tot, s_red[32];
+    __shared__ unsigned long long s_lo, s_hi;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    assign_small_body(p, sm, labels, out_iou, census, pos_list, pos_cap, s_lab);
+    const int K = p.gt_count[b];
+    const int lead = p.prepend_gt ? K : 0;
+    const int n_tot = lead + (p.box_count ? p.box_count[b] : (int)p.N);
+    const int npos = sm.cnt[0] + lead, nneg = sm.cnt[1];
+    const uint64_t sd = f.seed + 0x632BE59BD9B4E019ull * (uint64_t)(b + 1);
+    for (int i = tid; i < n_tot; i += kSmallThreads) s_flag[i] = 0;
+    // ---- positives: all of them, or the pos_num smallest (mix_key(sd, idx) << 32 | idx)
+    const int keep_pos = min(npos, f.pos_num);
+    uint64_t thr = ~0ull;
+    if (npos > f.pos_num) {
+        if (tid == 0) { s_lo = 0ull; s_hi = ~0ull; }
+        __syncthreads();
+        for (int it = 0; it < 64; ++it) {
+            const unsigned long long lo = s_lo, hi = s_hi;
+            if (lo >= hi) break;
+            const unsigned long long mid = lo + (hi - lo) / 2;
+            int c = 0;
+            for (int i = tid; i < n_tot; i += kSmallThreads)
+                if (s_lab[i] > 0) c += ((((uint64_t)mix_key(sd, (uint32_t)i) << 32) | (uint32_t)i) <= mid);
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0) s_red[warp] = c;
+            __syncthreads();
+            if (tid == 0) {
+                int tot = 0;
+                for (int w = 0; w < kSmallThreads / 32; ++w) tot += s_red[w];
+                if (tot >= f.pos_num) s_hi = mid; else s_lo = mid + 1;
+            }
+            __syncthreads();
+        }
+        thr = s_lo;
+    }
+    __syncthreads();
+    for (int i = tid; i < n_tot; i += kSmallThreads)
+        if (s_lab[i] > 0 && ((((uint64_t)mix_key(sd, (uint32_t)i) << 32) | (uint32_t)i) <= thr)) s_flag[i] = 1;
+    // ---- negatives: the first want_neg label-0 indices along the keyed Feistel permutation
+    const int want_neg = min(max(f.max_num - keep_pos, 0), nneg);
+    if (want_neg > 0) {
+        int bits = 2;
+        while ((1 << bits) < n_tot) ++bits;
+        if (bits & 1) ++bits;
+        const int half = bits >> 1, dom = 1 << bits;
+        int taken = 0;
+        for (int t0 = 0; t0 < dom && taken < want_neg; t0 += 4 * kSmallThreads) {
+            uint32_t y[4];
+            unsigned m[4];
+            bool hit[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int t = t0 + q * kSmallThreads + tid;
+                y[q] = feistel((uint32_t)t, half, sd ^ 0xA5A5A5A5DEADBEEFull);
+                hit[q] = t < dom && (int)y[q] < n_tot && s_lab[y[q]] == 0;
+                m[q] = __ballot_sync(0xffffffffu, hit[q]);
+                if (lane == 0) s_w[q][warp] = __popc(m[q]);
+            }
+            __syncthreads();
+            if (warp == 0) {                                        // exclusive scan of the 128 warp counts (t order)
+                int v[4], sum = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { v[e] = (&s_w[0][0])[lane * 4 + e]; sum += v[e]; }
+                int incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                int run = incl - sum;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { (&s_w[0][0])[lane * 4 + e] = run; run += v[e]; }
+                if (lane == 31) s_tot = incl;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int rank = taken + s_w[q][warp] + __popc(m[q] & ((1u << lane) - 1u));
+                if (hit[q] && rank < want_neg) s_flag[y[q]] = 1;
+            }
+            taken += s_tot;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // ---- ascending compaction of the flags
+    const int total = keep_pos + want_neg;
+    {
+        int c = 0;
+        const int i0 = tid * kFusedPer;
+#pragma unroll
+        for (int e = 0; e < kFusedPer; ++e) c += (i0 + e < n_tot) ? s_flag[i0 + e] : 0;
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_red[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = s_red[lane];
+            int iw = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, iw, d);
+                if (lane >= d) iw += t;
+            }
+            s_red[lane] = iw - v;
+        }
+        __syncthreads();
+        int pos = s_red[warp] + incl - c;
+#pragma unroll
+        for (int e = 0; e < kFusedPer; ++e)
+            if (i0 + e < n_tot && s_flag[i0 + e]) { if (pos < kSmallThreads) s_chosen[pos] = i0 + e; ++pos; }
+    }
+    __syncthreads();
+    // ---- gather + encode of the sampled rows (k_encode_targets)
+    if (tid == 0) f.n_chosen[b] = total;
+    const int t = tid;
+    if (t >= f.max_num) return;
+    const long long o = (long long)b * 4 * f.max_num;
+    const bool live = t < total;
+    Box bx{0, 0, 0, 0}, gb{0, 0, 0, 0};
+    float prm[4] = {0, 0, 0, 0};
+    int64_t lab_out = 0, isgt = 0;
+    int ci = -1;
+    if (live) {
+        const int i = s_chosen[t];
+        ci = i;
+        const int lab = s_lab[i];
+        if (i < lead) {
+            bx = sm.gt[i];
+            isgt = 1;
+        } else {
+            const float* src = p.boxes + (long long)b * 4 * p.box_ld;
+            const long long ii = i - lead;
+            bx = Box{src[ii], src[p.box_ld + ii], src[2 * p.box_ld + ii], src[3 * p.box_ld + ii]};
+        }
+        const int j = max(lab - 1, 0);                       // negatives point at GT 0 (lib/anchor.py:45-47)
+        gb = sm.gt[j];
+        const float bw = (bx.x2 - bx.x1) + 1.0f, bh = (bx.y2 - bx.y1) + 1.0f;
+        const float gw = (gb.x2 - gb.x1) + 1.0f, gh = (gb.y2 - gb.y1) + 1.0f;
+        const float bcx = (bx.x2 + bx.x1) / 2.0f, bcy = (bx.y2 + bx.y1) / 2.0f;
+        const float gcx = (gb.x2 + gb.x1) / 2.0f, gcy = (gb.y2 + gb.y1) / 2.0f;
+        prm[0] = ((gcx - bcx) / bw - f.ms[0]) / f.ms[4];
+        prm[1] = ((gcy - bcy) / bh - f.ms[1]) / f.ms[5];
+        prm[2] = (logf(gw / bw) - f.ms[2]) / f.ms[6];
+        prm[3] = (logf(gh / bh) - f.ms[3]) / f.ms[7];
+        if (f.gt_label) lab_out = (lab > 0) ? f.gt_label[(long long)b * p.gt_ld + j] : 0;
+        else lab_out = (lab > 0) ? 1 : 0;
+    }
+    const int mn = f.max_num;
+    f.chosen[(long long)b * mn + t] = ci;
+    if (f.tar_box) { f.tar_box[o + t] = bx.x1; f.tar_box[o + mn + t] = bx.y1; f.tar_box[o + 2 * mn + t] = bx.x2; f.tar_box[o + 3 * mn + t] = bx.y2; }
+    if (f.tar_gt) { f.tar_gt[o + t] = gb.x1; f.tar_gt[o + mn + t] = gb.y1; f.tar_gt[o + 2 * mn + t] = gb.x2; f.tar_gt[o + 3 * mn + t] = gb.y2; }
+    if (f.tar_param) { f.tar_param[o + t] = prm[0]; f.tar_param[o + mn + t] = prm[1]; f.tar_param[o + 2 * mn + t] = prm[2]; f.tar_param[o + 3 * mn + t] = prm[3]; }
+    if (f.tar_label) f.tar_label[(long long)b * mn + t] = lab_out;
+    if (f.tar_is_gt) f.tar_is_gt[(long long)b * mn + t] = isgt;
+}
+
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -918,6 +1123,33 @@ int b2d_encode_targets(float* tar_box, float* tar_gt, float* tar_param, int64_t*
     dim3 grid(cdiv(max_num, 128), B);
     k_encode_targets<<<grid, 128, 0, (cudaStream_t)stream>>>(p, pyr, tar_box, tar_gt, tar_param, tar_label, tar_is_gt);
     return check_launch("encode_targets");
+}
+
+int b2d_roi_targets_fused(int64_t* labels, float* max_iou, long long out_ld, const float* boxes, long long box_ld,
+                          const int* box_count, long long N, const float* gt, int gt_ld, const int* gt_count,
+                          const int64_t* gt_label, int B, float pos_iou, float neg_iou, float min_pos_iou,
+                          int prepend_gt, int* census, int* pos_list, int pos_cap, int* chosen, int* n_chosen,
+                          int max_num, int pos_num, unsigned long long seed, float* tar_box, float* tar_gt,
+                          float* tar_param, int64_t* tar_label, int64_t* tar_is_gt, const float* means_host,
+                          const float* stds_host, void* stream) {
+    B2D_REQUIRE(labels && max_iou && boxes && gt && gt_count && census && chosen && n_chosen, "roi_targets_fused: null pointer");
+    B2D_REQUIRE(B >= 1 && gt_ld >= 1 && gt_ld <= kGtChunk && N >= 0 && N <= kSmallThreads * kSmallBoxes,
+                "roi_targets_fused: need N <= 4096 and gt_ld <= 512");
+    B2D_REQUIRE(max_num >= 1 && max_num <= kSmallThreads && pos_num >= 0 && pos_num <= max_num,
+                "roi_targets_fused: need 1 <= max_num <= 1024 and pos_num <= max_num");
+    AssignArgs a;
+    a.boxes = boxes; a.box_ld = box_ld; a.box_count = box_count; a.N = N;
+    a.use_pyr = 0; a.img_hw = nullptr; a.border = 0.0f;
+    a.gt = gt; a.gt_ld = gt_ld; a.gt_count = gt_count;
+    a.pos_iou = pos_iou; a.neg_iou = neg_iou; a.min_pos_iou = min_pos_iou;
+    a.prepend_gt = prepend_gt; a.out_ld = out_ld;
+    FusedArgs f;
+    f.chosen = chosen; f.n_chosen = n_chosen; f.max_num = max_num; f.pos_num = pos_num; f.seed = seed;
+    f.gt_label = gt_label;
+    f.tar_box = tar_box; f.tar_gt = tar_gt; f.tar_param = tar_param; f.tar_label = tar_label; f.tar_is_gt = tar_is_gt;
+    for (int i = 0; i < 4; ++i) { f.ms[i] = means_host ? means_host[i] : 0.0f; f.ms[4 + i] = stds_host ? stds_host[i] : 1.0f; }
+    k_roi_targets_small<<<B, kSmallThreads, 0, (cudaStream_t)stream>>>(a, labels, max_iou, census, pos_list, pos_cap, f);
+    return check_launch("roi_targets_fused");
 }
 
 }  // extern "C"

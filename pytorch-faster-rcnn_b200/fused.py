@@ -124,8 +124,10 @@ class BatchedTargets(object):
         self.step = 0
         self.b0 = 0
         small = pyramid is None and self.N <= 4096 and self.gt_ld <= 512
-        # kernels: assign_small | (colmax_rect, label_rows) | (fill, colmax, label); then sample, encode
-        self.launches = 3 if small else (4 if pyramid is not None else 5)
+        # bbox_target in one launch (b2d_roi_targets_fused) when the problem fits one CTA per image
+        self.fused = small and self.max_num <= 1024
+        # kernels: roi_targets_small | assign_small | (colmax_rect, label_rows) | (fill, colmax, label); then sample, encode
+        self.launches = 1 if self.fused else (3 if small else (4 if pyramid is not None else 5))
 
     def slice(self, b0, b1):
         return _batch_view(self, b0, b1)
@@ -133,6 +135,16 @@ class BatchedTargets(object):
     def __call__(self, gt, gt_count, gt_label=None, boxes=None, box_count=None, img_hw=None):
         pyr = ctypes.byref(self.pyr.c) if boxes is None else None
         box_ld = boxes.shape[-1] if boxes is not None else 0
+        if self.fused and boxes is not None:
+            self.step += 1
+            _C.call("b2d_roi_targets_fused", _C.ptr(self.labels), _C.ptr(self.iou), self.out_ld, _C.ptr(boxes), box_ld,
+                    _C.ptr(box_count), self.N, _C.ptr(gt), self.gt_ld, _C.ptr(gt_count), _C.ptr(gt_label), self.B,
+                    float(self.pos_iou), float(self.neg_iou), float(self.min_pos), self.prepend, _C.ptr(self.census),
+                    _C.ptr(self.pos_list), self.out_ld, _C.ptr(self.chosen), _C.ptr(self.n_chosen), self.max_num,
+                    self.pos_num, (self.seed * 1000003 + self.step + 0x632BE59BD9B4E019 * self.b0) & 0xFFFFFFFFFFFFFFFF,
+                    _C.ptr(self.tar_box), _C.ptr(self.tar_gt), _C.ptr(self.tar_param), _C.ptr(self.tar_label),
+                    _C.ptr(self.tar_is_gt), self.means, self.stds, _C.stream())
+            return self
         _C.call("b2d_assign_max_iou", _C.ptr(self.labels), _C.ptr(self.iou), self.out_ld, _C.ptr(boxes), box_ld,
                 _C.ptr(box_count), self.N, pyr, _C.ptr(img_hw), self.border, _C.ptr(gt), self.gt_ld, _C.ptr(gt_count),
                 self.B, float(self.pos_iou), float(self.neg_iou), float(self.min_pos), self.prepend,

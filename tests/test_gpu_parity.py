@@ -435,6 +435,66 @@ def test_device_sampler_matches_its_spec_and_properties(n, max_num, pos_num):
     assert np.array_equal(out, out2)
 
 
+@pytest.mark.parametrize("n,K,max_num,pos_num,spread,prepend", [
+    (2000, 8, 512, 128, 1.0, True),        # config 2 (few positives)
+    (2000, 24, 512, 128, 0.15, True),      # proposals hug the GTs: #pos > pos_num -> threshold bisection
+    (4096, 64, 1024, 256, 0.3, True),      # largest supported problem, 16384-step permutation domain
+    (300, 3, 64, 16, 0.5, False),          # no GT prepend, fewer negatives than wanted
+    (40, 2, 512, 128, 0.2, True),          # fewer candidates than max_num
+])
+def test_roi_targets_fused_equals_three_kernel_path_and_spec(n, K, max_num, pos_num, spread, prepend):
+    """b2d_roi_targets_fused (one launch) == b2d_assign_max_iou + b2d_sample_labels + b2d_encode_targets,
+    and its `chosen` == the sampler specification (oracle/sampler_spec.py) on the oracle's labels."""
+    from oracle import sampler_spec
+    rng = np.random.default_rng(n + K)
+    B = 3
+    gt = np.zeros((B, 4, K), np.float32)
+    for b in range(B):
+        x1 = rng.uniform(0, 900, K); y1 = rng.uniform(0, 500, K)
+        gt[b] = np.stack([x1, y1, x1 + rng.uniform(30, 400, K), y1 + rng.uniform(30, 300, K)])
+    boxes = np.zeros((B, 4, n), np.float32)
+    for b in range(B):
+        j = rng.integers(0, K, n)
+        jit = rng.normal(0, spread * 120, (4, n))
+        far = rng.random(n) < 0.3
+        bb = gt[b][:, j] + jit
+        rnd = np.stack([rng.uniform(0, 900, n), rng.uniform(0, 500, n), rng.uniform(900, 1300, n), rng.uniform(500, 790, n)])
+        bb = np.where(far[None], rnd, bb)
+        boxes[b] = np.stack([np.minimum(bb[0], bb[2]), np.minimum(bb[1], bb[3]), np.maximum(bb[0], bb[2]) + 1, np.maximum(bb[1], bb[3]) + 1])
+    counts = np.array([n, max(n - 7, 1), n], np.int32)
+    gl = rng.integers(1, 21, (B, K)).astype(np.int64)
+    gcount = np.array([K, max(K - 1, 1), K], np.int32)
+    kw = dict(assigner=dict(pos_iou=0.5, neg_iou=0.5, min_pos_iou=0.5), sampler=dict(max_num=max_num, pos_num=pos_num),
+              means=(0, 0, 0, 0), stds=(0.1, 0.1, 0.2, 0.2), device=DEV, prepend_gt=prepend, seed=5)
+    a = fused.BatchedTargets(B, n, K, **kw)
+    c = fused.BatchedTargets(B, n, K, **kw)
+    assert a.fused
+    c.fused = False                                                       # three-kernel path
+    args = (T(gt), T(gcount), T(gl))
+    kws = dict(boxes=T(boxes), box_count=T(counts))
+    a(*args, **kws); c(*args, **kws)
+    torch.cuda.synchronize()
+    for name in ("census", "n_chosen", "chosen", "tar_box", "tar_gt", "tar_param", "tar_label", "tar_is_gt"):
+        x, y = N(getattr(a, name)), N(getattr(c, name))
+        if name == "census":
+            x, y = x[:, :2], y[:, :2]
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), name
+    seed = (5 * 1000003 + 1) & 0xFFFFFFFFFFFFFFFF
+    saw_bisect = False
+    for b in range(B):
+        lead = int(gcount[b]) if prepend else 0
+        nb = int(counts[b])
+        olab, _ = oracle.assign_max_iou(np.ascontiguousarray(boxes[b][:, :nb]), np.ascontiguousarray(gt[b][:, :gcount[b]]), 0.5, 0.5, 0.5)
+        full = np.concatenate([np.arange(1, lead + 1), olab]).astype(np.int64)
+        assert np.array_equal(N(a.labels[b, :lead + nb]), full)
+        saw_bisect |= int((full > 0).sum()) > pos_num
+        want = sampler_spec.sample(full, max_num, pos_num, seed, image_index=b)
+        m = int(a.n_chosen[b])
+        assert np.array_equal(N(a.chosen[b, :m]), want)
+    if spread <= 0.15:
+        assert saw_bisect, "case meant to exercise the positive-threshold bisection"
+
+
 # ------------------------------------------------------------------ fused train path vs oracle
 def test_fused_train_path_small_vs_oracle():
     import __graft_entry__
