@@ -30,6 +30,7 @@ namespace b2d {
 
 struct NmsSegs {
     int L;                              // levels per image (1 for the generic entry)
+    int lv0, lvn;                       // levels covered by this launch
     long long box_per_img, box_off[kMaxLevels];
     long long mask_per_img, mask_off[kMaxLevels];
     int wp[kMaxLevels];                 // mask row pitch in words
@@ -94,8 +95,8 @@ __global__ void __launch_bounds__(64) k_nms_mask_sym(NmsSegs s, int wmax) {
     __shared__ float4 s_row[64];
     __shared__ float s_ra[64];
     __shared__ uint32_t s_cw[2][64];
-    const int seg = blockIdx.y;
-    const int l = seg % s.L, b = seg / s.L;
+    int seg, b, l;
+    seg_of(s.lv0, s.lvn, s.L, blockIdx.y, seg, b, l);
     const int n = s.counts[seg];
     int rb, cb;
     tile_of(blockIdx.x, wmax, rb, cb);
@@ -190,8 +191,8 @@ constexpr int kFpEntries = 6;                        // non-zero words of a row 
 __global__ void __launch_bounds__(kFpThreads) k_nms_scan_fp(NmsSegs s, int max_keep, ScanOut o) {
     __shared__ uint32_t s_k[2][64];                  // kept bits, ping-pong (2048 bits each)
     __shared__ int s_prefix[65];
-    const int seg = blockIdx.x;
-    const int l = seg % s.L, b = seg / s.L;
+    int seg, b, l;
+    seg_of(s.lv0, s.lvn, s.L, blockIdx.x, seg, b, l);
     const int n = s.counts[seg];
     const long long base = (long long)b * s.box_per_img + s.box_off[l];
     const uint64_t* mask = s.mask + (long long)b * s.mask_per_img + s.mask_off[l];
@@ -288,8 +289,8 @@ __global__ void __launch_bounds__(kFpThreads) k_nms_scan_fp(NmsSegs s, int max_k
 // boxes of the same chunk that suppress j.
 __global__ void __launch_bounds__(64) k_nms_mask_dense(NmsSegs s, int wmax) {
     __shared__ float4 s_row[64];
-    const int seg = blockIdx.y;
-    const int l = seg % s.L, b = seg / s.L;
+    int seg, b, l;
+    seg_of(s.lv0, s.lvn, s.L, blockIdx.y, seg, b, l);
     const int n = s.counts[seg];
     int rb, cb;
     tile_of(blockIdx.x, wmax, rb, cb);
@@ -331,8 +332,8 @@ __global__ void __launch_bounds__(kScanThreads) k_nms_scan_seq(NmsSegs s, int ma
     __shared__ uint64_t s_keepw[kSortCap / 64];
     __shared__ int s_prefix[kSortCap / 64];
     __shared__ uint64_t s_keep;
-    const int seg = blockIdx.x;
-    const int l = seg % s.L, b = seg / s.L;
+    int seg, b, l;
+    seg_of(s.lv0, s.lvn, s.L, blockIdx.x, seg, b, l);
     const int n = s.counts[seg];
     const int W = (n + 63) / 64;
     const uint64_t* mask = s.mask + (long long)b * s.mask_per_img + s.mask_off[l];
@@ -471,7 +472,7 @@ __global__ void k_fill_i32(int* p, int v, int m) {
 int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st) {
     NmsSegs s;
     memset(&s, 0, sizeof(s));
-    s.L = p.L; s.box_per_img = p.sel_per_img; s.mask_per_img = p.mask_per_img;
+    s.L = p.L; s.lv0 = p.lv0; s.lvn = p.lvn; s.box_per_img = p.sel_per_img; s.mask_per_img = p.mask_per_img;
     int wmax = 1;
     for (int l = 0; l < p.L; ++l) {
         s.box_off[l] = p.sel_off[l]; s.mask_off[l] = p.mask_off[l];
@@ -480,9 +481,9 @@ int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st) {
     }
     s.boxes = p.sel_box; s.counts = p.sel_count; s.mask = p.mask; s.nz = p.nz;   // nz zeroed with the workspace head
     set_thr(s, p.nms_thr);
-    const int S = p.B * p.L;
+    const int S = p.B * p.lvn;
     int n_max = 1;
-    for (int l = 0; l < p.L; ++l) n_max = max(n_max, p.kcap[l]);
+    for (int l = p.lv0; l < p.lv0 + p.lvn; ++l) n_max = max(n_max, p.kcap[l]);
     (void)wmax;
     ScanOut o;
     memset(&o, 0, sizeof(o));
@@ -534,7 +535,7 @@ int b2d_nms(int64_t* keep, int* keep_count, const float* boxes, const float* sco
                                                      presorted);
     NmsSegs s;
     memset(&s, 0, sizeof(s));
-    s.L = 1; s.box_per_img = n_ld; s.mask_per_img = (long long)n_ld * wp; s.wp[0] = wp;
+    s.L = 1; s.lv0 = 0; s.lvn = 1; s.box_per_img = n_ld; s.mask_per_img = (long long)n_ld * wp; s.wp[0] = wp;
     s.boxes = sorted_box; s.counts = cnt; s.mask = mask; s.nz = nz;
     set_thr(s, thr_f);
     if (n <= kFpThreads * kFpRows) cudaMemsetAsync(nz, 0, (size_t)S * n_ld * 4, st);

@@ -17,6 +17,7 @@ struct RpnLaunch {
     const float* reg[kMaxLevels];
     const float* img_hw;
     int B, L;
+    int lv0, lvn;                       // this launch covers levels [lv0, lv0 + lvn) of every image (per-level chains)
     int n[kMaxLevels], kcap[kMaxLevels];
     long long sel_off[kMaxLevels], sel_per_img;
     long long mask_off[kMaxLevels], mask_per_img;
@@ -34,7 +35,14 @@ struct RpnLaunch {
     uint64_t* mask;
 };
 
-// nms.cu: suppression mask + scan over the sel_* arrays of every segment
+// launch-local segment index s (b-major over the launch's levels) -> global segment, image, level
+__device__ __forceinline__ void seg_of(int lv0, int lvn, int L, int s, int& seg, int& b, int& l) {
+    b = s / lvn;
+    l = lv0 + (s - b * lvn);
+    seg = b * L + l;
+}
+
+// nms.cu: suppression mask + scan over the sel_* arrays of the launch's segments
 int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st);
 
 }  // namespace b2d

@@ -40,7 +40,8 @@ __device__ __forceinline__ const float* seg_reg(const RpnLaunch& p, int b, int l
 // ---------------------------------------------------------------- k_hist
 __global__ void __launch_bounds__(256) k_hist(RpnLaunch p) {
     __shared__ uint32_t s_h[kHistBins];
-    const int seg = blockIdx.y, b = seg / p.L, l = seg - b * p.L;
+    int seg, b, l;
+    seg_of(p.lv0, p.lvn, p.L, blockIdx.y, seg, b, l);
     const int n = p.n[l], k = p.kcap[l];
     if (k >= n) return;                                  // no selection on this level
     const int start = blockIdx.x * kChunk;
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(256) k_compact(RpnLaunch p) {
     __shared__ uint32_t s_tmp[8];
     __shared__ uint64_t s_stageA[kCapA], s_stageB[kCapB];
     __shared__ int s_n, s_n2, s_base, s_base2;
-    const int seg = blockIdx.y, b = seg / p.L, l = seg - b * p.L;
+    int seg, b, l;
+    seg_of(p.lv0, p.lvn, p.L, blockIdx.y, seg, b, l);
     const int n = p.n[l], k = p.kcap[l];
     if (k >= n) return;
     const int start = blockIdx.x * kChunk;
@@ -247,7 +249,8 @@ __global__ void __launch_bounds__(kSelThreads) k_select(RpnLaunch p) {
     __shared__ __align__(16) uint32_t s_off[kHistBins + 4], s_cur[kHistBins], s_wsum[80];
     __shared__ int s_cnt, s_cnt2, s_digit, s_base;
     __shared__ int s_warp[kSelThreads / 32];
-    const int seg = blockIdx.x, b = seg / p.L, l = seg - b * p.L;
+    int seg, b, l;
+    seg_of(p.lv0, p.lvn, p.L, blockIdx.x, seg, b, l);
     const b2d_level& lv = p.pyr.lv[l];
     const int n = p.n[l], k = p.kcap[l];
     const float* cls = seg_cls(p, b, l);
@@ -610,6 +613,7 @@ bool rpn_plan(RpnLaunch& p, const b2d_pyramid* pyr, int B, const b2d_rpn_cfg* cf
     memset(&p, 0, sizeof(p));
     p.pyr = *pyr;
     p.B = B; p.L = pyr->num_levels;
+    p.lv0 = 0; p.lvn = p.L;
     p.pre_nms = cfg->pre_nms; p.post_nms = cfg->post_nms; p.max_num = cfg->max_num;
     p.score_mode = cfg->score_mode; p.cls_ch = cfg->num_cls_channels > 0 ? cfg->num_cls_channels : 1;
     p.nms_thr = cfg->nms_thr_f; p.min_size = cfg->min_size; p.do_nms = cfg->do_nms;
@@ -665,6 +669,39 @@ bool rpn_plan(RpnLaunch& p, const b2d_pyramid* pyr, int B, const b2d_rpn_cfg* cf
 
 }  // namespace b2d
 
+namespace {
+
+// Internal per-level streams of b2d_rpn_proposals (created once per device, on the first call; they only ever run
+// work that is ordered after / before the caller's stream through the fork / join events).
+struct LevelStreams {
+    cudaStream_t s[kMaxLevels];
+    cudaEvent_t fork, join[kMaxLevels];
+    bool ok;
+};
+
+LevelStreams* level_streams() {
+    static LevelStreams table[64];
+    static bool made[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    LevelStreams& t = table[dev];
+    if (!made[dev]) {
+        made[dev] = true;
+        t.ok = true;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        for (int l = 0; l < kMaxLevels; ++l) {
+            t.ok = t.ok && cudaStreamCreateWithPriority(&t.s[l], cudaStreamNonBlocking, hi) == cudaSuccess;
+            t.ok = t.ok && cudaEventCreateWithFlags(&t.join[l], cudaEventDisableTiming) == cudaSuccess;
+        }
+        t.ok = t.ok && cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) == cudaSuccess;
+        if (!t.ok) cudaGetLastError();
+    }
+    return t.ok ? &t : nullptr;
+}
+
+}  // namespace
+
 extern "C" {
 
 size_t b2d_rpn_proposals_workspace_bytes(const b2d_pyramid* pyr_host, int B, const b2d_rpn_cfg* cfg_host) {
@@ -698,24 +735,40 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
         attr_set = true;
     }
     cudaMemsetAsync(workspace, 0, p.zero_bytes, st);
-    const int S = B * p.L;
-    int max_chunks = 1;
-    bool any_select = false;
-    for (int l = 0; l < p.L; ++l) {
-        if (p.kcap[l] < p.n[l]) { any_select = true; max_chunks = max(max_chunks, cdiv(p.n[l], kChunk)); }
-    }
-    if (any_select) {
-        dim3 grid(max_chunks, S);
-        k_hist<<<grid, 256, 0, st>>>(p);
-        if (int rc = check_launch("rpn_proposals/k_hist")) return rc;
-        k_compact<<<grid, 256, 0, st>>>(p);
-        if (int rc = check_launch("rpn_proposals/k_compact")) return rc;
-    }
-    k_select<<<S, kSelThreads, kSortCap * 8, st>>>(p);
-    if (int rc = check_launch("rpn_proposals/k_select")) return rc;
-    if (p.do_nms) {
-        int rc = rpn_nms_launch(p, st);
-        if (rc != B2D_OK) return rc;
+    // Per-level chains.  hist -> compact -> select -> NMS mask -> scan of one level only depends on that level, and
+    // all of them but the mask are small latency-bound grids; run as ONE launch per kernel over all levels the step
+    // is the sum of the slowest segment of every kernel (166 us at config 2).  Each level therefore gets its own
+    // chain on an internal stream (parallel graph branches under capture): the mask work of one level fills the SMs
+    // while the other levels sit in their latency-bound kernels.  Joined before the merge.
+    int nchains = 1;
+    { const char* e = getenv("B2D_RPN_CHAINS"); const int want = e ? atoi(e) : 1; if (want && p.L > 1) nchains = p.L; }
+    LevelStreams* ls = nchains > 1 ? level_streams() : nullptr;
+    if (nchains > 1 && !ls) nchains = 1;
+    if (nchains > 1) cudaEventRecord(ls->fork, st);
+    for (int c = 0; c < nchains; ++c) {
+        RpnLaunch q = p;
+        cudaStream_t cs = st;
+        if (nchains > 1) { q.lv0 = c; q.lvn = 1; cs = ls->s[c]; cudaStreamWaitEvent(cs, ls->fork, 0); }
+        const int S = B * q.lvn;
+        int max_chunks = 1;
+        bool any_select = false;
+        for (int l = q.lv0; l < q.lv0 + q.lvn; ++l) {
+            if (q.kcap[l] < q.n[l]) { any_select = true; max_chunks = max(max_chunks, cdiv(q.n[l], kChunk)); }
+        }
+        if (any_select) {
+            dim3 grid(max_chunks, S);
+            k_hist<<<grid, 256, 0, cs>>>(q);
+            if (int rc = check_launch("rpn_proposals/k_hist")) return rc;
+            k_compact<<<grid, 256, 0, cs>>>(q);
+            if (int rc = check_launch("rpn_proposals/k_compact")) return rc;
+        }
+        k_select<<<S, kSelThreads, kSortCap * 8, cs>>>(q);
+        if (int rc = check_launch("rpn_proposals/k_select")) return rc;
+        if (q.do_nms) {
+            int rc = rpn_nms_launch(q, cs);
+            if (rc != B2D_OK) return rc;
+        }
+        if (nchains > 1) { cudaEventRecord(ls->join[c], cs); cudaStreamWaitEvent(st, ls->join[c], 0); }
     }
     bool sorted_lists = true;                            // see k_merge: unsorted only without NMS and without top-k
     int cat = 0;
