@@ -168,7 +168,7 @@ def run_b200(args):
     gt, gl = h_gt.to(dev), h_gl.to(dev)
     gcount = torch.full((B,), K_GT, dtype=torch.int32, device=dev)
     img_hw = torch.tensor([[float(w["img_shape"][0]), float(w["img_shape"][1])]] * B, device=dev)
-    hp = fused.TrainHotPath(B, grids, dev, gt_ld=K_GT, feat_channels=256, layout=1, overlap=True)
+    hp = fused.TrainHotPath(B, grids, dev, gt_ld=K_GT, feat_channels=256, layout=1, overlap=True, groups=args.groups)
 
     def step():
         return hp.step(cls, reg, feats, gt, gcount, gl, img_hw)
@@ -305,7 +305,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": WORKLOAD, "global_batch": total_imgs, "parallelism": "per-image partition, dp%d" % world,
-                                            "features": "fp32 NHWC (channels_last) resident in HBM", "cuda_graph": graph is not None,
+                                            "features": "fp32 NHWC (channels_last) resident in HBM", "cuda_graph": graph is not None, "image_groups": hp.groups,
                                             "l2": "inputs per step (755 MB/GPU) exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "layout": "pinned host fp32 NCHW (reference layout) -> H2D (copy stream) -> NCHW->NHWC -> hot path -> D2H of proposals/targets"},
@@ -320,6 +320,8 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--groups", type=int, default=int(os.environ.get("B2D_GROUPS", "1")),
+                    help="image groups with staggered stream priorities inside one step (fused.TrainHotPath)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()

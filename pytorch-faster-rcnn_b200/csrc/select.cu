@@ -38,7 +38,11 @@ __device__ __forceinline__ const float* seg_reg(const RpnLaunch& p, int b, int l
 }
 
 // ---------------------------------------------------------------- k_hist
-__global__ void __launch_bounds__(256) k_hist(RpnLaunch p) {
+// 1024 threads per 16384-element chunk: two rounds of 8 independent loads per thread.  (With 256 threads the chunk
+// took 8 dependent DRAM round trips -- 12 us for a kernel that moves 1 MB per image, r1g launch list.)
+constexpr int kHcThreads = 1024;
+
+__global__ void __launch_bounds__(kHcThreads) k_hist(RpnLaunch p) {
     __shared__ uint32_t s_h[kHistBins];
     int seg, b, l;
     seg_of(p.lv0, p.lvn, p.L, blockIdx.y, seg, b, l);
@@ -50,16 +54,17 @@ __global__ void __launch_bounds__(256) k_hist(RpnLaunch p) {
     __syncthreads();
     const float* cls = seg_cls(p, b, l);
     const int end = min(start + kChunk, n);
-    for (int r0 = start; r0 < end; r0 += 8 * 256) {
-        float v[8];                                       // 8 independent loads in flight per thread
+    {
+        constexpr int kPer = kChunk / kHcThreads;         // 16 independent loads in flight per thread
+        float v[kPer];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int i = r0 + q * 256 + threadIdx.x;
+        for (int q = 0; q < kPer; ++q) {
+            const int i = start + q * kHcThreads + threadIdx.x;
             v[q] = i < end ? load_logit(cls, n, i, p.score_mode, p.cls_ch) : 0.0f;
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-            if (r0 + q * 256 + (int)threadIdx.x < end) atomicAdd(&s_h[f2key(v[q]) >> (32 - kHistBits)], 1u);
+        for (int q = 0; q < kPer; ++q)
+            if (start + q * kHcThreads + (int)threadIdx.x < end) atomicAdd(&s_h[f2key(v[q]) >> (32 - kHistBits)], 1u);
     }
     __syncthreads();
     uint32_t* gh = p.hist + (long long)seg * kHistBins;
@@ -67,14 +72,14 @@ __global__ void __launch_bounds__(256) k_hist(RpnLaunch p) {
         if (s_h[t]) atomicAdd(&gh[t], s_h[t]);
 }
 
-// Find the largest bin t with sum_{bin >= t} hist[bin] >= k.  blockDim.x == 256.
-__device__ int find_threshold_bin(const uint32_t* __restrict__ gh, int k, uint32_t* s_tmp /*>= 8*/) {
-    constexpr int per = kHistBins / 256;
+// Find the largest bin t with sum_{bin >= t} hist[bin] >= k.  blockDim.x == kHcThreads.
+__device__ int find_threshold_bin(const uint32_t* __restrict__ gh, int k, uint32_t* s_tmp /*>= 32*/) {
+    constexpr int per = kHistBins / kHcThreads, kWarps = kHcThreads / 32;
     uint32_t loc[per];
     uint32_t sum = 0;
 #pragma unroll
     for (int q = 0; q < per; ++q) { loc[q] = gh[threadIdx.x * per + q]; sum += loc[q]; }
-    // suffix scan over the 256 partial sums: shuffles inside a warp, 8 warp totals through smem
+    // suffix scan over the partial sums: shuffles inside a warp, warp totals through smem
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t v = sum;
 #pragma unroll
@@ -87,7 +92,7 @@ __device__ int find_threshold_bin(const uint32_t* __restrict__ gh, int k, uint32
     if (threadIdx.x == 0) s_bin = 0;
     __syncthreads();
     uint32_t above = v - sum;                              // bins owned by higher lanes of this warp
-    for (int w = warp + 1; w < 8; ++w) above += s_tmp[w];  // ... and by higher warps
+    for (int w = warp + 1; w < kWarps; ++w) above += s_tmp[w];  // ... and by higher warps
     if (above < (uint32_t)k && above + sum >= (uint32_t)k) {
         uint32_t run = above;
         for (int q = per - 1; q >= 0; --q) {
@@ -106,9 +111,9 @@ __device__ int find_threshold_bin(const uint32_t* __restrict__ gh, int k, uint32
 // the chunk with 8 loads in flight per thread and NO barrier in the loop, then leaves with one
 // global atomic per list and a coalesced copy (order is irrelevant: they are sorted afterwards).
 // Stage overflow (dense candidates: degenerate score maps) appends straight to the global list.
-__global__ void __launch_bounds__(256) k_compact(RpnLaunch p) {
+__global__ void __launch_bounds__(kHcThreads) k_compact(RpnLaunch p) {
     constexpr int kCapA = 1536, kCapB = 512;
-    __shared__ uint32_t s_tmp[8];
+    __shared__ uint32_t s_tmp[32];
     __shared__ uint64_t s_stageA[kCapA], s_stageB[kCapB];
     __shared__ int s_n, s_n2, s_base, s_base2;
     int seg, b, l;
@@ -118,33 +123,33 @@ __global__ void __launch_bounds__(256) k_compact(RpnLaunch p) {
     const int start = blockIdx.x * kChunk;
     if (start >= n) return;
     if (threadIdx.x == 0) { s_n = 0; s_n2 = 0; }
+    const float* cls = seg_cls(p, b, l);
+    const int end = min(start + kChunk, n);
+    // the whole chunk (16 values per thread) is requested before the threshold search, whose latency it hides
+    constexpr int kPer = kChunk / kHcThreads;
+    float v[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int i = start + q * kHcThreads + threadIdx.x;
+        v[q] = i < end ? load_logit(cls, n, i, p.score_mode, p.cls_ch) : 0.0f;
+    }
     const int tb = find_threshold_bin(p.hist + (long long)seg * kHistBins, k, s_tmp);   // has barriers
     if (blockIdx.x == 0 && threadIdx.x == 0) p.thr_bin[seg] = tb;
-    const float* cls = seg_cls(p, b, l);
     uint64_t* cand = p.cand + ((long long)b * p.pyr.total + p.pyr.lv[l].offset);
     uint64_t* cand2 = p.cand2 + ((long long)b * p.pyr.total + p.pyr.lv[l].offset);
-    const int end = min(start + kChunk, n);
-    for (int r0 = start; r0 < end; r0 += 8 * 256) {
-        float v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int i = r0 + q * 256 + threadIdx.x;
-            v[q] = i < end ? load_logit(cls, n, i, p.score_mode, p.cls_ch) : 0.0f;
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int i = r0 + q * 256 + threadIdx.x;
-            const uint32_t key = f2key(v[q]);
-            const int bin = (int)(key >> (32 - kHistBits));
-            if (i < end && bin > tb) {
-                const int pos = atomicAdd(&s_n, 1);
-                if (pos < kCapA) s_stageA[pos] = make_comp(key, (uint32_t)i);
-                else cand[atomicAdd(&p.cand_count[seg], 1)] = make_comp(key, (uint32_t)i);
-            } else if (i < end && bin == tb) {
-                const int pos = atomicAdd(&s_n2, 1);
-                if (pos < kCapB) s_stageB[pos] = make_comp(key, (uint32_t)i);
-                else cand2[atomicAdd(&p.cand2_count[seg], 1)] = make_comp(key, (uint32_t)i);
-            }
+    for (int q = 0; q < kPer; ++q) {
+        const int i = start + q * kHcThreads + threadIdx.x;
+        const uint32_t key = f2key(v[q]);
+        const int bin = (int)(key >> (32 - kHistBits));
+        if (i < end && bin > tb) {
+            const int pos = atomicAdd(&s_n, 1);
+            if (pos < kCapA) s_stageA[pos] = make_comp(key, (uint32_t)i);
+            else cand[atomicAdd(&p.cand_count[seg], 1)] = make_comp(key, (uint32_t)i);
+        } else if (i < end && bin == tb) {
+            const int pos = atomicAdd(&s_n2, 1);
+            if (pos < kCapB) s_stageB[pos] = make_comp(key, (uint32_t)i);
+            else cand2[atomicAdd(&p.cand2_count[seg], 1)] = make_comp(key, (uint32_t)i);
         }
     }
     __syncthreads();
@@ -671,7 +676,7 @@ bool rpn_plan(RpnLaunch& p, const b2d_pyramid* pyr, int B, const b2d_rpn_cfg* cf
 
 namespace {
 
-// Internal per-level streams of b2d_rpn_proposals (created once per device, on the first call; they only ever run
+// Internal per-level streams of b2d_rpn_proposals (created once per device and priority, on the first call; they only ever run
 // work that is ordered after / before the caller's stream through the fork / join events).
 struct LevelStreams {
     cudaStream_t s[kMaxLevels];
@@ -679,19 +684,26 @@ struct LevelStreams {
     bool ok;
 };
 
-LevelStreams* level_streams() {
-    static LevelStreams table[64];
-    static bool made[64];
+// One stream set per (device, priority of the caller's stream): the chains inherit the caller's priority, so two
+// concurrent calls on streams of different priority (the staggered image groups of fused.TrainHotPath) neither share
+// internal streams nor lose their relative priority.
+LevelStreams* level_streams(cudaStream_t caller) {
+    constexpr int kPrio = 8;
+    static LevelStreams table[64][kPrio];
+    static bool made[64][kPrio];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    LevelStreams& t = table[dev];
-    if (!made[dev]) {
-        made[dev] = true;
+    int lo = 0, hi = 0, pr = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamGetPriority(caller, &pr) != cudaSuccess) { cudaGetLastError(); pr = lo; }
+    int slot = pr - hi;
+    slot = slot < 0 ? 0 : (slot >= kPrio ? kPrio - 1 : slot);
+    LevelStreams& t = table[dev][slot];
+    if (!made[dev][slot]) {
+        made[dev][slot] = true;
         t.ok = true;
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
         for (int l = 0; l < kMaxLevels; ++l) {
-            t.ok = t.ok && cudaStreamCreateWithPriority(&t.s[l], cudaStreamNonBlocking, hi) == cudaSuccess;
+            t.ok = t.ok && cudaStreamCreateWithPriority(&t.s[l], cudaStreamNonBlocking, pr) == cudaSuccess;
             t.ok = t.ok && cudaEventCreateWithFlags(&t.join[l], cudaEventDisableTiming) == cudaSuccess;
         }
         t.ok = t.ok && cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) == cudaSuccess;
@@ -742,7 +754,7 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
     // while the other levels sit in their latency-bound kernels.  Joined before the merge.
     int nchains = 1;
     { const char* e = getenv("B2D_RPN_CHAINS"); const int want = e ? atoi(e) : 1; if (want && p.L > 1) nchains = p.L; }
-    LevelStreams* ls = nchains > 1 ? level_streams() : nullptr;
+    LevelStreams* ls = nchains > 1 ? level_streams(st) : nullptr;
     if (nchains > 1 && !ls) nchains = 1;
     if (nchains > 1) cudaEventRecord(ls->fork, st);
     for (int c = 0; c < nchains; ++c) {
@@ -757,9 +769,9 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
         }
         if (any_select) {
             dim3 grid(max_chunks, S);
-            k_hist<<<grid, 256, 0, cs>>>(q);
+            k_hist<<<grid, kHcThreads, 0, cs>>>(q);
             if (int rc = check_launch("rpn_proposals/k_hist")) return rc;
-            k_compact<<<grid, 256, 0, cs>>>(q);
+            k_compact<<<grid, kHcThreads, 0, cs>>>(q);
             if (int rc = check_launch("rpn_proposals/k_compact")) return rc;
         }
         k_select<<<S, kSelThreads, kSortCap * 8, cs>>>(q);
@@ -846,8 +858,8 @@ int b2d_topk(int* idx, int* out_count, const float* values, long long ld, const 
     }
     cudaMemsetAsync(workspace, 0, p.zero_bytes, st);
     dim3 grid(cdiv(n, kChunk), S);
-    k_hist<<<grid, 256, 0, st>>>(p);
-    k_compact<<<grid, 256, 0, st>>>(p);
+    k_hist<<<grid, kHcThreads, 0, st>>>(p);
+    k_compact<<<grid, kHcThreads, 0, st>>>(p);
     k_select<<<S, kSelThreads, kSortCap * 8, st>>>(p);
     dim3 g2(cdiv(k, 256), S);
     k_topk_emit<<<g2, 256, 0, st>>>(p, idx, out_count, k);

@@ -59,6 +59,8 @@ def install(lib=None):
         _set(mods["heads.bbox_head"], "bbox_target", bbox.bbox_target)
     if mods["heads.rpn_head"]:
         _set(mods["heads.rpn_head"], "tvops", types.SimpleNamespace(nms=utils.nms))
+        if hasattr(mods["heads.rpn_head"], "RPNHead"):   # a9: the whole per-level loop as one fused K3 + K4 call
+            _set(mods["heads.rpn_head"].RPNHead, "predict_single_image", heads.rpn_predict_single_image)
     if mods["heads.fcos_head"] and hasattr(mods["heads.fcos_head"], "AnchorCreator"):
         _set(mods["heads.fcos_head"], "AnchorCreator", anchor.AnchorCreator)
     # head methods that are part of the path: rebind on the classes

@@ -10,6 +10,7 @@ Every stage is also reachable through the reference-signature functions in
 anchor.py / bbox.py / region.py / utils.py; this module only batches them.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -82,7 +83,10 @@ class RpnProposals(object):
         self.scores = torch.zeros((B, self.P), dtype=torch.float32, device=device)
         self.count = torch.zeros(B, dtype=torch.int32, device=device)
         self.prov = torch.zeros((B, self.P), dtype=torch.int32, device=device)
-        self.launches = 6 if do_nms else 4   # kernels: hist, compact, select, (mask, scan), merge  (+1 memset node)
+        # kernels: per level (hist, compact if the level is larger than pre_nms), select, (mask, scan); then merge (+1 memset node)
+        chains = len(pyramid.level_sizes) > 1 and os.environ.get("B2D_RPN_CHAINS", "1") != "0"
+        per_level = [(2 if 0 < c.pre_nms < n else 0) + 1 + (2 if do_nms else 0) for n in pyramid.level_sizes]
+        self.launches = (sum(per_level) if chains else max(per_level)) + 1
 
     def slice(self, b0, b1):
         v = _batch_view(self, b0, b1)
@@ -237,8 +241,12 @@ class TrainHotPath(object):
                 self.subs.append((b0, b1, self.proposals.slice(b0, b1) if groups > 1 else self.proposals,
                                   self.roi_targets.slice(b0, b1) if groups > 1 else self.roi_targets,
                                   self.roi_align.slice(b0, b1) if groups > 1 else self.roi_align,
-                                  torch.cuda.Stream(device=device, priority=-1),     # latency-bound chain
-                                  torch.cuda.Stream(device=device, priority=0)))     # RoIAlign (throughput)
+                                  # Priorities stagger the groups: group 0's chain wins every SM slot it asks for, so it
+                                  # reaches its RoIAlign (HBM-bound) while the later groups are still in their NMS masks
+                                  # (ALU-bound) -- the two overlap instead of running back to back.  RoIAlign streams
+                                  # rank below every chain, the RPN-target chain (off the critical path) lowest.
+                                  torch.cuda.Stream(device=device, priority=-5 + min(g, 2)),       # proposal / target chain
+                                  torch.cuda.Stream(device=device, priority=-2 + min(g, 1))))      # RoIAlign (throughput)
             self.s_rpn = torch.cuda.Stream(device=device, priority=0)
         per_group = self.proposals.launches + self.roi_targets.launches + 1
         self.launches = per_group * groups + self.rpn_targets.launches + 1

@@ -147,3 +147,36 @@ def predict_single_image(self, cls_outs, reg_outs, ctr_outs, img_meta, test_cfg)
     """Method form of FCOSHead.predict_single_image (DFL heads keep the reference path)."""
     return fcos_predict_single_image(cls_outs, reg_outs, ctr_outs, self.strides, img_meta, test_cfg, self.reg_mean,
                                      self.reg_std, self.use_centerness)
+
+
+# ---------------------------------------------------------------------------------- a9
+def rpn_predict_single_image(self, level_cls_outs, level_reg_outs, level_anchors, img_meta, test_cfg):
+    """Method form of RPNHead.predict_single_image (lib/heads/rpn_head.py:68-120): the per-level
+    sigmoid / top-k / decode / clamp / min-size / NMS / post-NMS loop and the final top-max_num as ONE
+    call of the fused K3 + K4 path (b2d_rpn_proposals, B = 1).  Same arguments and return value
+    `(bbox [4,k], score [k], None)`.  The anchors are regenerated in registers from the head's own
+    anchor parameters (anchor_strides / anchor_scales / anchor_ratios, lib/heads/anchor_head.py:29-36);
+    `level_anchors` is only used to read the grid sizes.  Selection happens on the logit (sigmoid and
+    softmax[1] are monotone in it), ties go to the lowest index."""
+    from . import fused
+    dev = level_cls_outs[0].device
+    _C.require_cuda(*level_cls_outs)
+    grids = tuple(tuple(int(v) for v in a.shape[-2:]) for a in level_anchors)
+    get = (lambda k, d=0: test_cfg.get(k, d)) if hasattr(test_cfg, "get") else (lambda k, d=0: getattr(test_cfg, k, d))
+    sf = float(img_meta.get('scale_factor', 1.0))
+    key = (grids, int(get('pre_nms')), int(get('post_nms')), int(get('max_num')), float(get('nms_iou', 0.7)),
+           float(get('min_bbox_size', 0)), sf, str(dev))
+    cache = self.__dict__.setdefault('_b2d_rpn_cache', {})
+    rp = cache.get(key)
+    if rp is None:
+        center_lt = bool(getattr(self.anchor_creators[0], 'center_lt', False)) if getattr(self, 'anchor_creators', None) else False
+        pyr = fused.AnchorPyramid(self.anchor_strides, grids, tuple(self.anchor_scales), tuple(self.anchor_ratios), center_lt)
+        rp = fused.RpnProposals(pyr, 1, test_cfg, self.target_means, self.target_stds, dev,
+                                score_mode=0 if self.use_sigmoid else 1, cls_channels=int(self.cls_channels),
+                                scale_factor=sf)
+        cache[key] = rp
+    cls = [_C.f32c(x).view(1, *x.shape[-3:]) for x in level_cls_outs]
+    reg = [_C.f32c(x).view(1, *x.shape[-3:]) for x in level_reg_outs]
+    props, scores, count = rp(cls, reg, _img_hw(img_meta['img_shape'][:2], dev))
+    k = int(count[0])
+    return props[0][:, :k].clone(), scores[0][:k].clone(), None

@@ -4,9 +4,11 @@ import collections, csv, io, json, subprocess, sys
 
 tag, rep, launches = sys.argv[1:4]
 bench = sys.argv[4] if len(sys.argv) > 4 else None
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, data = rows[0], rows[1], rows[2:]
+data_by_rep = []
+for one in rep.split(","):                      # several reports (one per kernel filter) may be given, comma-separated
+    raw = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    data_by_rep.append((rows[0], rows[1], rows[2:]))
 cols = collections.OrderedDict([
     ("kernel", "Kernel Name"), ("grid", "launch__grid_size"), ("block", "launch__block_size"),
     ("regs", "launch__registers_per_thread"), ("time_us", "gpu__time_duration.sum"),
@@ -26,13 +28,14 @@ def conv(v, u, want):
     if want == "time_us": x *= {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(u, 1.0)
     return round(x, 3)
 out = []
-for r in data:
-    rec = collections.OrderedDict()
-    for k, name in cols.items():
-        if name in hdr:
-            i = hdr.index(name)
-            rec[k] = r[i][:60] if k == "kernel" else conv(r[i], units[i], k)
-    out.append(rec)
+for hdr, units, data in data_by_rep:
+    for r in data:
+        rec = collections.OrderedDict()
+        for k, name in cols.items():
+            if name in hdr:
+                i = hdr.index(name)
+                rec[k] = r[i][:60] if k == "kernel" else conv(r[i], units[i], k)
+        out.append(rec)
 with open("profiles/%s_ncu_full.csv" % tag, "w", newline="") as f:
     w = csv.DictWriter(f, fieldnames=list(out[0].keys())); w.writeheader(); w.writerows(out)
 # launch list aggregate

@@ -149,6 +149,7 @@ def test_dropin_install_rebinds_reference_names():
         assert ah.anchor_target is b200det.anchor.anchor_target
         assert ah.AnchorCreator is b200det.anchor.AnchorCreator
         assert rh.tvops.nms is b200det.utils.nms
+        assert rh.RPNHead.predict_single_image is b200det.heads.rpn_predict_single_image
         assert sys.modules["lib.utils"].calc_iou is b200det.utils.calc_iou
         assert sys.modules["lib.utils"].tv.ops.nms is b200det.utils.nms
         assert sys.modules["lib.bbox"].bbox_target is b200det.bbox.bbox_target
@@ -157,3 +158,4 @@ def test_dropin_install_rebinds_reference_names():
     finally:
         b200det.uninstall()
     assert rb.MODULES["MaxIoUAssigner"] is orig
+    assert rh.RPNHead.predict_single_image is not b200det.heads.rpn_predict_single_image

@@ -213,6 +213,28 @@ def test_rpn_proposals_vs_reference():
             np.testing.assert_allclose(props[b, :, :n], ref_b, rtol=1e-5, atol=1e-3)
 
 
+def test_rpn_head_predict_single_image_method_form_vs_reference():
+    """heads.rpn_predict_single_image with the reference's own signature (lib/heads/rpn_head.py:68) on a stand-in
+    head object carrying the attributes RPNHead defines (lib/heads/anchor_head.py:29-50)."""
+    import types
+    from b200det import heads as bheads
+    g = load_golden("rpn")
+    grids = [(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)]
+    head = types.SimpleNamespace(anchor_strides=[4, 8, 16, 32, 64], anchor_scales=[8], anchor_ratios=[0.5, 1.0, 2.0],
+                                 target_means=[0.0] * 4, target_stds=[1.0] * 4, use_sigmoid=True, cls_channels=1,
+                                 anchor_creators=[banchor.AnchorCreator(base=s, scales=[8]) for s in (4, 8, 16, 32, 64)])
+    for ac in head.anchor_creators:
+        ac.to(DEV)                                                   # (returns None, like the reference's)
+    anchors = [ac(s, gr) for ac, s, gr in zip(head.anchor_creators, head.anchor_strides, grids)]
+    meta = dict(img_shape=tuple(int(v) for v in g["img_shape"]), pad_shape=tuple(int(v) for v in g["pad_shape"]), scale_factor=1.0)
+    cls, reg = [T(g["cls%d" % l]) for l in range(5)], [T(g["reg%d" % l]) for l in range(5)]
+    for i, c in enumerate(g["cfgs"]):
+        b, s_, extra = bheads.rpn_predict_single_image(head, cls, reg, anchors, meta, json.loads(str(c)))
+        assert extra is None and tuple(b.shape) == g["props%d" % i].shape
+        np.testing.assert_allclose(N(s_), g["scores%d" % i], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(N(b), g["props%d" % i], rtol=1e-5, atol=1e-3)
+
+
 def test_rpn_proposals_selection_bit_exact_vs_oracle():
     g = load_golden("rpn")
     grids = [(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)]
