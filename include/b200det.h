@@ -178,6 +178,23 @@ B2D_API int b2d_nms(int64_t* keep, int* keep_count, const float* boxes, const fl
             const int* counts, long long n, int S, float thr_f, int max_keep, int presorted, void* workspace,
             size_t ws_bytes, void* stream);
 
+/* ---- RCNN test-time detections, BBoxHead.predict_bboxes_single_image
+ * (lib/heads/bbox_head.py:122-146): softmax(cls_out) -> per-class decode + clamp
+ * (batched_param2bbox, lib/utils.py:96-106; reg channel = coord * C + class) ->
+ * multiclass_nms over classes 1..C-1 (lib/utils.py:224-269; strict != 0: arg-max class
+ * only) -> first max_per_img.  props [B][4][ld] (counts int32[B] or NULL => n),
+ * cls_out [B][ld][C] logits, reg_out [B][ld][4 * reg_classes] (reg_classes = C, or 1 for
+ * class-agnostic regression), img_hw float[B][2] or NULL (no clamp).  Outputs
+ * out_box [B][4][max_per_img], out_score / out_label [B][max_per_img], out_count int32[B].
+ * cap = candidate slots per image (<= 16384); *overflow is set to 1 if an image had more
+ * candidates (they are then truncated in enumeration order). */
+B2D_API size_t b2d_rcnn_detect_workspace_bytes(int cap, int B);
+B2D_API int b2d_rcnn_detect(float* out_box, float* out_score, int64_t* out_label, int* out_count, const float* props,
+                    long long ld, const int* counts, long long n, const float* cls_out, const float* reg_out, int C,
+                    int reg_classes, const float* means_host, const float* stds_host, const float* img_hw,
+                    float min_score, float nms_thr_f, int max_per_img, int strict, int cap, int B, int* overflow,
+                    void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- K5/K6: FPN level-mapped RoIAlign (BasicRoIExtractor, lib/region.py:243-306 +
  * torchvision RoIAlign aligned=False).  rois [4, R] column-major, roi_img int32[R]
  * (NULL => image 0).  feat_ptrs_host[l] -> level l features, fp32 NCHW [B,C,H,W]

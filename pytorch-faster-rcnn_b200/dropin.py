@@ -67,6 +67,7 @@ def install(lib=None):
     bh, fh = mods["heads.bbox_head"], mods["heads.fcos_head"]
     if bh and hasattr(bh, "BBoxHead"):
         _set(bh.BBoxHead, "refine_bboxes_single_image", heads.refine_bboxes_single_image)
+        _set(bh.BBoxHead, "predict_bboxes_single_image", heads.predict_bboxes_single_image)
     if fh and hasattr(fh, "FCOSHead"):
         _set(fh.FCOSHead, "single_image_targets_atss", heads.single_image_targets_atss)
         ref_predict = fh.FCOSHead.predict_single_image

@@ -245,9 +245,12 @@ class TrainHotPath(object):
                                   # reaches its RoIAlign (HBM-bound) while the later groups are still in their NMS masks
                                   # (ALU-bound) -- the two overlap instead of running back to back.  RoIAlign streams
                                   # rank below every chain, the RPN-target chain (off the critical path) lowest.
-                                  torch.cuda.Stream(device=device, priority=-5 + min(g, 2)),       # proposal / target chain
+                                  torch.cuda.Stream(device=device, priority=-4 + min(g, 2)),       # proposal / target chain
                                   torch.cuda.Stream(device=device, priority=-2 + min(g, 1))))      # RoIAlign (throughput)
-            self.s_rpn = torch.cuda.Stream(device=device, priority=0)
+            # RPN-target chain: its two ALU-bound kernels (colmax 17 us + label rows 35 us at config 2) should run
+            # while the proposal chains sit in hist / compact / select (latency-bound, ~50 us, SMs idle): lowest
+            # priority (the small critical kernels always get their SM slots) but enqueued first, see step()
+            self.s_rpn = torch.cuda.Stream(device=device, priority=int(os.environ.get("B2D_RPN_PRIO", "0")))
         per_group = self.proposals.launches + self.roi_targets.launches + 1
         self.launches = per_group * groups + self.rpn_targets.launches + 1
 
@@ -270,6 +273,11 @@ class TrainHotPath(object):
             self.roi_align(feats, bt.tar_box, bt.n_chosen)
         else:
             cur = torch.cuda.current_stream()
+            # enqueued FIRST: graph nodes launch in creation order, and these kernels should own the idle SMs while
+            # the proposal chains are in their latency-bound prefix (see __init__)
+            self.s_rpn.wait_stream(cur)
+            with torch.cuda.stream(self.s_rpn):
+                rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
             for (b0, b1, prop, tgt, ra, st, st_lo) in self.subs:
                 st.wait_stream(cur)
                 with torch.cuda.stream(st):
@@ -280,9 +288,6 @@ class TrainHotPath(object):
                     st_lo.wait_event(feats_ready)
                 with torch.cuda.stream(st_lo):
                     ra([f[b0:b1] for f in feats], t2.tar_box, t2.n_chosen)
-            self.s_rpn.wait_stream(cur)
-            with torch.cuda.stream(self.s_rpn):
-                rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
             for sub in self.subs:
                 cur.wait_stream(sub[-1])
             cur.wait_stream(self.s_rpn)

@@ -180,3 +180,52 @@ def rpn_predict_single_image(self, level_cls_outs, level_reg_outs, level_anchors
     props, scores, count = rp(cls, reg, _img_hw(img_meta['img_shape'][:2], dev))
     k = int(count[0])
     return props[0][:, :k].clone(), scores[0][:k].clone(), None
+
+
+# ---------------------------------------------------------------------------------- SURVEY 8(f-3)
+def rcnn_detect(props, cls_out, reg_out, img_size=None, target_means=None, target_stds=None, min_score=0.05,
+                nms_iou=0.5, max_per_img=100, nms_type='official', counts=None, cap=None):
+    """Batched RCNN test-time detections (b2d_rcnn_detect): props [B,4,n], cls_out [B,n,C] logits,
+    reg_out [B,n,4C] (or [B,n,4], class-agnostic) -> (boxes [B,4,max_per_img], scores [B,max_per_img],
+    labels int64 [B,max_per_img], count int32 [B]); softmax, per-class decode + clamp, class-offset NMS
+    over classes 1..C-1 and the top max_per_img in one candidate kernel + K4.  No host sync."""
+    _C.require_cuda(props, cls_out, reg_out)
+    props, cls_out, reg_out = _C.f32c(props), _C.f32c(cls_out), _C.f32c(reg_out)
+    B, _, n = props.shape
+    C = int(cls_out.shape[-1])
+    reg_c = int(reg_out.shape[-1]) // 4
+    dev = props.device
+    if cap is None:
+        cap = max(1, min(16384, n * ((C - 1) if nms_type == 'official' else 1)))
+    max_keep = max(1, min(int(max_per_img) if max_per_img is not None else cap, cap))
+    out_box = torch.zeros((B, 4, max_keep), dtype=torch.float32, device=dev)
+    out_score = torch.zeros((B, max_keep), dtype=torch.float32, device=dev)
+    out_label = torch.zeros((B, max_keep), dtype=torch.int64, device=dev)
+    out_count = torch.zeros(B, dtype=torch.int32, device=dev)
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = utils._workspace(_C.lib().b2d_rcnn_detect_workspace_bytes(cap, B), dev, "rcnn_detect")
+    hw = None
+    if img_size is not None:
+        hw = img_size if torch.is_tensor(img_size) else _img_hw(img_size[:2], dev, B)
+    _C.call("b2d_rcnn_detect", _C.ptr(out_box), _C.ptr(out_score), _C.ptr(out_label), _C.ptr(out_count), _C.ptr(props),
+            n, _C.ptr(counts), n, _C.ptr(cls_out), _C.ptr(reg_out), C, reg_c,
+            _C.host_f4(target_means, [0, 0, 0, 0]), _C.host_f4(target_stds, [1, 1, 1, 1]), _C.ptr(hw),
+            float(np.float32(min_score)), _C.floor_f32(float(nms_iou)), max_keep, int(nms_type == 'strict'), cap, B,
+            _C.ptr(overflow), _C.ptr(ws), ws.numel(), _C.stream())
+    return out_box, out_score, out_label, out_count, overflow
+
+
+def predict_bboxes_single_image(self, props, cls_out, reg_out, img_size=None, cfg=None):
+    """Method form of BBoxHead.predict_bboxes_single_image (lib/heads/bbox_head.py:122-146): same
+    arguments, returns `(preds [4,k], score [k], label int64 [k])`."""
+    if getattr(self, 'use_sigmoid', False):
+        raise NotImplementedError('Need to be implemented')            # as the reference (bbox_head.py:132)
+    get = (lambda k, d=None: cfg.get(k, d)) if hasattr(cfg, "get") else (lambda k, d=None: getattr(cfg, k, d))
+    with torch.no_grad():
+        b, s, l, cnt, ovf = rcnn_detect(props.unsqueeze(0), cls_out.unsqueeze(0), reg_out.unsqueeze(0), img_size,
+                                        self.target_means, self.target_stds, get('min_score'), get('nms_iou'),
+                                        get('max_per_img'), get('nms_type', 'official'))
+        k, o = int(cnt[0]), int(ovf[0])
+        if o:
+            raise _C.B200DetError("rcnn_detect: more than 16384 (box, class) candidates; raise min_score")
+    return b[0][:, :k], s[0][:k], l[0][:k]

@@ -430,6 +430,20 @@ def g_heads():
     for l in range(5):
         out["fc_cls%d" % l], out["fc_reg%d" % l], out["fc_ctr%d" % l] = cls[l], reg[l], ctr[l]
     out["fc_img"] = np.array(img_shape)
+    # ---- BBoxHead.predict_bboxes_single_image (lib/heads/bbox_head.py:122-146), 21 classes
+    n, C = 300, 21
+    dp = rand_boxes(rng, n, 400, 600, 16, 250)
+    dcls = rng.normal(0, 2.5, (n, C)).astype(np.float32)
+    dcls[:, 0] += 2.0                                       # most proposals are background
+    dreg = rng.normal(0, 0.6, (n, 4 * C)).astype(np.float32)
+    me = types.SimpleNamespace(use_sigmoid=False, reg_class_agnostic=False, num_classes=C,
+                               target_means=[0.0, 0.0, 0.0, 0.0], target_stds=[0.1, 0.1, 0.2, 0.2])
+    out.update(det_props=dp, det_cls=dcls, det_reg=dreg)
+    for i, cfg in enumerate([dict(min_score=0.05, nms_iou=0.5, max_per_img=100, nms_type="official"),
+                             dict(min_score=0.2, nms_iou=0.3, max_per_img=40, nms_type="strict")]):
+        b, sc, lab = bh.BBoxHead.predict_bboxes_single_image(me, T(dp), T(dcls), T(dreg), (400, 600), ref_shim.AttrDict(cfg))
+        out.update({"det_bbox%d" % i: b, "det_score%d" % i: sc, "det_label%d" % i: lab})
+        print("rcnn detect", i, "detections", int(sc.numel()))
     save("heads", **out)
 
 

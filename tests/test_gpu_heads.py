@@ -191,3 +191,51 @@ def test_cascade_three_stage_targets_refine_roialign_fwd_bwd():
     total.backward()
     assert all(f.grad is not None and torch.isfinite(f.grad).all() for f in feats)
     assert sum(float(f.grad.abs().sum()) for f in feats) > 0
+
+
+# ------------------------------------------------------------------ SURVEY 8(f-3)
+_DET_CFGS = [dict(min_score=0.05, nms_iou=0.5, max_per_img=100, nms_type="official"),
+             dict(min_score=0.2, nms_iou=0.3, max_per_img=40, nms_type="strict")]
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_rcnn_predict_bboxes_single_image_vs_reference(i):
+    """Method form with the reference's signature (lib/heads/bbox_head.py:122) against its golden output."""
+    g = load_golden("heads")
+    me = types.SimpleNamespace(use_sigmoid=False, reg_class_agnostic=False, num_classes=21,
+                               target_means=[0.0, 0.0, 0.0, 0.0], target_stds=[0.1, 0.1, 0.2, 0.2])
+    b, s, l = bheads.predict_bboxes_single_image(me, T(g["det_props"]), T(g["det_cls"]), T(g["det_reg"]), (400, 600),
+                                                 dict(_DET_CFGS[i]))
+    assert np.array_equal(N(l), g["det_label%d" % i])
+    np.testing.assert_allclose(N(s), g["det_score%d" % i], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(b), g["det_bbox%d" % i], rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("mode,agnostic", [("official", False), ("strict", False), ("official", True)])
+def test_rcnn_detect_batched_vs_oracle(mode, agnostic):
+    """ragged batch (1000 / 37 / 0 proposals), 21 and 81 classes, class-agnostic regression, no clamp."""
+    rng = np.random.default_rng(5 + len(mode) + agnostic)
+    B, n = 3, 1000
+    for C in (21, 81):
+        props = np.zeros((B, 4, n), np.float32)
+        for b in range(B):
+            cx, cy = rng.uniform(0, 1333, n), rng.uniform(0, 800, n)
+            w, h = rng.uniform(16, 400, n), rng.uniform(16, 400, n)
+            props[b] = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2])
+        cls = rng.normal(0, 2.5, (B, n, C)).astype(np.float32)
+        cls[..., 0] += 2.0
+        reg = rng.normal(0, 0.5, (B, n, 4 if agnostic else 4 * C)).astype(np.float32)
+        counts = np.array([n, 37, 0], np.int32)
+        img = (800, 1333) if C == 21 else None
+        ob, os_, ol, oc, ovf = bheads.rcnn_detect(T(props), T(cls), T(reg), img, [0, 0, 0, 0], [0.1, 0.1, 0.2, 0.2], 0.05, 0.5,
+                                                  100, mode, counts=T(counts))
+        assert int(ovf[0]) == 0
+        for b in range(B):
+            m = int(counts[b])
+            kb, ks, kl = oracle.rcnn_detect(np.ascontiguousarray(props[b][:, :m]), cls[b, :m], reg[b, :m], img, [0, 0, 0, 0],
+                                            [0.1, 0.1, 0.2, 0.2], 0.05, 0.5, 100, mode)
+            k = int(oc[b])
+            assert k == ks.shape[0], (C, b, k, ks.shape)
+            assert np.array_equal(N(ol[b, :k]), kl)
+            np.testing.assert_allclose(N(os_[b, :k]), ks, rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(N(ob[b, :, :k]), kb, rtol=1e-5, atol=1e-3)

@@ -175,3 +175,15 @@ def test_atss_oracle_vs_reference():
         assert np.array_equal(cls, g["cls_" + tag])
         assert np.array_equal(reg, g["reg_" + tag])
         np.testing.assert_allclose(ctr, g["ctr_" + tag], rtol=1e-5, atol=1e-6)
+
+
+def test_rcnn_detect_oracle_vs_reference():
+    """BBoxHead.predict_bboxes_single_image (lib/heads/bbox_head.py:122-146)."""
+    g = load_golden("heads")
+    for i, cfg in enumerate([dict(min_score=0.05, nms_iou=0.5, max_per_img=100, mode="official"),
+                             dict(min_score=0.2, nms_iou=0.3, max_per_img=40, mode="strict")]):
+        kb, ks, kl = oracle.rcnn_detect(g["det_props"], g["det_cls"], g["det_reg"], (400, 600), [0, 0, 0, 0],
+                                        [0.1, 0.1, 0.2, 0.2], **cfg)
+        assert np.array_equal(kl, g["det_label%d" % i])
+        np.testing.assert_allclose(ks, g["det_score%d" % i], rtol=1e-5, atol=1e-7)      # expf: libm vs Sleef
+        np.testing.assert_allclose(kb, g["det_bbox%d" % i], rtol=1e-5, atol=1e-3)
