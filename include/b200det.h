@@ -178,6 +178,14 @@ B2D_API int b2d_nms(int64_t* keep, int* keep_count, const float* boxes, const fl
             const int* counts, long long n, int S, float thr_f, int max_keep, int presorted, void* workspace,
             size_t ws_bytes, void* stream);
 
+/* ---- plain FCOS target assignment, FCOSHead.single_image_targets
+ * (lib/heads/fcos_head.py:371-416): per cell the smallest-area GT whose ltrb are all > 0 and
+ * whose max(ltrb) lies in [level_thr[l], level_thr[l+1]) (level_scale_thr, :167).  Same
+ * tensors and output layout as b2d_atss_assign; level_thr_host float[num_levels + 1]. */
+B2D_API int b2d_fcos_targets(int64_t* cls_tar, float* reg_tar, float* ctr_tar, const b2d_pyramid* pyr_host, const float* gt,
+                     int gt_ld, const int* gt_count, const int64_t* gt_label, const float* img_hw,
+                     const float* level_thr_host, int B, void* stream);
+
 /* ---- RCNN test-time detections, BBoxHead.predict_bboxes_single_image
  * (lib/heads/bbox_head.py:122-146): softmax(cls_out) -> per-class decode + clamp
  * (batched_param2bbox, lib/utils.py:96-106; reg channel = coord * C + class) ->

@@ -58,6 +58,7 @@ _SIGS = {
     "b2d_sample_labels": [_P, _P, _P, c_ll, _P, _P, c_ll, _P, _P, c_int, c_int, c_int, c_int, c_ull, _P],
     "b2d_roi_targets_fused": [_P, _P, c_ll, _P, c_ll, _P, c_ll, _P, c_int, _P, _P, c_int, c_float, c_float, c_float,
                               c_int, _P, _P, c_int, _P, _P, c_int, c_int, c_ull, _P, _P, _P, _P, _P, _P, _P, _P],
+    "b2d_fcos_targets": [_P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int, _P],
     "b2d_rcnn_detect": [_P, _P, _P, _P, _P, c_ll, _P, c_ll, _P, _P, c_int, c_int, _P, _P, _P, c_float, c_float, c_int,
                         c_int, c_int, c_int, _P, _P, c_size_t, _P],
     "b2d_gather_head_outputs": [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, _P],

@@ -199,6 +199,62 @@ __global__ void __launch_bounds__(256) k_atss_finalize(AtssArgs p, int64_t* __re
     reinterpret_cast<float4*>(reg)[o] = make_float4(r0, r1, r2, r3);
 }
 
+// ------------------------------------------------------------------ plain FCOS targets
+// FCOSHead.single_image_targets (lib/heads/fcos_head.py:371-416): GTs sorted by (+1) area, descending
+// (lib/utils.py:362-366), then painted one after the other on every level: a cell takes GT i iff all of
+// its ltrb > 0 and thr[level] <= max(ltrb) < thr[level + 1]; later (smaller) GTs overwrite earlier ones.
+// Order-free form: per cell the qualifying GT with the SMALLEST area wins (equal areas: the larger
+// original index, i.e. the later one of a stable sort; torch.sort leaves ties unspecified).
+struct FcosTarArgs {
+    b2d_pyramid pyr;
+    const float* gt; int gt_ld; const int* gt_count; const int64_t* gt_label;
+    const float* img_hw; float thr[kMaxLevels + 1]; long long total;
+};
+
+__global__ void __launch_bounds__(256) k_fcos_targets(FcosTarArgs p, int64_t* __restrict__ cls, float* __restrict__ reg,
+                                                      float* __restrict__ ctr) {
+    const int b = blockIdx.y;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.total) return;
+    int l = 0;
+    for (int q = 1; q < p.pyr.num_levels; ++q) if (c >= p.pyr.lv[q].offset) l = q;
+    const b2d_level& lv = p.pyr.lv[l];
+    const int i = (int)(c - lv.offset);
+    const int y = i / lv.W, x = i - y * lv.W;
+    const float sc = (float)(1.0 / (double)lv.stride);                       // paint_value, as k_atss_finalize
+    const float img_h = p.img_hw[2 * b], img_w = p.img_hw[2 * b + 1];
+    const bool in_img = (float)y <= rintf(img_h * sc) && (float)x <= rintf(img_w * sc);
+    float px, py;
+    cell_point(lv, y, x, px, py);
+    const float* g = p.gt + (long long)b * 4 * p.gt_ld;
+    const int K = p.gt_count[b];
+    const float lo = p.thr[l], hi = p.thr[l + 1];
+    int win = -1;
+    float win_area = 0.0f;
+    for (int j = 0; j < K; ++j) {
+        const float x1 = g[j], y1 = g[p.gt_ld + j], x2 = g[2 * p.gt_ld + j], y2 = g[3 * p.gt_ld + j];
+        const float r0 = px - x1, r1 = py - y1, r2 = x2 - px, r3 = y2 - py;
+        const float m = fmaxf(fmaxf(r0, r1), fmaxf(r2, r3));
+        const bool ok = r0 > 0.0f && r1 > 0.0f && r2 > 0.0f && r3 > 0.0f && m >= lo && m < hi;
+        const float area = ((x2 - x1) + 1.0f) * ((y2 - y1) + 1.0f);
+        if (ok && (win < 0 || area <= win_area)) { win = j; win_area = area; }
+    }
+    int64_t oc = in_img ? 0 : -1;
+    float r0 = -1.0f, r1 = -1.0f, r2 = -1.0f, r3 = -1.0f, oct = in_img ? 0.0f : -1.0f;
+    if (win >= 0) {
+        r0 = px - g[win]; r1 = py - g[p.gt_ld + win]; r2 = g[2 * p.gt_ld + win] - px; r3 = g[3 * p.gt_ld + win] - py;
+        oc = p.gt_label[(long long)b * p.gt_ld + win];
+        if (oc > 0) {
+            const float l_ = r0 + 1e-6f, t_ = r1 + 1e-6f, rr = r2 + 1e-6f, bb = r3 + 1e-6f;
+            oct = sqrtf((fminf(l_, rr) / fmaxf(l_, rr)) * (fminf(t_, bb) / fmaxf(t_, bb)));
+        }
+    }
+    const long long o = (long long)b * p.total + c;
+    cls[o] = oc; ctr[o] = oct;
+    reinterpret_cast<float4*>(reg)[o] = make_float4(r0, r1, r2, r3);
+}
+
+
 // ------------------------------------------------------------------ a19
 struct FcosArgs {
     b2d_pyramid pyr;
@@ -290,6 +346,23 @@ int b2d_atss_assign(int64_t* cls_tar, float* reg_tar, float* ctr_tar, const b2d_
     dim3 g2(cdiv(a.total, 256), B);
     k_atss_finalize<<<g2, 256, 0, st>>>(a, cls_tar, reg_tar, ctr_tar);
     return check_launch("atss_assign");
+}
+
+int b2d_fcos_targets(int64_t* cls_tar, float* reg_tar, float* ctr_tar, const b2d_pyramid* pyr_host, const float* gt,
+                     int gt_ld, const int* gt_count, const int64_t* gt_label, const float* img_hw,
+                     const float* level_thr_host, int B, void* stream) {
+    B2D_REQUIRE(cls_tar && reg_tar && ctr_tar && pyr_host && gt && gt_count && gt_label && img_hw && level_thr_host,
+                "fcos_targets: null pointer");
+    B2D_REQUIRE(B >= 1 && gt_ld >= 1 && pyr_host->num_levels >= 1 && pyr_host->num_levels <= B2D_MAX_LEVELS &&
+                pyr_host->total < (1ll << 31), "fcos_targets: bad sizes");
+    FcosTarArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pyr = *pyr_host; a.gt = gt; a.gt_ld = gt_ld; a.gt_count = gt_count; a.gt_label = gt_label; a.img_hw = img_hw;
+    a.total = pyr_host->total;
+    for (int l = 0; l <= pyr_host->num_levels; ++l) a.thr[l] = level_thr_host[l];
+    dim3 g(cdiv(a.total, 256), B);
+    k_fcos_targets<<<g, 256, 0, (cudaStream_t)stream>>>(a, cls_tar, reg_tar, ctr_tar);
+    return check_launch("fcos_targets");
 }
 
 int b2d_fcos_decode(float* boxes, float* key, float* score, float* ctr_score, const void* const* cls_ptrs_host,

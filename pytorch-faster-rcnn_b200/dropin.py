@@ -70,6 +70,7 @@ def install(lib=None):
         _set(bh.BBoxHead, "predict_bboxes_single_image", heads.predict_bboxes_single_image)
     if fh and hasattr(fh, "FCOSHead"):
         _set(fh.FCOSHead, "single_image_targets_atss", heads.single_image_targets_atss)
+        _set(fh.FCOSHead, "single_image_targets", heads.single_image_targets)
         ref_predict = fh.FCOSHead.predict_single_image
 
         def _predict(self, cls_outs, reg_outs, ctr_outs, img_meta, test_cfg):

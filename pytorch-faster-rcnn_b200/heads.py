@@ -229,3 +229,41 @@ def predict_bboxes_single_image(self, props, cls_out, reg_out, img_size=None, cf
         if o:
             raise _C.B200DetError("rcnn_detect: more than 16384 (box, class) candidates; raise min_score")
     return b[0][:, :k], s[0][:k], l[0][:k]
+
+
+# ---------------------------------------------------------------------------------- SURVEY 8(f-4)
+def fcos_targets(grids, strides, gt, gt_count, gt_label, img_hw, level_scale_thr=(0, 64, 128, 256, 512, 1e6)):
+    """Batched plain FCOS targets (b2d_fcos_targets): gt [B,4,K], gt_count int32[B], gt_label int64[B,K],
+    img_hw fp32[B,2] -> (cls int64 [B,total], reg fp32 [B,total,4], ctr fp32 [B,total]), cells level-major."""
+    _C.require_cuda(gt)
+    pyr = _point_pyramid(grids, strides, 8)
+    B, dev = int(gt.shape[0]), gt.device
+    total = int(pyr.total)
+    cls = torch.empty((B, total), dtype=torch.int64, device=dev)
+    reg = torch.empty((B, total, 4), dtype=torch.float32, device=dev)
+    ctr = torch.empty((B, total), dtype=torch.float32, device=dev)
+    thr = (ctypes.c_float * (len(grids) + 1))(*[float(v) for v in level_scale_thr[:len(grids) + 1]])
+    _C.call("b2d_fcos_targets", _C.ptr(cls), _C.ptr(reg), _C.ptr(ctr), ctypes.byref(pyr), _C.ptr(_C.f32c(gt)),
+            int(gt.shape[2]), _C.ptr(gt_count), _C.ptr(gt_label.to(torch.int64).contiguous()), _C.ptr(img_hw), thr, B,
+            _C.stream())
+    return cls, reg, ctr
+
+
+def single_image_targets(self, cls_outs, reg_outs, ctr_outs, gt_bboxes, gt_labels, img_meta, train_cfg):
+    """Method form of FCOSHead.single_image_targets (lib/heads/fcos_head.py:371-416): per-level lists of
+    [H,W,1] int64, [H,W,4] fp32, [H,W,1] fp32."""
+    grids = [tuple(int(v) for v in x.shape[-2:]) for x in cls_outs]
+    dev = cls_outs[0].device
+    K = int(gt_bboxes.shape[1])
+    gt = _C.f32c(gt_bboxes).view(1, 4, K)
+    cnt = torch.tensor([K], dtype=torch.int32, device=dev)
+    cls, reg, ctr = fcos_targets(grids, self.strides, gt, cnt, gt_labels.view(1, K), _img_hw(img_meta['img_shape'][:2], dev),
+                                 self.level_scale_thr)
+    cls_t, reg_t, ctr_t, off = [], [], [], 0
+    for (h, w) in grids:
+        n = h * w
+        cls_t.append(cls[0, off:off + n].view(h, w, 1))
+        reg_t.append(reg[0, off:off + n].view(h, w, 4))
+        ctr_t.append(ctr[0, off:off + n].view(h, w, 1))
+        off += n
+    return cls_t, reg_t, ctr_t

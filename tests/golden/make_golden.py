@@ -388,6 +388,15 @@ def g_atss():
                     "reg_" + tag: torch.cat([r.reshape(-1, 4) for r in reg_t]),
                     "ctr_" + tag: torch.cat([c.reshape(-1) for c in ctr_t])})
         print("atss", tag, "positives", int((out["cls_" + tag] > 0).sum()))
+        # plain FCOS targets (lib/heads/fcos_head.py:371-416) on the same GTs
+        me2 = types.SimpleNamespace(strides=strides, level_scale_thr=[0, 64, 128, 256, 512, 1e6])
+        with torch.no_grad():
+            cls_p, reg_p, ctr_p = fh.FCOSHead.single_image_targets(me2, dummy, dummy, dummy, T(gt), T(gl),
+                                                                   dict(img_shape=img_shape), None)
+        out.update({"pcls_" + tag: torch.cat([c.reshape(-1) for c in cls_p]),
+                    "preg_" + tag: torch.cat([r.reshape(-1, 4) for r in reg_p]),
+                    "pctr_" + tag: torch.cat([c.reshape(-1) for c in ctr_p])})
+        print("fcos plain", tag, "positives", int((out["pcls_" + tag] > 0).sum()))
     save("atss", **out)
 
 

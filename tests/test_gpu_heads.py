@@ -239,3 +239,40 @@ def test_rcnn_detect_batched_vs_oracle(mode, agnostic):
             assert np.array_equal(N(ol[b, :k]), kl)
             np.testing.assert_allclose(N(os_[b, :k]), ks, rtol=1e-5, atol=1e-7)
             np.testing.assert_allclose(N(ob[b, :, :k]), kb, rtol=1e-5, atol=1e-3)
+
+
+# ------------------------------------------------------------------ SURVEY 8(f-4)
+@pytest.mark.parametrize("tag", ["s", "f"])
+def test_fcos_plain_targets_vs_reference(tag):
+    g = load_golden("atss")
+    grids = [tuple(int(v) for v in x) for x in g["grids_" + tag]]
+    me = types.SimpleNamespace(strides=[8, 16, 32, 64, 128], level_scale_thr=[0, 64, 128, 256, 512, 1e6])
+    dummy = [torch.zeros((20,) + gr, device=DEV) for gr in grids]
+    cls_t, reg_t, ctr_t = bheads.single_image_targets(me, dummy, dummy, dummy, T(g["gt_" + tag]), T(g["gl_" + tag]),
+                                                      dict(img_shape=tuple(int(v) for v in g["img_" + tag])), None)
+    assert [tuple(c.shape) for c in cls_t] == [gr + (1,) for gr in grids]
+    cls = np.concatenate([N(c).reshape(-1) for c in cls_t])
+    reg = np.concatenate([N(r).reshape(-1, 4) for r in reg_t])
+    ctr = np.concatenate([N(c).reshape(-1) for c in ctr_t])
+    assert np.array_equal(cls, g["pcls_" + tag]) and np.array_equal(reg, g["preg_" + tag])
+    np.testing.assert_allclose(ctr, g["pctr_" + tag], rtol=1e-5, atol=1e-6)
+
+
+def test_fcos_plain_targets_batched_vs_oracle_ragged():
+    rng = np.random.default_rng(21)
+    strides = [8, 16, 32, 64, 128]
+    grids = [(-(-800 // s), -(-1344 // s)) for s in strides]
+    B, K = 3, 40
+    gt = np.zeros((B, 4, K), np.float32)
+    for b in range(B):
+        x1 = rng.uniform(0, 1000, K); y1 = rng.uniform(0, 600, K)
+        gt[b] = np.stack([x1, y1, np.minimum(x1 + rng.uniform(10, 700, K), 1332), np.minimum(y1 + rng.uniform(10, 500, K), 799)])
+    gl = rng.integers(1, 21, (B, K)).astype(np.int64)
+    cnt = np.array([K, 1, 7], np.int32)
+    img_hw = torch.tensor([[800.0, 1333.0]] * B, device=DEV)
+    cls, reg, ctr = bheads.fcos_targets(grids, strides, T(gt), T(cnt), T(gl), img_hw)
+    for b in range(B):
+        k = int(cnt[b])
+        c, r, t = oracle.fcos_targets(grids, strides, gt[b][:, :k], gl[b, :k], (800, 1333))
+        assert np.array_equal(N(cls[b]), c) and np.array_equal(N(reg[b]), r)
+        np.testing.assert_allclose(N(ctr[b]), t, rtol=1e-5, atol=1e-6)

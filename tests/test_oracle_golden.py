@@ -187,3 +187,13 @@ def test_rcnn_detect_oracle_vs_reference():
         assert np.array_equal(kl, g["det_label%d" % i])
         np.testing.assert_allclose(ks, g["det_score%d" % i], rtol=1e-5, atol=1e-7)      # expf: libm vs Sleef
         np.testing.assert_allclose(kb, g["det_bbox%d" % i], rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("tag", ["s", "f"])
+def test_fcos_plain_targets_oracle_vs_reference(tag):
+    """FCOSHead.single_image_targets (lib/heads/fcos_head.py:371-416)."""
+    g = load_golden("atss")
+    grids = [tuple(int(v) for v in x) for x in g["grids_" + tag]]
+    c, r, t = oracle.fcos_targets(grids, [8, 16, 32, 64, 128], g["gt_" + tag], g["gl_" + tag], tuple(g["img_" + tag][:2]))
+    assert np.array_equal(c, g["pcls_" + tag]) and np.array_equal(r, g["preg_" + tag])
+    np.testing.assert_allclose(t, g["pctr_" + tag], rtol=1e-5, atol=1e-6)
