@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -30
+B2D_ROI_IL=0 timeout 120 python scripts/bench_kernels.py il 2>&1 | tail -1
+B2D_ROI_IL=1 timeout 120 python scripts/bench_kernels.py il 2>&1 | tail -1
