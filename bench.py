@@ -153,6 +153,10 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # NCCL prints its version banner on stdout (NCCL_DEBUG=VERSION/WARN): keep fd 1 for the one JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _C.lib()
@@ -301,6 +305,8 @@ def run_b200(args):
             dt = time.perf_counter() - t0
             cpu = {"value": n / dt, "unit": "images/s", "cores": oracle.num_threads(), "kind": "port",
                    "sample": "image 0 of the batch, %d repetitions (%.1f s); C port of the reference path, OpenMP" % (n, dt)}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -309,7 +315,9 @@ def run_b200(args):
                                             "l2": "inputs per step (755 MB/GPU) exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "layout": "pinned host fp32 NCHW (reference layout) -> H2D (copy stream) -> NCHW->NHWC -> hot path -> D2H of proposals/targets"},
-            "gpu_launches": hp.launches * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}))
+            "gpu_launches": hp.launches * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}),
+            flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
