@@ -39,7 +39,18 @@ struct NmsSegs {
     uint64_t* mask;
     uint32_t* nz;                       // sym path: per row, bit w set iff word w of the row is non-zero (laid out like boxes)
     float thr, thr_lo, thr_hi;          // thr_lo/hi: decisive bounds that avoid the divide (see suppresses)
+    // fallback pass of the score-cut scheme (rpn_nms_launch): skip every image whose first pass already produced
+    // `need` survivors (chk = per-segment survivor counts of the first pass, L per image)
+    const int* chk; int need;
 };
+
+// true if the first (score-cut) pass of image b produced enough survivors: nothing left to do for this image
+__device__ __forceinline__ bool cut_pass_sufficient(const NmsSegs& s, int b) {
+    if (!s.chk) return false;
+    int tot = 0;
+    for (int l = 0; l < s.L; ++l) tot += s.chk[b * s.L + l];
+    return tot >= s.need;
+}
 
 // (double)iou > thr with iou = inter / ((aa + ab) - inter), evaluated exactly like the
 // reference.  The IEEE divide is only executed inside the narrow band |iou/thr - 1| <
@@ -91,15 +102,18 @@ __device__ __forceinline__ void tile_of(int t, int wmax, int& rb, int& cb) {
 }
 
 // ---- symmetric, sparse-output mask (n <= 2048) ------------------------------------------------
-__global__ void __launch_bounds__(64) k_nms_mask_sym(NmsSegs s, int wmax) {
-    __shared__ float4 s_row[64];
-    __shared__ float s_ra[64];
-    __shared__ uint32_t s_cw[2][64];
-    int seg, b, l;
-    seg_of(s.lv0, s.lvn, s.L, blockIdx.y, seg, b, l);
+struct MaskSmem {
+    float4 row[64];
+    float ra[64];
+    uint32_t cw[2][64];
+};
+
+// one 64 x 64 tile pair (rb <= cb) of segment (seg, b, l); all 64 threads of the CTA
+__device__ __forceinline__ void mask_tile(const NmsSegs& s, MaskSmem& sm, int seg, int b, int l, int rb, int cb) {
+    float4* s_row = sm.row;
+    float* s_ra = sm.ra;
+    uint32_t (*s_cw)[64] = sm.cw;
     const int n = s.counts[seg];
-    int rb, cb;
-    tile_of(blockIdx.x, wmax, rb, cb);
     const int r0 = rb * 64, c0 = cb * 64;
     if (r0 >= n || c0 >= n) return;
     const long long base = (long long)b * s.box_per_img + s.box_off[l];
@@ -165,12 +179,53 @@ __global__ void __launch_bounds__(64) k_nms_mask_sym(NmsSegs s, int wmax) {
     }
 }
 
+__global__ void __launch_bounds__(64) k_nms_mask_sym(NmsSegs s, int wmax) {
+    __shared__ MaskSmem sm;
+    int seg, b, l;
+    seg_of(s.lv0, s.lvn, s.L, blockIdx.y, seg, b, l);
+    int rb, cb;
+    tile_of(blockIdx.x, wmax, rb, cb);
+    mask_tile(s, sm, seg, b, l, rb, cb);
+}
+
+// Fallback pass of the score-cut scheme: a small persistent grid walks (segment, tile) work items and skips the
+// images whose first pass was sufficient -- when every image was (the normal case) the launch costs ~2 us instead
+// of the ~10 us that 21 000 immediately-exiting CTAs of the tile grid would.
+__global__ void __launch_bounds__(64) k_nms_mask_sym_fb(NmsSegs s, int wmax, int S) {
+    __shared__ MaskSmem sm;
+    __shared__ int s_todo[64];                          // per image: 1 if the first pass fell short
+    __shared__ int s_any;
+    const int nimg = S / s.lvn;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    for (int b = threadIdx.x; b < nimg; b += blockDim.x) {
+        const int todo = cut_pass_sufficient(s, b) ? 0 : 1;
+        if (b < 64) s_todo[b] = todo;
+        if (todo) s_any = 1;
+    }
+    __syncthreads();
+    if (!s_any) return;                                 // the normal case: nothing to do for any image
+    const int ntiles = wmax * (wmax + 1) / 2;
+    for (int sl = 0; sl < S; ++sl) {
+        int seg, b, l;
+        seg_of(s.lv0, s.lvn, s.L, sl, seg, b, l);
+        if (b < 64 ? !s_todo[b] : cut_pass_sufficient(s, b)) continue;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            int rb, cb;
+            tile_of(t, wmax, rb, cb);
+            mask_tile(s, sm, seg, b, l, rb, cb);
+            __syncthreads();                                                 // sm is reused by the next tile
+        }
+    }
+}
+
 struct ScanOut {
     // RPN pipeline: survivors are compacted (score order) from the sel_* arrays into kept_*
     const uint32_t* src_key; const int* src_idx; float4* dst_box; uint32_t* dst_key; int* dst_idx;
     // generic entry: int64 original indices
     int64_t* keep64; const int* sorted_idx; long long keep_ld;
     int* keep_count;
+    int* keep_count_aux;                // optional second copy of keep_count (first pass of the score-cut scheme)
 };
 
 __device__ __forceinline__ void emit_kept(const NmsSegs& s, const ScanOut& o, int seg, long long base, int r, int pos) {
@@ -193,6 +248,7 @@ __global__ void __launch_bounds__(kFpThreads) k_nms_scan_fp(NmsSegs s, int max_k
     __shared__ int s_prefix[65];
     int seg, b, l;
     seg_of(s.lv0, s.lvn, s.L, blockIdx.x, seg, b, l);
+    if (cut_pass_sufficient(s, b)) return;               // fallback pass: this image is already complete
     const int n = s.counts[seg];
     const long long base = (long long)b * s.box_per_img + s.box_off[l];
     const uint64_t* mask = s.mask + (long long)b * s.mask_per_img + s.mask_off[l];
@@ -280,7 +336,11 @@ __global__ void __launch_bounds__(kFpThreads) k_nms_scan_fp(NmsSegs s, int max_k
             if (max_keep <= 0 || pos < max_keep) emit_kept(s, o, seg, base, row, pos);
         }
     }
-    if (tid == 0) o.keep_count[seg] = (max_keep > 0 && s_prefix[64] > max_keep) ? max_keep : s_prefix[64];
+    if (tid == 0) {
+        const int kc = (max_keep > 0 && s_prefix[64] > max_keep) ? max_keep : s_prefix[64];
+        o.keep_count[seg] = kc;
+        if (o.keep_count_aux) o.keep_count_aux[seg] = kc;
+    }
 }
 
 // ---- dense upper-triangle mask + sequential scan (2048 < n <= 16384; generic entry) ------------
@@ -429,11 +489,13 @@ static void set_thr(NmsSegs& s, float thr) {
 }
 
 // mask + scan of S segments of at most n_max boxes; s.nz must be zeroed by the caller (sym path)
-static void launch_mask_scan(const NmsSegs& s, int S, int n_max, int max_keep, const ScanOut& o, cudaStream_t st) {
+static void launch_mask_scan(const NmsSegs& s, int S, int n_max, int max_keep, const ScanOut& o, cudaStream_t st,
+                             bool fallback = false) {
     const int wmax = (n_max + 63) / 64 > 0 ? (n_max + 63) / 64 : 1;
     dim3 grid(wmax * (wmax + 1) / 2, S);
     if (n_max <= kFpThreads * kFpRows) {
-        k_nms_mask_sym<<<grid, 64, 0, st>>>(s, wmax);
+        if (fallback) k_nms_mask_sym_fb<<<148 * 4, 64, 0, st>>>(s, wmax, S);
+        else k_nms_mask_sym<<<grid, 64, 0, st>>>(s, wmax);
         k_nms_scan_fp<<<S, kFpThreads, 0, st>>>(s, max_keep, o);
     } else {
         k_nms_mask_dense<<<grid, 64, 0, st>>>(s, wmax);
@@ -480,6 +542,8 @@ int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st) {
         wmax = max(wmax, s.wp[l]);
     }
     s.boxes = p.sel_box; s.counts = p.sel_count; s.mask = p.mask; s.nz = p.nz;   // nz zeroed with the workspace head
+    if (p.nms_phase == 1) s.counts = p.n_cut;
+    if (p.nms_phase == 2) { s.chk = p.keep1; s.need = p.max_num; }
     set_thr(s, p.nms_thr);
     const int S = p.B * p.lvn;
     int n_max = 1;
@@ -489,8 +553,126 @@ int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st) {
     memset(&o, 0, sizeof(o));
     o.src_key = p.sel_key; o.src_idx = p.sel_idx; o.dst_box = p.kept_box; o.dst_key = p.kept_key; o.dst_idx = p.kept_idx;
     o.keep_count = p.keep_count;
-    launch_mask_scan(s, S, n_max, p.post_nms, o, st);
+    if (p.nms_phase == 1) o.keep_count_aux = p.keep1;
+    launch_mask_scan(s, S, n_max, p.post_nms, o, st, p.nms_phase == 2);
     return check_launch("rpn_nms");
+}
+
+// ---- score cut (exact early termination of the per-level greedy NMS under a global top-k) ---------------------
+// RPNHead.predict_single_image keeps, after the per-level NMS, only the max_num best survivors of all levels
+// (lib/heads/rpn_head.py:112-118).  Whether a box survives depends only on HIGHER-scored boxes of its level, so the
+// NMS of the M globally best selected boxes (all levels, M >= max_num) already yields the final result whenever it
+// leaves >= max_num survivors: every box outside the M has a lower score than all of them.  k_nms_cut finds the key
+// of the M-th best box of an image to 16 bits (radix select over the <= 5 x 2048 keys in shared memory) and the
+// number of boxes per level at or above it (ties included); pass 1 runs mask + scan on those prefixes only, pass 2
+// (the full NMS) runs only for images whose pass 1 fell short.
+__global__ void __launch_bounds__(1024) k_nms_cut(RpnLaunch p, int M) {
+    extern __shared__ uint32_t s_keys[];                 // sel_per_img entries, level l at sel_off[l]
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_prefix, s_need;
+    __shared__ int s_cnt[kMaxLevels];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int total = 0;
+    {   // all levels' keys requested before the first use (<= 2 per level and thread: kcap <= 2048)
+        uint32_t v[kMaxLevels][2];
+        int nl[kMaxLevels];
+#pragma unroll
+        for (int l = 0; l < kMaxLevels; ++l) {
+            nl[l] = l < p.L ? p.sel_count[b * p.L + l] : 0;
+            total += nl[l];
+        }
+#pragma unroll
+        for (int l = 0; l < kMaxLevels; ++l) {
+            const uint32_t* src = p.sel_key + (long long)b * p.sel_per_img + p.sel_off[l < p.L ? l : 0];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int i = tid + r * 1024;
+                v[l][r] = i < nl[l] ? src[i] : 0u;
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < kMaxLevels; ++l)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int i = tid + r * 1024;
+                if (i < nl[l]) s_keys[p.sel_off[l] + i] = v[l][r];
+            }
+    }
+    if (total <= M) {                                    // uniform over the block
+        if (tid < p.L) p.n_cut[b * p.L + tid] = p.sel_count[b * p.L + tid];
+        return;
+    }
+    if (tid == 0) { s_prefix = 0u; s_need = (uint32_t)M; }
+    __syncthreads();
+    // Two radix passes (the 16 leading key bits) are enough: any threshold gives an exact result, a coarser one
+    // only admits a few more boxes than M (all keys whose leading bits tie with the M-th best).
+    for (int shift = 24; shift >= 16; shift -= 8) {
+        for (int t = tid; t < 256; t += blockDim.x) s_hist[t] = 0u;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        const uint32_t himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+        for (int l = 0; l < p.L; ++l) {
+            const int n = p.sel_count[b * p.L + l];
+            for (int i = tid; i < n; i += blockDim.x) {
+                const uint32_t k = s_keys[p.sel_off[l] + i];
+                // warp-aggregated: the keys of a score-sorted list share their leading bytes, a plain shared-memory
+                // atomic per key serialises on one or two bins (25 us for 8819 keys, timeline r1)
+                const bool in = (k & himask) == prefix;
+                const uint32_t bin = in ? ((k >> shift) & 255u) : 256u;
+                const unsigned peers = __match_any_sync(__activemask(), bin);
+                if (in && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (uint32_t)__popc(peers));
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {                                  // digit = largest d with sum_{bin >= d} hist >= need (warp suffix scan)
+            uint32_t loc[8], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { loc[q] = s_hist[tid * 8 + q]; sum += loc[q]; }
+            uint32_t v = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_down_sync(0xffffffffu, v, o);
+                if (tid + o < 32) v += t;
+            }
+            const uint32_t above = v - sum, need = s_need;
+            if (above < need && above + sum >= need) {
+                uint32_t run = above;
+#pragma unroll
+                for (int q = 7; q >= 0; --q) {
+                    if (run + loc[q] >= need) {
+                        s_need = need - run;
+                        s_prefix = prefix | ((uint32_t)(tid * 8 + q) << shift);
+                        break;
+                    }
+                    run += loc[q];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t tau = s_prefix;                       // leading 16 bits of the key of the M-th best box, rest 0
+    if (tid < kMaxLevels) s_cnt[tid] = 0;
+    __syncthreads();
+    for (int l = 0; l < p.L; ++l) {
+        const int n = p.sel_count[b * p.L + l];
+        int c = 0;
+        for (int i = tid; i < n; i += blockDim.x) c += s_keys[p.sel_off[l] + i] >= tau;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if ((tid & 31) == 0 && c) atomicAdd(&s_cnt[l], c);
+    }
+    __syncthreads();
+    if (tid < p.L) p.n_cut[b * p.L + tid] = s_cnt[tid];
+}
+
+int rpn_nms_cut_launch(const RpnLaunch& p, int M, cudaStream_t st) {
+    const size_t smem = (size_t)p.sel_per_img * 4;
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaFuncSetAttribute(k_nms_cut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = smem;
+    }
+    k_nms_cut<<<p.B, 1024, smem, st>>>(p, M);
+    return check_launch("rpn_nms_cut");
 }
 
 }  // namespace b2d

@@ -27,6 +27,8 @@ struct RpnLaunch {
     float nms_thr, min_size, ms[8];
     // workspace
     uint32_t* hist; int* cand_count; int* cand2_count; int* sel_count; int* keep_count; int* thr_bin;
+    int* n_cut; int* keep1;             // score-cut NMS: boxes per segment in the first pass, its survivor counts
+    int nms_phase;                      // 0: plain NMS of all selected boxes; 1: score-cut pass; 2: conditional full pass
     uint32_t* nz;                       // NMS: per selected box, bitmap of its non-zero mask words (nms.cu)
     size_t zero_bytes;
     uint64_t* cand; uint64_t* cand2;
@@ -44,5 +46,7 @@ __device__ __forceinline__ void seg_of(int lv0, int lvn, int L, int s, int& seg,
 
 // nms.cu: suppression mask + scan over the sel_* arrays of the launch's segments
 int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st);
+// nms.cu: per image the key of the M-th best selected box over all levels -> n_cut[segment]
+int rpn_nms_cut_launch(const RpnLaunch& p, int M, cudaStream_t st);
 
 }  // namespace b2d

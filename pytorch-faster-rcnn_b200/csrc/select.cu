@@ -656,6 +656,8 @@ bool rpn_plan(RpnLaunch& p, const b2d_pyramid* pyr, int B, const b2d_rpn_cfg* cf
     p.sel_count = (int*)carve((size_t)S * 4);
     p.keep_count = (int*)carve((size_t)S * 4);
     p.thr_bin = (int*)carve((size_t)S * 4);
+    p.n_cut = (int*)carve((size_t)S * 4);
+    p.keep1 = (int*)carve((size_t)S * 4);
     p.nz = (uint32_t*)carve(cfg->do_nms ? (size_t)B * p.sel_per_img * 4 : 0);
     p.zero_bytes = o;                                   // everything above is zeroed per call
     p.cand = (uint64_t*)carve((size_t)B * pyr->total * 8);
@@ -680,7 +682,7 @@ namespace {
 // work that is ordered after / before the caller's stream through the fork / join events).
 struct LevelStreams {
     cudaStream_t s[kMaxLevels];
-    cudaEvent_t fork, join[kMaxLevels];
+    cudaEvent_t fork, join[kMaxLevels], fork2, join2[kMaxLevels];
     bool ok;
 };
 
@@ -705,8 +707,10 @@ LevelStreams* level_streams(cudaStream_t caller) {
         for (int l = 0; l < kMaxLevels; ++l) {
             t.ok = t.ok && cudaStreamCreateWithPriority(&t.s[l], cudaStreamNonBlocking, pr) == cudaSuccess;
             t.ok = t.ok && cudaEventCreateWithFlags(&t.join[l], cudaEventDisableTiming) == cudaSuccess;
+            t.ok = t.ok && cudaEventCreateWithFlags(&t.join2[l], cudaEventDisableTiming) == cudaSuccess;
         }
         t.ok = t.ok && cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) == cudaSuccess;
+        t.ok = t.ok && cudaEventCreateWithFlags(&t.fork2, cudaEventDisableTiming) == cudaSuccess;
         if (!t.ok) cudaGetLastError();
     }
     return t.ok ? &t : nullptr;
@@ -756,6 +760,19 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
     { const char* e = getenv("B2D_RPN_CHAINS"); const int want = e ? atoi(e) : 1; if (want && p.L > 1) nchains = p.L; }
     LevelStreams* ls = nchains > 1 ? level_streams(st) : nullptr;
     if (nchains > 1 && !ls) nchains = 1;
+    // Score-cut NMS (nms.cu, k_nms_cut): pass 1 on the M = cut * max_num globally best boxes, full pass only for
+    // images that need it.  B2D_NMS_CUT = factor (default 1.5), 0 disables.
+    int cut_m = 0;
+    {
+        const char* e = getenv("B2D_NMS_CUT");
+        const double f = e ? atof(e) : 1.5;
+        int kmax = 0;
+        long long ksum = 0;
+        for (int l = 0; l < p.L; ++l) { kmax = max(kmax, p.kcap[l]); ksum += p.kcap[l]; }
+        if (f > 0.0 && p.do_nms && p.max_num > 0 && nchains > 1 && kmax <= 2048 && (double)ksum > f * p.max_num &&
+            p.sel_per_img * 4 <= 200 * 1024)
+            cut_m = (int)(f * p.max_num);
+    }
     if (nchains > 1) cudaEventRecord(ls->fork, st);
     for (int c = 0; c < nchains; ++c) {
         RpnLaunch q = p;
@@ -776,11 +793,26 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
         }
         k_select<<<S, kSelThreads, kSortCap * 8, cs>>>(q);
         if (int rc = check_launch("rpn_proposals/k_select")) return rc;
-        if (q.do_nms) {
+        if (q.do_nms && !cut_m) {
             int rc = rpn_nms_launch(q, cs);
             if (rc != B2D_OK) return rc;
         }
         if (nchains > 1) { cudaEventRecord(ls->join[c], cs); cudaStreamWaitEvent(st, ls->join[c], 0); }
+    }
+    if (cut_m) {
+        if (int rc = rpn_nms_cut_launch(p, cut_m, st)) return rc;
+        cudaEventRecord(ls->fork2, st);
+        for (int c = 0; c < nchains; ++c) {                  // pass 1: per-level chains on the cut prefixes
+            RpnLaunch q = p;
+            q.lv0 = c; q.lvn = 1; q.nms_phase = 1;
+            cudaStreamWaitEvent(ls->s[c], ls->fork2, 0);
+            if (int rc = rpn_nms_launch(q, ls->s[c])) return rc;
+            cudaEventRecord(ls->join2[c], ls->s[c]);
+            cudaStreamWaitEvent(st, ls->join2[c], 0);
+        }
+        RpnLaunch q = p;                                     // pass 2: all levels, skipped per image when pass 1 sufficed
+        q.nms_phase = 2;
+        if (int rc = rpn_nms_launch(q, st)) return rc;
     }
     bool sorted_lists = true;                            // see k_merge: unsorted only without NMS and without top-k
     int cat = 0;

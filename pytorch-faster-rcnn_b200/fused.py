@@ -87,6 +87,10 @@ class RpnProposals(object):
         chains = len(pyramid.level_sizes) > 1 and os.environ.get("B2D_RPN_CHAINS", "1") != "0"
         per_level = [(2 if 0 < c.pre_nms < n else 0) + 1 + (2 if do_nms else 0) for n in pyramid.level_sizes]
         self.launches = (sum(per_level) if chains else max(per_level)) + 1
+        kcaps = [(c.pre_nms if 0 < c.pre_nms < n else n) for n in pyramid.level_sizes]
+        cut = float(os.environ.get("B2D_NMS_CUT", "1.5"))
+        if chains and do_nms and c.max_num > 0 and cut > 0 and max(kcaps) <= 2048 and sum(kcaps) > cut * c.max_num:
+            self.launches += 3                       # score-cut NMS: k_nms_cut + the conditional full pass (mask, scan)
 
     def slice(self, b0, b1):
         v = _batch_view(self, b0, b1)

@@ -235,6 +235,35 @@ def test_rpn_head_predict_single_image_method_form_vs_reference():
         np.testing.assert_allclose(N(b), g["props%d" % i], rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("cut", ["0", "1.0", "1.3", "2"])
+def test_rpn_score_cut_nms_is_exact(cut, monkeypatch):
+    """Score-cut NMS (csrc/nms.cu k_nms_cut): pass 1 on the cut * max_num best boxes + conditional full pass must
+    give the selection of the plain per-level NMS for every cut factor (1.0: pass 1 always falls short -> the
+    fallback pass does the work; 2: the default; 0: disabled), on clustered boxes (low survival) and at config-2
+    sizes, against the oracle's provenance (level, index) of every proposal."""
+    monkeypatch.setenv("B2D_NMS_CUT", cut)
+    rng = np.random.default_rng(17)
+    grids = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+    strides = (4, 8, 16, 32, 64)
+    pyr = fused.AnchorPyramid(strides, grids)
+    cfg = dict(pre_nms=1000, post_nms=1000, max_num=1000, nms_iou=0.7, min_bbox_size=0)
+    B = 2
+    cls = [rng.normal(0, 1, (B, 3) + g).astype(np.float32) for g in grids]
+    reg = [rng.normal(0, 0.15, (B, 12) + g).astype(np.float32) for g in grids]         # small deltas: heavy overlap
+    rp = fused.RpnProposals(pyr, B, cfg, [0, 0, 0, 0], [1, 1, 1, 1], DEV)
+    img_hw = torch.tensor([[400.0, 666.0]] * B, device=DEV)
+    props, scores, count = rp([T(c) for c in cls], [T(r) for r in reg], img_hw)
+    torch.cuda.synchronize()
+    anc = [oracle.anchor_grid(s, gr, scales=[8]).reshape(4, -1) for s, gr in zip(strides, grids)]
+    offs = np.cumsum([0] + [a.shape[1] for a in anc])
+    for b in range(B):
+        _, _, lv, ix = oracle.rpn_proposals([c[b].reshape(-1) for c in cls], [r[b].reshape(4, -1) for r in reg], anc, cfg,
+                                            [0, 0, 0, 0], [1, 1, 1, 1], (400, 666))
+        n = int(count[b])
+        assert n == lv.shape[0]
+        assert np.array_equal(N(rp.prov[b, :n]), offs[lv] + ix), cut
+
+
 def test_rpn_proposals_selection_bit_exact_vs_oracle():
     g = load_golden("rpn")
     grids = [(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)]
