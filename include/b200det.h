@@ -178,6 +178,27 @@ B2D_API int b2d_nms(int64_t* keep, int* keep_count, const float* boxes, const fl
             const int* counts, long long n, int S, float thr_f, int max_keep, int presorted, void* workspace,
             size_t ws_bytes, void* stream);
 
+/* ---- loss reductions adjacent to the path, fused with the target gather.
+ * AnchorHead.calc_loss for a head without sampler (lib/heads/anchor_head.py:113-139):
+ * sigmoid_focal_loss (lib/losses.py:33-61) over every non-ignored anchor and
+ * smooth_l1_loss_v2 (:77-83) over the positives, read straight from the head maps
+ * (cls_ptrs_host[l] -> [B, A*C, H, W], reg_ptrs_host[l] -> [B, 4A, H, W]) with the class
+ * target / encoded deltas rebuilt from the assignment labels (int64 [B][label_ld], gt
+ * index + 1 / 0 / -1) -- no [C, s] gathers.  out3 = {sum focal, sum smooth-L1, #pos}
+ * (sums, not yet divided by the averaging factor).  _bwd writes scale2[0] * d(sum focal)/d(cls)
+ * and scale2[1] * d(sum smooth-L1)/d(reg) in the maps' layout (scale2: device float[2]). */
+B2D_API size_t b2d_anchor_loss_workspace_bytes(const b2d_pyramid* pyr_host, int B);
+B2D_API int b2d_anchor_loss_fwd(float* out3, const void* const* cls_ptrs_host, const void* const* reg_ptrs_host,
+                        const b2d_pyramid* pyr_host, const int64_t* labels, long long label_ld, const float* gt, int gt_ld,
+                        const int64_t* gt_label, int cls_channels, float alpha, float gamma, float beta,
+                        const float* means_host, const float* stds_host, int B, void* workspace, size_t ws_bytes,
+                        void* stream);
+B2D_API int b2d_anchor_loss_bwd(void* const* dcls_ptrs_host, void* const* dreg_ptrs_host, const float* scale2,
+                        const void* const* cls_ptrs_host, const void* const* reg_ptrs_host, const b2d_pyramid* pyr_host,
+                        const int64_t* labels, long long label_ld, const float* gt, int gt_ld, const int64_t* gt_label,
+                        int cls_channels, float alpha, float gamma, float beta, const float* means_host,
+                        const float* stds_host, int B, void* stream);
+
 /* ---- plain FCOS target assignment, FCOSHead.single_image_targets
  * (lib/heads/fcos_head.py:371-416): per cell the smallest-area GT whose ltrb are all > 0 and
  * whose max(ltrb) lies in [level_thr[l], level_thr[l+1]) (level_scale_thr, :167).  Same

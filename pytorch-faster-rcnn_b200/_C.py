@@ -58,6 +58,10 @@ _SIGS = {
     "b2d_sample_labels": [_P, _P, _P, c_ll, _P, _P, c_ll, _P, _P, c_int, c_int, c_int, c_int, c_ull, _P],
     "b2d_roi_targets_fused": [_P, _P, c_ll, _P, c_ll, _P, c_ll, _P, c_int, _P, _P, c_int, c_float, c_float, c_float,
                               c_int, _P, _P, c_int, _P, _P, c_int, c_int, c_ull, _P, _P, _P, _P, _P, _P, _P, _P],
+    "b2d_anchor_loss_fwd": [_P, _P, _P, _P, _P, c_ll, _P, c_int, _P, c_int, c_float, c_float, c_float, _P, _P, c_int, _P,
+                            c_size_t, _P],
+    "b2d_anchor_loss_bwd": [_P, _P, _P, _P, _P, _P, _P, c_ll, _P, c_int, _P, c_int, c_float, c_float, c_float, _P, _P,
+                            c_int, _P],
     "b2d_fcos_targets": [_P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int, _P],
     "b2d_rcnn_detect": [_P, _P, _P, _P, _P, c_ll, _P, c_ll, _P, _P, c_int, c_int, _P, _P, _P, c_float, c_float, c_int,
                         c_int, c_int, c_int, _P, _P, c_size_t, _P],
@@ -91,6 +95,7 @@ _SIZE_FNS = {
     "b2d_roi_align_bwd_workspace_bytes": [c_ll, c_int, _P],
     "b2d_atss_workspace_bytes": [_P, c_int],
     "b2d_rcnn_detect_workspace_bytes": [c_int, c_int],
+    "b2d_anchor_loss_workspace_bytes": [_P, c_int],
 }
 EXPORTS = sorted(list(_SIGS) + list(_SIZE_FNS) + ["b2d_last_error_string", "b2d_version"])
 

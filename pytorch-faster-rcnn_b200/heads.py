@@ -267,3 +267,61 @@ def single_image_targets(self, cls_outs, reg_outs, ctr_outs, gt_bboxes, gt_label
         ctr_t.append(ctr[0, off:off + n].view(h, w, 1))
         off += n
     return cls_t, reg_t, ctr_t
+
+
+# ---------------------------------------------------------------------------------- SURVEY 8(f-2)
+class _AnchorLossFn(torch.autograd.Function):
+    """{sum focal, sum smooth-L1, #pos} of an anchor head without sampler, differentiable in the head maps."""
+
+    @staticmethod
+    def forward(ctx, pyr, labels, gt, gt_label, meta, n, *maps):
+        cls, reg = maps[:n], maps[n:]
+        C, alpha, gamma, beta, means, stds = meta
+        B, dev = int(cls[0].shape[0]), cls[0].device
+        out = torch.empty(3, dtype=torch.float32, device=dev)
+        ws = utils._workspace(_C.lib().b2d_anchor_loss_workspace_bytes(ctypes.byref(pyr), B), dev, "anchor_loss")
+        _C.call("b2d_anchor_loss_fwd", _C.ptr(out), _ptrs(cls), _ptrs(reg), ctypes.byref(pyr), _C.ptr(labels),
+                int(labels.shape[1]), _C.ptr(gt), int(gt.shape[2]), _C.ptr(gt_label), C, alpha, gamma, beta, means, stds, B,
+                _C.ptr(ws), ws.numel(), _C.stream())
+        ctx.save_for_backward(labels, gt, gt_label, *maps)
+        ctx.misc = (pyr, meta, n)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        labels, gt, gt_label = ctx.saved_tensors[:3]
+        maps = ctx.saved_tensors[3:]
+        pyr, (C, alpha, gamma, beta, means, stds), n = ctx.misc
+        cls, reg = maps[:n], maps[n:]
+        scale = gout[:2].detach().to(torch.float32).contiguous()
+        dcls, dreg = [torch.empty_like(c) for c in cls], [torch.empty_like(r) for r in reg]
+        _C.call("b2d_anchor_loss_bwd", _ptrs(dcls), _ptrs(dreg), _C.ptr(scale), _ptrs(cls), _ptrs(reg), ctypes.byref(pyr),
+                _C.ptr(labels), int(labels.shape[1]), _C.ptr(gt), int(gt.shape[2]), _C.ptr(gt_label), C, alpha, gamma, beta,
+                means, stds, int(cls[0].shape[0]), _C.stream())
+        return (None,) * 6 + tuple(dcls) + tuple(dreg)
+
+
+def anchor_head_loss_sums(cls_outs, reg_outs, labels, pyramid, gt, gt_label, target_means=None, target_stds=None,
+                          alpha=0.25, gamma=2.0, beta=1.0 / 9.0):
+    """Fused AnchorHead.calc_loss pieces for a head without sampler (lib/heads/anchor_head.py:113-139;
+    sigmoid_focal_loss lib/losses.py:33-61, smooth_l1_loss_v2 :77-83): cls_outs[l] [B, A*C, H, W] logits,
+    reg_outs[l] [B, 4A, H, W], labels int64 [B, total] from the batched assignment (gt index + 1 / 0 / -1),
+    pyramid = fused.AnchorPyramid, gt [B,4,K], gt_label int64 [B,K] -> fp32[3] = {sum focal, sum smooth-L1,
+    #pos}, differentiable w.r.t. the maps.  No gathers, no host sync."""
+    _C.require_cuda(*cls_outs)
+    cls = [_C.f32c(x) for x in cls_outs]
+    reg = [_C.f32c(x) for x in reg_outs]
+    A = int(pyramid.num_anchors)
+    C = int(cls[0].shape[1]) // A
+    meta = (C, float(alpha), float(gamma), float(beta), _C.host_f4(target_means, [0, 0, 0, 0]),
+            _C.host_f4(target_stds, [1, 1, 1, 1]))
+    return _AnchorLossFn.apply(pyramid.c, labels.contiguous(), _C.f32c(gt), gt_label.to(torch.int64).contiguous(), meta,
+                               len(cls), *cls, *reg)
+
+
+def anchor_head_calc_loss(cls_outs, reg_outs, labels, pyramid, gt, gt_label, target_means=None, target_stds=None,
+                          alpha=0.25, gamma=2.0, beta=1.0 / 9.0, cls_weight=1.0, reg_weight=1.0):
+    """(cls_loss, reg_loss) of AnchorHead.calc_loss without sampler: both sums divided by #pos
+    (`avg_factor = pos_tars.sum()`, lib/heads/anchor_head.py:127-128)."""
+    s = anchor_head_loss_sums(cls_outs, reg_outs, labels, pyramid, gt, gt_label, target_means, target_stds, alpha, gamma, beta)
+    return cls_weight * s[0] / s[2], reg_weight * s[1] / s[2]

@@ -456,10 +456,46 @@ def g_heads():
     save("heads", **out)
 
 
+def g_loss():
+    """AnchorHead.calc_loss pieces without sampler (RetinaNet form): anchor_target (lib/anchor.py:11-76)
+    -> sigmoid_focal_loss (lib/losses.py:33-61) + smooth_l1_loss_v2 (:77-83), with torch autograd gradients
+    w.r.t. the head maps."""
+    from lib import losses as rlosses
+    rng = np.random.default_rng(SEED + 21)
+    strides, grids = [8, 16, 32], [(20, 28), (10, 14), (5, 7)]
+    scales, ratios, C, K = [4.0, 4.0 * 2 ** (1 / 3), 4.0 * 2 ** (2 / 3)], [0.5, 1.0, 2.0], 5, 6
+    A = 9
+    H, W = 160, 224
+    gt, _ = synth_gt(rng, K, H, W)
+    gl = rng.integers(1, C + 1, K).astype(np.int64)
+    creators = [ranchor.AnchorCreator(base=s, scales=scales, aspect_ratios=ratios) for s in strides]
+    anchors = torch.cat([creators[i](strides[i], grids[i]).view(4, -1) for i in range(3)], 1)
+    cls = [torch.from_numpy(rng.normal(-1.5, 1.5, (A * C,) + g).astype(np.float32)).requires_grad_(True) for g in grids]
+    reg = [torch.from_numpy(rng.normal(0, 0.5, (A * 4,) + g).astype(np.float32)).requires_grad_(True) for g in grids]
+    cls_out = torch.cat([c.view(C, -1) for c in cls], 1)
+    reg_out = torch.cat([r.view(4, -1) for r in reg], 1)
+    in_mask = torch.ones(anchors.shape[1], dtype=torch.bool)
+    means, stds = [0.0, 0.0, 0.0, 0.0], [1.0, 1.0, 1.0, 1.0]
+    tar_cls_out, tar_reg_out, tar_labels, _, _, tar_param = ranchor.anchor_target(
+        cls_out, reg_out, C, anchors, in_mask, T(gt), T(gl),
+        dict(type="MaxIoUAssigner", pos_iou=0.5, neg_iou=0.4, min_pos_iou=0.0), None, means, stds)
+    pos = tar_labels > 0
+    focal = rlosses.sigmoid_focal_loss(tar_cls_out.t(), tar_labels, alpha=0.25, gamma=2.0)
+    sl1 = rlosses.smooth_l1_loss_v2(tar_reg_out[:, pos], tar_param[:, pos], 1.0 / 9.0)
+    (2.0 * focal + 3.0 * sl1).backward()
+    out = dict(gt=gt, gl=gl, focal=focal.detach(), sl1=sl1.detach(), npos=np.array(int(pos.sum())),
+               scales=np.array(scales), tar_labels=tar_labels)
+    for l in range(3):
+        out["cls%d" % l], out["reg%d" % l] = cls[l].detach(), reg[l].detach()
+        out["dcls%d" % l], out["dreg%d" % l] = cls[l].grad, reg[l].grad
+    print("loss golden: focal %.4f sl1 %.4f npos %d kept %d" % (float(focal), float(sl1), int(pos.sum()), int(tar_labels.numel())))
+    save("loss", **out)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     gens = dict(anchors=g_anchors, iou_assign=g_iou_assign, deltas=g_deltas, nms=g_nms, rpn=g_rpn, roi=g_roi,
-                targets=g_targets, atss=g_atss, heads=g_heads)
+                targets=g_targets, atss=g_atss, heads=g_heads, loss=g_loss)
     for k, fn in gens.items():
         if not only or k in only:
             fn()

@@ -276,3 +276,61 @@ def test_fcos_plain_targets_batched_vs_oracle_ragged():
         c, r, t = oracle.fcos_targets(grids, strides, gt[b][:, :k], gl[b, :k], (800, 1333))
         assert np.array_equal(N(cls[b]), c) and np.array_equal(N(reg[b]), r)
         np.testing.assert_allclose(N(ctr[b]), t, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ SURVEY 8(f-2)
+def test_anchor_head_loss_fused_vs_reference():
+    """b2d_anchor_loss_fwd / _bwd against the reference's losses + torch autograd (golden `loss`)."""
+    g = load_golden("loss")
+    strides, grids = [8, 16, 32], [(20, 28), (10, 14), (5, 7)]
+    scales = [float(v) for v in g["scales"]]
+    pyr = fused.AnchorPyramid(strides, grids, scales=scales)
+    anc = np.concatenate([oracle.anchor_grid(s, gr, scales=scales).reshape(4, -1) for s, gr in zip(strides, grids)], 1)
+    lab, _ = oracle.assign_max_iou(anc, g["gt"], 0.5, 0.4, 0.0)
+    cls = [T(g["cls%d" % l][None]).requires_grad_(True) for l in range(3)]
+    reg = [T(g["reg%d" % l][None]).requires_grad_(True) for l in range(3)]
+    s = bheads.anchor_head_loss_sums(cls, reg, T(lab[None]), pyr, T(g["gt"][None]), T(g["gl"][None]))
+    (2.0 * s[0] + 3.0 * s[1]).backward()
+    assert int(s[2]) == int(g["npos"])
+    np.testing.assert_allclose(float(s[0].detach()), float(g["focal"]), rtol=1e-5)
+    np.testing.assert_allclose(float(s[1].detach()), float(g["sl1"]), rtol=1e-5)
+    for l in range(3):
+        np.testing.assert_allclose(N(cls[l].grad[0]), g["dcls%d" % l], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(N(reg[l].grad[0]), g["dreg%d" % l], rtol=1e-4, atol=1e-6)
+
+
+def test_anchor_head_loss_fused_config4_size_vs_oracle():
+    """RetinaNet sizes: 201 600 anchors x 20 classes per image, B = 2, labels from the GPU's own dense assignment."""
+    rng = np.random.default_rng(41)
+    strides = [8, 16, 32, 64, 128]
+    grids = [(-(-800 // s), -(-1344 // s)) for s in strides]
+    scales = [4.0, 4.0 * 2 ** (1 / 3), 4.0 * 2 ** (2 / 3)]
+    pyr = fused.AnchorPyramid(strides, grids, scales=scales)
+    B, K, C, A = 2, 12, 20, 9
+    gt = np.zeros((B, 4, K), np.float32)
+    for b in range(B):
+        x1 = rng.uniform(0, 1000, K); y1 = rng.uniform(0, 600, K)
+        gt[b] = np.stack([x1, y1, np.minimum(x1 + rng.uniform(20, 500, K), 1332), np.minimum(y1 + rng.uniform(20, 320, K), 799)])
+    gl = rng.integers(1, C + 1, (B, K)).astype(np.int64)
+    cls_np = [rng.normal(-2, 1.5, (B, A * C) + g).astype(np.float32) for g in grids]
+    reg_np = [rng.normal(0, 0.4, (B, A * 4) + g).astype(np.float32) for g in grids]
+    anc = np.concatenate([oracle.anchor_grid(s, gr, scales=scales).reshape(4, -1) for s, gr in zip(strides, grids)], 1)
+    assert anc.shape[1] == 201600
+    labs = np.stack([oracle.assign_max_iou(anc, gt[b], 0.5, 0.4, 0.0)[0] for b in range(B)])
+    cls = [T(c).requires_grad_(True) for c in cls_np]
+    reg = [T(r).requires_grad_(True) for r in reg_np]
+    closs, rloss = bheads.anchor_head_calc_loss(cls, reg, T(labs), pyr, T(gt), T(gl), beta=1.0 / 9.0)
+    (closs + rloss).backward()
+    f = s1 = 0.0
+    npos, dcs, drs = 0, [], []
+    for b in range(B):
+        fb, sb, nb, dc, dr = oracle.anchor_head_loss([c[b] for c in cls_np], [r[b] for r in reg_np], labs[b], anc, gt[b], gl[b])
+        f += fb; s1 += sb; npos += nb; dcs.append(dc); drs.append(dr)
+    assert npos > 50
+    np.testing.assert_allclose(float(closs.detach()), f / npos, rtol=1e-5)
+    np.testing.assert_allclose(float(rloss.detach()), s1 / npos, rtol=1e-5)
+    for l in range(5):
+        want_c = np.stack([dcs[b][l] for b in range(B)]) / npos
+        want_r = np.stack([drs[b][l] for b in range(B)]) / npos
+        np.testing.assert_allclose(N(cls[l].grad), want_c, rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(N(reg[l].grad), want_r, rtol=1e-4, atol=1e-7)

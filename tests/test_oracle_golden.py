@@ -197,3 +197,19 @@ def test_fcos_plain_targets_oracle_vs_reference(tag):
     c, r, t = oracle.fcos_targets(grids, [8, 16, 32, 64, 128], g["gt_" + tag], g["gl_" + tag], tuple(g["img_" + tag][:2]))
     assert np.array_equal(c, g["pcls_" + tag]) and np.array_equal(r, g["preg_" + tag])
     np.testing.assert_allclose(t, g["pctr_" + tag], rtol=1e-5, atol=1e-6)
+
+
+def test_anchor_head_loss_oracle_vs_reference():
+    """focal + smooth-L1 sums and their autograd gradients (lib/losses.py:33-61, 77-83)."""
+    g = load_golden("loss")
+    strides, grids = [8, 16, 32], [(20, 28), (10, 14), (5, 7)]
+    anc = np.concatenate([oracle.anchor_grid(s, gr, scales=list(g["scales"])).reshape(4, -1) for s, gr in zip(strides, grids)], 1)
+    lab, _ = oracle.assign_max_iou(anc, g["gt"], 0.5, 0.4, 0.0)
+    f, s1, npos, dc, dr = oracle.anchor_head_loss([g["cls%d" % l] for l in range(3)], [g["reg%d" % l] for l in range(3)], lab, anc,
+                                                  g["gt"], g["gl"])
+    assert npos == int(g["npos"])
+    np.testing.assert_allclose(f, float(g["focal"]), rtol=1e-6)
+    np.testing.assert_allclose(s1, float(g["sl1"]), rtol=1e-6)
+    for l in range(3):                                   # the golden backward was (2 focal + 3 sl1).backward()
+        np.testing.assert_allclose(2 * dc[l], g["dcls%d" % l], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(3 * dr[l], g["dreg%d" % l], rtol=1e-5, atol=1e-6)
