@@ -289,6 +289,8 @@ def run_b200(args):
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic(dom),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": stage_bytes[dom],
                     "stage_ms": stage_ms, "stage_algorithmic_bytes": stage_bytes,
+                    "stage_ms_note": "eager per-stage CUDA-event times; multi-kernel stages (proposals: 34 launches) are "
+                                     "host-launch-bound there, the step time above is the CUDA-graph replay",
                     "path_frac": (path_bytes / ((ms / args.steps) / 1e3) / 1e9) / peak}
         cpu = None
         if world == 1 and not args.no_cpu:
