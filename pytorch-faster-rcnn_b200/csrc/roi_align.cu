@@ -300,16 +300,19 @@ __global__ void __launch_bounds__(NT, MINB) k_roi_align_win(RoiArgs a, float* __
             for (int bin = grp; bin < bins; bin += NG) {
                 const BinTab* t = s_tab + bin;
                 VecF<V> acc;
-                switch (t->pat) {                          // uniform over the warps of a bin
-                    case 0: acc = bin_eval<FT, V, 0, 0>(fb, t); break;
-                    case 1: acc = bin_eval<FT, V, 0, 1>(fb, t); break;
-                    case 2: acc = bin_eval<FT, V, 0, 2>(fb, t); break;
-                    case 3: acc = bin_eval<FT, V, 1, 0>(fb, t); break;
-                    case 4: acc = bin_eval<FT, V, 1, 1>(fb, t); break;
-                    case 5: acc = bin_eval<FT, V, 1, 2>(fb, t); break;
-                    case 6: acc = bin_eval<FT, V, 2, 0>(fb, t); break;
-                    case 7: acc = bin_eval<FT, V, 2, 1>(fb, t); break;
-                    default: acc = bin_eval<FT, V, 2, 2>(fb, t); break;
+                const int pat = t->pat, py = pat / 3, px = pat - py * 3;   // uniform over the warps of a bin
+                if (py == 0) {
+                    if (px == 0) acc = bin_eval<FT, V, 0, 0>(fb, t);
+                    else if (px == 1) acc = bin_eval<FT, V, 0, 1>(fb, t);
+                    else acc = bin_eval<FT, V, 0, 2>(fb, t);
+                } else if (py == 1) {
+                    if (px == 0) acc = bin_eval<FT, V, 1, 0>(fb, t);
+                    else if (px == 1) acc = bin_eval<FT, V, 1, 1>(fb, t);
+                    else acc = bin_eval<FT, V, 1, 2>(fb, t);
+                } else {
+                    if (px == 0) acc = bin_eval<FT, V, 2, 0>(fb, t);
+                    else if (px == 1) acc = bin_eval<FT, V, 2, 1>(fb, t);
+                    else acc = bin_eval<FT, V, 2, 2>(fb, t);
                 }
                 float* st = s_tile + (cq * V) * bins + bin;    // x / 4 == x * 0.25 exactly
 #pragma unroll
