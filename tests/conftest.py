@@ -26,3 +26,15 @@ def golden():
 def fold0(a):
     """-0.0 -> +0.0 (the reference yields signed zeros in IoU tables)."""
     return np.asarray(a) + np.float32(0.0)
+
+
+def c4_inputs():
+    """Seeded inputs of BASELINE config 1 -- the same draws as tests/golden/make_golden.py:c4_inputs (SEED + 31)."""
+    rng = np.random.default_rng(2019 + 31)
+    cls = rng.normal(0, 1, (12, 38, 64)).astype(np.float32)
+    reg = rng.normal(0, 0.3, (48, 38, 64)).astype(np.float32)
+    feat = rng.standard_normal((1, 1024, 38, 64), dtype=np.float32)
+    cls_out = rng.normal(0, 2.5, (300, 21)).astype(np.float32)
+    cls_out[:, 0] += 2.0
+    reg_out = rng.normal(0, 0.5, (300, 84)).astype(np.float32)
+    return cls, reg, feat, cls_out, reg_out

@@ -492,10 +492,54 @@ def g_loss():
     save("loss", **out)
 
 
+def c4_inputs():
+    """Seeded inputs of BASELINE config 1 (faster_rcnn_r50 C4 inference, 600x1000 -> 608x1024, one level of 38x64x12
+    anchors, 1024-channel features); regenerated identically by tests/test_gpu_heads.py (the 10 MB feature map is not
+    stored)."""
+    rng = np.random.default_rng(SEED + 31)
+    cls = rng.normal(0, 1, (12, 38, 64)).astype(np.float32)
+    reg = rng.normal(0, 0.3, (48, 38, 64)).astype(np.float32)
+    feat = rng.standard_normal((1, 1024, 38, 64), dtype=np.float32)
+    cls_out = rng.normal(0, 2.5, (300, 21)).astype(np.float32)
+    cls_out[:, 0] += 2.0
+    reg_out = rng.normal(0, 0.5, (300, 84)).astype(np.float32)
+    return cls, reg, feat, cls_out, reg_out
+
+
+def g_c4():
+    """BASELINE config 1 end to end behind the backbone / head convolutions: RPNHead.predict_single_image with
+    test_cfg.rpn 6000/300/300/0.7 (configs/faster_rcnn_r50.py:96-102) -> BasicRoIExtractor(RoIPool 7x7 @1/16) ->
+    BBoxHead.predict_bboxes_single_image with test_cfg.rcnn (min_score .05, nms .3, 100)."""
+    import types
+    import lib.heads.bbox_head as bh
+    cls, reg, feat, cls_out, reg_out = c4_inputs()
+    head = build_module(dict(type="RPNHead", in_channels=8, feat_channels=8, anchor_scales=[4, 8, 16, 32],
+                             anchor_ratios=[0.5, 1.0, 2.0], anchor_strides=[16], target_means=[0.0] * 4, target_stds=[1.0] * 4,
+                             loss_cls=dict(type="CrossEntropyLoss", use_sigmoid=True, loss_weight=1.0),
+                             loss_bbox=dict(type="SmoothL1Loss", beta=1.0 / 9.0, loss_weight=1.0)))
+    meta = dict(img_shape=(600, 1000, 3), pad_shape=(608, 1024, 3), scale_factor=1.0)
+    anchors = head.create_anchors([(38, 64)])
+    with torch.no_grad():
+        props, scores, _ = head.predict_single_image([T(cls)], [T(reg)], anchors, meta,
+                                                     ref_shim.AttrDict(pre_nms=6000, post_nms=300, max_num=300, nms_iou=0.7,
+                                                                       min_bbox_size=0.0))
+        ext = build_module(dict(type="BasicRoIExtractor", roi_layers=[dict(type="RoIPool", spatial_scale=1 / 16)],
+                                output_size=(7, 7)))
+        pooled = ext([T(feat)], [props])[0]
+        n = props.shape[1]
+        me = types.SimpleNamespace(use_sigmoid=False, reg_class_agnostic=False, num_classes=21,
+                                   target_means=[0.0] * 4, target_stds=[0.1, 0.1, 0.2, 0.2])
+        db, ds, dl = bh.BBoxHead.predict_bboxes_single_image(me, props, T(cls_out[:n]), T(reg_out[:n]), (600, 1000),
+                                                             ref_shim.AttrDict(min_score=0.05, nms_iou=0.3, max_per_img=100))
+    print("c4: proposals", n, "pooled", tuple(pooled.shape), "detections", int(ds.numel()))
+    save("c4", props=props, scores=scores, pooled_sub=pooled[::7, ::37].contiguous(), pooled_sum=pooled.double().sum(),
+         det_bbox=db, det_score=ds, det_label=dl, cls_sha=sha(cls), feat_sha=sha(feat))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     gens = dict(anchors=g_anchors, iou_assign=g_iou_assign, deltas=g_deltas, nms=g_nms, rpn=g_rpn, roi=g_roi,
-                targets=g_targets, atss=g_atss, heads=g_heads, loss=g_loss)
+                targets=g_targets, atss=g_atss, heads=g_heads, loss=g_loss, c4=g_c4)
     for k, fn in gens.items():
         if not only or k in only:
             fn()

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import oracle
-from conftest import load_golden
+from conftest import c4_inputs, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -334,3 +334,41 @@ def test_anchor_head_loss_fused_config4_size_vs_oracle():
         want_r = np.stack([drs[b][l] for b in range(B)]) / npos
         np.testing.assert_allclose(N(cls[l].grad), want_c, rtol=1e-4, atol=1e-7)
         np.testing.assert_allclose(N(reg[l].grad), want_r, rtol=1e-4, atol=1e-7)
+
+
+# ------------------------------------------------------------------ BASELINE config 1 (C4), end to end
+def test_config1_c4_inference_path_vs_reference():
+    """faster_rcnn_r50 (C4) inference behind the convolutions, at the config's own sizes (600x1000 -> 608x1024,
+    29 184 anchors, test_cfg.rpn 6000/300/300/0.7 -> dense NMS path, RoIPool 7x7 @1/16 on 1024 channels, 21-class
+    detections with min_score .05 / nms .3 / 100): every stage against the unmodified reference's output."""
+    import hashlib
+    g = load_golden("c4")
+    cls, reg, feat, cls_out, reg_out = c4_inputs()
+    sha = lambda a: np.frombuffer(hashlib.sha1(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(sha(cls), g["cls_sha"]) and np.array_equal(sha(feat), g["feat_sha"]), "seeded inputs differ"
+    from b200det import anchor as banchor
+    head = types.SimpleNamespace(anchor_strides=[16], anchor_scales=[4, 8, 16, 32], anchor_ratios=[0.5, 1.0, 2.0],
+                                 target_means=[0.0] * 4, target_stds=[1.0] * 4, use_sigmoid=True, cls_channels=1,
+                                 anchor_creators=[banchor.AnchorCreator(base=16, scales=[4, 8, 16, 32])])
+    head.anchor_creators[0].to(DEV)
+    anchors = [head.anchor_creators[0](16, (38, 64))]
+    assert anchors[0].numel() == 4 * 29184
+    meta = dict(img_shape=(600, 1000, 3), pad_shape=(608, 1024, 3), scale_factor=1.0)
+    props, scores, _ = bheads.rpn_predict_single_image(head, [T(cls)], [T(reg)], anchors, meta,
+                                                       dict(pre_nms=6000, post_nms=300, max_num=300, nms_iou=0.7, min_bbox_size=0.0))
+    assert tuple(props.shape) == (4, 300)
+    np.testing.assert_allclose(N(scores), g["scores"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(props), g["props"], rtol=1e-5, atol=1e-3)
+    # RoIPool on the REFERENCE's proposals (so that a last-bit difference in a decoded box cannot move a bin edge)
+    ext = bregion.BasicRoIExtractor([dict(type="RoIPool", spatial_scale=1 / 16, sampling_ratio=2)], output_size=(7, 7))
+    pooled = ext([T(feat)], [T(g["props"])])[0]
+    assert tuple(pooled.shape) == (300, 1024, 7, 7)
+    assert np.array_equal(N(pooled[::7, ::37]), g["pooled_sub"])                     # max pooling: exact
+    np.testing.assert_allclose(float(pooled.double().sum()), float(g["pooled_sum"]), rtol=1e-9)
+    me = types.SimpleNamespace(use_sigmoid=False, reg_class_agnostic=False, num_classes=21,
+                               target_means=[0.0] * 4, target_stds=[0.1, 0.1, 0.2, 0.2])
+    db, ds, dl = bheads.predict_bboxes_single_image(me, T(g["props"]), T(cls_out), T(reg_out), (600, 1000),
+                                                    dict(min_score=0.05, nms_iou=0.3, max_per_img=100))
+    assert np.array_equal(N(dl), g["det_label"])
+    np.testing.assert_allclose(N(ds), g["det_score"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(db), g["det_bbox"], rtol=1e-5, atol=1e-3)

@@ -213,3 +213,21 @@ def test_anchor_head_loss_oracle_vs_reference():
     for l in range(3):                                   # the golden backward was (2 focal + 3 sl1).backward()
         np.testing.assert_allclose(2 * dc[l], g["dcls%d" % l], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(3 * dr[l], g["dreg%d" % l], rtol=1e-5, atol=1e-6)
+
+
+def test_config1_c4_oracle_vs_reference():
+    """BASELINE config 1 sizes through the oracle: proposals (29 184 anchors, 6000/300), RoIPool, detections."""
+    from conftest import c4_inputs
+    g = load_golden("c4")
+    cls, reg, feat, cls_out, reg_out = c4_inputs()
+    anc = oracle.anchor_grid(16, (38, 64), scales=[4, 8, 16, 32]).reshape(4, -1)
+    cfg = dict(pre_nms=6000, post_nms=300, max_num=300, nms_iou=0.7, min_bbox_size=0.0)
+    pb, ps, _, _ = oracle.rpn_proposals([cls.reshape(-1)], [reg.reshape(4, -1)], [anc], cfg, [0] * 4, [1] * 4, (600, 1000))
+    np.testing.assert_allclose(ps, g["scores"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(pb, g["props"], rtol=1e-5, atol=1e-3)
+    pooled, _ = oracle.roi_pool(feat[0], np.ascontiguousarray(g["props"][:, ::7]), 1 / 16)
+    assert np.array_equal(pooled[:, ::37], g["pooled_sub"])
+    kb, ks, kl = oracle.rcnn_detect(g["props"], cls_out, reg_out, (600, 1000), [0] * 4, [0.1, 0.1, 0.2, 0.2], 0.05, 0.3, 100)
+    assert np.array_equal(kl, g["det_label"])
+    np.testing.assert_allclose(ks, g["det_score"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(kb, g["det_bbox"], rtol=1e-5, atol=1e-3)
