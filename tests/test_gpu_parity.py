@@ -246,22 +246,23 @@ def test_rpn_score_cut_nms_is_exact(cut, monkeypatch):
     grids = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
     strides = (4, 8, 16, 32, 64)
     pyr = fused.AnchorPyramid(strides, grids)
-    cfg = dict(pre_nms=1000, post_nms=1000, max_num=1000, nms_iou=0.7, min_bbox_size=0)
     B = 2
     cls = [rng.normal(0, 1, (B, 3) + g).astype(np.float32) for g in grids]
     reg = [rng.normal(0, 0.15, (B, 12) + g).astype(np.float32) for g in grids]         # small deltas: heavy overlap
-    rp = fused.RpnProposals(pyr, B, cfg, [0, 0, 0, 0], [1, 1, 1, 1], DEV)
     img_hw = torch.tensor([[400.0, 666.0]] * B, device=DEV)
-    props, scores, count = rp([T(c) for c in cls], [T(r) for r in reg], img_hw)
-    torch.cuda.synchronize()
     anc = [oracle.anchor_grid(s, gr, scales=[8]).reshape(4, -1) for s, gr in zip(strides, grids)]
     offs = np.cumsum([0] + [a.shape[1] for a in anc])
-    for b in range(B):
-        _, _, lv, ix = oracle.rpn_proposals([c[b].reshape(-1) for c in cls], [r[b].reshape(4, -1) for r in reg], anc, cfg,
-                                            [0, 0, 0, 0], [1, 1, 1, 1], (400, 666))
-        n = int(count[b])
-        assert n == lv.shape[0]
-        assert np.array_equal(N(rp.prov[b, :n]), offs[lv] + ix), cut
+    for cfg in (dict(pre_nms=1000, post_nms=1000, max_num=1000, nms_iou=0.7, min_bbox_size=0),
+                dict(pre_nms=1000, post_nms=250, max_num=700, nms_iou=0.7, min_bbox_size=0)):   # per-level cap binds
+        rp = fused.RpnProposals(pyr, B, cfg, [0, 0, 0, 0], [1, 1, 1, 1], DEV)
+        props, scores, count = rp([T(c) for c in cls], [T(r) for r in reg], img_hw)
+        torch.cuda.synchronize()
+        for b in range(B):
+            _, _, lv, ix = oracle.rpn_proposals([c[b].reshape(-1) for c in cls], [r[b].reshape(4, -1) for r in reg], anc, cfg,
+                                                [0, 0, 0, 0], [1, 1, 1, 1], (400, 666))
+            n = int(count[b])
+            assert n == lv.shape[0]
+            assert np.array_equal(N(rp.prov[b, :n]), offs[lv] + ix), (cut, cfg)
 
 
 def test_rpn_proposals_selection_bit_exact_vs_oracle():
