@@ -1,0 +1,304 @@
+// roi_align_bwd_tile.cu -- K6, tile-gather form: deterministic, atomic-free RoIAlign backward for NHWC fp32
+// gradients and 2x2 samples per bin (every reference config).
+//
+// The first K6 (roi_bwd_pool.cu, k_roi_align_bwd: one thread per cell, every CTA scanning all RoIs and testing
+// all 14 x 14 samples of each) is bit-identical to torchvision's CPU kernel but takes 41 ms at config-2/3 sizes
+// (4096 RoIs x 256 channels: 23 GB/s).  Here the work is exactly the 784 taps of a RoI:
+//   k_bwd_meta      per RoI: level, sample geometry, cell bounding box of its taps
+//   k_bwd_bucket    per (image, level): the RoIs of that feature map, in ascending order ("sorted scatter" of the
+//                   RoI list by destination, ordered ballot compaction)
+//   k_roi_align_bwd_tile  one CTA per (16 x 16 cell tile, 64-channel group).  For every RoI of the bucket that
+//                   touches the tile (ascending): stage grad_out[roi][64 ch][bins] / 4 in shared memory as
+//                   [bin][channel]; per tile row / column list the sample rows / columns whose taps hit it with
+//                   their weights (hy or ly / hx or lx); then a thread (row, 4 channels) walks its 16 cells and adds
+//                   sum_{(sy, wy) in row} sum_{(sx, wx) in col} (wy * wx) * g[bin(sy, sx)] -- the same per-tap terms
+//                   as torchvision (grad / count * w), accumulated in registers in a fixed order.  Cells are owned
+//                   by exactly one thread: no atomics, no zero-fill pass, run-to-run bit-identical.
+// The summation order inside a cell differs from torchvision's sequential CPU order (RoI, ph, pw, iy, ix, tap), so
+// the result is equal within rounding (1e-5 relative, the north_star tolerance), not bit-identical; the generic kernel
+// remains for NCHW gradients / other sampling ratios.
+// HBM roofline: grad_out read (50 176 B/RoI, ~4x from L2: a RoI overlaps ~4 tiles) + every gradient cell written once.
+#include <cstring>
+
+#include "roi_common.cuh"
+
+namespace b2d {
+namespace {
+
+constexpr int kT = 16;                 // tile side in cells
+constexpr int kCg = 64;                // channels per CTA
+constexpr int kMaxS = 16;              // samples per axis (PH * 2, PW * 2 <= 16)
+constexpr int kPitch = kCg + 4;        // shared-memory pitch of a bin row (floats)
+constexpr int kMaxBinsT = 64;
+
+struct __align__(16) BwdMeta {
+    int img, lvl, y0, y1;
+    int x0, x1; float sx, sy;
+    float bw, bh; int _p0, _p1;
+};
+
+struct MetaArgs {
+    b2d_roi_cfg cfg;
+    const float* rois; long long roi_ld; const int* roi_img; const int* levels; long long R;
+};
+
+__global__ void __launch_bounds__(256) k_bwd_meta(MetaArgs a, BwdMeta* __restrict__ meta) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    const b2d_roi_cfg& c = a.cfg;
+    const float x1 = a.rois[r], y1 = a.rois[a.roi_ld + r], x2 = a.rois[2 * a.roi_ld + r], y2 = a.rois[3 * a.roi_ld + r];
+    BwdMeta m;
+    m.img = a.roi_img ? a.roi_img[r] : 0;
+    m.lvl = a.levels ? a.levels[r] : (c.num_levels > 1 ? roi_level(x1, y1, x2, y2, c.finest_scale, c.num_levels) : 0);
+    const int H = c.H[m.lvl], W = c.W[m.lvl];
+    const RoiGeom g = roi_geom(x1, y1, x2, y2, c.spatial_scale[m.lvl], c.PH, c.PW, 2, c.aligned);
+    m.sx = g.sx; m.sy = g.sy; m.bw = g.bw; m.bh = g.bh;
+    // cell bounding box of all taps (sample positions need not be monotone for malformed RoIs: take min / max)
+    int y0 = H, y1c = -1, x0 = W, x1c = -1;
+    for (int s = 0; s < 2 * c.PH; ++s) {
+        const AxisTap t = axis_tap(g.sy, g.bh, s >> 1, s & 1, 2, H);
+        if (t.valid) { y0 = min(y0, t.lo); y1c = max(y1c, t.hi); }
+    }
+    for (int s = 0; s < 2 * c.PW; ++s) {
+        const AxisTap t = axis_tap(g.sx, g.bw, s >> 1, s & 1, 2, W);
+        if (t.valid) { x0 = min(x0, t.lo); x1c = max(x1c, t.hi); }
+    }
+    m.y0 = y0; m.y1 = y1c; m.x0 = x0; m.x1 = x1c; m._p0 = m._p1 = 0;
+    meta[r] = m;
+}
+
+// bucket[(img * L + lvl) * R + k] = k-th RoI (ascending) of that feature map; bcount[img * L + lvl]
+__global__ void __launch_bounds__(256) k_bwd_bucket(const BwdMeta* __restrict__ meta, long long R, int L,
+                                                    int* __restrict__ bucket, int* __restrict__ bcount) {
+    __shared__ int s_warp[8], s_base;
+    const int img = blockIdx.x / L, lvl = blockIdx.x - img * L;
+    int* out = bucket + (long long)blockIdx.x * R;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (long long r0 = 0; r0 < R; r0 += 256) {
+        const long long r = r0 + threadIdx.x;
+        const bool hit = r < R && meta[r].img == img && meta[r].lvl == lvl;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = __popc(m);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += s_warp[w];
+        if (hit) out[before + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = (int)r;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_warp[w]; s_base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bcount[blockIdx.x] = s_base;
+}
+
+struct TileArgs {
+    b2d_roi_cfg cfg;
+    float* grad[kMaxLevels];
+    const float* gout; const BwdMeta* meta; const int* bucket; const int* bcount;
+    long long R;
+    int tile_off[kMaxLevels + 1], tiles_x[kMaxLevels];
+};
+
+struct __align__(8) ColTerm { float w; int off; };     // column weight, float offset of its bin column in s_g
+
+__global__ void __launch_bounds__(256, 2) k_roi_align_bwd_tile(TileArgs a) {
+    __shared__ __align__(16) float s_g[2][kMaxBinsT * kPitch];
+    __shared__ float s_roww[kT][kMaxS * 2];
+    __shared__ int s_rowb[kT][kMaxS * 2];                // float offset of the bin row in s_g
+    __shared__ ColTerm s_col[kT][kMaxS * 2];
+    __shared__ int s_rown[kT], s_coln[kT];
+    __shared__ int s_list[256], s_n, s_warp[8];
+    const b2d_roi_cfg& c = a.cfg;
+    const int tiles_per_img = a.tile_off[c.num_levels];
+    const int img = blockIdx.x / tiles_per_img;
+    int t = blockIdx.x - img * tiles_per_img, lvl = 0;
+    for (int q = 1; q < c.num_levels; ++q) if (t >= a.tile_off[q]) lvl = q;
+    t -= a.tile_off[lvl];
+    const int H = c.H[lvl], W = c.W[lvl], C = c.C, bins = c.PH * c.PW;
+    const int ty0 = (t / a.tiles_x[lvl]) * kT, tx0 = (t % a.tiles_x[lvl]) * kT;
+    const int cg = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int half = lane >> 4, cq = lane & 15;
+    const int row = warp * 2 + half;                     // tile row owned by this thread (with 4 channels)
+    float acc[kT][4];
+#pragma unroll
+    for (int x = 0; x < kT; ++x) { acc[x][0] = acc[x][1] = acc[x][2] = acc[x][3] = 0.0f; }
+    // staging map of this thread: channel tid % 64, bins tid / 64 + 4 k (no index arithmetic in the loops; the 32 B
+    // sectors a warp touches are re-used by its next 7 loads out of L1)
+    constexpr int kStage = (kMaxBinsT + 3) / 4;
+    const int sch = tid & (kCg - 1), sb0 = tid >> 6;
+    float sv[kStage];
+
+    const int* bl = a.bucket + (long long)(img * c.num_levels + lvl) * a.R;
+    const int nb = a.bcount[img * c.num_levels + lvl];
+    auto fetch = [&](int r) {                            // grad_out[r][cg * 64 .. + 64][bins] -> registers
+        const float* go = a.gout + ((long long)r * C + (long long)cg * kCg + sch) * bins + sb0;
+#pragma unroll
+        for (int k = 0; k < kStage; ++k) sv[k] = (sb0 + 4 * k < bins) ? go[4 * k] : 0.0f;
+    };
+    auto stash = [&](float* dst) {                       // registers -> [bin][channel] / 4
+        float* d = dst + sb0 * kPitch + sch;
+#pragma unroll
+        for (int k = 0; k < kStage; ++k)
+            if (sb0 + 4 * k < bins) d[4 * k * kPitch] = sv[k] * 0.25f;
+    };
+    for (int base = 0; base < nb; base += 256) {
+        // ---- RoIs of this chunk whose taps touch the tile, ascending
+        {
+            const int k = base + tid;
+            bool hit = false;
+            int r = 0;
+            if (k < nb) {
+                r = bl[k];
+                const BwdMeta m = a.meta[r];
+                hit = !(m.y1 < ty0 || m.y0 > ty0 + kT - 1 || m.x1 < tx0 || m.x0 > tx0 + kT - 1);
+            }
+            const unsigned bm = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_warp[warp] = __popc(bm);
+            __syncthreads();
+            int before = 0;
+            for (int w = 0; w < warp; ++w) before += s_warp[w];
+            if (hit) s_list[before + __popc(bm & ((1u << lane) - 1u))] = r;
+            if (tid == 0) { int tot = 0; for (int w = 0; w < 8; ++w) tot += s_warp[w]; s_n = tot; }
+            __syncthreads();
+        }
+        const int nhit = s_n;
+        if (nhit > 0) fetch(s_list[0]);
+        for (int e = 0; e < nhit; ++e) {
+            const int r = s_list[e];
+            float* sg = s_g[e & 1];
+            stash(sg);
+            if (e + 1 < nhit) fetch(s_list[e + 1]);      // next RoI's gradients are in flight during this one's math
+            // ---- per tile row / column: the samples whose taps hit it, in sample order (lo entry before hi entry).
+            // Thread (k = tid / 16, q = tid % 16) tests sample q against row / column k; the 16 lanes of a half-warp
+            // order their entries with two ballots.
+            {
+                const BwdMeta m = a.meta[r];
+                const int k = tid >> 4, q = lane & 15, hs = lane & 16;
+#pragma unroll
+                for (int ax = 0; ax < 2; ++ax) {
+                    const int ns = 2 * (ax ? c.PW : c.PH);
+                    const int coord = (ax ? tx0 : ty0) + k;
+                    bool hlo = false, hhi = false;
+                    float wl = 0.0f, wh = 0.0f;
+                    if (q < ns) {
+                        const AxisTap tp = ax ? axis_tap(m.sx, m.bw, q >> 1, q & 1, 2, W) : axis_tap(m.sy, m.bh, q >> 1, q & 1, 2, H);
+                        hlo = tp.valid && tp.lo == coord; hhi = tp.valid && tp.hi == coord;
+                        wl = tp.h; wh = tp.l;
+                    }
+                    const unsigned mlo = (__ballot_sync(0xffffffffu, hlo) >> hs) & 0xffffu;
+                    const unsigned mhi = (__ballot_sync(0xffffffffu, hhi) >> hs) & 0xffffu;
+                    const unsigned below = (1u << q) - 1u;
+                    int pos = __popc(mlo & below) + __popc(mhi & below);
+                    const int boff = ax ? (q >> 1) * kPitch : (q >> 1) * c.PW * kPitch;
+                    if (hlo) {
+                        if (ax) { s_col[k][pos].w = wl; s_col[k][pos].off = boff; } else { s_roww[k][pos] = wl; s_rowb[k][pos] = boff; }
+                        ++pos;
+                    }
+                    if (hhi) {
+                        if (ax) { s_col[k][pos].w = wh; s_col[k][pos].off = boff; } else { s_roww[k][pos] = wh; s_rowb[k][pos] = boff; }
+                    }
+                    if (q == 0) { if (ax) s_coln[k] = __popc(mlo) + __popc(mhi); else s_rown[k] = __popc(mlo) + __popc(mhi); }
+                }
+            }
+            __syncthreads();
+            const int nr = s_rown[row];
+            if (nr > 0) {
+                const float* gq = sg + cq * 4;
+                if (nr <= 4) {                           // the usual case: row terms live in registers
+                    float wy[4];
+                    const float* gr[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        wy[i] = i < nr ? s_roww[row][i] : 0.0f;
+                        gr[i] = gq + (i < nr ? s_rowb[row][i] : 0);
+                    }
+#pragma unroll
+                    for (int x = 0; x < kT; ++x) {
+                        const int nc = s_coln[x];
+                        for (int j = 0; j < nc; ++j) {
+                            const ColTerm ct = s_col[x][j];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                if (i < nr) {
+                                    const float w = wy[i] * ct.w;
+                                    const float4 g = *reinterpret_cast<const float4*>(gr[i] + ct.off);
+                                    acc[x][0] = fmaf(w, g.x, acc[x][0]); acc[x][1] = fmaf(w, g.y, acc[x][1]);
+                                    acc[x][2] = fmaf(w, g.z, acc[x][2]); acc[x][3] = fmaf(w, g.w, acc[x][3]);
+                                }
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int x = 0; x < kT; ++x) {
+                        const int nc = s_coln[x];
+                        if (nc == 0) continue;
+                        for (int i = 0; i < nr; ++i) {
+                            const float wy = s_roww[row][i];
+                            const float* gr = gq + s_rowb[row][i];
+                            for (int j = 0; j < nc; ++j) {
+                                const ColTerm ct = s_col[x][j];
+                                const float w = wy * ct.w;
+                                const float4 g = *reinterpret_cast<const float4*>(gr + ct.off);
+                                acc[x][0] = fmaf(w, g.x, acc[x][0]); acc[x][1] = fmaf(w, g.y, acc[x][1]);
+                                acc[x][2] = fmaf(w, g.z, acc[x][2]); acc[x][3] = fmaf(w, g.w, acc[x][3]);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();                             // tables are rebuilt for the next RoI
+        }
+    }
+    const int y = ty0 + row;
+    if (y < H) {
+        float* g = a.grad[lvl] + (((long long)img * H + y) * W + tx0) * C + (long long)cg * kCg + cq * 4;
+#pragma unroll
+        for (int x = 0; x < kT; ++x)
+            if (tx0 + x < W) *reinterpret_cast<float4*>(g + (long long)x * C) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+    }
+}
+
+}  // namespace
+
+size_t roi_align_bwd_tile_workspace(long long R, int B, int L) {
+    const size_t r = (size_t)(R > 0 ? R : 1);
+    return r * sizeof(BwdMeta) + 256 + (size_t)B * L * r * 4 + 256 + (size_t)B * L * 4 + 256;
+}
+
+// returns 1 if the configuration is not eligible (the caller then uses the generic kernel)
+int roi_align_bwd_tile_try(void* const* grad_feat_ptrs_host, const float* grad_out, const float* rois, long long roi_ld,
+                           const int* roi_img, const int* levels, long long R, int B, const b2d_roi_cfg& c, void* workspace,
+                           cudaStream_t st) {
+    if (c.layout != 1 || c.sampling_ratio != 2 || 2 * c.PH > kMaxS || 2 * c.PW > kMaxS || c.PH * c.PW > kMaxBinsT) return 1;
+    if (c.C % kCg != 0 || R < 1) return 1;
+    for (int l = 0; l < c.num_levels; ++l)
+        if (reinterpret_cast<uintptr_t>(grad_feat_ptrs_host[l]) & 15) return 1;
+    char* w = (char*)workspace;
+    BwdMeta* meta = (BwdMeta*)w; w += ((size_t)R * sizeof(BwdMeta) + 255) & ~(size_t)255;
+    int* bucket = (int*)w; w += ((size_t)B * c.num_levels * R * 4 + 255) & ~(size_t)255;
+    int* bcount = (int*)w;
+    MetaArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.cfg = c; ma.rois = rois; ma.roi_ld = roi_ld; ma.roi_img = roi_img; ma.levels = levels; ma.R = R;
+    k_bwd_meta<<<cdiv(R, 256), 256, 0, st>>>(ma, meta);
+    k_bwd_bucket<<<B * c.num_levels, 256, 0, st>>>(meta, R, c.num_levels, bucket, bcount);
+    TileArgs a;
+    memset(&a, 0, sizeof(a));
+    a.cfg = c;
+    int run = 0;
+    for (int l = 0; l < c.num_levels; ++l) {
+        a.grad[l] = (float*)grad_feat_ptrs_host[l];
+        a.tile_off[l] = run;
+        a.tiles_x[l] = cdiv(c.W[l], kT);
+        run += a.tiles_x[l] * cdiv(c.H[l], kT);
+    }
+    a.tile_off[c.num_levels] = run;
+    a.gout = grad_out; a.meta = meta; a.bucket = bucket; a.bcount = bcount; a.R = R;
+    dim3 grid((unsigned)(run * B), (unsigned)(c.C / kCg));
+    k_roi_align_bwd_tile<<<grid, 256, 0, st>>>(a);
+    return check_launch("roi_align_bwd(tile)");
+}
+
+}  // namespace b2d

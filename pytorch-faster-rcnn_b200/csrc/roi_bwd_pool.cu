@@ -10,11 +10,18 @@
 //
 // K7 follows torchvision.ops.roi_pool (rounded bounds, floor/ceil bins, argmax);
 // its backward is a per-cell ordered gather over the argmax table.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
 
 namespace b2d {
+
+// roi_align_bwd_tile.cu
+size_t roi_align_bwd_tile_workspace(long long R, int B, int L);
+int roi_align_bwd_tile_try(void* const* grad_feat_ptrs_host, const float* grad_out, const float* rois, long long roi_ld,
+                           const int* roi_img, const int* levels, long long R, int B, const b2d_roi_cfg& c, void* workspace,
+                           cudaStream_t st);
 
 struct AxisTapB { int lo, hi; float l, h; int valid; };
 
@@ -263,9 +270,11 @@ using namespace b2d;
 
 extern "C" {
 
+static size_t bwd_levels_bytes(long long R) { return (((size_t)(R > 0 ? R : 1) * 4 + 256) + 255) & ~(size_t)255; }
+
 size_t b2d_roi_align_bwd_workspace_bytes(long long R, int B, const b2d_roi_cfg* cfg_host) {
-    (void)B; (void)cfg_host;
-    return (size_t)(R > 0 ? R : 1) * 4 + 256;   // level ids
+    const int L = cfg_host ? cfg_host->num_levels : B2D_MAX_LEVELS;
+    return bwd_levels_bytes(R) + roi_align_bwd_tile_workspace(R, B > 0 ? B : 1, L);   // level ids + tile-kernel tables
 }
 
 int b2d_roi_align_bwd(void* const* grad_feat_ptrs_host, const float* grad_out, const float* rois, long long roi_ld,
@@ -279,6 +288,15 @@ int b2d_roi_align_bwd(void* const* grad_feat_ptrs_host, const float* grad_out, c
                 "roi_align_bwd: needs a fixed sampling_ratio with PH*sr, PW*sr <= 16");
     B2D_REQUIRE(workspace && ws_bytes >= b2d_roi_align_bwd_workspace_bytes(R, B, cfg_host), "roi_align_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
+    {   // tile-gather kernel (roi_align_bwd_tile.cu) for NHWC fp32 gradients with 2x2 samples; B2D_ROI_BWD_TILE=0 forces
+        // the generic, torchvision-bit-identical kernel below
+        const char* e = getenv("B2D_ROI_BWD_TILE");
+        if (!e || atoi(e) != 0) {
+            const int rc = roi_align_bwd_tile_try(grad_feat_ptrs_host, grad_out, rois, roi_ld, roi_img, levels, R, B, c,
+                                                  (char*)workspace + bwd_levels_bytes(R), st);
+            if (rc != 1) return rc;
+        }
+    }
     int* lv = (int*)workspace;
     if (levels) cudaMemcpyAsync(lv, levels, sizeof(int) * R, cudaMemcpyDeviceToDevice, st);
     else if (R > 0) {
