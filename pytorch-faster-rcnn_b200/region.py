@@ -232,6 +232,17 @@ def _feat_layout(feats):
     return _LAYOUT_NCHW, [_C.f32c(f) for f in feats]
 
 
+def _to_nhwc(feats):
+    """fp32 NCHW-contiguous level maps -> channels_last copies (b2d_nchw_to_nhwc), so that reference-layout
+    features (lib/necks.py FPN output) take the channel-vectorised K5 / K6 kernels instead of the generic ones."""
+    out = []
+    for f in feats:
+        d = torch.empty(f.shape, dtype=torch.float32, device=f.device, memory_format=torch.channels_last)
+        _C.call("b2d_nchw_to_nhwc", _C.ptr(d), _C.ptr(f), f.shape[0], f.shape[1], f.shape[2], f.shape[3], _C.stream())
+        out.append(d)
+    return out
+
+
 def _roi_cfg(feats, strides_or_scales, out_size, sampling_ratio, aligned, layout, finest_scale, scales=True):
     cfg = _C.RoiCfg()
     cfg.num_levels = len(feats)
@@ -259,6 +270,8 @@ class _RoIAlignFn(torch.autograd.Function):
     def forward(ctx, rois, roi_img, levels, meta, *feats):
         scales, out_size, sr, aligned, finest = meta
         layout, fl = _feat_layout(feats)
+        if layout == _LAYOUT_NCHW and sr == 2 and int(fl[0].shape[1]) % 4 == 0 and fl[0].shape[1] >= 16:
+            layout, fl = _LAYOUT_NHWC, _to_nhwc(fl)      # reference layout: transpose once, then the fast kernels
         cfg = _roi_cfg(fl, scales, out_size, sr, aligned, layout, finest)
         R = rois.shape[1]
         out = torch.empty((R, cfg.C, cfg.PH, cfg.PW), dtype=torch.float32, device=rois.device)

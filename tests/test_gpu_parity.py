@@ -424,6 +424,29 @@ def test_roi_align_backward_tile_kernel_vs_oracle_and_generic(C, K, monkeypatch)
             np.testing.assert_allclose(g1[l][b], ref, rtol=1e-5, atol=2e-6)
 
 
+def test_roi_align_reference_layout_takes_fast_kernels():
+    """fp32 NCHW features (the reference's FPN output layout, lib/necks.py) are transposed once and go through the same
+    K5 / K6 kernels as channels_last inputs: identical forward bits, identical gradients (returned for the NCHW input)."""
+    grids, feats, rois, img = _ring_case(14, 64, 200)
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    go = np.random.default_rng(2).standard_normal((200, 64, 7, 7)).astype(np.float32)
+    outs, grads = [], []
+    for cl in (False, True):
+        fs = [T(f) for f in feats]
+        if cl:
+            fs = [f.contiguous(memory_format=torch.channels_last) for f in fs]
+        fs = [f.requires_grad_(True) for f in fs]
+        o = bregion.roi_align_levels(fs, T(rois), T(img), scales)
+        (o * T(go)).sum().backward()
+        outs.append(N(o)); grads.append([N(f.grad) for f in fs])
+    assert np.array_equal(bits(outs[0]), bits(outs[1]))
+    for l in range(4):
+        assert np.array_equal(bits(grads[0][l]), bits(grads[1][l]))
+    for b in range(feats[0].shape[0]):
+        m = img == b
+        assert np.array_equal(bits(outs[0][m]), bits(oracle.roi_extract([f[b] for f in feats], np.ascontiguousarray(rois[:, m]))))
+
+
 def test_roi_pool_vs_torchvision():
     g = load_golden("roi")
     ext = bregion.BasicRoIExtractor([dict(type="RoIPool", spatial_scale=1 / 16, sampling_ratio=2)], output_size=(7, 7))
