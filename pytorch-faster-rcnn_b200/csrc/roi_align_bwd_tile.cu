@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(256, 2) k_roi_align_bwd_tile(TileArgs a) {
     const int cg = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int half = lane >> 4, cq = lane & 15;
-    const int row = warp * 2 + half;                     // tile row owned by this thread (with 4 channels)
+    const int row = warp + 8 * half;                     // tile row owned by this thread (with 4 channels); rows w and
+                                                         // w + 8 per warp: a RoI's contiguous row range loads all warps
     float acc[kT][4];
 #pragma unroll
     for (int x = 0; x < kT; ++x) { acc[x][0] = acc[x][1] = acc[x][2] = acc[x][3] = 0.0f; }
