@@ -649,3 +649,29 @@ def test_fused_train_path_full_size_properties():
         rois = N(bt.tar_box[b, :, :mm])
         ref = oracle.roi_extract([f[b] for f in w["feats"]], rois)
         assert np.array_equal(bits(N(out["roi_feats"][b * 512:b * 512 + mm])), bits(ref))
+
+
+def test_fused_step_is_run_to_run_deterministic():
+    """Five replays of the config-2-sized step (per-level chains on internal streams, score-cut NMS, fused targets)
+    give bit-identical proposals, samples, targets and RoI features -- a race between the chains would show here."""
+    B, K = 4, 8
+    w = workload.config2(B=B, K=K, channels=64)
+    hp = fused.TrainHotPath(B, w["grids"], DEV, gt_ld=K, feat_channels=64, overlap=True)
+    cls, reg = [T(c) for c in w["cls"]], [T(r) for r in w["reg"]]
+    feats = [T(f).contiguous(memory_format=torch.channels_last) for f in w["feats"]]
+    gt, gl = T(w["gt"]), T(w["gt_label"])
+    gcount = torch.full((B,), K, dtype=torch.int32, device=DEV)
+    img_hw = torch.tensor([[800.0, 1333.0]] * B, device=DEV)
+    ref = None
+    for it in range(5):
+        hp.rpn_targets.step = 0; hp.roi_targets.step = 0           # same sampler seed every replay
+        out = hp.step(cls, reg, feats, gt, gcount, gl, img_hw)
+        torch.cuda.synchronize()
+        snap = [N(out["props"]).copy(), N(out["scores"]).copy(), N(out["prop_count"]).copy(), N(out["rpn"].chosen).copy(),
+                N(out["rpn"].tar_param).copy(), N(out["rcnn"].chosen).copy(), N(out["rcnn"].tar_param).copy(),
+                N(out["roi_feats"]).copy()]
+        if ref is None:
+            ref = snap
+        else:
+            for a, b in zip(ref, snap):
+                assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), it
