@@ -100,13 +100,22 @@ struct TileArgs {
 };
 
 struct __align__(8) ColTerm { float w; int off; };     // column weight, float offset of its bin column in s_g
+constexpr size_t kTablesBytes = sizeof(float) * kT * kMaxS * 2 + sizeof(int) * kT * kMaxS * 2 + sizeof(ColTerm) * kT * kMaxS * 2 +
+                                2 * sizeof(int) * kT;
 
 __global__ void __launch_bounds__(256, 2) k_roi_align_bwd_tile(TileArgs a) {
-    __shared__ __align__(16) float s_g[2][kMaxBinsT * kPitch];
-    __shared__ float s_roww[kT][kMaxS * 2];
-    __shared__ int s_rowb[kT][kMaxS * 2];                // float offset of the bin row in s_g
-    __shared__ ColTerm s_col[kT][kMaxS * 2];
-    __shared__ int s_rown[kT], s_coln[kT];
+    // Everything a RoI needs (staged gradients + tap tables) is double-buffered, so ONE barrier per RoI is enough:
+    // a warp that is through with RoI e stages / tabulates RoI e + 1 into the other buffers while slower warps
+    // still accumulate RoI e; the barrier of e + 1 is what protects the buffers of e from RoI e + 2.
+    extern __shared__ __align__(16) char s_dyn[];
+    struct Tables {
+        float roww[kT][kMaxS * 2];
+        int rowb[kT][kMaxS * 2];                         // float offset of the bin row in the staged block
+        ColTerm col[kT][kMaxS * 2];
+        int rown[kT], coln[kT];
+    };
+    float (*s_g)[kMaxBinsT * kPitch] = reinterpret_cast<float (*)[kMaxBinsT * kPitch]>(s_dyn);
+    Tables* s_tab = reinterpret_cast<Tables*>(s_dyn + 2 * sizeof(float) * kMaxBinsT * kPitch);
     __shared__ int s_list[256], s_n, s_warp[8];
     const b2d_roi_cfg& c = a.cfg;
     const int tiles_per_img = a.tile_off[c.num_levels];
@@ -168,6 +177,7 @@ __global__ void __launch_bounds__(256, 2) k_roi_align_bwd_tile(TileArgs a) {
         for (int e = 0; e < nhit; ++e) {
             const int r = s_list[e];
             float* sg = s_g[e & 1];
+            Tables& tb = s_tab[e & 1];
             stash(sg);
             if (e + 1 < nhit) fetch(s_list[e + 1]);      // next RoI's gradients are in flight during this one's math
             // ---- per tile row / column: the samples whose taps hit it, in sample order (lo entry before hi entry).
@@ -193,17 +203,17 @@ __global__ void __launch_bounds__(256, 2) k_roi_align_bwd_tile(TileArgs a) {
                     int pos = __popc(mlo & below) + __popc(mhi & below);
                     const int boff = ax ? (q >> 1) * kPitch : (q >> 1) * c.PW * kPitch;
                     if (hlo) {
-                        if (ax) { s_col[k][pos].w = wl; s_col[k][pos].off = boff; } else { s_roww[k][pos] = wl; s_rowb[k][pos] = boff; }
+                        if (ax) { tb.col[k][pos].w = wl; tb.col[k][pos].off = boff; } else { tb.roww[k][pos] = wl; tb.rowb[k][pos] = boff; }
                         ++pos;
                     }
                     if (hhi) {
-                        if (ax) { s_col[k][pos].w = wh; s_col[k][pos].off = boff; } else { s_roww[k][pos] = wh; s_rowb[k][pos] = boff; }
+                        if (ax) { tb.col[k][pos].w = wh; tb.col[k][pos].off = boff; } else { tb.roww[k][pos] = wh; tb.rowb[k][pos] = boff; }
                     }
-                    if (q == 0) { if (ax) s_coln[k] = __popc(mlo) + __popc(mhi); else s_rown[k] = __popc(mlo) + __popc(mhi); }
+                    if (q == 0) { if (ax) tb.coln[k] = __popc(mlo) + __popc(mhi); else tb.rown[k] = __popc(mlo) + __popc(mhi); }
                 }
             }
             __syncthreads();
-            const int nr = s_rown[row];
+            const int nr = tb.rown[row];
             if (nr > 0) {
                 const float* gq = sg + cq * 4;
                 if (nr <= 4) {                           // the usual case: row terms live in registers
@@ -211,14 +221,14 @@ __global__ void __launch_bounds__(256, 2) k_roi_align_bwd_tile(TileArgs a) {
                     const float* gr[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        wy[i] = i < nr ? s_roww[row][i] : 0.0f;
-                        gr[i] = gq + (i < nr ? s_rowb[row][i] : 0);
+                        wy[i] = i < nr ? tb.roww[row][i] : 0.0f;
+                        gr[i] = gq + (i < nr ? tb.rowb[row][i] : 0);
                     }
 #pragma unroll
                     for (int x = 0; x < kT; ++x) {
-                        const int nc = s_coln[x];
+                        const int nc = tb.coln[x];
                         for (int j = 0; j < nc; ++j) {
-                            const ColTerm ct = s_col[x][j];
+                            const ColTerm ct = tb.col[x][j];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 if (i < nr) {
@@ -233,13 +243,13 @@ __global__ void __launch_bounds__(256, 2) k_roi_align_bwd_tile(TileArgs a) {
                 } else {
 #pragma unroll
                     for (int x = 0; x < kT; ++x) {
-                        const int nc = s_coln[x];
+                        const int nc = tb.coln[x];
                         if (nc == 0) continue;
                         for (int i = 0; i < nr; ++i) {
-                            const float wy = s_roww[row][i];
-                            const float* gr = gq + s_rowb[row][i];
+                            const float wy = tb.roww[row][i];
+                            const float* gr = gq + tb.rowb[row][i];
                             for (int j = 0; j < nc; ++j) {
-                                const ColTerm ct = s_col[x][j];
+                                const ColTerm ct = tb.col[x][j];
                                 const float w = wy * ct.w;
                                 const float4 g = *reinterpret_cast<const float4*>(gr + ct.off);
                                 acc[x][0] = fmaf(w, g.x, acc[x][0]); acc[x][1] = fmaf(w, g.y, acc[x][1]);
@@ -249,8 +259,8 @@ __global__ void __launch_bounds__(256, 2) k_roi_align_bwd_tile(TileArgs a) {
                     }
                 }
             }
-            __syncthreads();                             // tables are rebuilt for the next RoI
         }
+        __syncthreads();                                 // the hit list is rebuilt for the next chunk
     }
     const int y = ty0 + row;
     if (y < H) {
@@ -298,7 +308,10 @@ int roi_align_bwd_tile_try(void* const* grad_feat_ptrs_host, const float* grad_o
     a.tile_off[c.num_levels] = run;
     a.gout = grad_out; a.meta = meta; a.bucket = bucket; a.bcount = bcount; a.R = R;
     dim3 grid((unsigned)(run * B), (unsigned)(c.C / kCg));
-    k_roi_align_bwd_tile<<<grid, 256, 0, st>>>(a);
+    const size_t smem = 2 * sizeof(float) * kMaxBinsT * kPitch + 2 * kTablesBytes;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_roi_align_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    k_roi_align_bwd_tile<<<grid, 256, smem, st>>>(a);
     return check_launch("roi_align_bwd(tile)");
 }
 
