@@ -50,31 +50,59 @@ def ncu_traffic(stage):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md).  NVML through pynvml (sub-millisecond
+    per query, so that even a 6 ms timed region is sampled); `nvidia-smi` as a fallback."""
+
+    _BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag = index, [], False          # rows: (t, sm_mhz, sm_max_mhz, [reasons])
+        self.window = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
         self.q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    n = self.nvml
+                    mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    self.rows.append((time.perf_counter(), mhz, self.max_mhz, [k for k, b in self._BITS.items() if mask & b]))
+                    time.sleep(0.0005)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                c = [v.strip() for v in out.strip().split(",")]
+                if len(c) >= 6 and c[0].replace(".", "").isdigit():
+                    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                    self.rows.append((time.perf_counter(), float(c[0]), float(c[1]),
+                                      [k for k, v in zip(names, c[2:6]) if v.lower().startswith("active")]))
             except Exception:
                 pass
             time.sleep(0.05)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        rows = self.rows
+        inside = [r for r in rows if self.window and self.window[0] <= r[0] <= self.window[1]]
+        use = inside if inside else rows
+        sm = [r[1] for r in use]
+        mx = [r[2] for r in use]
+        reasons = sorted({k for r in use for k in r[3]})
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(sm))
+                    samples=len(sm), samples_in_timed_region=len(inside), source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 def touched_cell_bytes(rois_b4n, counts, grids, strides, C, finest=56.0):
@@ -204,6 +232,7 @@ def run_b200(args):
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         if graph is not None:
@@ -212,6 +241,7 @@ def run_b200(args):
             step()
     e1.record()
     barrier()
+    sampler.window = (t_host0, time.perf_counter())
     ms = e0.elapsed_time(e1)
     # ---- per-stage device times (eager, CUDA events on the launching stream)
     stages = ["proposals", "rpn_targets", "roi_targets", "roi_align"]
