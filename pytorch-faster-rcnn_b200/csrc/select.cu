@@ -1,10 +1,13 @@
 // select.cu -- K3: fused RPN proposal selection for all (image, level) segments:
 //   k_hist      12-bit radix histogram of the monotone logit keys   (multi-block)
 //   k_compact   threshold bin from the histogram + candidate compaction (multi-block)
-//   k_select    per segment: exact top-k by radix narrowing + in-smem bitonic sort,
-//               anchor generation in registers, delta decode, clip, min-size filter
-//   (NMS: nms.cu)
-//   k_merge     per image: concat levels, global top-max_num, sigmoid, [4,k] output
+//   k_select    per segment: exact top-k of the candidates by an in-smem linear-key bucket sort (bitonic
+//               network / radix narrowing only for heavily tied score maps), anchor generation in
+//               registers, delta decode, clip, min-size filter
+//   (NMS: nms.cu -- score cut, mask, scan)
+//   k_merge_rank  per surviving box: global rank by binary searches over the other levels' lists,
+//               scatter to [4, max_num] + sigmoid   (k_merge: single-block form for unsorted lists)
+// The launcher runs one chain per FPN level on library-owned streams (see b2d_rpn_proposals).
 // Reference: RPNHead.predict_single_image (lib/heads/rpn_head.py:68-120).
 //
 // Selection and ordering use the *logit* (sigmoid is monotone), ties broken by the
