@@ -369,3 +369,69 @@ class TrainHotPath(object):
             if k in h_out:
                 h_out[k].copy_(t, non_blocking=True)
         return h_out
+
+
+class CascadeHotPath(object):
+    """The stage loop of CascadeRCNN.forward_train (lib/detectors/cascade_rcnn.py:119-153; BASELINE config 3) minus
+    the head convolutions and losses, batched: per stage bbox_target on the current boxes (b2d_roi_targets_fused,
+    thresholds .5/.6/.7) -> FPN RoIAlign of the sampled RoIs (K5) -> [RCNN head: the caller's reg_out] ->
+    BBoxHead.refine_bboxes (b2d_refine_bboxes, stage stds, GT columns dropped) -> next stage's boxes; and the RoIAlign
+    backward of every stage (K6).  Allocation- and sync-free after construction (CUDA-graph capturable)."""
+
+    def __init__(self, B, n_props, grids, device, strides=(4, 8, 16, 32), gt_ld=64, feat_channels=256,
+                 thresholds=(0.5, 0.6, 0.7),
+                 stage_stds=((0.1, 0.1, 0.2, 0.2), (0.05, 0.05, 0.1, 0.1), (0.033, 0.033, 0.067, 0.067)),
+                 sampler=None, num_classes=21, layout=1, seed=0):
+        sampler = sampler or dict(max_num=512, pos_num=128)
+        z4 = (0.0, 0.0, 0.0, 0.0)
+        self.B, self.m, self.C = B, int(sampler["max_num"]), int(num_classes)
+        shapes = [(feat_channels, g[0], g[1]) for g in grids[:len(strides)]]
+        self.stages = []
+        n = int(n_props)
+        for s, (thr, sd) in enumerate(zip(thresholds, stage_stds)):
+            tg = BatchedTargets(B, n, gt_ld, dict(pos_iou=thr, neg_iou=thr, min_pos_iou=thr), sampler, z4, sd, device,
+                                prepend_gt=True, seed=seed + s)
+            ra = BatchedRoIAlign(B, self.m, shapes, list(strides), device, layout=layout)
+            refined = torch.zeros((B, 4, self.m), dtype=torch.float32, device=device)
+            rcount = torch.zeros(B, dtype=torch.int32, device=device)
+            self.stages.append((tg, ra, refined, rcount, _C.host_f4(sd, [1, 1, 1, 1])))
+            n = self.m
+        self.roi_img = torch.arange(B, dtype=torch.int32, device=device).repeat_interleave(self.m).contiguous()
+        self.rois_flat = [torch.zeros((4, B * self.m), dtype=torch.float32, device=device) for _ in self.stages]
+        mf = torch.channels_last if layout != 0 else torch.contiguous_format
+        self.grads = [[torch.zeros((B,) + shp, dtype=torch.float32, device=device).contiguous(memory_format=mf) for shp in shapes]
+                      for _ in self.stages]
+        self.bwd_cfg = self.stages[0][1].cfg
+        nb = _C.lib().b2d_roi_align_bwd_workspace_bytes(B * self.m, B, ctypes.byref(self.bwd_cfg))
+        self.bwd_ws = torch.empty(nb, dtype=torch.uint8, device=device)
+        self.zero4 = _C.host_f4(z4, [0, 0, 0, 0])
+        self.launches = len(self.stages) * (1 + 1 + 1)
+
+    def step(self, props, prop_count, feats, gt, gt_count, gt_label, img_hw, reg_outs):
+        """props [B,4,n_props] + prop_count; reg_outs[s]: the stage head's regression output [B, max_num, 4*num_classes]
+        (rows in the order of the stage's sampled RoIs).  Returns the per-stage (targets, roi features, refined boxes,
+        counts)."""
+        outs = []
+        boxes, count = props, prop_count
+        for s, (tg, ra, refined, rcount, stds) in enumerate(self.stages):
+            bt = tg(gt, gt_count, gt_label, boxes=boxes, box_count=count)
+            ra(feats, bt.tar_box, bt.n_chosen)
+            _C.call("b2d_refine_bboxes", _C.ptr(refined), _C.ptr(rcount), _C.ptr(bt.tar_box), self.m, _C.ptr(bt.n_chosen),
+                    self.m, _C.ptr(bt.tar_label), _C.ptr(reg_outs[s]), self.C, _C.ptr(bt.tar_is_gt), self.zero4, stds, 1,
+                    _C.ptr(img_hw), self.B, _C.stream())
+            outs.append((bt, ra.out, refined, rcount))
+            boxes, count = refined, rcount
+        return outs
+
+    def backward(self, grad_feats):
+        """grad_feats[s] [B*max_num, C, 7, 7] (zero rows for unused slots) -> per-stage feature gradients (K6);
+        the caller (autograd in the reference) adds the stages."""
+        for s, (tg, ra, _, _, _) in enumerate(self.stages):
+            self.rois_flat[s].copy_(tg.tar_box.permute(1, 0, 2).reshape(4, -1))
+            arr = (_C.c_void_p * _C.MAX_LEVELS)()
+            for i, g in enumerate(self.grads[s]):
+                arr[i] = g.data_ptr()
+            _C.call("b2d_roi_align_bwd", arr, _C.ptr(grad_feats[s]), _C.ptr(self.rois_flat[s]), self.B * self.m,
+                    _C.ptr(self.roi_img), None, self.B * self.m, self.B, ctypes.byref(self.bwd_cfg), _C.ptr(self.bwd_ws),
+                    self.bwd_ws.numel(), _C.stream())
+        return self.grads

@@ -372,3 +372,82 @@ def test_config1_c4_inference_path_vs_reference():
     assert np.array_equal(N(dl), g["det_label"])
     np.testing.assert_allclose(N(ds), g["det_score"], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(N(db), g["det_bbox"], rtol=1e-5, atol=1e-3)
+
+
+# ------------------------------------------------------------------ BASELINE config 3, batched
+def test_cascade_hot_path_batched_vs_oracle():
+    """fused.CascadeHotPath at config-3 geometry (800x1344 pyramid, 2000 proposals, 512 samples, 3 stages; B = 2,
+    64 channels to keep the oracle fast): every stage's assignment, sampling (device-sampler spec), encoded deltas, RoI
+    features, refined boxes and the RoIAlign backward against the oracle."""
+    from oracle import sampler_spec
+    rng = np.random.default_rng(77)
+    B, K, C, NC = 2, 6, 64, 21
+    strides = (4, 8, 16, 32)
+    grids = [(-(-800 // s), -(-1344 // s)) for s in strides]
+    feats_np = [rng.standard_normal((B, C) + g).astype(np.float32) for g in grids]
+    feats = [T(f).contiguous(memory_format=torch.channels_last) for f in feats_np]
+    gt = np.zeros((B, 4, K), np.float32); gl = np.zeros((B, K), np.int64)
+    for b in range(B):
+        gt[b], gl[b] = workload.synth_gt(rng, K, 800, 1333)
+    n = 2000
+    props = np.zeros((B, 4, n), np.float32)
+    for b in range(B):
+        j = rng.integers(0, K, n)
+        jit = rng.normal(0, 25, (4, n))
+        far = rng.random(n) < 0.5
+        cx, cy = rng.uniform(0, 1333, n), rng.uniform(0, 800, n)
+        w, h = rng.uniform(16, 300, n), rng.uniform(16, 300, n)
+        rnd = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2])
+        bb = np.where(far[None], rnd, gt[b][:, j] + jit)
+        props[b] = np.stack([np.clip(np.minimum(bb[0], bb[2]), 0, 1332), np.clip(np.minimum(bb[1], bb[3]), 0, 799),
+                             np.clip(np.maximum(bb[0], bb[2]) + 1, 0, 1332), np.clip(np.maximum(bb[1], bb[3]) + 1, 0, 799)])
+    cp = fused.CascadeHotPath(B, n, grids, DEV, strides=strides, gt_ld=K, feat_channels=C, num_classes=NC, seed=3)
+    m = cp.m
+    reg_np = [rng.normal(0, 1, (B, m, 4 * NC)).astype(np.float32) for _ in range(3)]
+    gcount = torch.full((B,), K, dtype=torch.int32, device=DEV)
+    pcount = torch.full((B,), n, dtype=torch.int32, device=DEV)
+    img_hw = torch.tensor([[800.0, 1333.0]] * B, device=DEV)
+    outs = cp.step(T(props), pcount, feats, T(gt), gcount, T(gl), img_hw, [T(r) for r in reg_np])
+    torch.cuda.synchronize()
+    thresholds = (0.5, 0.6, 0.7)
+    stds = ((0.1, 0.1, 0.2, 0.2), (0.05, 0.05, 0.1, 0.1), (0.033, 0.033, 0.067, 0.067))
+    cur = [np.ascontiguousarray(props[b]) for b in range(B)]
+    for s, (bt, roi_feats, refined, rcount) in enumerate(outs):
+        for b in range(B):
+            olab, _ = oracle.assign_max_iou(cur[b], gt[b], thresholds[s], thresholds[s], thresholds[s])
+            full = np.concatenate([np.arange(1, K + 1), olab]).astype(np.int64)
+            nb = full.shape[0]
+            assert np.array_equal(N(bt.labels[b, :nb]), full), (s, b)
+            seed = ((3 + s) * 1000003 + 1) & 0xFFFFFFFFFFFFFFFF
+            want = sampler_spec.sample(full, m, 128, seed, image_index=b)
+            k = int(bt.n_chosen[b])
+            assert np.array_equal(N(bt.chosen[b, :k]), want), (s, b)
+            allb = np.concatenate([gt[b], cur[b]], 1)
+            tb = allb[:, want]
+            np.testing.assert_array_equal(N(bt.tar_box[b, :, :k]), tb)
+            tg_ = gt[b][:, np.maximum(full[want] - 1, 0)]
+            np.testing.assert_allclose(N(bt.tar_param[b, :, :k]), oracle.bbox2param(tb, tg_, [0.0] * 4, list(stds[s])), rtol=1e-5, atol=1e-5)
+            ref = oracle.roi_extract([f[b] for f in feats_np], tb)
+            assert np.array_equal(N(roi_feats[b * m:b * m + k]).view(np.uint32), ref.view(np.uint32)), (s, b)
+            lab_cls = np.where(full[want] > 0, gl[b][np.maximum(full[want] - 1, 0)], 0)
+            keep = want >= K                                       # GT columns (the first K candidates) are dropped
+            reg = reg_np[s][b, :k].reshape(k, 4, NC)[np.arange(k), :, lab_cls].T       # [4, k]
+            dec = oracle.param2bbox(np.ascontiguousarray(tb[:, keep]), np.ascontiguousarray(reg[:, keep]), [0.0] * 4, list(stds[s]), (800, 1333))
+            kr = int(rcount[b])
+            assert kr == int(keep.sum())
+            np.testing.assert_allclose(N(refined[b, :, :kr]), dec, rtol=1e-5, atol=1e-3)
+            cur[b] = np.ascontiguousarray(N(refined[b, :, :kr]))
+    # backward of the three RoIAlign stages
+    go = [rng.standard_normal((B * m, C, 7, 7)).astype(np.float32) for _ in range(3)]
+    grads = cp.backward([T(g) for g in go])
+    torch.cuda.synchronize()
+    s = 2
+    bt = outs[s][0]
+    for b in range(B):
+        k = int(bt.n_chosen[b])
+        assert k == m
+        tb = N(bt.tar_box[b, :, :k])
+        lv = oracle.level_map(tb)
+        for l, st in enumerate(strides):
+            ref = oracle.roi_align_bwd(go[s][b * m:(b + 1) * m][lv == l], (C,) + grids[l], np.ascontiguousarray(tb[:, lv == l]), 1.0 / st)
+            np.testing.assert_allclose(N(grads[s][l][b]), ref, rtol=1e-5, atol=2e-6)
