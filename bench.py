@@ -97,7 +97,12 @@ class ClockSampler(threading.Thread):
     def summary(self):
         rows = self.rows
         inside = [r for r in rows if self.window and self.window[0] <= r[0] <= self.window[1]]
-        use = inside if inside else rows
+        use = inside
+        if not use and self.window and rows:             # the region is a few ms: fall back to the samples closest to it
+            mid = 0.5 * (self.window[0] + self.window[1])
+            use = sorted(rows, key=lambda r: abs(r[0] - mid))[:8]
+        if not use:
+            use = rows
         sm = [r[1] for r in use]
         mx = [r[2] for r in use]
         reasons = sorted({k for r in use for k in r[3]})
