@@ -7,10 +7,10 @@
 //   k_bwd_meta      per RoI: level, sample geometry, cell bounding box of its taps
 //   k_bwd_bucket    per (image, level): the RoIs of that feature map, in ascending order ("sorted scatter" of the
 //                   RoI list by destination, ordered ballot compaction)
-//   k_roi_align_bwd_tile  one CTA per (16 x 16 cell tile, 64-channel group).  For every RoI of the bucket that
-//                   touches the tile (ascending): stage grad_out[roi][64 ch][bins] / 4 in shared memory as
+//   k_roi_align_bwd_tile  one 512-thread CTA per (16 x 16 cell tile, 128-channel group).  For every RoI of the bucket that
+//                   touches the tile (ascending): stage grad_out[roi][128 ch][bins] / 4 in shared memory as
 //                   [bin][channel]; per tile row / column list the sample rows / columns whose taps hit it with
-//                   their weights (hy or ly / hx or lx); then a thread (row, 4 channels) walks its 16 cells and adds
+//                   their weights (hy or ly / hx or lx); then a thread (warp = tile row, lane = 4 channels) walks its 16 cells and adds
 //                   sum_{(sy, wy) in row} sum_{(sx, wx) in col} (wy * wx) * g[bin(sy, sx)] -- the same per-tap terms
 //                   as torchvision (grad / count * w), accumulated in registers in a fixed order.  Cells are owned
 //                   by exactly one thread: no atomics, no zero-fill pass, run-to-run bit-identical.
@@ -26,7 +26,8 @@ namespace b2d {
 namespace {
 
 constexpr int kT = 16;                 // tile side in cells
-constexpr int kCg = 64;                // channels per CTA
+constexpr int kCg = 128;               // channels per CTA
+constexpr int kBT = 512;               // threads per CTA: warp w owns tile row w, lane l channels 4l .. 4l + 3
 constexpr int kMaxS = 16;              // samples per axis (PH * 2, PW * 2 <= 16)
 constexpr int kPitch = kCg + 4;        // shared-memory pitch of a bin row (floats)
 constexpr int kMaxBinsT = 64;
@@ -103,7 +104,7 @@ struct __align__(8) ColTerm { float w; int off; };     // column weight, float o
 constexpr size_t kTablesBytes = sizeof(float) * kT * kMaxS * 2 + sizeof(int) * kT * kMaxS * 2 + sizeof(ColTerm) * kT * kMaxS * 2 +
                                 2 * sizeof(int) * kT;
 
-__global__ void __launch_bounds__(256, 2) k_roi_align_bwd_tile(TileArgs a) {
+__global__ void __launch_bounds__(kBT, 1) k_roi_align_bwd_tile(TileArgs a) {
     // Everything a RoI needs (staged gradients + tap tables) is double-buffered, so ONE barrier per RoI is enough:
     // a warp that is through with RoI e stages / tabulates RoI e + 1 into the other buffers while slower warps
     // still accumulate RoI e; the barrier of e + 1 is what protects the buffers of e from RoI e + 2.
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(256, 2) k_roi_align_bwd_tile(TileArgs a) {
     };
     float (*s_g)[kMaxBinsT * kPitch] = reinterpret_cast<float (*)[kMaxBinsT * kPitch]>(s_dyn);
     Tables* s_tab = reinterpret_cast<Tables*>(s_dyn + 2 * sizeof(float) * kMaxBinsT * kPitch);
-    __shared__ int s_list[256], s_n, s_warp[8];
+    __shared__ int s_list[kBT], s_n, s_warp[kBT / 32];
     const b2d_roi_cfg& c = a.cfg;
     const int tiles_per_img = a.tile_off[c.num_levels];
     const int img = blockIdx.x / tiles_per_img;
@@ -127,16 +128,15 @@ __global__ void __launch_bounds__(256, 2) k_roi_align_bwd_tile(TileArgs a) {
     const int ty0 = (t / a.tiles_x[lvl]) * kT, tx0 = (t % a.tiles_x[lvl]) * kT;
     const int cg = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int half = lane >> 4, cq = lane & 15;
-    const int row = warp + 8 * half;                     // tile row owned by this thread (with 4 channels); rows w and
-                                                         // w + 8 per warp: a RoI's contiguous row range loads all warps
+    const int cq = lane;
+    const int row = warp;                                // tile row owned by this warp (lane: 4 channels)
     float acc[kT][4];
 #pragma unroll
     for (int x = 0; x < kT; ++x) { acc[x][0] = acc[x][1] = acc[x][2] = acc[x][3] = 0.0f; }
     // staging map of this thread: channel tid % 64, bins tid / 64 + 4 k (no index arithmetic in the loops; the 32 B
     // sectors a warp touches are re-used by its next 7 loads out of L1)
     constexpr int kStage = (kMaxBinsT + 3) / 4;
-    const int sch = tid & (kCg - 1), sb0 = tid >> 6;
+    const int sch = tid & (kCg - 1), sb0 = tid >> 7;
     float sv[kStage];
 
     const int* bl = a.bucket + (long long)(img * c.num_levels + lvl) * a.R;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256, 2) k_roi_align_bwd_tile(TileArgs a) {
         for (int k = 0; k < kStage; ++k)
             if (sb0 + 4 * k < bins) d[4 * k * kPitch] = sv[k] * 0.25f;
     };
-    for (int base = 0; base < nb; base += 256) {
+    for (int base = 0; base < nb; base += kBT) {
         // ---- RoIs of this chunk whose taps touch the tile, ascending
         {
             const int k = base + tid;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256, 2) k_roi_align_bwd_tile(TileArgs a) {
             int before = 0;
             for (int w = 0; w < warp; ++w) before += s_warp[w];
             if (hit) s_list[before + __popc(bm & ((1u << lane) - 1u))] = r;
-            if (tid == 0) { int tot = 0; for (int w = 0; w < 8; ++w) tot += s_warp[w]; s_n = tot; }
+            if (tid == 0) { int tot = 0; for (int w = 0; w < kBT / 32; ++w) tot += s_warp[w]; s_n = tot; }
             __syncthreads();
         }
         const int nhit = s_n;
@@ -185,9 +185,9 @@ __global__ void __launch_bounds__(256, 2) k_roi_align_bwd_tile(TileArgs a) {
             // order their entries with two ballots.
             {
                 const BwdMeta m = a.meta[r];
-                const int k = tid >> 4, q = lane & 15, hs = lane & 16;
-#pragma unroll
-                for (int ax = 0; ax < 2; ++ax) {
+                const int ax = tid >> 8;                             // first 256 threads: rows, the others: columns
+                const int k = (tid >> 4) & 15, q = lane & 15, hs = lane & 16;
+                {
                     const int ns = 2 * (ax ? c.PW : c.PH);
                     const int coord = (ax ? tx0 : ty0) + k;
                     bool hlo = false, hhi = false;
@@ -311,7 +311,7 @@ int roi_align_bwd_tile_try(void* const* grad_feat_ptrs_host, const float* grad_o
     const size_t smem = 2 * sizeof(float) * kMaxBinsT * kPitch + 2 * kTablesBytes;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_roi_align_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    k_roi_align_bwd_tile<<<grid, 256, smem, st>>>(a);
+    k_roi_align_bwd_tile<<<grid, kBT, smem, st>>>(a);
     return check_launch("roi_align_bwd(tile)");
 }
 
