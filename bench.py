@@ -267,6 +267,23 @@ def run_b200(args):
     torch.cuda.synchronize()
     stage_ms = {s: float(np.mean([evs[it][i].elapsed_time(evs[it][i + 1]) for it in range(args.steps)]))
                 for i, s in enumerate(stages)}
+    # ---- the same RoIAlign on bf16 NHWC features (north_star: "NHWC bf16/fp32 features"; reported separately: it halves
+    # the input bytes but cannot meet the 1e-5 parity bar against the fp32 reference)
+    bf16_ms = None
+    if rank == 0:
+        feats16 = [f.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for f in feats[:4]]
+        ra16 = fused.BatchedRoIAlign(B, hp.roi_align.ld, [(256, g[0], g[1]) for g in grids[:4]], list(strides[:4]), dev, layout=2)
+        bt16 = out["rcnn"]
+        for _ in range(3):
+            ra16(feats16, bt16.tar_box, bt16.n_chosen)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            ra16(feats16, bt16.tar_box, bt16.n_chosen)
+        g1.record()
+        torch.cuda.synchronize()
+        bf16_ms = g0.elapsed_time(g1) / args.steps
+        del feats16, ra16
     # ---- end-to-end through the public API with HOST buffers (fp32 NCHW, the reference layout):
     # TrainHotPath.step_from_host = pinned host inputs -> H2D -> NCHW->NHWC -> hot path -> D2H of the results
     def e2e_step():
@@ -326,7 +343,12 @@ def run_b200(args):
                     "stage_ms": stage_ms, "stage_algorithmic_bytes": stage_bytes,
                     "stage_ms_note": "eager per-stage CUDA-event times; multi-kernel stages (proposals: 34 launches) are "
                                      "host-launch-bound there, the step time above is the CUDA-graph replay",
-                    "path_frac": (path_bytes / ((ms / args.steps) / 1e3) / 1e9) / peak}
+                    "path_frac": (path_bytes / ((ms / args.steps) / 1e3) / 1e9) / peak,
+                    "roi_align_bf16_features": None if bf16_ms is None else {
+                        "ms": bf16_ms, "algorithmic_bytes": in_bytes // 2 + out_bytes + int(counts.sum()) * 16,
+                        "achieved": (in_bytes // 2 + out_bytes + int(counts.sum()) * 16) / (bf16_ms / 1e3) / 1e9,
+                        "frac": (in_bytes // 2 + out_bytes + int(counts.sum()) * 16) / (bf16_ms / 1e3) / 1e9 / peak,
+                        "note": "same kernel, bf16 NHWC inputs, fp32 accumulation and output; not the parity path"}}
         cpu = None
         if world == 1 and not args.no_cpu:
             import oracle
