@@ -218,12 +218,65 @@ __device__ __forceinline__ VecF<V> bin_eval(const char* fb, const BinTab* t) {
     return acc;
 }
 
+// Packed-add variant (fp32 features, 4 channels per lane): the same products and sums in the same order, with the
+// additions two channels per instruction (add.rn.f32x2 -> FADD2).  The products stay scalar FMULs on purpose:
+// ptxas (CUDA 12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false, which would change
+// the rounding; a scalar product feeding a packed add is left alone (checked in SASS).
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+template <int PY, int PX>
+__device__ __forceinline__ VecF<4> bin_eval_x2(const char* fb, const BinTab* t) {
+    const int4 ry = *reinterpret_cast<const int4*>(t->ry);
+    const int4 cx = *reinterpret_cast<const int4*>(t->cx);
+    const int ryv[4] = {ry.x, ry.y, ry.z, ry.w}, cxv[4] = {cx.x, cx.y, cx.z, cx.w};
+    float4 v[4][4];
+#pragma unroll
+    for (int r = 0; r < PY + 2; ++r) {
+        const char* rp = fb + (unsigned)ryv[r];      // offsets are non-negative: zero-extend, no sign shifts
+#pragma unroll
+        for (int c = 0; c < PX + 2; ++c) v[r][c] = __ldg(reinterpret_cast<const float4*>(rp + (unsigned)cxv[c]));
+    }
+    unsigned long long a01 = 0ull, a23 = 0ull;      // (+0, +0)
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy) {
+#pragma unroll
+        for (int ix = 0; ix < 2; ++ix) {
+            const int r0 = iy ? PY : 0, c0 = ix ? PX : 0;
+            const float4 w = *reinterpret_cast<const float4*>(&t->w[(iy * 2 + ix) * 4]);
+            const float4 &v1 = v[r0][c0], &v2 = v[r0][c0 + 1], &v3 = v[r0 + 1][c0], &v4 = v[r0 + 1][c0 + 1];
+            a01 = add2(a01, add2(add2(add2(pack2(w.x * v1.x, w.x * v1.y), pack2(w.y * v2.x, w.y * v2.y)),
+                                      pack2(w.z * v3.x, w.z * v3.y)), pack2(w.w * v4.x, w.w * v4.y)));
+            a23 = add2(a23, add2(add2(add2(pack2(w.x * v1.z, w.x * v1.w), pack2(w.y * v2.z, w.y * v2.w)),
+                                      pack2(w.z * v3.z, w.z * v3.w)), pack2(w.w * v4.z, w.w * v4.w)));
+        }
+    }
+    VecF<4> acc;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.f[0]), "=f"(acc.f[1]) : "l"(a01));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.f[2]), "=f"(acc.f[3]) : "l"(a23));
+    return acc;
+}
+
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 // NT threads per CTA, CT channels per CTA (grid.y = C / CT tiles), MINB = min resident CTAs/SM
 // (the register bound that keeps the window loads batched, see the notes above).
-template <typename FT, int NT, int CT, int MINB, int V>
+template <typename FT, int NT, int CT, int MINB, int V, int X2 = 0>
 __global__ void __launch_bounds__(NT, MINB) k_roi_align_win(RoiArgs a, float* __restrict__ out) {
+    static_assert(!X2 || (sizeof(FT) == 4 && V == 4), "packed path: fp32 features, 4 channels per lane");
+    using Tab = BinTab;
     extern __shared__ __align__(16) float s_tile[];                      // [CT][bins] (+ bin table behind it)
-    const long long r = blockIdx.x;
+    const long long r = a.tiles > 0 ? blockIdx.x / a.tiles : blockIdx.x;
+    const int tile = a.tiles > 0 ? blockIdx.x % a.tiles : blockIdx.y;
     const b2d_roi_cfg& c = a.cfg;
     float x1, y1, x2, y2;
     int img;
@@ -233,7 +286,7 @@ __global__ void __launch_bounds__(NT, MINB) k_roi_align_win(RoiArgs a, float* __
     else lvl = c.num_levels > 1 ? roi_level(x1, y1, x2, y2, c.finest_scale, c.num_levels) : 0;
     const int H = c.H[lvl], W = c.W[lvl], C = c.C;
     const int bins = c.PH * c.PW;
-    BinTab* s_tab = reinterpret_cast<BinTab*>(s_tile + CT * bins);
+    Tab* s_tab = reinterpret_cast<Tab*>(s_tile + CT * bins);
     const RoiGeom g = roi_geom(x1, y1, x2, y2, c.spatial_scale[lvl], c.PH, c.PW, 2, c.aligned);
     // L2 prefetch for the RoI that runs `pf_dist` CTAs later: one bulk prefetch per feature row of
     // its tap rectangle (rows are contiguous in NHWC).  Costs no registers, and turns the DRAM
@@ -264,7 +317,7 @@ __global__ void __launch_bounds__(NT, MINB) k_roi_align_win(RoiArgs a, float* __
         const AxisTap ty0 = axis_tap(g.sy, g.bh, ph, 0, 2, H), ty1 = axis_tap(g.sy, g.bh, ph, 1, 2, H);
         const AxisTap tx0 = axis_tap(g.sx, g.bw, pw, 0, 2, W), tx1 = axis_tap(g.sx, g.bw, pw, 1, 2, W);
         const int es = (int)sizeof(FT);
-        BinTab t;
+        Tab t;
         // window rows: PY in {0,1}: lo0 + {0..PY+1} clamped like the taps; PY = 2: {lo0, hi0, lo1, hi1}
         const int dy = ty1.lo - ty0.lo, dx = tx1.lo - tx0.lo;
         const int py = (dy >= 0 && dy < 2) ? dy : 2, px = (dx >= 0 && dx < 2) ? dx : 2;   // 2 = explicit {lo0,hi0,lo1,hi1}
@@ -280,12 +333,16 @@ __global__ void __launch_bounds__(NT, MINB) k_roi_align_win(RoiArgs a, float* __
             for (int ix = 0; ix < 2; ++ix) {
                 const AxisTap& ty = *tys[iy];
                 const AxisTap& tx = *txs[ix];
-                float* w = &t.w[(iy * 2 + ix) * 4];
-                if (ty.valid && tx.valid) { w[0] = ty.h * tx.h; w[1] = ty.h * tx.l; w[2] = ty.l * tx.h; w[3] = ty.l * tx.l; }
-                else { w[0] = w[1] = w[2] = w[3] = 0.0f; }
+                const bool ok = ty.valid && tx.valid;
+                const float wv[4] = {ok ? ty.h * tx.h : 0.0f, ok ? ty.h * tx.l : 0.0f, ok ? ty.l * tx.h : 0.0f,
+                                     ok ? ty.l * tx.l : 0.0f};
+                for (int k = 0; k < 4; ++k) t.w[(iy * 2 + ix) * 4 + k] = wv[k];
             }
         t.pat = py * 3 + px; t._p0 = t._p1 = t._p2 = 0;
         s_tab[bin] = t;
+    } else if ((int)threadIdx.x >= NT - 16) {           // byte offsets of the rotated tile stores: [rot][step]
+        const int k = threadIdx.x - (NT - 16);
+        reinterpret_cast<int*>(s_tab + bins)[k] = (((k & 3) + (k >> 2)) & 3) * bins * 4;
     }
     __syncthreads();
     const FT* feat = reinterpret_cast<const FT*>(a.feat[lvl]) + (long long)img * H * W * C;
@@ -293,30 +350,57 @@ __global__ void __launch_bounds__(NT, MINB) k_roi_align_win(RoiArgs a, float* __
     const int cq = threadIdx.x % LG, grp = threadIdx.x / LG;
     float* o = out + r * (long long)C * bins;
     {
-        const int c0 = blockIdx.y * CT;
+        const int c0 = tile * CT;
         const int ch = c0 + cq * V;
         if (ch < C) {
             const char* fb = reinterpret_cast<const char*>(feat + ch);
+            // The lanes of a warp are 4 * bins floats apart in the [channel][bin] tile, i.e. on 8 banks only; lane
+            // group j = cq / 8 therefore stores component (s + j) % 4 at step s, which spreads every store over
+            // all 32 banks (bins odd).  The rotation is two rounds of selects on the results.
+            // Their four tile offsets come from a 16-entry table in shared memory (one LDS.128 per bin) so that
+            // they occupy no registers while the window is live.
+            const int rot = (cq >> 3) & 3;
+            const bool r1 = rot & 1, r2 = rot & 2;
+            const int4* s_rot = reinterpret_cast<const int4*>(s_tab + bins) + rot;
+            const unsigned st_base = (unsigned)__cvta_generic_to_shared(s_tile + (cq * V) * bins);
             for (int bin = grp; bin < bins; bin += NG) {
-                const BinTab* t = s_tab + bin;
+                const Tab* t = s_tab + bin;
                 VecF<V> acc;
                 const int pat = t->pat, py = pat / 3, px = pat - py * 3;   // uniform over the warps of a bin
+#define B2D_BIN(PY_, PX_)                                                  \
+    do {                                                                   \
+        if constexpr (X2) acc = bin_eval_x2<PY_, PX_>(fb, t);              \
+        else acc = bin_eval<FT, V, PY_, PX_>(fb, t);                       \
+    } while (0)
                 if (py == 0) {
-                    if (px == 0) acc = bin_eval<FT, V, 0, 0>(fb, t);
-                    else if (px == 1) acc = bin_eval<FT, V, 0, 1>(fb, t);
-                    else acc = bin_eval<FT, V, 0, 2>(fb, t);
+                    if (px == 0) B2D_BIN(0, 0);
+                    else if (px == 1) B2D_BIN(0, 1);
+                    else B2D_BIN(0, 2);
                 } else if (py == 1) {
-                    if (px == 0) acc = bin_eval<FT, V, 1, 0>(fb, t);
-                    else if (px == 1) acc = bin_eval<FT, V, 1, 1>(fb, t);
-                    else acc = bin_eval<FT, V, 1, 2>(fb, t);
+                    if (px == 0) B2D_BIN(1, 0);
+                    else if (px == 1) B2D_BIN(1, 1);
+                    else B2D_BIN(1, 2);
                 } else {
-                    if (px == 0) acc = bin_eval<FT, V, 2, 0>(fb, t);
-                    else if (px == 1) acc = bin_eval<FT, V, 2, 1>(fb, t);
-                    else acc = bin_eval<FT, V, 2, 2>(fb, t);
+                    if (px == 0) B2D_BIN(2, 0);
+                    else if (px == 1) B2D_BIN(2, 1);
+                    else B2D_BIN(2, 2);
                 }
-                float* st = s_tile + (cq * V) * bins + bin;    // x / 4 == x * 0.25 exactly
+#undef B2D_BIN
+                // x / 4 == x * 0.25 exactly; rotated stores, see st_rot above
+                if constexpr (V == 4) {
+                    const float f0 = acc.f[0] * 0.25f, f1 = acc.f[1] * 0.25f, f2 = acc.f[2] * 0.25f, f3 = acc.f[3] * 0.25f;
+                    const float g0 = r1 ? f1 : f0, g1 = r1 ? f2 : f1, g2 = r1 ? f3 : f2, g3 = r1 ? f0 : f3;
+                    const int4 ro = *s_rot;
+                    const unsigned sb = st_base + bin * 4;
+                    sts_f32(sb + ro.x, r2 ? g2 : g0);       // f[(s + rot) % 4] at step s
+                    sts_f32(sb + ro.y, r2 ? g3 : g1);
+                    sts_f32(sb + ro.z, r2 ? g0 : g2);
+                    sts_f32(sb + ro.w, r2 ? g1 : g3);
+                } else {
+                    float* st = s_tile + (cq * V) * bins + bin;
 #pragma unroll
-                for (int e = 0; e < V; ++e) st[e * bins] = acc.f[e] * 0.25f;
+                    for (int e = 0; e < V; ++e) st[e * bins] = acc.f[e] * 0.25f;
+                }
             }
         }
         __syncthreads();
@@ -441,16 +525,21 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
         }
         { const char* e = getenv("B2D_ROI_PF"); a.pf_dist = e ? atoi(e) : 0; }   // dev knob (L2 prefetch: measured slower, r1)
         auto launch5 = [&](auto kern, int nt, int ct) {
-            const size_t smem5 = (size_t)ct * bins * 4 + (size_t)bins * sizeof(BinTab);
+            const size_t smem5 = (size_t)ct * bins * 4 + (size_t)bins * sizeof(BinTab) + 64;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
-            dim3 grid((unsigned)R, (unsigned)cdiv(c.C, ct));
+            const int tiles = cdiv(c.C, ct);
+            const char* e_ord = getenv("B2D_ROI_ORDER");
+            a.tiles = (e_ord && atoi(e_ord) == 1 && R * tiles < (1ll << 31)) ? tiles : 0;
+            dim3 grid(a.tiles ? (unsigned)(R * tiles) : (unsigned)R, a.tiles ? 1u : (unsigned)tiles);
             kern<<<grid, nt, smem5, st>>>(a, out);
         };
         // 128 threads x 4 channels = 128 channels per CTA, 6 CTAs/SM: fastest of the measured
         // (threads, channels/CTA, CTAs/SM, channels/thread) points -- (256,256,2,4) 200 us,
         // (256,256,3,4) 169, (128,128,4,4) 169, (128,128,6,4) 159, (128,128,7,4) 186 (spills),
         // (256,128,5,2) 175, (128,64,8,2) 186, (128,64,10,2) 173 (config 2, 4096 RoIs)
-        if (c.layout == 1) launch5(k_roi_align_win<float, 128, 128, 6, 4>, 128, 128);
+        const char* e_x2 = getenv("B2D_ROI_X2");       // dev knob: 0 = scalar adds (157 vs 151 us, config 2)
+        if (c.layout == 1 && !(e_x2 && atoi(e_x2) == 0)) launch5(k_roi_align_win<float, 128, 128, 6, 4, 1>, 128, 128);
+        else if (c.layout == 1) launch5(k_roi_align_win<float, 128, 128, 6, 4>, 128, 128);
         else launch5(k_roi_align_win<__nv_bfloat16, 128, 128, 6, 4>, 128, 128);
     } else if (fast) {
         const size_t smem = (size_t)bins * (kCTile + 4) * 4;

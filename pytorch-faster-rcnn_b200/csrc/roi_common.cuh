@@ -14,6 +14,7 @@ struct RoiArgs {
     long long R;
     long long batched_ld;          // > 0: rois are image-major [B][4][ld], counts per image
     const int* counts;
+    int tiles;                     // window kernel: > 0 = 1-D grid, channel tiles of a RoI adjacent (bid = r * tiles + tile)
     int pf_dist;                   // window kernel: L2-prefetch the RoI pf_dist CTAs ahead (0 = off)
 };
 

@@ -33,10 +33,11 @@ def main():
     which = sys.argv[1:] or ["roi"]
     if "roi" in which:
         ref = None
-        for v in os.environ.get("VARIANTS", "0,4,3,2,1").split(","):
+        # VARIANTS: comma list of <order><x2>[:pf], e.g. "00,10,01,11" -> B2D_ROI_ORDER, B2D_ROI_X2 dev knobs
+        for v in os.environ.get("VARIANTS", "00,10,01,11").split(","):
             if ":" in v:
                 v, pf = v.split(":"); os.environ["B2D_ROI_PF"] = pf
-            os.environ["B2D_ROI_VARIANT"] = v
+            os.environ["B2D_ROI_ORDER"] = v[0]; os.environ["B2D_ROI_X2"] = v[1] if len(v) > 1 else "0"
             hp.roi_align.out.zero_()
             us = timeit(lambda: hp.roi_align(feats, bt.tar_box, bt.n_chosen))
             o = hp.roi_align.out.clone()
