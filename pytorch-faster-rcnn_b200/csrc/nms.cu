@@ -42,11 +42,13 @@ struct NmsSegs {
     // fallback pass of the score-cut scheme (rpn_nms_launch): skip every image whose first pass already produced
     // `need` survivors (chk = per-segment survivor counts of the first pass, L per image)
     const int* chk; int need;
+    int* force_fb;                      // per image: set by the sweep kernel of the first pass when it gives up
 };
 
 // true if the first (score-cut) pass of image b produced enough survivors: nothing left to do for this image
 __device__ __forceinline__ bool cut_pass_sufficient(const NmsSegs& s, int b) {
     if (!s.chk) return false;
+    if (s.force_fb && s.force_fb[b]) return false;
     int tot = 0;
     for (int l = 0; l < s.L; ++l) tot += s.chk[b * s.L + l];
     return tot >= s.need;
@@ -216,6 +218,162 @@ __global__ void __launch_bounds__(64) k_nms_mask_sym_fb(NmsSegs s, int wmax, int
             mask_tile(s, sm, seg, b, l, rb, cb);
             __syncthreads();                                                 // sm is reused by the next tile
         }
+    }
+}
+
+// ---- sweep mask (first pass of the score-cut scheme) -----------------------------------------------------------
+// iou > thr forces the x-extents to overlap: with i the box whose x1 is smaller, inter > thr * u >= thr * area_i
+// gives x1_j < x2_i - thr * w_i.  A CTA buckets the boxes of its segment by x1 (256 uniform cells, counting sort in
+// shared memory) and a box only meets the boxes whose x1 lies in [x1_i, x1_i + (1 - 0.9 thr) w_i + slack] -- a few
+// dozen candidates instead of 2000 on config 2.  The 0.9 and the absolute slack are far larger than any fp32
+// rounding of the quantities involved, so no pair that `suppresses` accepts is skipped; the decision itself is the
+// same function on the same operands (it is symmetric in the two boxes).  kSweepSlices CTAs share a segment: each
+// repeats the (cheap) bucketing and sweeps the boxes i = slice, slice + kSweepSlices, ..., a warp per box with the
+// lanes striding its candidate range.  Bits are OR-ed into the mask, which the launcher zeroes at the start of the step.
+// Gives up -- force_fb[image] = 1, the full dense pass then runs for the image -- on malformed boxes or when the
+// x1 distribution is so concentrated that the cells stop pruning.
+constexpr int kSweepThreads = 256, kSweepCells = 256, kSweepCap = 2048, kSweepSlices = 16;
+__global__ void __launch_bounds__(kSweepThreads) k_nms_sweep(NmsSegs s, float prune) {
+    __shared__ float4 s_box[kSweepCap];
+    __shared__ uint16_t s_ord[kSweepCap];
+    __shared__ int s_start[kSweepCells + 1], s_cur[kSweepCells];
+    __shared__ float s_mn[kSweepThreads / 32], s_mx[kSweepThreads / 32];
+    __shared__ int s_ok, s_heavy;
+    int seg, b, l;
+    seg_of(s.lv0, s.lvn, s.L, blockIdx.x, seg, b, l);
+    const int n = s.counts[seg];
+    if (n <= 0) return;
+    const long long base = (long long)b * s.box_per_img + s.box_off[l];
+    const float4* boxes = s.boxes + base;
+    uint32_t* nz = s.nz + base;
+    uint64_t* mask = s.mask + (long long)b * s.mask_per_img + s.mask_off[l];
+    const int wp = s.wp[l];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_ok = 1; s_heavy = 0; }
+    for (int c = tid; c <= kSweepCells; c += kSweepThreads) s_start[c] = 0;
+    float mn = INFINITY, mx = -INFINITY;
+    bool ok = true;
+    for (int i = tid; i < n; i += kSweepThreads) {
+        const float4 bx = boxes[i];
+        s_box[i] = bx;
+        ok = ok && well_formed(bx);
+        mn = fminf(mn, bx.x); mx = fmaxf(mx, bx.x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (!ok) s_ok = 0;
+    mn = s_mn[0]; mx = s_mx[0];
+    for (int w = 1; w < kSweepThreads / 32; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+    const float inv = (mx > mn) ? (float)kSweepCells / (mx - mn) : 0.0f;
+    auto cell = [&](float x) { return min(kSweepCells - 1, max(0, (int)((x - mn) * inv))); };   // monotone in x
+    __syncthreads();
+    if (!s_ok) {                                                         // malformed box: the dense pass decides
+        if (tid == 0 && blockIdx.y == 0) s.force_fb[b] = 1;
+        return;
+    }
+    for (int i = tid; i < n; i += kSweepThreads) atomicAdd(&s_start[cell(s_box[i].x) + 1], 1);
+    __syncthreads();
+    if (warp == 0) {                                                     // inclusive scan of the 256 counts, 8 per lane
+        int c[8], sum = 0;
+        long long sq = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { c[q] = s_start[lane * 8 + q + 1]; sum += c[q]; sq += (long long)c[q] * c[q]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        int run = incl - sum;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { s_cur[lane * 8 + q] = run; run += c[q]; s_start[lane * 8 + q + 1] = run; }
+        if (lane == 0 && sq > (long long)n * 192) s_heavy = 1;           // cells no longer prune: ~n^2 / 10 pair tests
+    }
+    __syncthreads();
+    if (s_heavy) {
+        if (tid == 0 && blockIdx.y == 0) s.force_fb[b] = 1;
+        return;
+    }
+    for (int i = tid; i < n; i += kSweepThreads) s_ord[atomicAdd(&s_cur[cell(s_box[i].x)], 1)] = (uint16_t)i;
+    __syncthreads();
+    // a warp per box, lanes stride its candidate range (the ranges are heavy-tailed: mean 40, max ~600 on config 2)
+    for (int i = blockIdx.y + kSweepSlices * warp; i < n; i += kSweepSlices * (kSweepThreads / 32)) {
+        const float4 bi = s_box[i];
+        const float wi = bi.z - bi.x;
+        if (!(wi > 0.0f) || !(bi.w - bi.y > 0.0f)) continue;              // empty box: inter == 0 with everything
+        const float ai = area_of(bi);
+        const float xhi = bi.x + prune * wi + 1.0e-4f * (fabsf(bi.z) + 1.0f);
+        const int k1 = s_start[cell(xhi) + 1];
+        for (int k = s_start[cell(bi.x)] + lane; k < k1; k += 32) {
+            const int j = s_ord[k];
+            const float4 bj = s_box[j];
+            if (bj.x < bi.x || (bj.x == bi.x && j <= i) || bj.x > xhi) continue;   // every unordered pair once
+            if (!(bj.y < bi.w && bi.y < bj.w)) continue;                           // no y overlap: inter == 0
+            if (!suppresses_wf(bi, ai, bj, area_of(bj), s.thr, s.thr_lo, s.thr_hi)) continue;
+            atomicOr(reinterpret_cast<unsigned long long*>(&mask[(long long)i * wp + (j >> 6)]), 1ull << (j & 63));
+            atomicOr(reinterpret_cast<unsigned long long*>(&mask[(long long)j * wp + (i >> 6)]), 1ull << (i & 63));
+            atomicOr(&nz[i], 1u << (j >> 6));
+            atomicOr(&nz[j], 1u << (i >> 6));
+        }
+    }
+}
+
+// The tile grid of k_nms_mask_sym is sized by the level capacity (528 tiles per segment at 2000 boxes) while the cut
+// prefixes need a fraction of them, and a CTA that exits at once still costs ~2.6 ns of CTA dispatch.  Here a fixed
+// grid walks the (segment, tile) items that exist: every CTA builds the per-segment tile prefix from the device-side
+// counts (S <= kItemSegs) and takes items blockIdx.x, blockIdx.x + gridDim.x, ...
+constexpr int kItemSegs = 1024;
+// (A 256-thread variant of the tile -- 8 warps x 8 rows, column words assembled from per-warp bytes -- and grids of
+// 8..32 CTAs per SM were measured: 31-38 us for the ~5000 tiles of config 2 either way; the pass is bound by the
+// pair arithmetic itself, ~25 instructions per pair at IPC ~1.5.)
+constexpr int kItemCtasPerSm = 16;
+__global__ void __launch_bounds__(64, kItemCtasPerSm) k_nms_mask_sym_items(NmsSegs s, int S) {
+    __shared__ MaskSmem sm;
+    __shared__ int s_first[kItemSegs + 1];              // first item of segment slot sl (exclusive prefix of the tile counts)
+    for (int sl = threadIdx.x; sl < S; sl += blockDim.x) {
+        int seg, b, l;
+        seg_of(s.lv0, s.lvn, s.L, sl, seg, b, l);
+        const int w = (s.counts[seg] + 63) >> 6;
+        s_first[sl + 1] = w * (w + 1) / 2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {                             // inclusive scan, one warp, 32 slots per round
+        int carry = 0;
+        for (int base = 0; base < S; base += 32) {
+            const int i = base + (int)threadIdx.x;
+            int v = i < S ? s_first[i + 1] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if ((int)threadIdx.x >= o) v += t;
+            }
+            if (i < S) s_first[i + 1] = carry + v;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (threadIdx.x == 0) s_first[0] = 0;
+    }
+    __syncthreads();
+    const int total = s_first[S];
+    for (int it = blockIdx.x; it < total; it += gridDim.x) {
+        int lo = 0, hi = S - 1;                         // last slot with s_first[slot] <= it
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_first[mid] <= it) lo = mid; else hi = mid - 1;
+        }
+        int seg, b, l;
+        seg_of(s.lv0, s.lvn, s.L, lo, seg, b, l);
+        const int w = (s.counts[seg] + 63) >> 6;
+        int rb, cb;
+        tile_of(it - s_first[lo], w, rb, cb);
+        mask_tile(s, sm, seg, b, l, rb, cb);
+        __syncthreads();                                // sm is reused by the next item
     }
 }
 
@@ -490,11 +648,17 @@ static void set_thr(NmsSegs& s, float thr) {
 
 // mask + scan of S segments of at most n_max boxes; s.nz must be zeroed by the caller (sym path)
 static void launch_mask_scan(const NmsSegs& s, int S, int n_max, int max_keep, const ScanOut& o, cudaStream_t st,
-                             bool fallback = false) {
+                             bool fallback = false, bool items = false) {
     const int wmax = (n_max + 63) / 64 > 0 ? (n_max + 63) / 64 : 1;
     dim3 grid(wmax * (wmax + 1) / 2, S);
     if (n_max <= kFpThreads * kFpRows) {
         if (fallback) k_nms_mask_sym_fb<<<148 * 4, 64, 0, st>>>(s, wmax, S);
+        else if (items && S <= kItemSegs) {
+            // sweep: needs a pruning bound (0 < thr < 1), a zeroed mask and a place to report "gave up"
+            const bool sweep = s.force_fb != nullptr;
+            if (sweep) k_nms_sweep<<<dim3(S, kSweepSlices), kSweepThreads, 0, st>>>(s, 1.0f - 0.9f * s.thr);
+            else k_nms_mask_sym_items<<<148 * kItemCtasPerSm, 64, 0, st>>>(s, S);
+        }
         else k_nms_mask_sym<<<grid, 64, 0, st>>>(s, wmax);
         k_nms_scan_fp<<<S, kFpThreads, 0, st>>>(s, max_keep, o);
     } else {
@@ -531,6 +695,15 @@ __global__ void k_fill_i32(int* p, int v, int m) {
     if (i < m) p[i] = v;
 }
 
+// true if pass 1 of the score-cut scheme will use the sweep kernel (the launcher then zeroes the mask for the step)
+bool rpn_nms_sweep_active(const RpnLaunch& p) {
+    const char* e = getenv("B2D_NMS_SWEEP");
+    int n_max = 1;
+    for (int l = 0; l < p.L; ++l) n_max = max(n_max, p.kcap[l]);
+    return !(e && atoi(e) == 0) && p.nms_thr >= 0.05f && p.nms_thr < 1.0f && n_max <= kSweepCap &&
+           p.B * p.L <= kItemSegs;
+}
+
 int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st) {
     NmsSegs s;
     memset(&s, 0, sizeof(s));
@@ -542,8 +715,8 @@ int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st) {
         wmax = max(wmax, s.wp[l]);
     }
     s.boxes = p.sel_box; s.counts = p.sel_count; s.mask = p.mask; s.nz = p.nz;   // nz zeroed with the workspace head
-    if (p.nms_phase == 1) s.counts = p.n_cut;
-    if (p.nms_phase == 2) { s.chk = p.keep1; s.need = p.max_num; }
+    if (p.nms_phase == 1) { s.counts = p.n_cut; s.force_fb = rpn_nms_sweep_active(p) ? p.force_fb : nullptr; }
+    if (p.nms_phase == 2) { s.chk = p.keep1; s.need = p.max_num; s.force_fb = p.force_fb; }
     set_thr(s, p.nms_thr);
     const int S = p.B * p.lvn;
     int n_max = 1;
@@ -554,7 +727,7 @@ int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st) {
     o.src_key = p.sel_key; o.src_idx = p.sel_idx; o.dst_box = p.kept_box; o.dst_key = p.kept_key; o.dst_idx = p.kept_idx;
     o.keep_count = p.keep_count;
     if (p.nms_phase == 1) o.keep_count_aux = p.keep1;
-    launch_mask_scan(s, S, n_max, p.post_nms, o, st, p.nms_phase == 2);
+    launch_mask_scan(s, S, n_max, p.post_nms, o, st, p.nms_phase == 2, p.nms_phase == 1);
     return check_launch("rpn_nms");
 }
 

@@ -28,6 +28,7 @@ struct RpnLaunch {
     // workspace
     uint32_t* hist; int* cand_count; int* cand2_count; int* sel_count; int* keep_count; int* thr_bin;
     int* n_cut; int* keep1;             // score-cut NMS: boxes per segment in the first pass, its survivor counts
+    int* force_fb;                      // score-cut NMS: per image, 1 = the first pass gave up (sweep kernel), run the full pass
     int nms_phase;                      // 0: plain NMS of all selected boxes; 1: score-cut pass; 2: conditional full pass
     uint32_t* nz;                       // NMS: per selected box, bitmap of its non-zero mask words (nms.cu)
     size_t zero_bytes;
@@ -48,5 +49,7 @@ __device__ __forceinline__ void seg_of(int lv0, int lvn, int L, int s, int& seg,
 int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st);
 // nms.cu: per image the key of the M-th best selected box over all levels -> n_cut[segment]
 int rpn_nms_cut_launch(const RpnLaunch& p, int M, cudaStream_t st);
+// nms.cu: pass 1 of the score-cut scheme uses the sweep kernel -> the mask must be zero when it starts
+bool rpn_nms_sweep_active(const RpnLaunch& p);
 
 }  // namespace b2d

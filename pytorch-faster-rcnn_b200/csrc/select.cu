@@ -661,6 +661,7 @@ bool rpn_plan(RpnLaunch& p, const b2d_pyramid* pyr, int B, const b2d_rpn_cfg* cf
     p.thr_bin = (int*)carve((size_t)S * 4);
     p.n_cut = (int*)carve((size_t)S * 4);
     p.keep1 = (int*)carve((size_t)S * 4);
+    p.force_fb = (int*)carve((size_t)B * 4);
     p.nz = (uint32_t*)carve(cfg->do_nms ? (size_t)B * p.sel_per_img * 4 : 0);
     p.zero_bytes = o;                                   // everything above is zeroed per call
     p.cand = (uint64_t*)carve((size_t)B * pyr->total * 8);
@@ -781,6 +782,9 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
         RpnLaunch q = p;
         cudaStream_t cs = st;
         if (nchains > 1) { q.lv0 = c; q.lvn = 1; cs = ls->s[c]; cudaStreamWaitEvent(cs, ls->fork, 0); }
+        // the sweep kernel of NMS pass 1 ORs into a zeroed mask: cleared on the (short) chain of the coarsest level
+        if (cut_m && c == nchains - 1 && rpn_nms_sweep_active(p))
+            cudaMemsetAsync(p.mask, 0, (size_t)B * p.mask_per_img * 8, cs);
         const int S = B * q.lvn;
         int max_chunks = 1;
         bool any_select = false;
@@ -804,14 +808,23 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
     }
     if (cut_m) {
         if (int rc = rpn_nms_cut_launch(p, cut_m, st)) return rc;
-        cudaEventRecord(ls->fork2, st);
-        for (int c = 0; c < nchains; ++c) {                  // pass 1: per-level chains on the cut prefixes
+        // pass 1 on the cut prefixes: one item-walking mask launch + one scan launch over all levels
+        // (B2D_NMS_P1_CHAINS=1: the older per-level chains with capacity-sized tile grids, dispatch-bound)
+        const char* e_p1 = getenv("B2D_NMS_P1_CHAINS");
+        if (e_p1 && atoi(e_p1) == 1) {
+            cudaEventRecord(ls->fork2, st);
+            for (int c = 0; c < nchains; ++c) {
+                RpnLaunch q = p;
+                q.lv0 = c; q.lvn = 1; q.nms_phase = 1;
+                cudaStreamWaitEvent(ls->s[c], ls->fork2, 0);
+                if (int rc = rpn_nms_launch(q, ls->s[c])) return rc;
+                cudaEventRecord(ls->join2[c], ls->s[c]);
+                cudaStreamWaitEvent(st, ls->join2[c], 0);
+            }
+        } else {
             RpnLaunch q = p;
-            q.lv0 = c; q.lvn = 1; q.nms_phase = 1;
-            cudaStreamWaitEvent(ls->s[c], ls->fork2, 0);
-            if (int rc = rpn_nms_launch(q, ls->s[c])) return rc;
-            cudaEventRecord(ls->join2[c], ls->s[c]);
-            cudaStreamWaitEvent(st, ls->join2[c], 0);
+            q.nms_phase = 1;
+            if (int rc = rpn_nms_launch(q, st)) return rc;
         }
         RpnLaunch q = p;                                     // pass 2: all levels, skipped per image when pass 1 sufficed
         q.nms_phase = 2;

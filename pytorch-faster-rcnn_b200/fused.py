@@ -91,6 +91,8 @@ class RpnProposals(object):
         cut = float(os.environ.get("B2D_NMS_CUT", "1.5"))
         if chains and do_nms and c.max_num > 0 and cut > 0 and max(kcaps) <= 2048 and sum(kcaps) > cut * c.max_num:
             self.launches += 3                       # score-cut NMS: k_nms_cut + the conditional full pass (mask, scan)
+            if os.environ.get("B2D_NMS_P1_CHAINS", "0") != "1":
+                self.launches -= 2 * (len(kcaps) - 1)    # pass 1 is one (mask, scan) pair over all levels
 
     def slice(self, b0, b1):
         v = _batch_view(self, b0, b1)
