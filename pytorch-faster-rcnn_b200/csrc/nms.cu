@@ -233,11 +233,12 @@ __global__ void __launch_bounds__(64) k_nms_mask_sym_fb(NmsSegs s, int wmax, int
 // Gives up -- force_fb[image] = 1, the full dense pass then runs for the image -- on malformed boxes or when the
 // x1 distribution is so concentrated that the cells stop pruning.
 constexpr int kSweepThreads = 256, kSweepCells = 256, kSweepCap = 2048, kSweepSlices = 16;
-__global__ void __launch_bounds__(kSweepThreads) k_nms_sweep(NmsSegs s, float prune) {
+__global__ void __launch_bounds__(1024) k_nms_sweep(NmsSegs s, float prune) {
+    const int nthr = blockDim.x, nslice = gridDim.y;      // launch shape: kSweepThreads x kSweepSlices (dev knobs below)
     __shared__ float4 s_box[kSweepCap];
     __shared__ uint16_t s_ord[kSweepCap];
     __shared__ int s_start[kSweepCells + 1], s_cur[kSweepCells];
-    __shared__ float s_mn[kSweepThreads / 32], s_mx[kSweepThreads / 32];
+    __shared__ float s_mn[32], s_mx[32];
     __shared__ int s_ok, s_heavy;
     int seg, b, l;
     seg_of(s.lv0, s.lvn, s.L, blockIdx.x, seg, b, l);
@@ -250,10 +251,10 @@ __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep(NmsSegs s, float pr
     const int wp = s.wp[l];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { s_ok = 1; s_heavy = 0; }
-    for (int c = tid; c <= kSweepCells; c += kSweepThreads) s_start[c] = 0;
+    for (int c = tid; c <= kSweepCells; c += nthr) s_start[c] = 0;
     float mn = INFINITY, mx = -INFINITY;
     bool ok = true;
-    for (int i = tid; i < n; i += kSweepThreads) {
+    for (int i = tid; i < n; i += nthr) {
         const float4 bx = boxes[i];
         s_box[i] = bx;
         ok = ok && well_formed(bx);
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep(NmsSegs s, float pr
     __syncthreads();
     if (!ok) s_ok = 0;
     mn = s_mn[0]; mx = s_mx[0];
-    for (int w = 1; w < kSweepThreads / 32; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+    for (int w = 1; w < nthr / 32; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
     const float inv = (mx > mn) ? (float)kSweepCells / (mx - mn) : 0.0f;
     auto cell = [&](float x) { return min(kSweepCells - 1, max(0, (int)((x - mn) * inv))); };   // monotone in x
     __syncthreads();
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep(NmsSegs s, float pr
         if (tid == 0 && blockIdx.y == 0) s.force_fb[b] = 1;
         return;
     }
-    for (int i = tid; i < n; i += kSweepThreads) atomicAdd(&s_start[cell(s_box[i].x) + 1], 1);
+    for (int i = tid; i < n; i += nthr) atomicAdd(&s_start[cell(s_box[i].x) + 1], 1);
     __syncthreads();
     if (warp == 0) {                                                     // inclusive scan of the 256 counts, 8 per lane
         int c[8], sum = 0;
@@ -301,10 +302,10 @@ __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep(NmsSegs s, float pr
         if (tid == 0 && blockIdx.y == 0) s.force_fb[b] = 1;
         return;
     }
-    for (int i = tid; i < n; i += kSweepThreads) s_ord[atomicAdd(&s_cur[cell(s_box[i].x)], 1)] = (uint16_t)i;
+    for (int i = tid; i < n; i += nthr) s_ord[atomicAdd(&s_cur[cell(s_box[i].x)], 1)] = (uint16_t)i;
     __syncthreads();
     // a warp per box, lanes stride its candidate range (the ranges are heavy-tailed: mean 40, max ~600 on config 2)
-    for (int i = blockIdx.y + kSweepSlices * warp; i < n; i += kSweepSlices * (kSweepThreads / 32)) {
+    for (int i = blockIdx.y + nslice * warp; i < n; i += nslice * (nthr / 32)) {
         const float4 bi = s_box[i];
         const float wi = bi.z - bi.x;
         if (!(wi > 0.0f) || !(bi.w - bi.y > 0.0f)) continue;              // empty box: inter == 0 with everything
@@ -656,7 +657,12 @@ static void launch_mask_scan(const NmsSegs& s, int S, int n_max, int max_keep, c
         else if (items && S <= kItemSegs) {
             // sweep: needs a pruning bound (0 < thr < 1), a zeroed mask and a place to report "gave up"
             const bool sweep = s.force_fb != nullptr;
-            if (sweep) k_nms_sweep<<<dim3(S, kSweepSlices), kSweepThreads, 0, st>>>(s, 1.0f - 0.9f * s.thr);
+            if (sweep) {
+                const char* et = getenv("B2D_SWEEP_T");
+                const char* eg = getenv("B2D_SWEEP_G");
+                const int nt = et ? atoi(et) : kSweepThreads, ng = eg ? atoi(eg) : kSweepSlices;
+                k_nms_sweep<<<dim3(S, ng), nt, 0, st>>>(s, 1.0f - 0.9f * s.thr);
+            }
             else k_nms_mask_sym_items<<<148 * kItemCtasPerSm, 64, 0, st>>>(s, S);
         }
         else k_nms_mask_sym<<<grid, 64, 0, st>>>(s, wmax);

@@ -265,6 +265,35 @@ def test_rpn_score_cut_nms_is_exact(cut, monkeypatch):
             assert np.array_equal(N(rp.prov[b, :n]), offs[lv] + ix), (cut, cfg)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("sweep", ["1", "0"])
+def test_rpn_sweep_nms_concentrated_boxes(sweep, monkeypatch):
+    """The x-sweep mask kernel of NMS pass 1 (csrc/nms.cu k_nms_sweep) gives up when the x1 values of a segment are
+    concentrated (here: huge deltas, every box clips to the full image or to the same left edge) and the dense pass
+    must then produce the reference selection; same check with the sweep disabled."""
+    monkeypatch.setenv("B2D_NMS_SWEEP", sweep)
+    rng = np.random.default_rng(23)
+    grids = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+    strides = (4, 8, 16, 32, 64)
+    pyr = fused.AnchorPyramid(strides, grids)
+    B = 2
+    cls = [rng.normal(0, 1, (B, 3) + g).astype(np.float32) for g in grids]
+    anc = [oracle.anchor_grid(s, gr, scales=[8]).reshape(4, -1) for s, gr in zip(strides, grids)]
+    offs = np.cumsum([0] + [a.shape[1] for a in anc])
+    cfg = dict(pre_nms=1000, post_nms=1000, max_num=1000, nms_iou=0.7, min_bbox_size=0)
+    for shift in (4.0, 1.5):                      # 4: every box is the whole image; 1.5: wide boxes sharing clipped edges
+        reg = [(rng.normal(0, 0.05, (B, 12) + g) + shift).astype(np.float32) for g in grids]
+        rp = fused.RpnProposals(pyr, B, cfg, [0, 0, 0, 0], [1, 1, 1, 1], DEV)
+        props, scores, count = rp([T(c) for c in cls], [T(r) for r in reg], torch.tensor([[400.0, 666.0]] * B, device=DEV))
+        torch.cuda.synchronize()
+        for b in range(B):
+            _, _, lv, ix = oracle.rpn_proposals([c[b].reshape(-1) for c in cls], [r[b].reshape(4, -1) for r in reg], anc, cfg,
+                                                [0, 0, 0, 0], [1, 1, 1, 1], (400, 666))
+            n = int(count[b])
+            assert n == lv.shape[0], (sweep, shift)
+            assert np.array_equal(N(rp.prov[b, :n]), offs[lv] + ix), (sweep, shift)
+
+
 def test_rpn_proposals_selection_bit_exact_vs_oracle():
     g = load_golden("rpn")
     grids = [(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)]
