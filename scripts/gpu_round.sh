@@ -10,6 +10,6 @@ $B > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --steps 3 --warmup 3 --no-graph --no-cpu > gpurun_out/ncu.log 2>&1; echo ncu_rc=$?
 N="ncu --set full --clock-control none --import-source on"
 $N -k regex:k_roi_align_win -s 3 -c 1 -o gpurun_out/prof_${tag}_roi $B > gpurun_out/ncu_a.log 2>&1; echo rc=$?
-$N -k regex:'k_nms_mask_sym|k_nms_cut|k_nms_scan' -s 30 -c 12 -o gpurun_out/prof_${tag}_nms $B > gpurun_out/ncu_b.log 2>&1; echo rc=$?
-$N -k regex:'k_label_rows|k_colmax_rect|k_roi_targets_small|k_merge_rank|k_sample|k_hist|k_compact|k_select' -s 45 -c 17 -o gpurun_out/prof_${tag}_tgt $B > gpurun_out/ncu_c.log 2>&1; echo rc=$?
+$N -k regex:'k_nms_sweep|k_nms_mask_sym|k_nms_cut|k_nms_scan' -s 10 -c 5 -o gpurun_out/prof_${tag}_nms $B > gpurun_out/ncu_b.log 2>&1; echo rc=$?
+$N -k regex:'k_label_rows|k_colmax_rect|k_roi_targets_small|k_merge_rank|k_sample|k_hist|k_compact|k_select' -s 34 -c 17 -o gpurun_out/prof_${tag}_tgt $B > gpurun_out/ncu_c.log 2>&1; echo rc=$?
 python scripts/timeline.py 1 > gpurun_out/timeline_$tag.txt 2>&1; echo tl_rc=$?
