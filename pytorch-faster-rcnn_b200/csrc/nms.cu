@@ -745,12 +745,23 @@ int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st) {
 // of the M-th best box of an image to 16 bits (radix select over the <= 5 x 2048 keys in shared memory) and the
 // number of boxes per level at or above it (ties included); pass 1 runs mask + scan on those prefixes only, pass 2
 // (the full NMS) runs only for images whose pass 1 fell short.
-__global__ void __launch_bounds__(1024) k_nms_cut(RpnLaunch p, int M) {
+__global__ void __launch_bounds__(1024) k_nms_cut(RpnLaunch p, int M, int zero_ctas) {
     extern __shared__ uint32_t s_keys[];                 // sel_per_img entries, level l at sel_off[l]
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_prefix, s_need;
     __shared__ int s_cnt[kMaxLevels];
     const int b = blockIdx.x, tid = threadIdx.x;
+    if (b >= p.B) {
+        // CTAs past the images clear the suppression mask for the sweep kernel of pass 1 (it ORs bits into it) while
+        // the B selecting CTAs are in their latency-bound radix passes: 13 MB at config 2, off the critical path.
+        // (A cudaMemsetAsync on a level chain took 18 us next to the RPN-target kernels and delayed k_select.)
+        const long long words = (long long)p.B * p.mask_per_img;
+        uint4* m16 = reinterpret_cast<uint4*>(p.mask);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (long long i = (long long)(b - p.B) * 1024 + tid; i < words / 2; i += (long long)zero_ctas * 1024) m16[i] = z;
+        if ((words & 1) && b == p.B && tid == 0) p.mask[words - 1] = 0ull;
+        return;
+    }
     int total = 0;
     {   // all levels' keys requested before the first use (<= 2 per level and thread: kcap <= 2048)
         uint32_t v[kMaxLevels][2];
@@ -850,7 +861,8 @@ int rpn_nms_cut_launch(const RpnLaunch& p, int M, cudaStream_t st) {
         cudaFuncSetAttribute(k_nms_cut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = smem;
     }
-    k_nms_cut<<<p.B, 1024, smem, st>>>(p, M);
+    const int zero_ctas = rpn_nms_sweep_active(p) ? 148 : 0;
+    k_nms_cut<<<p.B + zero_ctas, 1024, smem, st>>>(p, M, zero_ctas);
     return check_launch("rpn_nms_cut");
 }
 

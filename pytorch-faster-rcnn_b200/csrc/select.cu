@@ -782,9 +782,6 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
         RpnLaunch q = p;
         cudaStream_t cs = st;
         if (nchains > 1) { q.lv0 = c; q.lvn = 1; cs = ls->s[c]; cudaStreamWaitEvent(cs, ls->fork, 0); }
-        // the sweep kernel of NMS pass 1 ORs into a zeroed mask: cleared on the (short) chain of the coarsest level
-        if (cut_m && c == nchains - 1 && rpn_nms_sweep_active(p))
-            cudaMemsetAsync(p.mask, 0, (size_t)B * p.mask_per_img * 8, cs);
         const int S = B * q.lvn;
         int max_chunks = 1;
         bool any_select = false;
