@@ -366,6 +366,27 @@ __global__ void __launch_bounds__(kSelThreads) k_select(RpnLaunch p) {
     float4* sel_box = p.sel_box + so;
     uint32_t* sel_key = p.sel_key + so;
     int* sel_idx = p.sel_idx + so;
+    if (p.raw || !(p.min_size > 0.0f)) {
+        // no size filter (min_bbox_size = 0, every reference RPN config): every selected box is kept at its rank, so
+        // the order-preserving compaction below (three block barriers per 1024 boxes) is not needed, and the
+        // scattered delta loads of a thread's boxes are independent of each other
+#pragma unroll 2
+        for (int r = threadIdx.x; r < kk; r += blockDim.x) {
+            const uint64_t c = s_buf[r < split_at ? r : split_off + (r - split_at)];
+            const uint32_t idx = comp_idx(c);
+            const uint32_t key = identity ? f2key(load_logit(cls, n, (int)idx, p.score_mode, p.cls_ch)) : comp_key(c);
+            Box o{0, 0, 0, 0};
+            if (!p.raw) {
+                const Box a = anchor_flat(lv, (int)idx);
+                o = decode_box(a, reg[idx], reg[n + idx], reg[2 * n + idx], reg[3 * n + idx], p.ms, true, img_h, img_w);
+            }
+            sel_box[r] = make_float4(o.x1, o.y1, o.x2, o.y2);
+            sel_key[r] = key;
+            sel_idx[r] = (int)idx;
+        }
+        if (threadIdx.x == 0) p.sel_count[seg] = kk;
+        return;
+    }
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
     for (int r0 = 0; r0 < kk; r0 += blockDim.x) {
