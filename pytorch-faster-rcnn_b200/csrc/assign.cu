@@ -1072,11 +1072,8 @@ int b2d_sample_labels(int* chosen, int* n_chosen, const int64_t* labels, long lo
     B2D_REQUIRE(B >= 1 && max_num >= 1 && max_num <= kSampleSortCap && pos_num >= 0 && pos_num <= max_num,
                 "sample_labels: need 1 <= max_num <= 4096 and pos_num <= max_num");
     B2D_REQUIRE(n < (1ll << 31), "sample_labels: n too large");
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSortCap * 8);
-        attr_set = true;
-    }
+    // function attributes are per device: set on every call (a process may drive several GPUs)
+    cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSortCap * 8);
     k_sample<<<B, kSampleThreads, kSampleSortCap * 8, (cudaStream_t)stream>>>(
         chosen, n_chosen, labels, ld, count, count_add, n, census, pos_list, pos_cap, max_num, pos_num, seed);
     return check_launch("sample_labels");

@@ -543,12 +543,11 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
         else launch5(k_roi_align_win<__nv_bfloat16, 128, 128, 6, 4>, 128, 128);
     } else if (fast) {
         const size_t smem = (size_t)bins * (kCTile + 4) * 4;
-        static size_t attr_f32 = 0, attr_bf16 = 0;
         if (c.layout == 1) {
-            if (smem > attr_f32) { cudaFuncSetAttribute(k_roi_align_nhwc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_f32 = smem; }
+            cudaFuncSetAttribute(k_roi_align_nhwc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
             k_roi_align_nhwc<float><<<(unsigned)R, 256, smem, st>>>(a, out);
         } else {
-            if (smem > attr_bf16) { cudaFuncSetAttribute(k_roi_align_nhwc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_bf16 = smem; }
+            cudaFuncSetAttribute(k_roi_align_nhwc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             k_roi_align_nhwc<__nv_bfloat16><<<(unsigned)R, 256, smem, st>>>(a, out);
         }
     } else {

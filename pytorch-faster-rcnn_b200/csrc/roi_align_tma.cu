@@ -449,14 +449,12 @@ int roi_align_tma_try(const RoiArgs& a, float* out, cudaStream_t st) {
     const size_t smem = (size_t)kNS * kSlotBytes + (size_t)c.C * bins * 4 + 2 * (size_t)bins * sizeof(TBin) + 2 * sizeof(Hdr) +
                         (2 * kNS + 4) * sizeof(uint64_t) + (kNS + 32 * kProdWarps) * sizeof(int);
     if (smem > 227 * 1024) return 1;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_roi_align_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k_roi_align_tma<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    }
+    int sms = 0, dev = 0;                                  // per device, every call (a process may drive several GPUs)
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_roi_align_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_roi_align_tma<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (sms <= 0) sms = 1;
     const unsigned grid = (unsigned)(a.R < sms ? a.R : sms);
     RoiArgs b = a;
     { const char* e = getenv("B2D_ROI_TMA_DEV"); b.pf_dist = e ? atoi(e) : 0; }

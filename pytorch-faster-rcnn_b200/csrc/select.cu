@@ -769,12 +769,9 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
     p.img_hw = img_hw;
     { const char* e = getenv("B2D_DBG"); p.dbg = e ? atoi(e) : 0; }
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
-        cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
-        attr_set = true;
-    }
+    // function attributes are per device: set on every call (a process may drive several GPUs)
+    cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
+    cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
     cudaMemsetAsync(workspace, 0, p.zero_bytes, st);
     // Per-level chains.  hist -> compact -> select -> NMS mask -> scan of one level only depends on that level, and
     // all of them but the mask are small latency-bound grids; run as ONE launch per kernel over all levels the step
@@ -899,11 +896,7 @@ int b2d_topk(int* idx, int* out_count, const float* values, long long ld, const 
     B2D_REQUIRE(idx && out_count && values && S >= 1 && k >= 1, "topk: bad args");
     cudaStream_t st = (cudaStream_t)stream;
     if (n <= kSortCap) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_topk_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
-            attr_set = true;
-        }
+        cudaFuncSetAttribute(k_topk_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);   // per device
         k_topk_small<<<S, kSelThreads, kSortCap * 8, st>>>(idx, out_count, values, ld, counts, n, k);
         return check_launch("topk");
     }
@@ -917,11 +910,7 @@ int b2d_topk(int* idx, int* out_count, const float* values, long long ld, const 
     B2D_REQUIRE(rpn_plan(p, &pyr, S, &cfg, (char*)workspace, &need), "topk: unsupported size");
     B2D_REQUIRE(workspace && ws_bytes >= need, "topk: workspace too small");
     p.cls[0] = values; p.reg[0] = nullptr; p.img_hw = nullptr; p.raw = 1;
-    static bool attr2 = false;
-    if (!attr2) {
-        cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
-        attr2 = true;
-    }
+    cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);   // per device
     cudaMemsetAsync(workspace, 0, p.zero_bytes, st);
     dim3 grid(cdiv(n, kChunk), S);
     k_hist<<<grid, kHcThreads, 0, st>>>(p);
