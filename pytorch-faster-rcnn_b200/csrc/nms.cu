@@ -660,7 +660,9 @@ static void launch_mask_scan(const NmsSegs& s, int S, int n_max, int max_keep, c
             if (sweep) {
                 const char* et = getenv("B2D_SWEEP_T");
                 const char* eg = getenv("B2D_SWEEP_G");
-                const int nt = et ? atoi(et) : kSweepThreads, ng = eg ? atoi(eg) : kSweepSlices;
+                int nt = et ? atoi(et) : kSweepThreads, ng = eg ? atoi(eg) : kSweepSlices;
+                if (nt < 32 || nt > 1024 || (nt & 31)) nt = kSweepThreads;       // dev knobs: ignore unusable values
+                if (ng < 1 || ng > 64) ng = kSweepSlices;
                 k_nms_sweep<<<dim3(S, ng), nt, 0, st>>>(s, 1.0f - 0.9f * s.thr);
             }
             else k_nms_mask_sym_items<<<148 * kItemCtasPerSm, 64, 0, st>>>(s, S);
