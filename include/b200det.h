@@ -57,6 +57,8 @@ typedef struct b2d_pyramid {
 
 B2D_API const char* b2d_last_error_string(void);
 B2D_API int b2d_version(void);
+/* re-read the B2D_* development knobs from the environment (they are otherwise read once, at first use) */
+B2D_API void b2d_reload_knobs(void);
 
 /* ---- K1: AnchorCreator.__call__ (lib/anchor.py:107-129) -> out [4, A, H, W] */
 B2D_API int b2d_anchor_grid(float* out, const float* ws, const float* hs, int A, int H, int W, float stride,

@@ -97,7 +97,7 @@ _SIZE_FNS = {
     "b2d_rcnn_detect_workspace_bytes": [c_int, c_int],
     "b2d_anchor_loss_workspace_bytes": [_P, c_int],
 }
-EXPORTS = sorted(list(_SIGS) + list(_SIZE_FNS) + ["b2d_last_error_string", "b2d_version"])
+EXPORTS = sorted(list(_SIGS) + list(_SIZE_FNS) + ["b2d_last_error_string", "b2d_version", "b2d_reload_knobs"])
 
 
 def lib():
@@ -120,8 +120,14 @@ def lib():
         fn.restype = c_size_t
     L.b2d_last_error_string.restype = ctypes.c_char_p
     L.b2d_version.restype = c_int
+    L.b2d_reload_knobs.restype = None
     _lib = L
     return L
+
+
+def reload_knobs():
+    """Re-read the B2D_* development knobs from the environment (the library reads them once, at first use)."""
+    lib().b2d_reload_knobs()
 
 
 def check(rc, what):

@@ -1031,7 +1031,7 @@ int b2d_assign_max_iou(int64_t* labels, float* max_iou, long long out_ld, const 
         k_assign_small<<<B, kSmallThreads, 0, st>>>(a, labels, max_iou, census, pos_list, pos_cap);
         return check_launch("assign_max_iou");
     }
-    if (a.use_pyr && !prepend_gt && !getenv("B2D_ASSIGN_OLD")) {
+    if (a.use_pyr && !prepend_gt && !knobs().assign_old) {
         uint32_t* cmx = (uint32_t*)workspace;
         cudaMemsetAsync(census, 0, sizeof(int) * 4 * B, st);
         cudaMemsetAsync(cmx, 0, sizeof(uint32_t) * (size_t)B * gt_ld, st);

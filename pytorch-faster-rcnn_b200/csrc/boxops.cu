@@ -19,9 +19,40 @@ void set_error(const char* msg) {
     g_err = msg ? msg : "";
 }
 
+static Knobs g_knobs;
+static std::once_flag g_knobs_once;
+
+static void load_knobs() {
+    auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    Knobs k;
+    k.dbg = geti("B2D_DBG", 0);
+    k.rpn_chains = geti("B2D_RPN_CHAINS", 1);
+    k.rpn_front = geti("B2D_RPN_FRONT", 1);
+    k.rpn_back = geti("B2D_RPN_BACK", 1);
+    { const char* e = getenv("B2D_NMS_CUT"); k.nms_cut = e ? atof(e) : 1.5; }
+    k.nms_p1_chains = geti("B2D_NMS_P1_CHAINS", 0);
+    k.nms_sweep = geti("B2D_NMS_SWEEP", 1);
+    k.sweep_t = geti("B2D_SWEEP_T", 0);
+    k.sweep_g = geti("B2D_SWEEP_G", 0);
+    k.roi_tma = geti("B2D_ROI_TMA", 0);
+    k.roi_pf = geti("B2D_ROI_PF", 0);
+    k.roi_order = geti("B2D_ROI_ORDER", 0);
+    k.roi_x2 = geti("B2D_ROI_X2", 1);
+    k.roi_tma_dev = geti("B2D_ROI_TMA_DEV", 0);
+    k.roi_bwd_tile = geti("B2D_ROI_BWD_TILE", 1);
+    k.assign_old = getenv("B2D_ASSIGN_OLD") != nullptr;
+    k.pdl = geti("B2D_PDL", 1);
+    k.debug_sync = getenv("B2D_DEBUG_SYNC") != nullptr;
+    g_knobs = k;
+}
+
+const Knobs& knobs() {
+    std::call_once(g_knobs_once, load_knobs);
+    return g_knobs;
+}
+
 int check_launch(const char* what) {
-    static const bool debug_sync = getenv("B2D_DEBUG_SYNC") != nullptr;   // debugging aid: localise a faulting kernel
-    if (debug_sync) cudaDeviceSynchronize();
+    if (knobs().debug_sync) cudaDeviceSynchronize();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         char buf[512];
@@ -140,7 +171,9 @@ const char* b2d_last_error_string(void) {
     return copy.c_str();
 }
 
-int b2d_version(void) { return 100; }
+int b2d_version(void) { return 200; }
+
+void b2d_reload_knobs(void) { knobs(); load_knobs(); }
 
 int b2d_anchor_grid(float* out, const float* ws_host, const float* hs_host, int A, int H, int W, float stride,
                     int center_lt, void* stream) {

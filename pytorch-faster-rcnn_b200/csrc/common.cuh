@@ -18,6 +18,29 @@ constexpr int kMaxAnchorsPerCell = B2D_MAX_ANCHORS;
 void set_error(const char* msg);
 int check_launch(const char* what);
 
+// Development knobs (DESIGN.md "Development knobs").  Read from the environment ONCE, when the library is first used
+// (b2d_reload_knobs() re-reads them: tests only) -- no launcher calls getenv on the hot path.
+struct Knobs {
+    int dbg;               // B2D_DBG            select.cu debug switch
+    int rpn_chains;        // B2D_RPN_CHAINS     1: per-level chains on internal streams (multi-kernel path)
+    int rpn_front;         // B2D_RPN_FRONT      1: cluster kernel k_rpn_front (hist + threshold + compact + sort + decode)
+    int rpn_back;          // B2D_RPN_BACK       1: cluster kernel k_rpn_back (cut + sweep + scan + merge)
+    double nms_cut;        // B2D_NMS_CUT        score-cut factor (default 1.5), 0 disables
+    int nms_p1_chains;     // B2D_NMS_P1_CHAINS
+    int nms_sweep;         // B2D_NMS_SWEEP      0 disables the x-sweep mask kernel
+    int sweep_t, sweep_g;  // B2D_SWEEP_T / _G   launch shape of k_nms_sweep
+    int roi_tma;           // B2D_ROI_TMA        1: TMA-ring RoIAlign, 2: tensor-map window RoIAlign
+    int roi_pf;            // B2D_ROI_PF         L2 prefetch distance of k_roi_align_win
+    int roi_order;         // B2D_ROI_ORDER
+    int roi_x2;            // B2D_ROI_X2         0: scalar adds in k_roi_align_win
+    int roi_tma_dev;       // B2D_ROI_TMA_DEV
+    int roi_bwd_tile;      // B2D_ROI_BWD_TILE   0: generic backward kernel
+    int assign_old;        // B2D_ASSIGN_OLD     1: round-1a assignment kernels in pyramid mode
+    int pdl;               // B2D_PDL            0: no programmatic dependent launch edges
+    int debug_sync;        // B2D_DEBUG_SYNC     synchronise after every launch (localise a faulting kernel)
+};
+const Knobs& knobs();
+
 #define B2D_REQUIRE(cond, msg)            \
     do {                                  \
         if (!(cond)) {                    \

@@ -658,9 +658,7 @@ static void launch_mask_scan(const NmsSegs& s, int S, int n_max, int max_keep, c
             // sweep: needs a pruning bound (0 < thr < 1), a zeroed mask and a place to report "gave up"
             const bool sweep = s.force_fb != nullptr;
             if (sweep) {
-                const char* et = getenv("B2D_SWEEP_T");
-                const char* eg = getenv("B2D_SWEEP_G");
-                int nt = et ? atoi(et) : kSweepThreads, ng = eg ? atoi(eg) : kSweepSlices;
+                int nt = knobs().sweep_t ? knobs().sweep_t : kSweepThreads, ng = knobs().sweep_g ? knobs().sweep_g : kSweepSlices;
                 if (nt < 32 || nt > 1024 || (nt & 31)) nt = kSweepThreads;       // dev knobs: ignore unusable values
                 if (ng < 1 || ng > 64) ng = kSweepSlices;
                 k_nms_sweep<<<dim3(S, ng), nt, 0, st>>>(s, 1.0f - 0.9f * s.thr);
@@ -705,10 +703,9 @@ __global__ void k_fill_i32(int* p, int v, int m) {
 
 // true if pass 1 of the score-cut scheme will use the sweep kernel (the launcher then zeroes the mask for the step)
 bool rpn_nms_sweep_active(const RpnLaunch& p) {
-    const char* e = getenv("B2D_NMS_SWEEP");
     int n_max = 1;
     for (int l = 0; l < p.L; ++l) n_max = max(n_max, p.kcap[l]);
-    return !(e && atoi(e) == 0) && p.nms_thr >= 0.05f && p.nms_thr < 1.0f && n_max <= kSweepCap &&
+    return knobs().nms_sweep != 0 && p.nms_thr >= 0.05f && p.nms_thr < 1.0f && n_max <= kSweepCap &&
            p.B * p.L <= kItemSegs;
 }
 

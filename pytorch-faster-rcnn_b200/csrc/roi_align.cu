@@ -517,19 +517,17 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
     if (win) {
         // TMA-ring kernel (roi_align_tma.cu): opt-in with B2D_ROI_TMA=1.  Bit-identical, but measured slower than
         // the L1-path kernel below on config 2 (380 vs 159 us, round 1: issue-bound consumers).
-        const char* e_tma = getenv("B2D_ROI_TMA");
-        const int use_tma = e_tma ? atoi(e_tma) : 0;
+        const int use_tma = knobs().roi_tma;
         if (use_tma) {
             const int rc = roi_align_tma_try(a, out, st);
             if (rc != 1) return rc;
         }
-        { const char* e = getenv("B2D_ROI_PF"); a.pf_dist = e ? atoi(e) : 0; }   // dev knob (L2 prefetch: measured slower, r1)
+        a.pf_dist = knobs().roi_pf;   // dev knob (L2 prefetch: measured slower, r1)
         auto launch5 = [&](auto kern, int nt, int ct) {
             const size_t smem5 = (size_t)ct * bins * 4 + (size_t)bins * sizeof(BinTab) + 64;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
             const int tiles = cdiv(c.C, ct);
-            const char* e_ord = getenv("B2D_ROI_ORDER");
-            a.tiles = (e_ord && atoi(e_ord) == 1 && R * tiles < (1ll << 31)) ? tiles : 0;
+            a.tiles = (knobs().roi_order == 1 && R * tiles < (1ll << 31)) ? tiles : 0;
             dim3 grid(a.tiles ? (unsigned)(R * tiles) : (unsigned)R, a.tiles ? 1u : (unsigned)tiles);
             kern<<<grid, nt, smem5, st>>>(a, out);
         };
@@ -537,8 +535,8 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
         // (threads, channels/CTA, CTAs/SM, channels/thread) points -- (256,256,2,4) 200 us,
         // (256,256,3,4) 169, (128,128,4,4) 169, (128,128,6,4) 159, (128,128,7,4) 186 (spills),
         // (256,128,5,2) 175, (128,64,8,2) 186, (128,64,10,2) 173 (config 2, 4096 RoIs)
-        const char* e_x2 = getenv("B2D_ROI_X2");       // dev knob: 0 = scalar adds (157 vs 151 us, config 2)
-        if (c.layout == 1 && !(e_x2 && atoi(e_x2) == 0)) launch5(k_roi_align_win<float, 128, 128, 6, 4, 1>, 128, 128);
+        // B2D_ROI_X2=0 (dev knob): scalar adds (157 vs 151 us, config 2)
+        if (c.layout == 1 && knobs().roi_x2 != 0) launch5(k_roi_align_win<float, 128, 128, 6, 4, 1>, 128, 128);
         else if (c.layout == 1) launch5(k_roi_align_win<float, 128, 128, 6, 4>, 128, 128);
         else launch5(k_roi_align_win<__nv_bfloat16, 128, 128, 6, 4>, 128, 128);
     } else if (fast) {

@@ -457,7 +457,7 @@ int roi_align_tma_try(const RoiArgs& a, float* out, cudaStream_t st) {
     if (sms <= 0) sms = 1;
     const unsigned grid = (unsigned)(a.R < sms ? a.R : sms);
     RoiArgs b = a;
-    { const char* e = getenv("B2D_ROI_TMA_DEV"); b.pf_dist = e ? atoi(e) : 0; }
+    b.pf_dist = knobs().roi_tma_dev;
     if (c.layout == 1) k_roi_align_tma<float><<<grid, kThreads, smem, st>>>(b, out);
     else k_roi_align_tma<__nv_bfloat16><<<grid, kThreads, smem, st>>>(b, out);
     return check_launch("roi_align_fwd(tma)");

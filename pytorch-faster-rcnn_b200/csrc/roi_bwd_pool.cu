@@ -290,8 +290,7 @@ int b2d_roi_align_bwd(void* const* grad_feat_ptrs_host, const float* grad_out, c
     cudaStream_t st = (cudaStream_t)stream;
     {   // tile-gather kernel (roi_align_bwd_tile.cu) for NHWC fp32 gradients with 2x2 samples; B2D_ROI_BWD_TILE=0 forces
         // the generic, torchvision-bit-identical kernel below
-        const char* e = getenv("B2D_ROI_BWD_TILE");
-        if (!e || atoi(e) != 0) {
+        if (knobs().roi_bwd_tile != 0) {
             const int rc = roi_align_bwd_tile_try(grad_feat_ptrs_host, grad_out, rois, roi_ld, roi_img, levels, R, B, c,
                                                   (char*)workspace + bwd_levels_bytes(R), st);
             if (rc != 1) return rc;

@@ -38,3 +38,19 @@ def c4_inputs():
     cls_out[:, 0] += 2.0
     reg_out = rng.normal(0, 0.5, (300, 84)).astype(np.float32)
     return cls, reg, feat, cls_out, reg_out
+
+
+@pytest.fixture
+def setknob(monkeypatch):
+    """Set B2D_* development knobs for one test: the library reads its knobs once, so the environment change is
+    followed by b2d_reload_knobs(); both are undone at teardown."""
+    from b200det import _C
+
+    def _set(**kv):
+        for k, v in kv.items():
+            monkeypatch.setenv(k, str(v))
+        _C.reload_knobs()
+
+    yield _set
+    monkeypatch.undo()
+    _C.reload_knobs()

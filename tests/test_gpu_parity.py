@@ -236,12 +236,12 @@ def test_rpn_head_predict_single_image_method_form_vs_reference():
 
 
 @pytest.mark.parametrize("cut", ["0", "1.0", "1.3", "2"])
-def test_rpn_score_cut_nms_is_exact(cut, monkeypatch):
+def test_rpn_score_cut_nms_is_exact(cut, setknob):
     """Score-cut NMS (csrc/nms.cu k_nms_cut): pass 1 on the cut * max_num best boxes + conditional full pass must
     give the selection of the plain per-level NMS for every cut factor (1.0: pass 1 always falls short -> the
     fallback pass does the work; 2: the default; 0: disabled), on clustered boxes (low survival) and at config-2
     sizes, against the oracle's provenance (level, index) of every proposal."""
-    monkeypatch.setenv("B2D_NMS_CUT", cut)
+    setknob(B2D_NMS_CUT=cut)
     rng = np.random.default_rng(17)
     grids = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
     strides = (4, 8, 16, 32, 64)
@@ -267,11 +267,11 @@ def test_rpn_score_cut_nms_is_exact(cut, monkeypatch):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("sweep", ["1", "0"])
-def test_rpn_sweep_nms_concentrated_boxes(sweep, monkeypatch):
+def test_rpn_sweep_nms_concentrated_boxes(sweep, setknob):
     """The x-sweep mask kernel of NMS pass 1 (csrc/nms.cu k_nms_sweep) gives up when the x1 values of a segment are
     concentrated (here: huge deltas, every box clips to the full image or to the same left edge) and the dense pass
     must then produce the reference selection; same check with the sweep disabled."""
-    monkeypatch.setenv("B2D_NMS_SWEEP", sweep)
+    setknob(B2D_NMS_SWEEP=sweep)
     rng = np.random.default_rng(23)
     grids = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
     strides = (4, 8, 16, 32, 64)
@@ -306,6 +306,35 @@ def test_rpn_proposals_selection_bit_exact_vs_oracle():
         _, _, count, prov = _rpn_run(g, c, B=1)
         _, _, lv, ix = oracle.rpn_proposals(lg, dl, anc, c, [0, 0, 0, 0], [1, 1, 1, 1], tuple(g["img_shape"][:2]))
         assert np.array_equal(prov[0, :count[0]], offs[lv] + ix), i
+
+
+
+@pytest.mark.parametrize("knobs", [{}, {"B2D_NMS_CUT": "0"}, {"B2D_NMS_SWEEP": "0"}, {"B2D_RPN_FRONT": "0", "B2D_RPN_BACK": "0"}])
+def test_rpn_proposals_benchmarked_config2_full_size_vs_oracle(knobs, setknob):
+    """The configuration bench.py times -- workload.config2(B=8): 200x336 ... 13x21 grids, 268 569 anchors per image,
+    pre/post/max 2000, thr 0.7 -- through fused.RpnProposals against oracle.rpn_proposals for EVERY image: provenance
+    (level, anchor index) of every proposal bit-exact, boxes / scores within 1e-5.  Default knobs (fused cluster
+    kernels, score-cut + sweep NMS), score cut off, sweep off, and the round-1 multi-kernel chain."""
+    setknob(**knobs)
+    B = 8
+    w = workload.config2(B=B, K=8, with_feats=False)
+    grids, strides = w["grids"], w["strides"]
+    pyr = fused.AnchorPyramid(strides, grids)
+    cfg = dict(pre_nms=2000, post_nms=2000, max_num=2000, nms_iou=0.7, min_bbox_size=0)
+    rp = fused.RpnProposals(pyr, B, cfg, [0, 0, 0, 0], [1, 1, 1, 1], DEV)
+    img_hw = torch.tensor([[800.0, 1333.0]] * B, device=DEV)
+    props, scores, count = rp([T(c) for c in w["cls"]], [T(r) for r in w["reg"]], img_hw)
+    torch.cuda.synchronize()
+    anc = [oracle.anchor_grid(s, gr, scales=[8]).reshape(4, -1) for s, gr in zip(strides, grids)]
+    offs = np.cumsum([0] + [a.shape[1] for a in anc])
+    for b in range(B):
+        ob, osc, lv, ix = oracle.rpn_proposals([c[b].reshape(-1) for c in w["cls"]], [r[b].reshape(4, -1) for r in w["reg"]],
+                                               anc, cfg, [0, 0, 0, 0], [1, 1, 1, 1], (800, 1333))
+        n = int(count[b])
+        assert n == lv.shape[0] == 2000, (b, n)
+        assert np.array_equal(N(rp.prov[b, :n]), offs[lv] + ix), (knobs, b)
+        np.testing.assert_allclose(N(scores[b, :n]), osc, rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(N(props[b, :, :n]), ob, rtol=1e-5, atol=1e-3)
 
 
 def test_topk_large_and_ties():
@@ -391,8 +420,8 @@ def _ring_case(seed, C, K, B=2):
 
 
 @pytest.mark.parametrize("C,K", [(256, 700), (128, 333)])
-def test_roi_align_tma_ring_bit_exact_vs_oracle(C, K, monkeypatch):
-    monkeypatch.setenv("B2D_ROI_TMA", "1")                                # opt-in kernel
+def test_roi_align_tma_ring_bit_exact_vs_oracle(C, K, setknob):
+    setknob(B2D_ROI_TMA=1)                                                # opt-in kernel
     grids, feats, rois, img = _ring_case(11, C, K)
     fs = [T(f).contiguous(memory_format=torch.channels_last) for f in feats]
     out = N(bregion.roi_align_levels(fs, T(rois), T(img), [1 / 4, 1 / 8, 1 / 16, 1 / 32]))
@@ -407,12 +436,12 @@ def test_roi_align_tma_ring_bit_exact_vs_oracle(C, K, monkeypatch):
     assert np.array_equal(bits(o1), bits(ref1))
 
 
-def test_roi_align_tma_ring_bf16_and_l1_path_agree(monkeypatch):
+def test_roi_align_tma_ring_bf16_and_l1_path_agree(setknob):
     grids, feats, rois, img = _ring_case(12, 256, 500)
     fs = [T(f).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for f in feats]
-    monkeypatch.setenv("B2D_ROI_TMA", "1")
+    setknob(B2D_ROI_TMA=1)
     out = N(bregion.roi_align_levels(fs, T(rois), T(img), [1 / 4, 1 / 8, 1 / 16, 1 / 32]))
-    monkeypatch.setenv("B2D_ROI_TMA", "0")                                # L1-path kernel (k_roi_align_win)
+    setknob(B2D_ROI_TMA=0)                                                # L1-path kernel (k_roi_align_win)
     out_l1 = N(bregion.roi_align_levels(fs, T(rois), T(img), [1 / 4, 1 / 8, 1 / 16, 1 / 32]))
     assert np.array_equal(bits(out), bits(out_l1))
     for b in range(2):
@@ -422,7 +451,7 @@ def test_roi_align_tma_ring_bf16_and_l1_path_agree(monkeypatch):
 
 
 @pytest.mark.parametrize("C,K", [(128, 300), (256, 500)])
-def test_roi_align_backward_tile_kernel_vs_oracle_and_generic(C, K, monkeypatch):
+def test_roi_align_backward_tile_kernel_vs_oracle_and_generic(C, K, setknob):
     """K6 tile-gather kernel (csrc/roi_align_bwd_tile.cu): against the oracle's sequential backward (1e-5 relative:
     the summation order inside a cell differs from torchvision's), against the generic torchvision-ordered kernel,
     and run-to-run bit-identical; RoIs incl. borders / outside / sub-cell / wider than the map."""
@@ -442,7 +471,7 @@ def test_roi_align_backward_tile_kernel_vs_oracle_and_generic(C, K, monkeypatch)
     g2 = run()
     for l in range(4):
         assert np.array_equal(bits(g1[l]), bits(g2[l])), "backward must be run-to-run deterministic"
-    monkeypatch.setenv("B2D_ROI_BWD_TILE", "0")                           # generic kernel (torchvision's order)
+    setknob(B2D_ROI_BWD_TILE=0)                                           # generic kernel (torchvision's order)
     g0 = run()
     lv = oracle.level_map(rois)
     for l, s_ in enumerate((4, 8, 16, 32)):
