@@ -90,6 +90,7 @@ _SIGS = {
 }
 _SIZE_FNS = {
     "b2d_rpn_proposals_workspace_bytes": [_P, c_int, _P],
+    "b2d_rpn_proposals_debug_offset": [_P, c_int, _P],
     "b2d_topk_workspace_bytes": [c_ll, c_int, c_int],
     "b2d_nms_workspace_bytes": [c_ll, c_int],
     "b2d_roi_align_bwd_workspace_bytes": [c_ll, c_int, _P],

@@ -31,12 +31,22 @@ struct RpnLaunch {
     int* force_fb;                      // score-cut NMS: per image, 1 = the first pass gave up (sweep kernel), run the full pass
     int nms_phase;                      // 0: plain NMS of all selected boxes; 1: score-cut pass; 2: conditional full pass
     uint32_t* nz;                       // NMS: per selected box, bitmap of its non-zero mask words (nms.cu)
-    size_t zero_bytes;
+    size_t zero_bytes, dbg_off;
     uint64_t* cand; uint64_t* cand2;
     float4* sel_box; uint32_t* sel_key; int* sel_idx;
     float4* kept_box; uint32_t* kept_key; int* kept_idx;   // NMS survivors, compacted in score order
     uint64_t* mask;
+    // development aid (B2D_DBG=10): globaltimer stamps of the cluster kernels, [B][kDbgCtas][kDbgStamps]
+    unsigned long long* dbg_t;
 };
+constexpr int kDbgCtas = 64, kDbgStamps = 16;
+__device__ __forceinline__ void dbg_stamp(const RpnLaunch& p, int b, int cta, int k) {
+    if (p.dbg_t && threadIdx.x == 0 && cta < kDbgCtas && k < kDbgStamps) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.dbg_t[((long long)b * kDbgCtas + cta) * kDbgStamps + k] = t;
+    }
+}
 
 // launch-local segment index s (b-major over the launch's levels) -> global segment, image, level
 __device__ __forceinline__ void seg_of(int lv0, int lvn, int L, int s, int& seg, int& b, int& l) {
@@ -45,6 +55,9 @@ __device__ __forceinline__ void seg_of(int lv0, int lvn, int L, int s, int& seg,
     seg = b * L + l;
 }
 
+// rpn_front.cu: cluster kernel for hist + threshold + compact + sort + decode of every segment.
+// 1: launched; 0: not applicable (run the multi-kernel path); anything else: error code
+int rpn_front_launch(const RpnLaunch& p, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
 // nms.cu: suppression mask + scan over the sel_* arrays of the launch's segments
 int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st);
 // nms.cu: per image the key of the M-th best selected box over all levels -> n_cut[segment]

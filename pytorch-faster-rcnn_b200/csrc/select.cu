@@ -592,6 +592,8 @@ bool rpn_plan(RpnLaunch& p, const b2d_pyramid* pyr, int B, const b2d_rpn_cfg* cf
     p.kept_key = (uint32_t*)carve(kept * 4);
     p.kept_idx = (int*)carve(kept * 4);
     p.mask = (uint64_t*)carve(cfg->do_nms ? (size_t)B * p.mask_per_img * 8 : 0);
+    p.dbg_off = o;
+    p.dbg_t = (unsigned long long*)carve((size_t)B * kDbgCtas * kDbgStamps * 8);
     *bytes = o;
     return true;
 }
@@ -642,6 +644,14 @@ LevelStreams* level_streams(cudaStream_t caller) {
 
 extern "C" {
 
+size_t b2d_rpn_proposals_debug_offset(const b2d_pyramid* pyr_host, int B, const b2d_rpn_cfg* cfg_host) {
+    if (!pyr_host || !cfg_host || B < 1) return 0;
+    RpnLaunch p;
+    size_t bytes = 0;
+    if (!rpn_plan(p, pyr_host, B, cfg_host, nullptr, &bytes)) return 0;
+    return p.dbg_off;
+}
+
 size_t b2d_rpn_proposals_workspace_bytes(const b2d_pyramid* pyr_host, int B, const b2d_rpn_cfg* cfg_host) {
     if (!pyr_host || !cfg_host || B < 1) return 0;
     RpnLaunch p;
@@ -665,6 +675,7 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
     for (int l = 0; l < p.L; ++l) { p.cls[l] = (const float*)cls_ptrs_host[l]; p.reg[l] = (const float*)reg_ptrs_host[l]; }
     p.img_hw = img_hw;
     p.dbg = knobs().dbg;
+    if (p.dbg != 10) p.dbg_t = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     // function attributes are per device: set on every call (a process may drive several GPUs)
     cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
@@ -691,8 +702,16 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
             p.sel_per_img * 4 <= 200 * 1024)
             cut_m = (int)(f * p.max_num);
     }
-    if (nchains > 1) cudaEventRecord(ls->fork, st);
-    for (int c = 0; c < nchains; ++c) {
+    // K3 as one cluster kernel (rpn_front.cu) when the plan fits; the per-level chains below otherwise
+    bool front_done = false;
+    if (knobs().rpn_front && !p.raw) {
+        const int rc = ls ? rpn_front_launch(p, st, ls->s[0], ls->fork, ls->join[0])
+                          : rpn_front_launch(p, st, nullptr, nullptr, nullptr);
+        if (rc == 1) front_done = true;
+        else if (rc != 0) return rc;
+    }
+    if (nchains > 1 && !front_done) cudaEventRecord(ls->fork, st);
+    for (int c = 0; c < nchains && !front_done; ++c) {
         RpnLaunch q = p;
         cudaStream_t cs = st;
         if (nchains > 1) { q.lv0 = c; q.lvn = 1; cs = ls->s[c]; cudaStreamWaitEvent(cs, ls->fork, 0); }
@@ -716,6 +735,9 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
             if (rc != B2D_OK) return rc;
         }
         if (nchains > 1) { cudaEventRecord(ls->join[c], cs); cudaStreamWaitEvent(st, ls->join[c], 0); }
+    }
+    if (front_done && p.do_nms && !cut_m) {
+        if (int rc = rpn_nms_launch(p, st)) return rc;       // plain NMS of all selected boxes, all levels in one launch pair
     }
     if (cut_m) {
         if (int rc = rpn_nms_cut_launch(p, cut_m, st)) return rc;

@@ -15,11 +15,13 @@ T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 cls, reg = [T(c) for c in w["cls"]], [T(r) for r in w["reg"]]
 img_hw = torch.tensor([[800.0, 1333.0]] * B, device=dev)
 hp = fused.TrainHotPath(B, w["grids"], dev, gt_ld=K, feat_channels=256, layout=1)
+hp.proposals.ws.zero_()
 step = lambda: hp.proposals(cls, reg, img_hw)
 ref = None
 for setting in (sys.argv[1:] or [""]):
     kv = dict(x.split("=") for x in setting.split(";") if x)
     for k, v in kv.items(): os.environ[k] = v
+    b200det._C.reload_knobs()
     for _ in range(3): step()
     torch.cuda.synchronize()
     side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
@@ -53,4 +55,15 @@ for setting in (sys.argv[1:] or [""]):
     reps.append(cur)
     last = reps[-1]; t0 = last[0][0]
     for s, e, n in last: print("   %7.1f %7.1f  %6.1f  %s" % (s - t0, e - t0, e - s, n[:48]))
+    if kv.get("B2D_DBG") == "10":
+        import ctypes
+        off = b200det._C.lib().b2d_rpn_proposals_debug_offset(ctypes.byref(hp.pyr.c), B, ctypes.byref(hp.proposals.cfg))
+        tt = hp.proposals.ws[off:off + B * 64 * 16 * 8].view(torch.int64).view(B, 64, 16).cpu().numpy()
+        t0 = tt[tt > 0].min()
+        for b_ in (0, B - 1):
+            for c in range(64):
+                row = tt[b_, c]
+                if (row > 0).any():
+                    print("   img %d cta %2d: %s" % (b_, c, " ".join("%6.1f" % ((v - t0) / 1e3) if v > 0 else "     -" for v in row[:12])))
     for k in kv: os.environ.pop(k, None)
+    b200det._C.reload_knobs()

@@ -337,6 +337,50 @@ def test_rpn_proposals_benchmarked_config2_full_size_vs_oracle(knobs, setknob):
         np.testing.assert_allclose(N(props[b, :, :n]), ob, rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("front", ["1", "0"])
+@pytest.mark.parametrize("kind", ["all_equal", "few_values", "near_constant", "normal_small_k", "keep_all"])
+def test_rpn_front_degenerate_score_maps_vs_oracle(kind, front, setknob):
+    """The cluster selection kernel (csrc/rpn_front.cu) on score maps that defeat the 12-bit radix pass: every score
+    equal (zero-initialised head: the lowest indices must win), five distinct values (exact ties beyond the sort
+    capacity), scores inside one float octave (narrowing passes resolve them), plus a small top-k and a level that
+    keeps everything -- against the oracle's provenance; same inputs through the multi-kernel path (front=0)."""
+    setknob(B2D_RPN_FRONT=front)
+    rng = np.random.default_rng(5)
+    grids = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+    strides = (4, 8, 16, 32, 64)
+    pyr = fused.AnchorPyramid(strides, grids)
+    B = 2
+    shape = lambda g: (B, 3) + g
+    if kind == "all_equal":
+        cls = [np.zeros(shape(g), np.float32) for g in grids]
+    elif kind == "few_values":
+        cls = [rng.integers(0, 5, shape(g)).astype(np.float32) for g in grids]
+    elif kind == "near_constant":
+        cls = [(1.0 + rng.uniform(0, 1e-3, shape(g))).astype(np.float32) for g in grids]
+    else:
+        cls = [rng.normal(0, 1, shape(g)).astype(np.float32) for g in grids]
+    reg = [rng.normal(0, 0.5, (B, 12) + g).astype(np.float32) for g in grids]
+    cfg = dict(pre_nms=1000, post_nms=1000, max_num=1000, nms_iou=0.7, min_bbox_size=0)
+    if kind == "normal_small_k":
+        cfg = dict(pre_nms=37, post_nms=20, max_num=60, nms_iou=0.7, min_bbox_size=0)
+    if kind == "keep_all":
+        grids = grids[2:]; strides = strides[2:]; cls = cls[2:]; reg = reg[2:]
+        pyr = fused.AnchorPyramid(strides, grids)
+        cfg = dict(pre_nms=4000, post_nms=4000, max_num=3000, nms_iou=0.7, min_bbox_size=8)
+    anc = [oracle.anchor_grid(s, gr, scales=[8]).reshape(4, -1) for s, gr in zip(strides, grids)]
+    offs = np.cumsum([0] + [a.shape[1] for a in anc])
+    rp = fused.RpnProposals(pyr, B, cfg, [0, 0, 0, 0], [1, 1, 1, 1], DEV)
+    props, scores, count = rp([T(c) for c in cls], [T(r) for r in reg], torch.tensor([[400.0, 666.0]] * B, device=DEV))
+    torch.cuda.synchronize()
+    for b in range(B):
+        ob, osc, lv, ix = oracle.rpn_proposals([c[b].reshape(-1) for c in cls], [r[b].reshape(4, -1) for r in reg], anc, cfg,
+                                               [0, 0, 0, 0], [1, 1, 1, 1], (400, 666))
+        n = int(count[b])
+        assert n == lv.shape[0], (kind, front, n, lv.shape)
+        assert np.array_equal(N(rp.prov[b, :n]), offs[lv] + ix), (kind, front)
+        np.testing.assert_allclose(N(props[b, :, :n]), ob, rtol=1e-5, atol=1e-3)
+
+
 def test_topk_large_and_ties():
     rng = np.random.default_rng(7)
     v = rng.standard_normal(201600).astype(np.float32)
