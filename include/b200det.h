@@ -162,6 +162,8 @@ typedef struct b2d_rpn_cfg {
 B2D_API size_t b2d_rpn_proposals_workspace_bytes(const b2d_pyramid* pyr_host, int B, const b2d_rpn_cfg* cfg_host);
 /* development aid: byte offset inside the workspace of the globaltimer stamps written when B2D_DBG=10
  * (u64 [B][64 CTAs][16 stamps]) */
+/* kernels + memset nodes the last b2d_rpn_proposals call of this thread issued (bench.py gpu_launches) */
+B2D_API int b2d_last_launch_count(void);
 B2D_API size_t b2d_rpn_proposals_debug_offset(const b2d_pyramid* pyr_host, int B, const b2d_rpn_cfg* cfg_host);
 B2D_API int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const void* const* cls_ptrs_host,
                       const void* const* reg_ptrs_host, const b2d_pyramid* pyr_host, const float* img_hw,

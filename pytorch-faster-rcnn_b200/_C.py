@@ -98,7 +98,7 @@ _SIZE_FNS = {
     "b2d_rcnn_detect_workspace_bytes": [c_int, c_int],
     "b2d_anchor_loss_workspace_bytes": [_P, c_int],
 }
-EXPORTS = sorted(list(_SIGS) + list(_SIZE_FNS) + ["b2d_last_error_string", "b2d_version", "b2d_reload_knobs"])
+EXPORTS = sorted(list(_SIGS) + list(_SIZE_FNS) + ["b2d_last_error_string", "b2d_version", "b2d_reload_knobs", "b2d_last_launch_count"])
 
 
 def lib():
@@ -122,6 +122,7 @@ def lib():
     L.b2d_last_error_string.restype = ctypes.c_char_p
     L.b2d_version.restype = c_int
     L.b2d_reload_knobs.restype = None
+    L.b2d_last_launch_count.restype = c_int
     _lib = L
     return L
 

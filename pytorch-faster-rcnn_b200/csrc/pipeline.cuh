@@ -58,6 +58,10 @@ __device__ __forceinline__ void seg_of(int lv0, int lvn, int L, int s, int& seg,
 // rpn_front.cu: cluster kernel for hist + threshold + compact + sort + decode of every segment.
 // 1: launched; 0: not applicable (run the multi-kernel path); anything else: error code
 int rpn_front_launch(const RpnLaunch& p, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
+int rpn_front_launch_count(const RpnLaunch& p);      // kernels rpn_front_launch issues for this plan (1 or 2)
+// rpn_back.cu: cluster kernel for score cut + sweep mask + scan + merge (one cluster per image)
+bool rpn_back_applicable(const RpnLaunch& p);
+int rpn_back_launch(const RpnLaunch& p, int cut_m, float* props, float* scores, int* count, int* prov, cudaStream_t st);
 // nms.cu: suppression mask + scan over the sel_* arrays of the launch's segments
 int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st);
 // nms.cu: per image the key of the M-th best selected box over all levels -> n_cut[segment]

@@ -501,6 +501,12 @@ static int front_launch_one(const RpnLaunch& p, const FrontPlan& fp, cudaStream_
     return check_launch("rpn_proposals/k_rpn_front");
 }
 
+int rpn_front_launch_count(const RpnLaunch& p) {
+    FrontPlan big, small;
+    if (!front_plan(p, big, small)) return 0;
+    return (big.slots > 0) + (small.slots > 0);
+}
+
 // 1: launched; 0: not applicable (the caller runs the multi-kernel path); anything else: error code.
 // `side`, `fork`, `join`: a library-owned stream and two events for the second launch (may be null: both launches
 // then go to `st` one after the other).

@@ -642,6 +642,8 @@ LevelStreams* level_streams(cudaStream_t caller) {
 
 }  // namespace
 
+static thread_local int g_last_launches = 0;
+
 extern "C" {
 
 size_t b2d_rpn_proposals_debug_offset(const b2d_pyramid* pyr_host, int B, const b2d_rpn_cfg* cfg_host) {
@@ -680,7 +682,8 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
     // function attributes are per device: set on every call (a process may drive several GPUs)
     cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
     cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
-    cudaMemsetAsync(workspace, 0, p.zero_bytes, st);
+    int nl = 0;                                           // launches (kernels + memset nodes) of this call
+    cudaMemsetAsync(workspace, 0, p.zero_bytes, st); ++nl;
     // Per-level chains.  hist -> compact -> select -> NMS mask -> scan of one level only depends on that level, and
     // all of them but the mask are small latency-bound grids; run as ONE launch per kernel over all levels the step
     // is the sum of the slowest segment of every kernel (166 us at config 2).  Each level therefore gets its own
@@ -693,12 +696,13 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
     // Score-cut NMS (nms.cu, k_nms_cut): pass 1 on the M = cut * max_num globally best boxes, full pass only for
     // images that need it.  B2D_NMS_CUT = factor (default 1.5), 0 disables.
     int cut_m = 0;
+    const bool use_back = rpn_back_applicable(p);        // K4 + merge as one cluster kernel (rpn_back.cu)
     {
         const double f = knobs().nms_cut;
         int kmax = 0;
         long long ksum = 0;
         for (int l = 0; l < p.L; ++l) { kmax = max(kmax, p.kcap[l]); ksum += p.kcap[l]; }
-        if (f > 0.0 && p.do_nms && p.max_num > 0 && nchains > 1 && kmax <= 2048 && (double)ksum > f * p.max_num &&
+        if (f > 0.0 && p.do_nms && p.max_num > 0 && (nchains > 1 || use_back) && kmax <= 2048 && (double)ksum > f * p.max_num &&
             p.sel_per_img * 4 <= 200 * 1024)
             cut_m = (int)(f * p.max_num);
     }
@@ -707,7 +711,7 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
     if (knobs().rpn_front && !p.raw) {
         const int rc = ls ? rpn_front_launch(p, st, ls->s[0], ls->fork, ls->join[0])
                           : rpn_front_launch(p, st, nullptr, nullptr, nullptr);
-        if (rc == 1) front_done = true;
+        if (rc == 1) { front_done = true; nl += rpn_front_launch_count(p); }
         else if (rc != 0) return rc;
     }
     if (nchains > 1 && !front_done) cudaEventRecord(ls->fork, st);
@@ -723,24 +727,35 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
         }
         if (any_select) {
             dim3 grid(max_chunks, S);
+            nl += 2;
             k_hist<<<grid, kHcThreads, 0, cs>>>(q);
             if (int rc = check_launch("rpn_proposals/k_hist")) return rc;
             k_compact<<<grid, kHcThreads, 0, cs>>>(q);
             if (int rc = check_launch("rpn_proposals/k_compact")) return rc;
         }
+        ++nl;
         k_select<<<S, kSelThreads, kSortCap * 8, cs>>>(q);
         if (int rc = check_launch("rpn_proposals/k_select")) return rc;
-        if (q.do_nms && !cut_m) {
+        if (q.do_nms && !cut_m && !use_back) {
             int rc = rpn_nms_launch(q, cs);
             if (rc != B2D_OK) return rc;
+            nl += 2;
         }
         if (nchains > 1) { cudaEventRecord(ls->join[c], cs); cudaStreamWaitEvent(st, ls->join[c], 0); }
     }
+    if (use_back) {
+        const int rc = rpn_back_launch(p, cut_m, props, scores, count, prov, st);
+        if (rc == 1) { g_last_launches = nl + 1; return B2D_OK; }
+        return rc == 0 ? B2D_ERR_ARG : rc;
+    }
     if (front_done && p.do_nms && !cut_m) {
         if (int rc = rpn_nms_launch(p, st)) return rc;       // plain NMS of all selected boxes, all levels in one launch pair
+        nl += 2;
     }
     if (cut_m) {
         if (int rc = rpn_nms_cut_launch(p, cut_m, st)) return rc;
+        nl += 1 + 2 + 2;                                     // cut, pass 1 (mask, scan), conditional pass 2 (mask, scan)
+        if (knobs().nms_p1_chains == 1) nl += 2 * (nchains - 1);
         // pass 1 on the cut prefixes: one item-walking mask launch + one scan launch over all levels
         // (B2D_NMS_P1_CHAINS=1: the older per-level chains with capacity-sized tile grids, dispatch-bound)
         if (knobs().nms_p1_chains == 1) {
@@ -774,8 +789,11 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
     } else {
         k_merge<<<B, kSelThreads, kSortCap * 8, st>>>(p, props, scores, count, prov);
     }
+    g_last_launches = nl + 1;
     return check_launch("rpn_proposals");
 }
+
+int b2d_last_launch_count(void) { return g_last_launches; }
 
 static void topk_cfg(long long n, int k, b2d_pyramid& pyr, b2d_rpn_cfg& cfg) {
     memset(&pyr, 0, sizeof(pyr));

@@ -83,16 +83,7 @@ class RpnProposals(object):
         self.scores = torch.zeros((B, self.P), dtype=torch.float32, device=device)
         self.count = torch.zeros(B, dtype=torch.int32, device=device)
         self.prov = torch.zeros((B, self.P), dtype=torch.int32, device=device)
-        # kernels: per level (hist, compact if the level is larger than pre_nms), select, (mask, scan); then merge (+1 memset node)
-        chains = len(pyramid.level_sizes) > 1 and os.environ.get("B2D_RPN_CHAINS", "1") != "0"
-        per_level = [(2 if 0 < c.pre_nms < n else 0) + 1 + (2 if do_nms else 0) for n in pyramid.level_sizes]
-        self.launches = (sum(per_level) if chains else max(per_level)) + 1
-        kcaps = [(c.pre_nms if 0 < c.pre_nms < n else n) for n in pyramid.level_sizes]
-        cut = float(os.environ.get("B2D_NMS_CUT", "1.5"))
-        if chains and do_nms and c.max_num > 0 and cut > 0 and max(kcaps) <= 2048 and sum(kcaps) > cut * c.max_num:
-            self.launches += 3                       # score-cut NMS: k_nms_cut + the conditional full pass (mask, scan)
-            if os.environ.get("B2D_NMS_P1_CHAINS", "0") != "1":
-                self.launches -= 2 * (len(kcaps) - 1)    # pass 1 is one (mask, scan) pair over all levels
+        self.launches = 0                       # kernels + memset nodes per call: reported by the library after the first call
 
     def slice(self, b0, b1):
         v = _batch_view(self, b0, b1)
@@ -104,6 +95,7 @@ class RpnProposals(object):
         _C.call("b2d_rpn_proposals", _C.ptr(self.props), _C.ptr(self.scores), _C.ptr(self.count), _C.ptr(self.prov),
                 _ptrs(cls_outs), _ptrs(reg_outs), ctypes.byref(self.pyr.c), _C.ptr(img_hw), self.B,
                 ctypes.byref(self.cfg), _C.ptr(self.ws), self.ws.numel(), _C.stream())
+        self.launches = int(_C.lib().b2d_last_launch_count())
         return self.props, self.scores, self.count
 
 
@@ -209,8 +201,9 @@ class TrainHotPath(object):
     def __init__(self, B, grids, device, strides=(4, 8, 16, 32, 64), gt_ld=64, feat_channels=256,
                  rpn_proposal=None, rpn_assigner=None, rpn_sampler=None, rcnn_assigner=None, rcnn_sampler=None,
                  rpn_stds=(1.0, 1.0, 1.0, 1.0), rcnn_stds=(0.1, 0.1, 0.2, 0.2), allowed_border=0, layout=1, seed=0,
-                 groups=1, overlap=False):
+                 groups=1, overlap=False, order=None):
         z4 = (0.0, 0.0, 0.0, 0.0)
+        self.order = order or os.environ.get("B2D_STEP_ORDER", "rpn_first")
         rpn_proposal = rpn_proposal or dict(pre_nms=2000, post_nms=2000, max_num=2000, nms_iou=0.7, min_bbox_size=0)
         rpn_assigner = rpn_assigner or dict(pos_iou=0.7, neg_iou=0.3, min_pos_iou=0.3)
         rpn_sampler = rpn_sampler or dict(max_num=256, pos_num=128)
@@ -257,8 +250,7 @@ class TrainHotPath(object):
             # while the proposal chains sit in hist / compact / select (latency-bound, ~50 us, SMs idle): lowest
             # priority (the small critical kernels always get their SM slots) but enqueued first, see step()
             self.s_rpn = torch.cuda.Stream(device=device, priority=int(os.environ.get("B2D_RPN_PRIO", "0")))
-        per_group = self.proposals.launches + self.roi_targets.launches + 1
-        self.launches = per_group * groups + self.rpn_targets.launches + 1
+        self.launches = 0
 
     def _rpn_target_chain(self, cls_outs, reg_outs, gt, gt_count, img_hw):
         rt = self.rpn_targets(gt, gt_count, None, img_hw=img_hw)
@@ -279,15 +271,23 @@ class TrainHotPath(object):
             self.roi_align(feats, bt.tar_box, bt.n_chosen)
         else:
             cur = torch.cuda.current_stream()
-            # enqueued FIRST: graph nodes launch in creation order, and these kernels should own the idle SMs while
-            # the proposal chains are in their latency-bound prefix (see __init__)
+            # Graph nodes launch in creation order.  order "rpn_first" (default): the RPN-target kernels (ALU-bound,
+            # thousands of CTAs) are enqueued before the proposal stage; "chain_first": the proposal stage's cluster
+            # kernels (1024-thread CTAs that need whole SMs) first.  Measured at config 2 (r2l): 257 vs 275 us per step --
+            # enqueued second, the RPN-target grid only gets the SMs the clusters leave and spills into RoIAlign.
+            rpn_first = self.order == "rpn_first"
             self.s_rpn.wait_stream(cur)
-            with torch.cuda.stream(self.s_rpn):
-                rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
-            for (b0, b1, prop, tgt, ra, st, st_lo) in self.subs:
+            if rpn_first:
+                with torch.cuda.stream(self.s_rpn):
+                    rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
+            for gi, (b0, b1, prop, tgt, ra, st, st_lo) in enumerate(self.subs):
                 st.wait_stream(cur)
                 with torch.cuda.stream(st):
                     p, _, c = prop([t[b0:b1] for t in cls_outs], [t[b0:b1] for t in reg_outs], img_hw[b0:b1])
+                if gi == 0 and not rpn_first:
+                    with torch.cuda.stream(self.s_rpn):
+                        rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
+                with torch.cuda.stream(st):
                     t2 = tgt(gt[b0:b1], gt_count[b0:b1], gt_label[b0:b1], boxes=p, box_count=c)
                 st_lo.wait_stream(st)
                 if feats_ready is not None:
@@ -297,6 +297,8 @@ class TrainHotPath(object):
             for sub in self.subs:
                 cur.wait_stream(sub[-1])
             cur.wait_stream(self.s_rpn)
+        self.launches = (sum(sub[2].launches for sub in self.subs) if self.groups > 1 else self.proposals.launches) + \
+            (self.roi_targets.launches + 1) * self.groups + self.rpn_targets.launches + 1
         return dict(props=self.proposals.props, scores=self.proposals.scores, prop_count=self.proposals.count,
                     rpn=self.rpn_targets, rpn_tar_cls=self.tar_cls, rpn_tar_reg=self.tar_reg, rcnn=self.roi_targets,
                     roi_feats=self.roi_align.out)

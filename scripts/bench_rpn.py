@@ -64,6 +64,6 @@ for setting in (sys.argv[1:] or [""]):
             for c in range(64):
                 row = tt[b_, c]
                 if (row > 0).any():
-                    print("   img %d cta %2d: %s" % (b_, c, " ".join("%6.1f" % ((v - t0) / 1e3) if v > 0 else "     -" for v in row[:12])))
+                    print("   img %d cta %2d: %s" % (b_, c, " ".join("%6.1f" % ((v - t0) / 1e3) if v > 0 else "     -" for v in row[:16])))
     for k in kv: os.environ.pop(k, None)
     b200det._C.reload_knobs()
