@@ -98,7 +98,10 @@ B2D_API int b2d_assign_max_iou(int64_t* labels, float* max_iou, long long out_ld
  * b2d_assign_max_iou or b2d_label_census. */
 B2D_API int b2d_sample_labels(int* chosen, int* n_chosen, const int64_t* labels, long long ld, const int* count,
                       const int* count_add /* optional int32[B] added to count */, long long n, const int* census, const int* pos_list, int pos_cap, int B, int max_num,
-                      int pos_num, unsigned long long seed, void* stream);
+                      int pos_num, unsigned long long seed, const unsigned long long* seed_step /* optional device counter added to seed */, void* stream);
+/* *cell += inc on the stream: the per-step counter of the device-RNG samplers lives in device memory, so that a step
+ * captured in a CUDA graph draws a fresh random stream on every replay (a by-value seed is frozen by the capture) */
+B2D_API int b2d_counter_add(unsigned long long* cell, unsigned long long inc, void* stream);
 /* census + positive list of an arbitrary labels vector (for the sampler classes) */
 B2D_API int b2d_label_census(int* census, int* pos_list, int pos_cap, const int64_t* labels, long long ld,
                      const int* count, long long n, int B, void* stream);
@@ -131,9 +134,9 @@ B2D_API int b2d_roi_targets_fused(int64_t* labels, float* max_iou, long long out
                           const int* box_count, long long N, const float* gt, int gt_ld, const int* gt_count,
                           const int64_t* gt_label, int B, float pos_iou, float neg_iou, float min_pos_iou,
                           int prepend_gt, int* census, int* pos_list, int pos_cap, int* chosen, int* n_chosen,
-                          int max_num, int pos_num, unsigned long long seed, float* tar_box, float* tar_gt,
-                          float* tar_param, int64_t* tar_label, int64_t* tar_is_gt, const float* means_host,
-                          const float* stds_host, void* stream);
+                          int max_num, int pos_num, unsigned long long seed, const unsigned long long* seed_step,
+                          float* tar_box, float* tar_gt, float* tar_param, int64_t* tar_label, int64_t* tar_is_gt,
+                          const float* means_host, const float* stds_host, void* stream);
 
 /* gather of the head outputs at the sampled anchors (lib/anchor.py:49-56), batched:
  * cls_ptrs_host[l] -> [B, C, n_l], reg_ptrs_host[l] -> [B, 4, n_l] (the views of
@@ -148,7 +151,8 @@ B2D_API int b2d_gather_head_outputs(float* tar_cls, float* tar_reg, const void* 
  * cls_ptrs_host[l] -> [B, A*C, H, W] logits, reg_ptrs_host[l] -> [B, 4A, H, W]
  * (channel = coord*A + a, lib/heads/anchor_head.py:82-83).  score_mode: 0 = one
  * sigmoid channel, 1 = two-channel softmax (score = p[1]), 2 = max over C sigmoid
- * channels.  Outputs: props [B][4][max_num], scores [B][max_num], count int32[B]
+ * channels (selection on the best class logit), 3 = max over the foreground classes
+ * c >= 1 of a C-channel softmax (AnchorHead with use_sigmoid = False).  Outputs: props [B][4][max_num], scores [B][max_num], count int32[B]
  * (plus, if non-NULL, prov int32[B][max_num] = flattened anchor index). */
 typedef struct b2d_rpn_cfg {
     int pre_nms, post_nms, max_num; /* <= 0 means "no limit" like the reference */
@@ -184,6 +188,43 @@ B2D_API size_t b2d_nms_workspace_bytes(long long n_max, int S);
 B2D_API int b2d_nms(int64_t* keep, int* keep_count, const float* boxes, const float* scores, long long n_ld,
             const int* counts, long long n, int S, float thr_f, int max_keep, int presorted, void* workspace,
             size_t ws_bytes, void* stream);
+
+/* ---- index glue as kernels (round 2): multiclass / batched NMS front-end, RoI scaling, IoU-balanced sampler.
+ * utils.multiclass_nms (lib/utils.py:224-269): bbox [n][4] (box_classes 1) or [n][4*C] viewed (n,4,C), score [n][C],
+ * chan_mask_host = 2 x u64 bitmap of nms_channel, score_factor [n] or NULL, strict = mode 'strict'.  Outputs ROW-major
+ * like the reference returns them: out_box [max_keep][4], out_score, out_label int64, out_count int32[1];
+ * *overflow = 1 if more than `cap` (<= 16384) candidates passed the test. */
+B2D_API size_t b2d_multiclass_nms_workspace_bytes(int cap);
+B2D_API int b2d_multiclass_nms(float* out_box, float* out_score, int64_t* out_label, int* out_count, const float* bbox,
+                       int box_classes, const float* score, long long n, int C, const unsigned long long* chan_mask_host,
+                       float min_score, const float* score_factor, int strict, float nms_thr_f, int max_keep, int cap,
+                       int* overflow, void* workspace, size_t ws_bytes, void* stream);
+/* the candidate stage of b2d_multiclass_nms alone, into caller arrays of `cap` entries (cand_box / nms_box [cap][4]):
+ * for candidate sets larger than b2d_nms takes (16384) */
+B2D_API int b2d_multiclass_candidates(float* cand_box, float* nms_box, float* cand_score, int* cand_label, int* cand_count,
+                              int* overflow, const float* bbox, int box_classes, const float* score, long long n, int C,
+                              const unsigned long long* chan_mask_host, float min_score, const float* score_factor,
+                              int strict, int cap, void* stream);
+/* utils.batched_nms (lib/utils.py:211-221): out [n][4] = bbox + fp32(label * max(bbox)) -- the boxes handed to nms */
+B2D_API int b2d_batched_nms_boxes(float* out, const float* bbox, const int64_t* label, long long n, void* stream);
+/* ScalableRoICrop.scale_bbox (lib/region.py:220-225) on [4][ld] boxes */
+B2D_API int b2d_scale_rois(float* out, const float* rois, long long ld, long long n, float scale, void* stream);
+/* IoUBalancedNegSampler (lib/region.py:128-172).  Bins are given HIGHEST IoU range first (the reference's walk order),
+ * bounds already rounded to fp32 like torch's tensor-vs-python-scalar comparison.  ids: 0 positive, 1 + j bin j, -1 none. */
+B2D_API int b2d_iou_bin_ids(int* ids, const int64_t* labels, const float* iou, long long n, int num_bins,
+                    const float* bin_lo_host, const float* bin_hi_host, void* stream);
+B2D_API int b2d_sample_iou_balanced(int64_t* out_labels, const int64_t* labels, const float* iou, long long n, int max_num,
+                            int pos_num, int num_bins, const float* bin_lo_host, const float* bin_hi_host,
+                            unsigned long long seed, void* stream);
+/* CrossEntropyLoss on sampled rows (lib/losses.py:129-156; callers lib/heads/anchor_head.py:113-139 and
+ * lib/heads/bbox_head.py:56-80): logits [C][ld] (row_major 0: the reference's tar_cls_out) or [rows][ld] (row_major 1),
+ * target int64[rows] (< 0: ignored).  fwd: partial [64][2] = per-block (sum of row losses, rows counted);
+ * bwd: grad (same layout as logits) = scale[0] * dloss/dlogit. */
+B2D_API size_t b2d_sampled_ce_workspace_bytes(void);
+B2D_API int b2d_sampled_ce_fwd(float* partial, const float* logits, long long ld, int C, int row_major, int sigmoid,
+                       const int64_t* target, long long rows, void* stream);
+B2D_API int b2d_sampled_ce_bwd(float* grad, const float* scale, const float* logits, long long ld, int C, int row_major,
+                       int sigmoid, const int64_t* target, long long rows, void* stream);
 
 /* ---- loss reductions adjacent to the path, fused with the target gather.
  * AnchorHead.calc_loss for a head without sampler (lib/heads/anchor_head.py:113-139):

@@ -55,9 +55,10 @@ _SIGS = {
     "b2d_elem_iou": [_P, _P, _P, c_ll, _P],
     "b2d_assign_max_iou": [_P, _P, c_ll, _P, c_ll, _P, c_ll, _P, _P, c_float, _P, c_int, _P, c_int, c_float,
                            c_float, c_float, c_int, _P, _P, c_int, _P, c_size_t, _P],
-    "b2d_sample_labels": [_P, _P, _P, c_ll, _P, _P, c_ll, _P, _P, c_int, c_int, c_int, c_int, c_ull, _P],
+    "b2d_sample_labels": [_P, _P, _P, c_ll, _P, _P, c_ll, _P, _P, c_int, c_int, c_int, c_int, c_ull, _P, _P],
+    "b2d_counter_add": [_P, c_ull, _P],
     "b2d_roi_targets_fused": [_P, _P, c_ll, _P, c_ll, _P, c_ll, _P, c_int, _P, _P, c_int, c_float, c_float, c_float,
-                              c_int, _P, _P, c_int, _P, _P, c_int, c_int, c_ull, _P, _P, _P, _P, _P, _P, _P, _P],
+                              c_int, _P, _P, c_int, _P, _P, c_int, c_int, c_ull, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "b2d_anchor_loss_fwd": [_P, _P, _P, _P, _P, c_ll, _P, c_int, _P, c_int, c_float, c_float, c_float, _P, _P, c_int, _P,
                             c_size_t, _P],
     "b2d_anchor_loss_bwd": [_P, _P, _P, _P, _P, _P, _P, c_ll, _P, c_int, _P, c_int, c_float, c_float, c_float, _P, _P,
@@ -85,6 +86,15 @@ _SIGS = {
     "b2d_atss_assign": [_P, _P, _P, _P, _P, c_int, _P, _P, _P, c_int, c_int, _P, c_size_t, _P],
     "b2d_fcos_decode": [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_float, c_float, c_float, _P, c_int, _P],
     "b2d_roi_pool_fwd": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_ll, _P, c_ll, c_float, c_int, c_int, _P],
+    "b2d_multiclass_nms": [_P, _P, _P, _P, _P, c_int, _P, c_ll, c_int, _P, c_float, _P, c_int, c_float, c_int, c_int, _P, _P,
+                           c_size_t, _P],
+    "b2d_multiclass_candidates": [_P, _P, _P, _P, _P, _P, _P, c_int, _P, c_ll, c_int, _P, c_float, _P, c_int, c_int, _P],
+    "b2d_batched_nms_boxes": [_P, _P, _P, c_ll, _P],
+    "b2d_scale_rois": [_P, _P, c_ll, c_ll, c_float, _P],
+    "b2d_iou_bin_ids": [_P, _P, _P, c_ll, c_int, _P, _P, _P],
+    "b2d_sample_iou_balanced": [_P, _P, _P, c_ll, c_int, c_int, c_int, _P, _P, c_ull, _P],
+    "b2d_sampled_ce_fwd": [_P, _P, c_ll, c_int, c_int, c_int, _P, c_ll, _P],
+    "b2d_sampled_ce_bwd": [_P, _P, _P, c_ll, c_int, c_int, c_int, _P, c_ll, _P],
     "b2d_roi_pool_bwd": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_ll, _P, c_ll, c_float, c_int, c_int, _P,
                          c_size_t, _P],
 }
@@ -97,6 +107,8 @@ _SIZE_FNS = {
     "b2d_atss_workspace_bytes": [_P, c_int],
     "b2d_rcnn_detect_workspace_bytes": [c_int, c_int],
     "b2d_anchor_loss_workspace_bytes": [_P, c_int],
+    "b2d_multiclass_nms_workspace_bytes": [c_int],
+    "b2d_sampled_ce_workspace_bytes": [],
 }
 EXPORTS = sorted(list(_SIGS) + list(_SIZE_FNS) + ["b2d_last_error_string", "b2d_version", "b2d_reload_knobs", "b2d_last_launch_count"])
 

@@ -611,8 +611,10 @@ __global__ void __launch_bounds__(kSampleThreads) k_sample(int* __restrict__ cho
                                                            const int* __restrict__ count_add, long long n,
                                                            const int* __restrict__ census,
                                                            const int* __restrict__ pos_list, int pos_cap,
-                                                           int max_num, int pos_num, unsigned long long seed) {
+                                                           int max_num, int pos_num, unsigned long long seed,
+                                                           const unsigned long long* __restrict__ seed_step) {
     extern __shared__ __align__(16) uint64_t s_sort[];          // kSampleSortCap entries
+    if (seed_step) seed += *seed_step;                            // per-step counter in device memory (CUDA-graph replays)
     __shared__ int s_n, s_warp[kSampleThreads / 32], s_take;
     __shared__ unsigned long long s_lo, s_hi;
     const int b = blockIdx.x;
@@ -822,6 +824,7 @@ constexpr int kFusedPer = (kFusedMaxN + kSmallThreads - 1) / kSmallThreads;
 struct FusedArgs {
     int* chosen; int* n_chosen; int max_num, pos_num;
     unsigned long long seed;
+    const unsigned long long* seed_step;      // optional device counter added to seed (advanced by b2d_counter_add)
     const int64_t* gt_label;
     float* tar_box; float* tar_gt; float* tar_param; int64_t* tar_label; int64_t* tar_is_gt;
     float ms[8];
@@ -844,7 +847,7 @@ __global__ void __launch_bounds__(kSmallThreads) k_roi_targets_small(AssignArgs 
     const int lead = p.prepend_gt ? K : 0;
     const int n_tot = lead + (p.box_count ? p.box_count[b] : (int)p.N);
     const int npos = sm.cnt[0] + lead, nneg = sm.cnt[1];
-    const uint64_t sd = f.seed + 0x632BE59BD9B4E019ull * (uint64_t)(b + 1);
+    const uint64_t sd = f.seed + (f.seed_step ? *f.seed_step : 0ull) + 0x632BE59BD9B4E019ull * (uint64_t)(b + 1);
     for (int i = tid; i < n_tot; i += kSmallThreads) s_flag[i] = 0;
     // ---- positives: all of them, or the pos_num smallest (mix_key(sd, idx) << 32 | idx)
     const int keep_pos = min(npos, f.pos_num);
@@ -997,6 +1000,8 @@ __global__ void __launch_bounds__(kSmallThreads) k_roi_targets_small(AssignArgs 
     if (f.tar_is_gt) f.tar_is_gt[(long long)b * mn + t] = isgt;
 }
 
+__global__ void k_counter_add(unsigned long long* cell, unsigned long long inc) { *cell += inc; }
+
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -1067,7 +1072,7 @@ int b2d_label_census(int* census, int* pos_list, int pos_cap, const int64_t* lab
 
 int b2d_sample_labels(int* chosen, int* n_chosen, const int64_t* labels, long long ld, const int* count,
                       const int* count_add, long long n, const int* census, const int* pos_list, int pos_cap, int B, int max_num,
-                      int pos_num, unsigned long long seed, void* stream) {
+                      int pos_num, unsigned long long seed, const unsigned long long* seed_step, void* stream) {
     B2D_REQUIRE(chosen && n_chosen && labels && census && pos_list, "sample_labels: null pointer");
     B2D_REQUIRE(B >= 1 && max_num >= 1 && max_num <= kSampleSortCap && pos_num >= 0 && pos_num <= max_num,
                 "sample_labels: need 1 <= max_num <= 4096 and pos_num <= max_num");
@@ -1075,8 +1080,14 @@ int b2d_sample_labels(int* chosen, int* n_chosen, const int64_t* labels, long lo
     // function attributes are per device: set on every call (a process may drive several GPUs)
     cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSortCap * 8);
     k_sample<<<B, kSampleThreads, kSampleSortCap * 8, (cudaStream_t)stream>>>(
-        chosen, n_chosen, labels, ld, count, count_add, n, census, pos_list, pos_cap, max_num, pos_num, seed);
+        chosen, n_chosen, labels, ld, count, count_add, n, census, pos_list, pos_cap, max_num, pos_num, seed, seed_step);
     return check_launch("sample_labels");
+}
+
+int b2d_counter_add(unsigned long long* cell, unsigned long long inc, void* stream) {
+    B2D_REQUIRE(cell, "counter_add: null pointer");
+    k_counter_add<<<1, 1, 0, (cudaStream_t)stream>>>(cell, inc);
+    return check_launch("counter_add");
 }
 
 int b2d_scatter_sampled(int64_t* out, const int64_t* labels, long long ld, long long n, const int* chosen,
@@ -1126,9 +1137,9 @@ int b2d_roi_targets_fused(int64_t* labels, float* max_iou, long long out_ld, con
                           const int* box_count, long long N, const float* gt, int gt_ld, const int* gt_count,
                           const int64_t* gt_label, int B, float pos_iou, float neg_iou, float min_pos_iou,
                           int prepend_gt, int* census, int* pos_list, int pos_cap, int* chosen, int* n_chosen,
-                          int max_num, int pos_num, unsigned long long seed, float* tar_box, float* tar_gt,
-                          float* tar_param, int64_t* tar_label, int64_t* tar_is_gt, const float* means_host,
-                          const float* stds_host, void* stream) {
+                          int max_num, int pos_num, unsigned long long seed, const unsigned long long* seed_step,
+                          float* tar_box, float* tar_gt, float* tar_param, int64_t* tar_label, int64_t* tar_is_gt,
+                          const float* means_host, const float* stds_host, void* stream) {
     B2D_REQUIRE(labels && max_iou && boxes && gt && gt_count && census && chosen && n_chosen, "roi_targets_fused: null pointer");
     B2D_REQUIRE(B >= 1 && gt_ld >= 1 && gt_ld <= kGtChunk && N >= 0 && N <= kSmallThreads * kSmallBoxes,
                 "roi_targets_fused: need N <= 4096 and gt_ld <= 512");
@@ -1141,7 +1152,7 @@ int b2d_roi_targets_fused(int64_t* labels, float* max_iou, long long out_ld, con
     a.pos_iou = pos_iou; a.neg_iou = neg_iou; a.min_pos_iou = min_pos_iou;
     a.prepend_gt = prepend_gt; a.out_ld = out_ld;
     FusedArgs f;
-    f.chosen = chosen; f.n_chosen = n_chosen; f.max_num = max_num; f.pos_num = pos_num; f.seed = seed;
+    f.chosen = chosen; f.n_chosen = n_chosen; f.max_num = max_num; f.pos_num = pos_num; f.seed = seed; f.seed_step = seed_step;
     f.gt_label = gt_label;
     f.tar_box = tar_box; f.tar_gt = tar_gt; f.tar_param = tar_param; f.tar_label = tar_label; f.tar_is_gt = tar_is_gt;
     for (int i = 0; i < 4; ++i) { f.ms[i] = means_host ? means_host[i] : 0.0f; f.ms[4 + i] = stds_host ? stds_host[i] : 1.0f; }

@@ -10,7 +10,15 @@ __device__ __forceinline__ float load_logit(const float* __restrict__ cls, int n
     if (mode == 1) return cls[n + i] - cls[i];            // softmax[1] == sigmoid(l1 - l0)
     float m = cls[i];
     for (int c = 1; c < C; ++c) m = fmaxf(m, cls[(long long)c * n + i]);
-    return m;
+    if (mode == 2) return m;                              // best class logit (sigmoid heads: sigmoid is monotone)
+    // mode 3, softmax heads (lib/heads/anchor_head.py:232-236): max over the foreground classes c >= 1 of softmax_c
+    float s = 0.0f, fg = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+        const float v = cls[(long long)c * n + i];
+        s += expf(v - m);
+        if (c >= 1) fg = fmaxf(fg, v);
+    }
+    return expf(fg - m) / s;
 }
 
 __device__ __forceinline__ const float* seg_cls(const RpnLaunch& p, int b, int l) {

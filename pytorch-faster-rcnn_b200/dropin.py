@@ -9,6 +9,27 @@ import types
 _saved = []
 
 
+def _grad_safe(fast, reference):
+    """The kernels have no autograd graph and no CPU path.  A rebinding of a reference function that the reference
+    also uses on differentiable tensors (IoULoss -> utils.elem_iou, lib/losses.py:7-10; GuidedAnchor ->
+    utils.param2bbox, lib/heads/guided_head.py:129) or on CPU tensors therefore keeps the reference implementation
+    for exactly those calls: any tensor argument that requires grad while grad mode is on, or that is not on a CUDA
+    device, routes the call to the saved original."""
+    import functools
+
+    import torch
+
+    @functools.wraps(reference)
+    def call(*args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and ((a.requires_grad and torch.is_grad_enabled()) or not a.is_cuda):
+                return reference(*args, **kwargs)
+        return fast(*args, **kwargs)
+
+    call.b2d_fast, call.b2d_reference = fast, reference
+    return call
+
+
 def _set(obj, name, value):
     if hasattr(obj, name) or isinstance(obj, dict):
         old = obj[name] if isinstance(obj, dict) else getattr(obj, name)
@@ -19,8 +40,26 @@ def _set(obj, name, value):
             setattr(obj, name, value)
 
 
-def install(lib=None):
-    """lib: the reference's imported `lib` package (default: sys.modules['lib'])."""
+def _channels_last_fpn(necks):
+    """make the reference FPN (lib/necks.py:7-90) EMIT channels_last feature maps.  Its convolutions
+    are switched to channels_last weights and fed channels_last inputs, so cuDNN runs NHWC kernels and the outputs
+    arrive in the layout the RoIAlign kernels read (one contiguous channel vector per cell) -- no transposition
+    kernel anywhere; lateral adds, nearest upsampling and max pooling preserve the memory format."""
+    import torch
+    ref_forward = necks.FPN.forward
+
+    def forward(self, feats):
+        if not getattr(self, "_b2d_channels_last", False):
+            self.to(memory_format=torch.channels_last)
+            self._b2d_channels_last = True
+        return ref_forward(self, [f.contiguous(memory_format=torch.channels_last) for f in feats])
+
+    _set(necks.FPN, "forward", forward)
+
+
+def install(lib=None, channels_last=False):
+    """lib: the reference's imported `lib` package (default: sys.modules['lib']).  channels_last=True additionally
+    makes the FPN neck produce channels_last (NHWC) feature maps, the layout K5 / K6 read without a transposition."""
     from . import anchor, bbox, heads, region, utils
     lib = lib or sys.modules.get("lib")
     if lib is None:
@@ -33,7 +72,8 @@ def install(lib=None):
                   "batched_nms", "multiclass_nms"]
     if mods["utils"]:
         for n in util_names:
-            _set(mods["utils"], n, getattr(utils, n))
+            if hasattr(mods["utils"], n):
+                _set(mods["utils"], n, _grad_safe(getattr(utils, n), getattr(mods["utils"], n)))
         # lib.utils calls tv.ops.nms: give it a module-like shim whose .ops.nms is ours
         tvshim = types.SimpleNamespace(ops=types.SimpleNamespace(nms=utils.nms), transforms=mods["utils"].tv.transforms)
         _set(mods["utils"], "tv", tvshim)
@@ -51,6 +91,8 @@ def install(lib=None):
     # names bound with `from .. import x` inside the heads
     ah = mods["heads.anchor_head"]
     if ah:
+        if hasattr(ah, "AnchorHead"):                    # RetinaNet test path (BASELINE config 4): per-level top-k + multiclass NMS
+            _set(ah.AnchorHead, "predict_single_image", heads.anchor_head_predict_single_image)
         _set(ah, "AnchorCreator", anchor.AnchorCreator)
         _set(ah, "anchor_target", anchor.anchor_target)
         _set(ah, "inside_grid_mask", region.inside_grid_mask)
@@ -79,6 +121,19 @@ def install(lib=None):
             return heads.predict_single_image(self, cls_outs, reg_outs, ctr_outs, img_meta, test_cfg)
 
         _set(fh.FCOSHead, "predict_single_image", _predict)
+    necks = sys.modules.get("lib.necks")
+    if channels_last and necks is not None and hasattr(necks, "FPN"):
+        _channels_last_fpn(necks)
+    losses = sys.modules.get("lib.losses")
+    if losses is not None and hasattr(losses, "CrossEntropyLoss"):      # CE / BCE on the sampled rows
+        ref_ce = losses.CrossEntropyLoss.forward
+
+        def _ce_forward(self, pred, label):
+            if not pred.is_cuda:
+                return ref_ce(self, pred, label)
+            return heads.cross_entropy_loss_forward(self, pred, label)
+
+        _set(losses.CrossEntropyLoss, "forward", _ce_forward)
     if mods["builder"]:
         reg = mods["builder"].MODULES
         for n in ("MaxIoUAssigner", "RandomSampler", "IoUBalancedNegSampler", "BasicRoIExtractor",

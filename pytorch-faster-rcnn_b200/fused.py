@@ -33,7 +33,7 @@ def _batch_view(obj, b0, b1, rows_per_image=None):
     v = copy.copy(obj)
     rows_per_image = rows_per_image or {}
     for k, t in list(vars(obj).items()):
-        if isinstance(t, torch.Tensor) and t.dim() >= 1 and k != "ws":
+        if isinstance(t, torch.Tensor) and t.dim() >= 1 and k not in ("ws", "step_cell"):
             r = rows_per_image.get(k, 1)
             v.__dict__[k] = t[b0 * r:b1 * r]
     v.B, v.b0 = b1 - b0, getattr(obj, "b0", 0) + b0
@@ -123,13 +123,20 @@ class BatchedTargets(object):
         self.tar_label = torch.zeros((B, self.max_num), dtype=i64, device=device)
         self.tar_is_gt = torch.zeros((B, self.max_num), dtype=i64, device=device)
         self.means, self.stds = _C.host_f4(means, [0, 0, 0, 0]), _C.host_f4(stds, [1, 1, 1, 1])
-        self.step = 0
+        # per-step counter of the device sampler, in DEVICE memory: a CUDA-graph replay re-reads it, a by-value
+        # seed would be frozen by the capture (every replay would keep the same positives / negative walk)
+        self.step_cell = torch.zeros(1, dtype=torch.int64, device=device)
+        self.auto_bump = True                   # False: the owner (TrainHotPath) advances a shared cell once per step
         self.b0 = 0
         small = pyramid is None and self.N <= 4096 and self.gt_ld <= 512
         # bbox_target in one launch (b2d_roi_targets_fused) when the problem fits one CTA per image
         self.fused = small and self.max_num <= 1024
         # kernels: roi_targets_small | assign_small | (colmax_rect, label_rows) | (fill, colmax, label); then sample, encode
-        self.launches = 1 if self.fused else (3 if small else (4 if pyramid is not None else 5))
+        self.launches = 1 if self.fused else (3 if small else (4 if pyramid is not None else 5))      # (+1: counter, if auto_bump)
+
+    def reset_step(self):
+        """Restart the device sampler's step counter (tests: the same random stream again)."""
+        self.step_cell.zero_()
 
     def slice(self, b0, b1):
         return _batch_view(self, b0, b1)
@@ -137,13 +144,15 @@ class BatchedTargets(object):
     def __call__(self, gt, gt_count, gt_label=None, boxes=None, box_count=None, img_hw=None):
         pyr = ctypes.byref(self.pyr.c) if boxes is None else None
         box_ld = boxes.shape[-1] if boxes is not None else 0
+        if self.auto_bump:
+            _C.call("b2d_counter_add", _C.ptr(self.step_cell), 1, _C.stream())
+        base_seed = (self.seed * 1000003 + 0x632BE59BD9B4E019 * self.b0) & 0xFFFFFFFFFFFFFFFF
         if self.fused and boxes is not None:
-            self.step += 1
             _C.call("b2d_roi_targets_fused", _C.ptr(self.labels), _C.ptr(self.iou), self.out_ld, _C.ptr(boxes), box_ld,
                     _C.ptr(box_count), self.N, _C.ptr(gt), self.gt_ld, _C.ptr(gt_count), _C.ptr(gt_label), self.B,
                     float(self.pos_iou), float(self.neg_iou), float(self.min_pos), self.prepend, _C.ptr(self.census),
                     _C.ptr(self.pos_list), self.out_ld, _C.ptr(self.chosen), _C.ptr(self.n_chosen), self.max_num,
-                    self.pos_num, (self.seed * 1000003 + self.step + 0x632BE59BD9B4E019 * self.b0) & 0xFFFFFFFFFFFFFFFF,
+                    self.pos_num, base_seed, _C.ptr(self.step_cell),
                     _C.ptr(self.tar_box), _C.ptr(self.tar_gt), _C.ptr(self.tar_param), _C.ptr(self.tar_label),
                     _C.ptr(self.tar_is_gt), self.means, self.stds, _C.stream())
             return self
@@ -152,14 +161,12 @@ class BatchedTargets(object):
                 self.B, float(self.pos_iou), float(self.neg_iou), float(self.min_pos), self.prepend,
                 _C.ptr(self.census), _C.ptr(self.pos_list), self.out_ld, _C.ptr(self.colmax), self.colmax.numel() * 4,
                 _C.stream())
-        self.step += 1
         cnt, cnt_add = (box_count, gt_count) if (self.prepend and box_count is not None) else \
             ((None, gt_count) if self.prepend else (box_count, None))
         n = self.N if cnt is None else 0
         _C.call("b2d_sample_labels", _C.ptr(self.chosen), _C.ptr(self.n_chosen), _C.ptr(self.labels), self.out_ld,
                 _C.ptr(cnt), _C.ptr(cnt_add), n, _C.ptr(self.census), _C.ptr(self.pos_list), self.out_ld, self.B,
-                self.max_num, self.pos_num,
-                (self.seed * 1000003 + self.step + 0x632BE59BD9B4E019 * self.b0) & 0xFFFFFFFFFFFFFFFF, _C.stream())
+                self.max_num, self.pos_num, base_seed, _C.ptr(self.step_cell), _C.stream())
         _C.call("b2d_encode_targets", _C.ptr(self.tar_box), _C.ptr(self.tar_gt), _C.ptr(self.tar_param),
                 _C.ptr(self.tar_label), _C.ptr(self.tar_is_gt), _C.ptr(self.chosen), _C.ptr(self.n_chosen),
                 self.max_num, _C.ptr(self.labels), self.out_ld, _C.ptr(boxes), box_ld, pyr, _C.ptr(gt), self.gt_ld,
@@ -216,6 +223,10 @@ class TrainHotPath(object):
                                           pyramid=self.pyr, border=allowed_border, seed=seed)
         self.roi_targets = BatchedTargets(B, self.proposals.P, gt_ld, rcnn_assigner, rcnn_sampler, z4, rcnn_stds,
                                           device, prepend_gt=True, seed=seed + 1)
+        # one device-side step counter for both samplers, advanced once at the start of step() (graph-replay safe)
+        self.step_cell = torch.zeros(1, dtype=torch.int64, device=device)
+        for t in (self.rpn_targets, self.roi_targets):
+            t.step_cell, t.auto_bump = self.step_cell, False
         roi_strides = list(strides[:4])
         shapes = [(feat_channels, g[0], g[1]) for g in grids[:4]]
         self.roi_align = BatchedRoIAlign(B, rcnn_sampler["max_num"], shapes, roi_strides, device, layout=layout)
@@ -252,6 +263,10 @@ class TrainHotPath(object):
             self.s_rpn = torch.cuda.Stream(device=device, priority=int(os.environ.get("B2D_RPN_PRIO", "0")))
         self.launches = 0
 
+    def reset_step(self):
+        """Restart the samplers' step counter (tests: the same random stream again)."""
+        self.step_cell.zero_()
+
     def _rpn_target_chain(self, cls_outs, reg_outs, gt, gt_count, img_hw):
         rt = self.rpn_targets(gt, gt_count, None, img_hw=img_hw)
         _C.call("b2d_gather_head_outputs", _C.ptr(self.tar_cls), _C.ptr(self.tar_reg), _ptrs(cls_outs), _ptrs(reg_outs),
@@ -262,6 +277,7 @@ class TrainHotPath(object):
         """One pass of the hot path over the batch (device-resident inputs).  `feats_ready`: optional
         CUDA event after which `feats` may be read (lets the proposal / target chains start while
         the feature maps are still arriving, see step_from_host)."""
+        _C.call("b2d_counter_add", _C.ptr(self.step_cell), 1, _C.stream())      # before the streams fork
         if not self.subs:
             if feats_ready is not None:
                 torch.cuda.current_stream().wait_event(feats_ready)
@@ -298,7 +314,7 @@ class TrainHotPath(object):
                 cur.wait_stream(sub[-1])
             cur.wait_stream(self.s_rpn)
         self.launches = (sum(sub[2].launches for sub in self.subs) if self.groups > 1 else self.proposals.launches) + \
-            (self.roi_targets.launches + 1) * self.groups + self.rpn_targets.launches + 1
+            (self.roi_targets.launches + 1) * self.groups + self.rpn_targets.launches + 1 + 1
         return dict(props=self.proposals.props, scores=self.proposals.scores, prop_count=self.proposals.count,
                     rpn=self.rpn_targets, rpn_tar_cls=self.tar_cls, rpn_tar_reg=self.tar_reg, rcnn=self.roi_targets,
                     roi_feats=self.roi_align.out)
@@ -400,6 +416,9 @@ class CascadeHotPath(object):
             rcount = torch.zeros(B, dtype=torch.int32, device=device)
             self.stages.append((tg, ra, refined, rcount, _C.host_f4(sd, [1, 1, 1, 1])))
             n = self.m
+        self.step_cell = torch.zeros(1, dtype=torch.int64, device=device)        # one step counter for all stages
+        for st in self.stages:
+            st[0].step_cell, st[0].auto_bump = self.step_cell, False
         self.roi_img = torch.arange(B, dtype=torch.int32, device=device).repeat_interleave(self.m).contiguous()
         self.rois_flat = [torch.zeros((4, B * self.m), dtype=torch.float32, device=device) for _ in self.stages]
         mf = torch.channels_last if layout != 0 else torch.contiguous_format
@@ -409,7 +428,7 @@ class CascadeHotPath(object):
         nb = _C.lib().b2d_roi_align_bwd_workspace_bytes(B * self.m, B, ctypes.byref(self.bwd_cfg))
         self.bwd_ws = torch.empty(nb, dtype=torch.uint8, device=device)
         self.zero4 = _C.host_f4(z4, [0, 0, 0, 0])
-        self.launches = len(self.stages) * (1 + 1 + 1)
+        self.launches = len(self.stages) * (1 + 1 + 1) + 1
 
     def step(self, props, prop_count, feats, gt, gt_count, gt_label, img_hw, reg_outs):
         """props [B,4,n_props] + prop_count; reg_outs[s]: the stage head's regression output [B, max_num, 4*num_classes]
@@ -417,6 +436,7 @@ class CascadeHotPath(object):
         counts)."""
         outs = []
         boxes, count = props, prop_count
+        _C.call("b2d_counter_add", _C.ptr(self.step_cell), 1, _C.stream())
         for s, (tg, ra, refined, rcount, stds) in enumerate(self.stages):
             bt = tg(gt, gt_count, gt_label, boxes=boxes, box_count=count)
             ra(feats, bt.tar_box, bt.n_chosen)

@@ -76,8 +76,9 @@ def atss_assign(grids, strides, gt, gt_count, gt_label, img_hw, topk=9, scale=8)
     ctr = torch.empty((B, total), dtype=torch.float32, device=dev)
     wsb = _C.lib().b2d_atss_workspace_bytes(ctypes.byref(pyr), B)
     ws = utils._workspace(wsb, dev, "atss")
-    _C.call("b2d_atss_assign", _C.ptr(cls), _C.ptr(reg), _C.ptr(ctr), ctypes.byref(pyr), _C.ptr(_C.f32c(gt)),
-            int(gt.shape[2]), _C.ptr(gt_count), _C.ptr(gt_label.to(torch.int64).contiguous()), _C.ptr(img_hw), B, int(topk),
+    gt_c, gl_c = _C.f32c(gt), gt_label.to(torch.int64).contiguous()      # locals: temporaries must outlive the launch
+    _C.call("b2d_atss_assign", _C.ptr(cls), _C.ptr(reg), _C.ptr(ctr), ctypes.byref(pyr), _C.ptr(gt_c),
+            int(gt.shape[2]), _C.ptr(gt_count), _C.ptr(gl_c), _C.ptr(img_hw), B, int(topk),
             _C.ptr(ws), ws.numel(), _C.stream())
     return cls, reg, ctr
 
@@ -122,9 +123,10 @@ def fcos_predict_single_image(cls_outs, reg_outs, ctr_outs, strides, img_meta, t
     cl, rg = [_C.f32c(x) for x in cls_outs], [_C.f32c(x) for x in reg_outs]
     ct = [_C.f32c(x) for x in ctr_outs] if use_centerness else None
     min_size = float(np.float32(img_meta['scale_factor'] * get('min_bbox_size', 0)))
+    hw_t = _img_hw(img_meta['img_shape'][:2], dev)
     _C.call("b2d_fcos_decode", _C.ptr(boxes), _C.ptr(key), _C.ptr(score), _C.ptr(ctrs), _ptrs(cl), _ptrs(rg),
             _ptrs(ct) if ct is not None else None, ctypes.byref(pyr), C, float(reg_mean), float(reg_std), min_size,
-            _C.ptr(_img_hw(img_meta['img_shape'][:2], dev)), 1, _C.stream())
+            _C.ptr(hw_t), 1, _C.stream())
     pre_nms = int(get('pre_nms', 0))
     sel, off = [], 0
     for (h, w) in grids:                                  # per-level filter + top-k (lib/heads/fcos_head.py:602-613)
@@ -180,6 +182,101 @@ def rpn_predict_single_image(self, level_cls_outs, level_reg_outs, level_anchors
     props, scores, count = rp(cls, reg, _img_hw(img_meta['img_shape'][:2], dev))
     k = int(count[0])
     return props[0][:, :k].clone(), scores[0][:k].clone(), None
+
+
+# ---------------------------------------------------------------------------------- RetinaNet test path (BASELINE config 4)
+def anchor_head_predict_single_image(self, level_cls_outs, level_reg_outs, level_anchors, img_meta, test_cfg):
+    """Method form of AnchorHead.predict_single_image (lib/heads/anchor_head.py:207-258), same arguments and return
+    value `(bbox [4,k], score [k], label int64 [k])`.  Per level the best class score of every anchor, the top
+    `pre_nms` of them, delta decode + clamp and the min-size filter are ONE call of the fused K3 path
+    (b2d_rpn_proposals with score_mode 2 / 3 and do_nms 0; the anchors are regenerated in registers from the head's
+    anchor parameters, `level_anchors` only gives the grid sizes); the class scores of the selected anchors are then
+    gathered and handed to utils.multiclass_nms (one library call).  Selection happens on the best class LOGIT for a
+    sigmoid head (sigmoid is monotone) and on max_{c>=1} softmax_c for a softmax head; ties go to the lowest index."""
+    from . import fused
+    dev = level_cls_outs[0].device
+    _C.require_cuda(*level_cls_outs)
+    grids = tuple(tuple(int(v) for v in a.shape[-2:]) for a in level_anchors)
+    get = (lambda k, d=0: test_cfg.get(k, d)) if hasattr(test_cfg, "get") else (lambda k, d=0: getattr(test_cfg, k, d))
+    sf = float(img_meta.get('scale_factor', 1.0))
+    C = int(self.cls_channels)
+    key = (grids, int(get('pre_nms')), float(get('min_bbox_size', 0)), sf, str(dev), C, bool(self.use_sigmoid))
+    cache = self.__dict__.setdefault('_b2d_pred_cache', {})
+    rp = cache.get(key)
+    if rp is None:
+        center_lt = bool(getattr(self.anchor_creators[0], 'center_lt', False)) if getattr(self, 'anchor_creators', None) else False
+        pyr = fused.AnchorPyramid(self.anchor_strides, grids, tuple(self.anchor_scales), tuple(self.anchor_ratios), center_lt)
+        sel_cfg = dict(pre_nms=int(get('pre_nms')), post_nms=0, max_num=0, nms_iou=0.5, min_bbox_size=get('min_bbox_size', 0))
+        rp = fused.RpnProposals(pyr, 1, sel_cfg, self.target_means, self.target_stds, dev,
+                                score_mode=2 if self.use_sigmoid else 3, cls_channels=C, do_nms=False, scale_factor=sf)
+        cache[key] = rp
+    cls = [_C.f32c(x).view(1, *x.shape[-3:]) for x in level_cls_outs]
+    reg = [_C.f32c(x).view(1, *x.shape[-3:]) for x in level_reg_outs]
+    props, _, count = rp(cls, reg, _img_hw(img_meta['img_shape'][:2], dev))
+    k = int(count[0])
+    boxes = props[0][:, :k]
+    prov = rp.prov[0, :k].to(torch.int64)                 # flattened anchor index (level-major concat)
+    flat = torch.cat([c.view(C, -1) for c in cls], dim=1)  # [C, total] logits
+    picked = flat.index_select(1, prov)
+    score = picked.sigmoid() if self.use_sigmoid else picked.softmax(dim=0)
+    if self.use_sigmoid:
+        nms_label_set, label_adjust = list(range(0, self.num_classes - 1)), 1
+    else:
+        nms_label_set, label_adjust = list(range(1, self.num_classes)), 0
+    kb, ks, kl = utils.multiclass_nms(boxes.t().contiguous(), score.t().contiguous(), nms_label_set, get('nms_iou'),
+                                      get('min_score'), get('max_per_img'), mode=get('nms_type', 'official'))
+    return kb.t(), ks, kl + label_adjust
+
+
+# ---------------------------------------------------------------------------------- SURVEY 8(f-2): CE / BCE on sampled rows
+class _SampledCEFn(torch.autograd.Function):
+    """sum over the rows of cross_entropy(pred, label) (softmax) or binary_cross_entropy_with_logits (sigmoid)."""
+
+    @staticmethod
+    def forward(ctx, pred, label, use_sigmoid):
+        n, C = int(pred.shape[0]), int(pred.shape[1])
+        # two layouts are read in place: contiguous [n, C], and the transposed view of a contiguous [C, n] tensor
+        # (the reference's tar_cls_out.t(), lib/heads/anchor_head.py:129); anything else is made contiguous first
+        if pred.is_contiguous():
+            row_major, ld, src = 1, C, pred
+        elif pred.t().is_contiguous():
+            row_major, ld, src = 0, n, pred
+        else:
+            row_major, ld, src = 1, C, pred.contiguous()
+        lab = label.to(torch.int64).contiguous()
+        partial = torch.empty(int(_C.lib().b2d_sampled_ce_workspace_bytes()) // 4, dtype=torch.float32, device=pred.device)
+        _C.call("b2d_sampled_ce_fwd", _C.ptr(partial), _C.ptr(src), ld, C, row_major, int(bool(use_sigmoid)), _C.ptr(lab), n,
+                _C.stream())
+        ctx.save_for_backward(src, lab)
+        ctx.meta = (ld, C, row_major, int(bool(use_sigmoid)), n)
+        return partial.view(-1, 2)[:, 0].sum()
+
+    @staticmethod
+    def backward(ctx, gout):
+        src, lab = ctx.saved_tensors
+        ld, C, row_major, sig, n = ctx.meta
+        dev = src.device
+        grad = torch.empty((n, C), dtype=torch.float32, device=dev) if row_major else \
+            torch.empty((C, n), dtype=torch.float32, device=dev).t()
+        scale = gout.detach().to(torch.float32).reshape(1).contiguous()
+        _C.call("b2d_sampled_ce_bwd", _C.ptr(grad), _C.ptr(scale), _C.ptr(src), ld, C, row_major, sig, _C.ptr(lab), n, _C.stream())
+        return grad, None, None
+
+
+def sampled_cross_entropy(pred, label, use_sigmoid=False, loss_weight=1.0):
+    """CrossEntropyLoss.forward (lib/losses.py:129-156) on the sampled rows: pred [n, C] (any strides: the RPN's
+    `tar_cls_out.t()` is read in place), label int64 [n] -> loss_weight * sum of the row losses, differentiable in
+    pred.  One kernel forward, one backward; callers divide by avg_factor like the reference
+    (lib/heads/anchor_head.py:127-131, lib/heads/bbox_head.py:62-71)."""
+    _C.require_cuda(pred, label)
+    if pred.dtype != torch.float32:
+        pred = pred.float()
+    return _SampledCEFn.apply(pred, label, use_sigmoid) * loss_weight
+
+
+def cross_entropy_loss_forward(self, pred, label):
+    """Method form bound onto the reference's losses.CrossEntropyLoss by dropin.install()."""
+    return sampled_cross_entropy(pred, label, self.use_sigmoid, self.loss_weight)
 
 
 # ---------------------------------------------------------------------------------- SURVEY 8(f-3)
@@ -243,8 +340,9 @@ def fcos_targets(grids, strides, gt, gt_count, gt_label, img_hw, level_scale_thr
     reg = torch.empty((B, total, 4), dtype=torch.float32, device=dev)
     ctr = torch.empty((B, total), dtype=torch.float32, device=dev)
     thr = (ctypes.c_float * (len(grids) + 1))(*[float(v) for v in level_scale_thr[:len(grids) + 1]])
-    _C.call("b2d_fcos_targets", _C.ptr(cls), _C.ptr(reg), _C.ptr(ctr), ctypes.byref(pyr), _C.ptr(_C.f32c(gt)),
-            int(gt.shape[2]), _C.ptr(gt_count), _C.ptr(gt_label.to(torch.int64).contiguous()), _C.ptr(img_hw), thr, B,
+    gt_c, gl_c = _C.f32c(gt), gt_label.to(torch.int64).contiguous()      # locals: temporaries must outlive the launch
+    _C.call("b2d_fcos_targets", _C.ptr(cls), _C.ptr(reg), _C.ptr(ctr), ctypes.byref(pyr), _C.ptr(gt_c),
+            int(gt.shape[2]), _C.ptr(gt_count), _C.ptr(gl_c), _C.ptr(img_hw), thr, B,
             _C.stream())
     return cls, reg, ctr
 

@@ -116,7 +116,7 @@ class RandomSampler(object):
         self._calls += 1
         _C.call("b2d_sample_labels", _C.ptr(chosen), _C.ptr(n_chosen), _C.ptr(lab), n, None, None, n, _C.ptr(census),
                 _C.ptr(pos_list), max(n, 1), 1, self.max_num, self.pos_num,
-                (int(self.seed) * 1000003 + self._calls) & 0xFFFFFFFFFFFFFFFF, _C.stream())
+                (int(self.seed) * 1000003 + self._calls) & 0xFFFFFFFFFFFFFFFF, None, _C.stream())
         out = torch.full_like(lab, -1)
         _C.call("b2d_scatter_sampled", _C.ptr(out), _C.ptr(lab), n, n, _C.ptr(chosen), _C.ptr(n_chosen),
                 self.max_num, 1, _C.stream())
@@ -135,42 +135,68 @@ class RandomSampler(object):
 
 
 class IoUBalancedNegSampler(object):
-    """lib/region.py:128-172 (host numpy RNG, like the reference; floor_thr /
-    floor_fraction are accepted and ignored exactly as there)."""
+    """lib/region.py:128-172: positives capped at pos_num, negatives drawn per IoU bin of [0, max_iou) from the highest
+    bin down (int(num_neg / num_bins) each, the lowest bin takes what is left, no back-fill).  floor_thr /
+    floor_fraction are accepted and ignored exactly as there.
 
-    def __init__(self, max_num, pos_num, num_bins=3, max_iou=0.5, floor_thr=-1, floor_fraction=0):
+    rng='device' (default): one kernel (b2d_sample_iou_balanced), no host sync; a class over its quota keeps the
+    members with the smallest keyed hash, the RandomSampler device rule.  rng='numpy': the reference's host stream
+    -- the class of every element comes from b2d_iou_bin_ids, one copy to the host, then np.random.choice with the
+    reference's arguments in the reference's order, one upload, b2d_scatter_sampled."""
+    default_rng = "device"
+
+    def __init__(self, max_num, pos_num, num_bins=3, max_iou=0.5, floor_thr=-1, floor_fraction=0, rng=None, seed=0):
         assert max_num >= pos_num
         assert max_iou > 0 and max_iou <= 1
         self.max_num, self.pos_num, self.num_bins, self.max_iou = max_num, pos_num, num_bins, max_iou
+        self.rng, self.seed, self._calls = rng or self.default_rng, seed, 0
+        # bin bounds as torch compares them: python doubles i * bin_size and s + bin_size, rounded to the fp32 of
+        # `overlaps` (tensor-vs-scalar comparison); handed over highest bin first, the order of the reference's walk
+        width = self.max_iou / self.num_bins
+        lo = [np.float32(i * width) for i in range(self.num_bins)][::-1]
+        hi = [np.float32(i * width + width) for i in range(self.num_bins)][::-1]
+        self._lo = (_C.c_float * self.num_bins)(*[float(v) for v in lo])
+        self._hi = (_C.c_float * self.num_bins)(*[float(v) for v in hi])
 
-    @staticmethod
-    def _select(places, num):
-        idx = np.random.choice(places.shape[0], num, False)
-        return places.index_select(0, torch.as_tensor(idx, device=places.device))
-
-    def __call__(self, labels, overlaps, props_bbox, gt_bbox):
-        pos_places = (labels > 0).nonzero()
-        if pos_places.shape[0] > self.pos_num:
-            pos_places = self._select(pos_places, self.pos_num)
-        num_neg = self.max_num - pos_places.shape[0]
-        num_per_bin = int(num_neg / self.num_bins)
-        bin_size = self.max_iou / self.num_bins
-        starts = [i * bin_size for i in range(self.num_bins)]
-        ends = [s + bin_size for s in starts]
-        neg_chosen, neg_places = 0, []
-        for i, (s, e) in enumerate(zip(starts[::-1], ends[::-1])):
-            cur = ((labels == 0) & (overlaps >= s) & (overlaps < e)).nonzero()
-            allowed = num_per_bin if i < self.num_bins - 1 else num_neg - neg_chosen
-            if cur.shape[0] > allowed:
-                cur = self._select(cur, allowed)
-            neg_chosen += cur.shape[0]
-            neg_places.append(cur)
-        tot = torch.cat([pos_places] + neg_places)
-        if tot.shape[0] < self.max_num:
-            logging.warning('Sampler can not sample max number of samples, instead: {}'.format(tot.shape[0]))
-        res = torch.full_like(labels, -1)
-        res[tot] = labels[tot]
-        return res
+    def __call__(self, labels, overlaps, props_bbox=None, gt_bbox=None):
+        _C.require_cuda(labels, overlaps)
+        lab, iou = labels.to(torch.int64).contiguous(), _C.f32c(overlaps)
+        n, dev = int(lab.numel()), lab.device
+        if self.rng != "numpy":
+            out = torch.empty_like(lab)
+            self._calls += 1
+            _C.call("b2d_sample_iou_balanced", _C.ptr(out), _C.ptr(lab), _C.ptr(iou), n, self.max_num, self.pos_num,
+                    self.num_bins, self._lo, self._hi, (int(self.seed) * 1000003 + self._calls) & 0xFFFFFFFFFFFFFFFF,
+                    _C.stream())
+            return out
+        ids = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        _C.call("b2d_iou_bin_ids", _C.ptr(ids), _C.ptr(lab), _C.ptr(iou), n, self.num_bins, self._lo, self._hi, _C.stream())
+        cls = ids[:n].cpu().numpy()
+        members = [np.flatnonzero(cls == c) for c in range(self.num_bins + 1)]      # ascending, like nonzero()
+        picked = members[0]
+        if picked.shape[0] > self.pos_num:
+            picked = picked[np.random.choice(picked.shape[0], self.pos_num, False)]
+        budget = self.max_num - picked.shape[0]
+        share, taken, parts = int(budget / self.num_bins), 0, [picked]
+        for j in range(self.num_bins):
+            m = members[1 + j]
+            quota = share if j < self.num_bins - 1 else budget - taken
+            if m.shape[0] > quota:
+                m = m[np.random.choice(m.shape[0], quota, False)]
+            taken += m.shape[0]
+            parts.append(m)
+        chosen = np.concatenate(parts).astype(np.int32)
+        if chosen.shape[0] < self.max_num:
+            logging.warning('Sampler can not sample max number of samples, instead: {}'.format(chosen.shape[0]))
+        out = torch.empty_like(lab)
+        cap = max(int(chosen.shape[0]), 1)
+        d_chosen = torch.zeros(cap, dtype=torch.int32, device=dev)
+        d_chosen[:chosen.shape[0]] = torch.from_numpy(chosen).to(dev)
+        d_n = torch.tensor([chosen.shape[0]], dtype=torch.int32, device=dev)
+        out.fill_(-1)
+        if n:
+            _C.call("b2d_scatter_sampled", _C.ptr(out), _C.ptr(lab), n, n, _C.ptr(d_chosen), _C.ptr(d_n), cap, 1, _C.stream())
+        return out
 
 
 def topk_desc(values, k):
@@ -269,6 +295,11 @@ class _RoIAlignFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rois, roi_img, levels, meta, *feats):
         scales, out_size, sr, aligned, finest = meta
+        if any(ctx.needs_input_grad[4:]) and (sr <= 0 or out_size[0] * sr > 16 or out_size[1] * sr > 16):
+            # fail at the forward call, not at loss.backward(): K6 has no adaptive-sampling / large-grid form
+            raise _C.B200DetError("roi_align: gradients w.r.t. the features need a fixed sampling_ratio with "
+                                  "output_size * sampling_ratio <= 16 per axis (got output_size=%s, sampling_ratio=%d)"
+                                  % (tuple(out_size), sr))
         layout, fl = _feat_layout(feats)
         if layout == _LAYOUT_NCHW and sr == 2 and int(fl[0].shape[1]) % 4 == 0 and fl[0].shape[1] >= 16:
             layout, fl = _LAYOUT_NHWC, _to_nhwc(fl)      # reference layout: transpose once, then the fast kernels
@@ -297,7 +328,8 @@ class _RoIAlignFn(torch.autograd.Function):
             return (None, None, None, None) + tuple(torch.zeros_like(g) for g in grads)
         wsb = _C.lib().b2d_roi_align_bwd_workspace_bytes(R, B, _C.ctypes.byref(cfg))
         ws = utils._workspace(wsb, dev, "roi_bwd")
-        _C.call("b2d_roi_align_bwd", _ptr_array(grads), _C.ptr(_C.f32c(gout)), _C.ptr(rois), rois.shape[1],
+        gout_c = _C.f32c(gout)
+        _C.call("b2d_roi_align_bwd", _ptr_array(grads), _C.ptr(gout_c), _C.ptr(rois), rois.shape[1],
                 _C.ptr(roi_img), _C.ptr(levels), R, B, _C.ctypes.byref(cfg), _C.ptr(ws), ws.numel(), _C.stream())
         grads = [g if d == torch.float32 else g.to(d) for g, d in zip(grads, dtypes)]
         return (None, None, None, None) + tuple(grads)
@@ -336,7 +368,8 @@ class _RoIPoolFn(torch.autograd.Function):
         R = rois.shape[1]
         if R == 0:
             return torch.zeros_like(g), None, None, None, None
-        _C.call("b2d_roi_pool_bwd", _C.ptr(g), _C.ptr(_C.f32c(gout)), _C.ptr(arg), B, C, H, W, _C.ptr(rois), R,
+        gout_c = _C.f32c(gout)
+        _C.call("b2d_roi_pool_bwd", _C.ptr(g), _C.ptr(gout_c), _C.ptr(arg), B, C, H, W, _C.ptr(rois), R,
                 _C.ptr(roi_img), R, scale, out_size[0], out_size[1], None, 0, _C.stream())
         return g, None, None, None, None
 
@@ -357,10 +390,12 @@ class RoIAlign(nn.Module):
         self.output_size = utils.to_pair(output_size)
         self.spatial_scale, self.sampling_ratio, self.aligned = spatial_scale, sampling_ratio, aligned
 
-    def forward(self, input, rois):
-        r4, idx = _split_rois5(rois)
+    def crop(self, input, r4, idx):
         return roi_align_levels([input], r4, idx, [self.spatial_scale], self.output_size, self.sampling_ratio,
                                 self.aligned)
+
+    def forward(self, input, rois):
+        return self.crop(input, *_split_rois5(rois))
 
 
 class RoIPool(nn.Module):
@@ -371,10 +406,12 @@ class RoIPool(nn.Module):
         self.output_size = utils.to_pair(output_size)
         self.spatial_scale = spatial_scale
 
-    def forward(self, input, rois):
+    def crop(self, input, r4, idx):
         _C.require_cuda(input)
-        r4, idx = _split_rois5(rois)
         return _RoIPoolFn.apply(input, r4.detach(), idx, self.spatial_scale, self.output_size)
+
+    def forward(self, input, rois):
+        return self.crop(input, *_split_rois5(rois))
 
 
 def roi_align(input, boxes, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=False):
@@ -386,7 +423,8 @@ def roi_pool(input, boxes, output_size, spatial_scale=1.0):
 
 
 class ScalableRoICrop(nn.Module):
-    """lib/region.py:212-233: rescale each RoI about its centre (+1 sizes), then crop."""
+    """lib/region.py:212-233: every RoI is rescaled about its centre (half sizes with the +1 convention, times
+    `scale`) by b2d_scale_rois, then cropped by the wrapped RoI layer.  rois: torchvision's [n,5] or a list of [L,4]."""
     ROI_OP = None
 
     def __init__(self, scale=1.0, **kwargs):
@@ -395,16 +433,13 @@ class ScalableRoICrop(nn.Module):
         self.scale = scale
         self.kwargs = kwargs
 
-    def scale_bbox(self, bbox, scale):
-        ctr_x, ctr_y = (bbox[:, 2] + bbox[:, 0]) / 2, (bbox[:, 3] + bbox[:, 1]) / 2
-        half_w, half_h = (bbox[:, 2] - bbox[:, 0] + 1) / 2, (bbox[:, 3] - bbox[:, 1] + 1) / 2
-        half_w, half_h = half_w * scale, half_h * scale
-        return torch.stack([ctr_x - half_w, ctr_y - half_h, ctr_x + half_w, ctr_y + half_h], dim=1)
-
     def forward(self, feats, rois):
-        batch_idx, bboxes = rois[:, 0:1], rois[:, 1:]
-        rois = torch.cat([batch_idx, self.scale_bbox(bboxes, self.scale)], dim=1)
-        return self.roi_op(feats, rois)
+        r4, idx = _split_rois5(rois)                      # [4,n] + image index
+        n = int(r4.shape[1])
+        scaled = torch.empty_like(r4)
+        _C.require_cuda(r4)
+        _C.call("b2d_scale_rois", _C.ptr(scaled), _C.ptr(r4), n, n, float(self.scale), _C.stream())
+        return self.roi_op.crop(feats, scaled, idx)
 
 
 class ScalableRoIPool(ScalableRoICrop):

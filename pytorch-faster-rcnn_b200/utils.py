@@ -122,10 +122,15 @@ def clamp_bbox(bbox, img_size):
 
 # ---- a11 / a12 ---------------------------------------------------------------------
 _ws_cache = {}
+NMS_MAX_BOXES = 16384        # b2d_nms: boxes per call (dense mask above 2048 boxes); see INTEGRATION.md
 
 
 def _workspace(nbytes, device, tag):
-    key = (tag, device)
+    """Scratch buffer for one entry point, cached per (tag, device, CURRENT STREAM): two streams never share scratch
+    memory, and a buffer is only ever replaced by a larger one allocated on the same stream (the caching allocator
+    then keeps the old block alive until that stream has passed the kernels that use it)."""
+    stream = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0
+    key = (tag, device, stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
@@ -133,13 +138,21 @@ def _workspace(nbytes, device, tag):
     return buf
 
 
+def _tv_nms(boxes, scores, iou_threshold):
+    import torchvision
+    return torchvision.ops.nms(boxes, scores, iou_threshold)
+
+
 def nms(boxes, scores, iou_threshold):
     """Drop-in for torchvision.ops.nms (CPU semantics): boxes [n,4], scores [n] ->
-    int64 indices of kept boxes, in decreasing score order (ties: lower index first)."""
+    int64 indices of kept boxes, in decreasing score order (ties: lower index first).
+    More than NMS_MAX_BOXES boxes (torchvision has no limit) are handed to torchvision's CUDA kernel."""
     _C.require_cuda(boxes, scores)
     n = int(scores.numel())
     if n == 0:
         return torch.zeros(0, dtype=torch.int64, device=boxes.device)
+    if n > NMS_MAX_BOXES:
+        return _tv_nms(boxes.reshape(n, 4).float(), scores.reshape(n).float(), float(iou_threshold))
     b, s = _C.f32c(boxes.reshape(n, 4)), _C.f32c(scores.reshape(n))
     keep = torch.empty(n, dtype=torch.int64, device=boxes.device)
     cnt = torch.empty(1, dtype=torch.int32, device=boxes.device)
@@ -151,55 +164,77 @@ def nms(boxes, scores, iou_threshold):
 
 
 def batched_nms(bbox, score, label, nms_iou, class_agnostic=False):
-    """lib/utils.py:211-221 (class-offset trick; the fp32 add is part of the result)."""
-    numel = score.numel()
-    if numel == 0:
+    """lib/utils.py:211-221: class-aware NMS through the coordinate offset label * bbox.max() (the fp32 add is part
+    of the reference result); bbox [n,4], score [n], label int64 [n] -> the kept rows of all three, score order.
+    The maximum and the shifted boxes come from one kernel (b2d_batched_nms_boxes)."""
+    n = int(score.numel())
+    if n == 0:
         return bbox, score, label
-    if class_agnostic:
-        nms_bbox = bbox
-    else:
-        max_range = bbox.max()
-        nms_bbox = bbox + (label * max_range).to(bbox).view(numel, 1)
-    keep = nms(nms_bbox, score, nms_iou)
-    return bbox[keep, :], score[keep], label[keep]
+    _C.require_cuda(bbox, score, label)
+    boxes = _C.f32c(bbox.reshape(n, 4))
+    if not class_agnostic:
+        shifted = torch.empty_like(boxes)
+        lab64 = label.to(torch.int64).contiguous()          # (kept in a local: a temporary would be freed before the launch)
+        _C.call("b2d_batched_nms_boxes", _C.ptr(shifted), _C.ptr(boxes), _C.ptr(lab64), n, _C.stream())
+        boxes = shifted
+    keep = nms(boxes, score, nms_iou)
+    return bbox.index_select(0, keep), score.index_select(0, keep), label.index_select(0, keep)
 
 
 def multiclass_nms(bbox, score, nms_channel, nms_iou, min_score=-1, max_num=None, score_factor=None,
                    mode='official'):
-    """lib/utils.py:224-269.  Candidate enumeration is index glue; the NMS is K4."""
+    """lib/utils.py:224-269 as ONE library call (b2d_multiclass_nms): bbox [n,4] or [n,4*C], score [n,C] ->
+    (bbox [k,4], score [k], label int64 [k]).  Candidate test, ordered compaction, class offsets, NMS and the
+    max_num cut run on the device; the only host read is the survivor count."""
     assert mode in ['official', 'strict']
     assert score.dim() == 2, 'multiclass_nms only applies to multi-channel score'
-    cls_channel = score.shape[1]
-    num_bbox = bbox.shape[0]
-    simple_bbox = bbox.shape[1] == 4
-    nms_channel = list(nms_channel)
-    if mode == 'official':
-        chan = torch.zeros(cls_channel, dtype=torch.bool, device=score.device)
-        chan[torch.as_tensor(nms_channel, dtype=torch.long, device=score.device)] = True
-        label = torch.arange(cls_channel, device=score.device).view(1, -1).expand(num_bbox, -1)
-        if simple_bbox:
-            bbox = bbox.unsqueeze(2).expand(-1, -1, cls_channel)
-        else:
-            bbox = bbox.view(num_bbox, 4, cls_channel)
-        bbox = bbox.permute(0, 2, 1)
-        chosen = (score >= min_score) & chan.view(1, -1)
-        if score_factor is not None:
-            if score_factor.dim() == 1:
-                score_factor = score_factor.unsqueeze(1)
-            score = score * score_factor
-        nms_bbox, nms_score, nms_label = bbox[chosen], score[chosen], label[chosen]
-    else:
-        score, label = score.max(1)
-        chosen = torch.zeros_like(label, dtype=torch.bool)
-        for cha in nms_channel:
-            chosen = chosen | (label == cha)
-        if not simple_bbox:
-            bbox = bbox.view(num_bbox, 4, cls_channel)[torch.arange(num_bbox, device=bbox.device), :, label]
-        chosen = (score >= min_score) & chosen
-        if score_factor is not None:
-            score = score * score_factor
-        nms_bbox, nms_score, nms_label = bbox[chosen, :], score[chosen], label[chosen]
-    keep_bbox, keep_score, keep_label = batched_nms(nms_bbox, nms_score, nms_label, nms_iou)
-    if max_num is not None and keep_score.numel() > max_num:
-        keep_bbox, keep_score, keep_label = keep_bbox[:max_num], keep_score[:max_num], keep_label[:max_num]
-    return keep_bbox, keep_score, keep_label
+    _C.require_cuda(bbox, score)
+    n, C = int(score.shape[0]), int(score.shape[1])
+    dev = score.device
+    if n == 0:
+        return bbox.new_zeros((0, 4)), score.new_zeros((0,)), torch.zeros(0, dtype=torch.int64, device=dev)
+    box_classes = 1 if bbox.shape[1] == 4 else C
+    assert bbox.shape[1] == 4 * box_classes and C <= 128
+    chan = [0, 0]
+    for c in nms_channel:
+        c = int(c)
+        if 0 <= c < C:
+            chan[c >> 6] |= 1 << (c & 63)
+    cand_max = n * (len(list(nms_channel)) if mode == 'official' else 1)
+    # contiguous fp32 copies are held in locals until the call returns: a temporary created inside the argument list is
+    # freed at once and the next temporary may reuse (and overwrite) its block before the kernel runs
+    box_c, score_c = _C.f32c(bbox), _C.f32c(score)
+    factor = None
+    if score_factor is not None:
+        factor = _C.f32c(score_factor.reshape(-1))
+        assert factor.numel() == n
+    chan_arr = (_C.c_ull * 2)(*chan)
+    min_f = float(torch.tensor(min_score, dtype=torch.float32))          # the fp32 torch compares the scores with
+    thr = _C.floor_f32(float(nms_iou))
+    if cand_max > NMS_MAX_BOXES:
+        # more (box, class) pairs than b2d_nms takes could pass the test: candidate kernel alone, then the NMS by size
+        cbox = torch.empty((cand_max, 4), dtype=torch.float32, device=dev)
+        nbox = torch.empty((cand_max, 4), dtype=torch.float32, device=dev)
+        cscore = torch.empty(cand_max, dtype=torch.float32, device=dev)
+        clabel = torch.empty(cand_max, dtype=torch.int32, device=dev)
+        meta = torch.empty(2, dtype=torch.int32, device=dev)
+        _C.call("b2d_multiclass_candidates", _C.ptr(cbox), _C.ptr(nbox), _C.ptr(cscore), _C.ptr(clabel), _C.ptr(meta[0:1]),
+                _C.ptr(meta[1:2]), _C.ptr(box_c), box_classes, _C.ptr(score_c), n, C, chan_arr, min_f, _C.ptr(factor),
+                int(mode == 'strict'), cand_max, _C.stream())
+        m = int(meta[0])
+        keep = nms(nbox[:m], cscore[:m], nms_iou)
+        if max_num is not None:
+            keep = keep[:int(max_num)]
+        return cbox.index_select(0, keep), cscore.index_select(0, keep), clabel.index_select(0, keep).to(torch.int64)
+    cap = max(1, cand_max)
+    max_keep = cap if max_num is None else max(1, min(int(max_num), cap))
+    out_box = torch.empty((max_keep, 4), dtype=torch.float32, device=dev)
+    out_score = torch.empty(max_keep, dtype=torch.float32, device=dev)
+    out_label = torch.empty(max_keep, dtype=torch.int64, device=dev)
+    meta = torch.empty(2, dtype=torch.int32, device=dev)              # survivor count, overflow flag
+    ws = _workspace(_C.lib().b2d_multiclass_nms_workspace_bytes(cap), dev, "multiclass_nms")
+    _C.call("b2d_multiclass_nms", _C.ptr(out_box), _C.ptr(out_score), _C.ptr(out_label), _C.ptr(meta[0:1]),
+            _C.ptr(box_c), box_classes, _C.ptr(score_c), n, C, chan_arr, min_f, _C.ptr(factor), int(mode == 'strict'),
+            thr, max_keep, cap, _C.ptr(meta[1:2]), _C.ptr(ws), ws.numel(), _C.stream())
+    k = int(meta[0])
+    return out_box[:k], out_score[:k], out_label[:k]

@@ -536,10 +536,92 @@ def g_c4():
          det_bbox=db, det_score=ds, det_label=dl, cls_sha=sha(cls), feat_sha=sha(feat))
 
 
+def g_heads2():
+    """Round 2: AnchorHead.predict_single_image at BASELINE config-4 sizes (lib/heads/anchor_head.py:207-258), the
+    softmax RPN (lib/heads/rpn_head.py:83-86), Scalable RoI layers (lib/region.py:212-239), IoUBalancedNegSampler
+    (lib/region.py:128-172, numpy stream)."""
+    import types
+    import hashlib
+    import inputs as gin
+    import lib.heads.anchor_head as ah
+    import lib.heads.rpn_head as rh
+    out = {}
+    # ---- RetinaNet test path: 151 200 / 37 800 / 9 450 / 2 457 / 693 anchors x 20 classes (inputs regenerated by the test)
+    cls, reg = gin.retina_inputs(20)
+    acs = [ranchor.AnchorCreator(base=s, scales=gin.RETINA_SCALES, aspect_ratios=[0.5, 1.0, 2.0]) for s in gin.RETINA_STRIDES]
+    anchors = [ac(s, g) for ac, s, g in zip(acs, gin.RETINA_STRIDES, gin.RETINA_GRIDS)]
+    meta = dict(img_shape=(800, 1333, 3), pad_shape=(800, 1344, 3), scale_factor=1.0)
+    me = types.SimpleNamespace(cls_channels=20, use_sigmoid=True, num_classes=21, target_means=[0.0] * 4, target_stds=[1.0] * 4)
+    cfgs = [dict(pre_nms=1000, min_bbox_size=0, min_score=0.05, nms_iou=0.5, nms_type="strict", max_per_img=100),
+            dict(pre_nms=300, min_bbox_size=24, min_score=0.9, nms_iou=0.4, nms_type="official", max_per_img=250)]
+    out["ret_cfgs"] = np.array([json.dumps(c) for c in cfgs])
+    out["ret_cls_sha"], out["ret_reg_sha"] = sha(cls[0]), sha(reg[4])
+    for i, c in enumerate(cfgs):
+        with torch.no_grad():
+            b, sc, lab = ah.AnchorHead.predict_single_image(me, [T(x) for x in cls], [T(x) for x in reg], anchors, meta,
+                                                            ref_shim.AttrDict(c))
+        out.update({"ret_bbox%d" % i: b, "ret_score%d" % i: sc, "ret_label%d" % i: lab})
+        print("retina predict", i, "detections", int(sc.numel()))
+    # softmax AnchorHead (use_sigmoid False, 21 channels) on a small pyramid
+    rng = np.random.default_rng(SEED + 42)
+    sgrids = [(20, 28), (10, 14), (5, 7)]
+    scls = [rng.normal(0, 2, (3 * 5,) + g).astype(np.float32) for g in sgrids]
+    sreg = [rng.normal(0, 0.3, (12,) + g).astype(np.float32) for g in sgrids]
+    sacs = [ranchor.AnchorCreator(base=s, scales=[8], aspect_ratios=[0.5, 1.0, 2.0]) for s in (8, 16, 32)]
+    sanchors = [ac(s, g) for ac, s, g in zip(sacs, (8, 16, 32), sgrids)]
+    me = types.SimpleNamespace(cls_channels=5, use_sigmoid=False, num_classes=5, target_means=[0.0] * 4, target_stds=[1.0] * 4)
+    scfg = dict(pre_nms=200, min_bbox_size=0, min_score=0.3, nms_iou=0.5, nms_type="official", max_per_img=80)
+    with torch.no_grad():
+        b, sc, lab = ah.AnchorHead.predict_single_image(me, [T(x) for x in scls], [T(x) for x in sreg], sanchors,
+                                                        dict(img_shape=(160, 213, 3), scale_factor=1.0), ref_shim.AttrDict(scfg))
+    print("softmax anchor head", "detections", int(sc.numel()))
+    out.update(sm_bbox=b, sm_score=sc, sm_label=lab, sm_cfg=np.array(json.dumps(scfg)))
+    for l in range(3):
+        out["sm_cls%d" % l], out["sm_reg%d" % l] = scls[l], sreg[l]
+    # ---- RPN with a two-channel softmax classifier (use_sigmoid False, lib/heads/rpn_head.py:83-86)
+    grids = [(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)]
+    rcls = [rng.normal(0, 1, (6,) + g).astype(np.float32) for g in grids]
+    rreg = [rng.normal(0, 0.5, (12,) + g).astype(np.float32) for g in grids]
+    racs = [ranchor.AnchorCreator(base=s, scales=[8], aspect_ratios=[0.5, 1.0, 2.0]) for s in (4, 8, 16, 32, 64)]
+    ranchors = [ac(s, g) for ac, s, g in zip(racs, (4, 8, 16, 32, 64), grids)]
+    me = types.SimpleNamespace(cls_channels=2, use_sigmoid=False, target_means=[0.0] * 4, target_stds=[1.0] * 4)
+    rcfg = dict(pre_nms=300, post_nms=200, max_num=400, nms_iou=0.7, min_bbox_size=0)
+    with torch.no_grad():
+        b, sc, _ = rh.RPNHead.predict_single_image(me, [T(x) for x in rcls], [T(x) for x in rreg], ranchors,
+                                                   dict(img_shape=(160, 213, 3), pad_shape=(160, 224, 3), scale_factor=1.0),
+                                                   ref_shim.AttrDict(rcfg))
+    out.update(rs_props=b, rs_scores=sc, rs_cfg=np.array(json.dumps(rcfg)))
+    for l in range(5):
+        out["rs_cls%d" % l], out["rs_reg%d" % l] = rcls[l], rreg[l]
+    # ---- ScalableRoIPool / ScalableRoIAlign (lib/region.py:212-239)
+    feat = rng.normal(0, 1, (2, 8, 20, 28)).astype(np.float32)
+    bx = rand_boxes(rng, 40, 160, 213, 8, 120)
+    rois5 = np.concatenate([rng.integers(0, 2, (40, 1)).astype(np.float32), bx.T], 1)
+    with torch.no_grad():
+        sp = rregion.ScalableRoIPool(scale=1.3, output_size=(7, 7), spatial_scale=1 / 8)(T(feat), T(rois5))
+        sa = rregion.ScalableRoIAlign(scale=0.8, output_size=(7, 7), spatial_scale=1 / 8, sampling_ratio=2)(T(feat), T(rois5))
+    out.update(sc_feat=feat, sc_rois=rois5, sc_pool=sp, sc_align=sa)
+    # ---- IoUBalancedNegSampler, numpy stream
+    n = 3000
+    lab = np.where(rng.uniform(size=n) < 0.1, rng.integers(1, 9, n), 0).astype(np.int64)
+    lab[rng.uniform(size=n) < 0.05] = -1
+    iou = np.where(lab > 0, rng.uniform(0.5, 1.0, n), rng.uniform(0, 0.5, n) ** 2).astype(np.float32)
+    out.update(ib_labels=lab, ib_iou=iou)
+    for i, (mx, ps, nb) in enumerate([(512, 128, 3), (256, 400, 5)]):
+        if ps > mx:
+            ps = mx
+        np.random.seed(7 + i)
+        res = rregion.IoUBalancedNegSampler(mx, ps, num_bins=nb, max_iou=0.5)(T(lab), T(iou), None, None)
+        out["ib_out%d" % i] = res
+        out["ib_cfg%d" % i] = np.array([mx, ps, nb])
+        print("iou-balanced", i, "kept", int((res >= 0).sum()), "pos", int((res > 0).sum()))
+    save("heads2", **out)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     gens = dict(anchors=g_anchors, iou_assign=g_iou_assign, deltas=g_deltas, nms=g_nms, rpn=g_rpn, roi=g_roi,
-                targets=g_targets, atss=g_atss, heads=g_heads, loss=g_loss, c4=g_c4)
+                targets=g_targets, atss=g_atss, heads=g_heads, loss=g_loss, c4=g_c4, heads2=g_heads2)
     for k, fn in gens.items():
         if not only or k in only:
             fn()

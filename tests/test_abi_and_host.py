@@ -150,7 +150,8 @@ def test_dropin_install_rebinds_reference_names():
         assert ah.AnchorCreator is b200det.anchor.AnchorCreator
         assert rh.tvops.nms is b200det.utils.nms
         assert rh.RPNHead.predict_single_image is b200det.heads.rpn_predict_single_image
-        assert sys.modules["lib.utils"].calc_iou is b200det.utils.calc_iou
+        assert sys.modules["lib.utils"].calc_iou.b2d_fast is b200det.utils.calc_iou         # grad-safe wrapper
+        assert ah.AnchorHead.predict_single_image is b200det.heads.anchor_head_predict_single_image
         assert sys.modules["lib.utils"].tv.ops.nms is b200det.utils.nms
         assert sys.modules["lib.bbox"].bbox_target is b200det.bbox.bbox_target
         built = rb.build_module(dict(type="MaxIoUAssigner", pos_iou=0.7, neg_iou=0.3, min_pos_iou=0.3))
@@ -159,3 +160,59 @@ def test_dropin_install_rebinds_reference_names():
         b200det.uninstall()
     assert rb.MODULES["MaxIoUAssigner"] is orig
     assert rh.RPNHead.predict_single_image is not b200det.heads.rpn_predict_single_image
+
+
+def test_dropin_keeps_gradients_and_cpu_tensors_on_the_reference_path():
+    """install() must not cut autograd.  IoULoss is -utils.elem_iou(a, b).log() (lib/losses.py:7-10); after
+    install() its gradient is still there, and CPU tensors still work (both routed to the saved reference code)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference checkout not present on this machine")
+    import torch
+    lib = ref_shim.install()
+    import b200det
+    import lib.losses as rl
+    import lib.utils as ru
+    b200det.install(lib)
+    try:
+        a = torch.tensor([[10.0, 20.0], [10.0, 30.0], [50.0, 80.0], [60.0, 90.0]], requires_grad=True)
+        b = torch.tensor([[12.0, 25.0], [11.0, 28.0], [55.0, 70.0], [58.0, 95.0]])
+        loss = rl.iou_loss(a, b).sum() if hasattr(rl, "iou_loss") else (-ru.elem_iou(a, b).log()).sum()
+        loss.backward()
+        assert a.grad is not None and float(a.grad.abs().sum()) > 0.0
+        with torch.no_grad():
+            p = ru.param2bbox(b, torch.zeros_like(b))            # CPU tensors: reference implementation, no raise
+        assert tuple(p.shape) == (4, 2)
+        ce = rl.CrossEntropyLoss(use_sigmoid=False)
+        x = torch.randn(5, 3, requires_grad=True)
+        ce(x, torch.tensor([0, 1, 2, 1, 0])).backward()           # CPU: the reference's forward
+        assert x.grad is not None
+    finally:
+        b200det.uninstall()
+
+
+def test_install_channels_last_makes_the_reference_fpn_emit_nhwc():
+    """install(channels_last=True) -> lib.necks.FPN outputs are channels_last and numerically the same."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference checkout not present on this machine")
+    import torch
+    lib = ref_shim.install()
+    import b200det
+    import lib.necks as rn
+    torch.manual_seed(0)
+    fpn = rn.FPN(in_channels=[8, 16, 32, 64], out_channels=8, num_outs=5)
+    feats = [torch.randn(2, c, 64 // s, 96 // s) for c, s in zip([8, 16, 32, 64], [1, 2, 4, 8])]
+    with torch.no_grad():
+        ref = fpn(feats)
+    b200det.install(lib, channels_last=True)
+    try:
+        with torch.no_grad():
+            out = fpn(feats)
+        for a, b in zip(ref, out):
+            assert b.is_contiguous(memory_format=torch.channels_last) or b.shape[1] == 1 or b.shape[2] * b.shape[3] == 1
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+    finally:
+        b200det.uninstall()

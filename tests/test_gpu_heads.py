@@ -451,3 +451,252 @@ def test_cascade_hot_path_batched_vs_oracle():
         for l, st in enumerate(strides):
             ref = oracle.roi_align_bwd(go[s][b * m:(b + 1) * m][lv == l], (C,) + grids[l], np.ascontiguousarray(tb[:, lv == l]), 1.0 / st)
             np.testing.assert_allclose(N(grads[s][l][b]), ref, rtol=1e-5, atol=2e-6)
+
+
+# ------------------------------------------------------------------ round 2: RetinaNet test path, softmax heads, glue kernels
+def _gin():
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import inputs as gin
+    return gin
+
+
+def _sha(a):
+    import hashlib
+    return np.frombuffer(hashlib.sha1(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_anchor_head_predict_retinanet_config4_vs_reference(i):
+    """AnchorHead.predict_single_image (lib/heads/anchor_head.py:207-258) at BASELINE config-4 sizes -- 201 600 anchors x
+    20 classes, per-level top-1000 on the best class score (score_mode 2, do_nms 0), decode, strict / official
+    multiclass NMS, max_per_img -- through the reference-signature method against the reference's own output."""
+    import json
+    from b200det import anchor as banchor
+    gin = _gin()
+    g = load_golden("heads2")
+    cls, reg = gin.retina_inputs(20)
+    assert np.array_equal(_sha(cls[0]), g["ret_cls_sha"]) and np.array_equal(_sha(reg[4]), g["ret_reg_sha"]), "seeded inputs differ"
+    head = types.SimpleNamespace(anchor_strides=list(gin.RETINA_STRIDES), anchor_scales=gin.RETINA_SCALES,
+                                 anchor_ratios=[0.5, 1.0, 2.0], target_means=[0.0] * 4, target_stds=[1.0] * 4,
+                                 use_sigmoid=True, cls_channels=20, num_classes=21, anchor_creators=None)
+    anchors = [torch.empty((4, 9) + gr, device=DEV) for gr in gin.RETINA_GRIDS]       # only the grid sizes are read
+    meta = dict(img_shape=(800, 1333, 3), pad_shape=(800, 1344, 3), scale_factor=1.0)
+    cfg = json.loads(str(g["ret_cfgs"][i]))
+    b, s, l = bheads.anchor_head_predict_single_image(head, [T(x) for x in cls], [T(x) for x in reg], anchors, meta, cfg)
+    assert tuple(b.shape) == g["ret_bbox%d" % i].shape
+    assert np.array_equal(N(l), g["ret_label%d" % i])
+    np.testing.assert_allclose(N(s), g["ret_score%d" % i], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(b), g["ret_bbox%d" % i], rtol=1e-5, atol=1e-3)
+
+
+def test_anchor_head_predict_softmax_head_vs_reference():
+    """use_sigmoid False: per-level top-k on max_{c>=1} softmax_c (score_mode 3), softmax scores, classes 1..C-1."""
+    import json
+    g = load_golden("heads2")
+    head = types.SimpleNamespace(anchor_strides=[8, 16, 32], anchor_scales=[8], anchor_ratios=[0.5, 1.0, 2.0],
+                                 target_means=[0.0] * 4, target_stds=[1.0] * 4, use_sigmoid=False, cls_channels=5,
+                                 num_classes=5, anchor_creators=None)
+    grids = [(20, 28), (10, 14), (5, 7)]
+    anchors = [torch.empty((4, 3) + gr, device=DEV) for gr in grids]
+    cfg = json.loads(str(g["sm_cfg"]))
+    b, s, l = bheads.anchor_head_predict_single_image(head, [T(g["sm_cls%d" % k]) for k in range(3)],
+                                                      [T(g["sm_reg%d" % k]) for k in range(3)], anchors,
+                                                      dict(img_shape=(160, 213, 3), scale_factor=1.0), cfg)
+    assert tuple(b.shape) == g["sm_bbox"].shape
+    assert np.array_equal(N(l), g["sm_label"])
+    np.testing.assert_allclose(N(s), g["sm_score"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(b), g["sm_bbox"], rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("front", ["1", "0"])
+def test_rpn_two_channel_softmax_vs_reference(front, setknob):
+    """RPNHead with use_sigmoid False (lib/heads/rpn_head.py:83-86): score = softmax[1] = sigmoid(l1 - l0), score_mode 1,
+    through the cluster kernel and the multi-kernel chain."""
+    import json
+    from b200det import anchor as banchor
+    setknob(B2D_RPN_FRONT=front)
+    g = load_golden("heads2")
+    grids = [(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)]
+    head = types.SimpleNamespace(anchor_strides=[4, 8, 16, 32, 64], anchor_scales=[8], anchor_ratios=[0.5, 1.0, 2.0],
+                                 target_means=[0.0] * 4, target_stds=[1.0] * 4, use_sigmoid=False, cls_channels=2,
+                                 anchor_creators=None)
+    anchors = [torch.empty((4, 3) + gr, device=DEV) for gr in grids]
+    b, s, extra = bheads.rpn_predict_single_image(head, [T(g["rs_cls%d" % k]) for k in range(5)],
+                                                  [T(g["rs_reg%d" % k]) for k in range(5)], anchors,
+                                                  dict(img_shape=(160, 213, 3), pad_shape=(160, 224, 3), scale_factor=1.0),
+                                                  json.loads(str(g["rs_cfg"])))
+    assert extra is None and tuple(b.shape) == g["rs_props"].shape
+    np.testing.assert_allclose(N(s), g["rs_scores"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(b), g["rs_props"], rtol=1e-5, atol=1e-3)
+
+
+def test_scalable_roi_layers_vs_reference():
+    """ScalableRoIPool / ScalableRoIAlign (lib/region.py:212-239): RoIs rescaled by b2d_scale_rois, then K7 / K5."""
+    g = load_golden("heads2")
+    feat, rois = T(g["sc_feat"]), T(g["sc_rois"])
+    sp = bregion.ScalableRoIPool(scale=1.3, output_size=(7, 7), spatial_scale=1 / 8)(feat, rois)
+    sa = bregion.ScalableRoIAlign(scale=0.8, output_size=(7, 7), spatial_scale=1 / 8, sampling_ratio=2)(feat, rois)
+    np.testing.assert_allclose(N(sp), g["sc_pool"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(N(sa), g["sc_align"], rtol=1e-5, atol=1e-6)
+    sa_nhwc = bregion.ScalableRoIAlign(scale=0.8, output_size=(7, 7), spatial_scale=1 / 8, sampling_ratio=2)(
+        feat.contiguous(memory_format=torch.channels_last), rois)
+    assert np.array_equal(N(sa_nhwc), N(sa))
+
+
+def test_roi_align_nhwc_kernel_fixed_ratio_three():
+    """k_roi_align_nhwc (channels_last, fixed sampling ratio != 2) against the generic NCHW kernel and the oracle."""
+    rng = np.random.default_rng(11)
+    feat = rng.standard_normal((2, 8, 24, 30)).astype(np.float32)
+    n = 50
+    x1, y1 = rng.uniform(0, 180, n), rng.uniform(0, 140, n)
+    rois = np.stack([x1, y1, x1 + rng.uniform(4, 90, n), y1 + rng.uniform(4, 70, n)]).astype(np.float32)
+    idx = rng.integers(0, 2, n).astype(np.int32)
+    f = T(feat)
+    a = bregion.roi_align_levels([f], T(rois), T(idx), [1 / 8], (5, 5), 3, False)
+    b = bregion.roi_align_levels([f.contiguous(memory_format=torch.channels_last)], T(rois), T(idx), [1 / 8], (5, 5), 3, False)
+    assert np.array_equal(N(a), N(b))
+    for img in range(2):
+        m = idx == img
+        ref = oracle.roi_align(feat[img], np.ascontiguousarray(rois[:, m]), 1 / 8, (5, 5), 3, False)
+        np.testing.assert_allclose(N(b)[m], ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_iou_balanced_sampler_numpy_stream_vs_reference(i):
+    g = load_golden("heads2")
+    mx, ps, nb = (int(v) for v in g["ib_cfg%d" % i])
+    np.random.seed(7 + i)
+    out = bregion.IoUBalancedNegSampler(mx, ps, num_bins=nb, max_iou=0.5, rng="numpy")(T(g["ib_labels"]), T(g["ib_iou"]), None, None)
+    assert np.array_equal(N(out), g["ib_out%d" % i])
+
+
+def test_iou_balanced_sampler_device_properties():
+    """Device RNG mode (one kernel, no host sync): same cardinalities per class as the reference's rule, kept labels
+    unchanged, everything else -1, deterministic for a seed, different for another."""
+    g = load_golden("heads2")
+    lab, iou = g["ib_labels"], g["ib_iou"]
+    for (mx, ps, nb) in [(512, 128, 3), (256, 256, 5), (64, 0, 2)]:
+        smp = bregion.IoUBalancedNegSampler(mx, ps, num_bins=nb, max_iou=0.5, seed=3)
+        out = N(smp(T(lab), T(iou)))
+        kept = out >= 0
+        assert np.array_equal(out[kept], lab[kept]) and (out[~kept] == -1).all()
+        npos = int((lab > 0).sum())
+        kp = min(npos, ps)
+        assert int((out > 0).sum()) == kp
+        num_neg, per = mx - kp, int((mx - kp) / nb)
+        width = 0.5 / nb
+        lo = [np.float32(j * width) for j in range(nb)][::-1]
+        hi = [np.float32(j * width + width) for j in range(nb)][::-1]
+        taken = 0
+        for j in range(nb):
+            member = (lab == 0) & (iou >= lo[j]) & (iou < hi[j])
+            quota = per if j < nb - 1 else num_neg - taken
+            want = min(int(member.sum()), quota)
+            assert int((kept & member).sum()) == want, (mx, ps, nb, j)
+            taken += want
+        out2 = N(bregion.IoUBalancedNegSampler(mx, ps, num_bins=nb, max_iou=0.5, seed=3)(T(lab), T(iou)))
+        assert np.array_equal(out, out2)
+        out3 = N(bregion.IoUBalancedNegSampler(mx, ps, num_bins=nb, max_iou=0.5, seed=4)(T(lab), T(iou)))
+        assert not np.array_equal(out, out3)
+
+
+@pytest.mark.parametrize("use_sigmoid,C", [(False, 21), (True, 1), (True, 6)])
+@pytest.mark.parametrize("layout", ["rows", "transposed"])
+def test_sampled_cross_entropy_vs_torch(use_sigmoid, C, layout):
+    """CrossEntropyLoss.forward on sampled rows (lib/losses.py:129-156) against plain PyTorch fp32, forward and gradient;
+    the transposed layout is the RPN's tar_cls_out.t() read in place.  Tolerance 1e-5 relative (expf / logf)."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(C)
+    n = 777
+    x = rng.normal(0, 2, (n, C)).astype(np.float32)
+    lab = rng.integers(0, 2 if (use_sigmoid and C == 1) else (C + 1 if use_sigmoid else C), n).astype(np.int64)
+    base = T(x) if layout == "rows" else T(np.ascontiguousarray(x.T))
+    base.requires_grad_(True)
+    pred = base if layout == "rows" else base.t()
+    loss = bheads.sampled_cross_entropy(pred, T(lab), use_sigmoid, 0.5)
+    loss.backward()
+    ref_in = T(x).requires_grad_(True)
+    if use_sigmoid and C == 1:
+        ref = F.binary_cross_entropy_with_logits(ref_in, T(lab).view(-1, 1).float(), reduction="none").sum() * 0.5
+    elif use_sigmoid:
+        onehot = F.one_hot(T(lab), C + 1)[:, 1:].float()
+        ref = F.binary_cross_entropy_with_logits(ref_in, onehot, reduction="none").sum() * 0.5
+    else:
+        ref = F.cross_entropy(ref_in, T(lab), reduction="none").sum() * 0.5
+    ref.backward()
+    np.testing.assert_allclose(float(loss), float(ref), rtol=1e-5)
+    got = N(base.grad) if layout == "rows" else N(base.grad).T
+    np.testing.assert_allclose(got, N(ref_in.grad), rtol=1e-4, atol=1e-6)
+
+
+def test_sampler_step_counter_survives_cuda_graph_replay():
+    """the device sampler's per-step counter lives in device memory, so two replays of a captured step on
+    identical labels draw different samples (a by-value seed would be frozen by the capture)."""
+    B, n, K = 2, 3000, 8
+    rng = np.random.default_rng(3)
+    gt, gl = workload.synth_gt(rng, K, 800, 1333)
+    cx, cy = rng.uniform(0, 1333, n), rng.uniform(0, 800, n)
+    w, h = rng.uniform(8, 400, n), rng.uniform(8, 400, n)
+    boxes = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2]).astype(np.float32)
+    bt = fused.BatchedTargets(B, n, K, dict(pos_iou=0.5, neg_iou=0.5, min_pos_iou=0.5), dict(max_num=256, pos_num=64),
+                              [0, 0, 0, 0], [0.1, 0.1, 0.2, 0.2], DEV, prepend_gt=True, seed=9)
+    bx = T(np.stack([boxes] * B)); g = T(np.stack([gt] * B)); lab = T(np.stack([gl] * B))
+    cnt = torch.full((B,), n, dtype=torch.int32, device=DEV); gc = torch.full((B,), K, dtype=torch.int32, device=DEV)
+    run = lambda: bt(g, gc, lab, boxes=bx, box_count=cnt)
+    run(); torch.cuda.synchronize()
+    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            run()
+    torch.cuda.current_stream().wait_stream(side)
+    graph.replay(); torch.cuda.synchronize()
+    first = N(bt.chosen).copy()
+    graph.replay(); torch.cuda.synchronize()
+    second = N(bt.chosen).copy()
+    assert (N(bt.n_chosen) == 256).all()
+    assert not np.array_equal(first, second)
+    bt.reset_step(); graph.replay(); torch.cuda.synchronize()
+    third = N(bt.chosen).copy()
+    bt.reset_step(); graph.replay(); torch.cuda.synchronize()
+    assert np.array_equal(third, N(bt.chosen))            # same counter value -> same sample (reproducible)
+
+
+@pytest.mark.parametrize("mode", ["official", "strict"])
+@pytest.mark.parametrize("n,use_factor,per_class", [(1500, True, False), (400, False, True), (40, True, False)])
+def test_multiclass_nms_kernel_vs_oracle_incl_more_than_16384_candidates(mode, n, use_factor, per_class):
+    """utils.multiclass_nms (lib/utils.py:224-269) as one library call: candidates enumerated in numpy (row-major
+    boolean-mask order), class-offset NMS by the oracle.  n = 1500 x 20 classes at min_score 0.05 gives ~20 000
+    (box, class) candidates: beyond b2d_nms's 16384 boxes, the candidate kernel + large-n NMS path must agree too."""
+    rng = np.random.default_rng(n)
+    C = 20
+    cx, cy = rng.uniform(0, 300, n), rng.uniform(0, 250, n)
+    w, h = rng.uniform(8, 100, n), rng.uniform(8, 100, n)
+    base = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1).astype(np.float32)
+    if per_class:                                                      # [n, 4*C] viewed (n, 4, C)
+        bbox = (base[:, :, None] + rng.normal(0, 3, (n, 4, C))).astype(np.float32).reshape(n, 4 * C)
+    else:
+        bbox = base
+    score = (1 / (1 + np.exp(-rng.normal(-2, 2, (n, C))))).astype(np.float32)
+    fac = (1 / (1 + np.exp(-rng.normal(0, 1, n)))).astype(np.float32) if use_factor else None
+    chans = list(range(1, C))
+    kb, ks, kl = butils.multiclass_nms(T(bbox), T(score), chans, 0.6, 0.05, 100, T(fac) if use_factor else None, mode=mode)
+    # numpy restatement of the candidate enumeration
+    bb3 = bbox.reshape(n, 4, C) if per_class else np.repeat(base[:, :, None], C, 2)
+    if mode == "official":
+        chosen = (score >= np.float32(0.05)) & np.isin(np.arange(C), chans)[None, :]
+        sc = score * fac[:, None] if use_factor else score
+        ii, cc = np.nonzero(chosen)
+    else:
+        cc_all = score.argmax(1)
+        best = score[np.arange(n), cc_all]
+        chosen = (best >= np.float32(0.05)) & np.isin(cc_all, chans)
+        ii = np.nonzero(chosen)[0]
+        cc = cc_all[ii]
+        sc = np.zeros_like(score)
+        sc[np.arange(n), cc_all] = best * fac if use_factor else best
+    cb, cs = bb3[ii, :, cc].astype(np.float32), sc[ii, cc].astype(np.float32)
+    keep = oracle.batched_nms(cb, cs, cc.astype(np.int64), 0.6)[:100]
+    assert np.array_equal(N(kl), cc[keep])
+    assert np.array_equal(N(ks), cs[keep]) and np.array_equal(N(kb), cb[keep])
