@@ -58,6 +58,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False          # rows: (t, sm_mhz, sm_max_mhz, [reasons])
+        self.spin = False                                                   # True while a timed region runs: no sleep between queries
         self.window = None
         self.nvml = None
         try:
@@ -81,7 +82,8 @@ class ClockSampler(threading.Thread):
                     mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
                     mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
                     self.rows.append((time.perf_counter(), mhz, self.max_mhz, [k for k, b in self._BITS.items() if mask & b]))
-                    time.sleep(0.0005)
+                    if not self.spin:
+                        time.sleep(0.0005)
                     continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -235,19 +237,135 @@ def run_b200(args):
 
     sampler = ClockSampler(local)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, n):
+        """n calls of fn bracketed by barrier + synchronize on both sides, timed with CUDA events on the launching stream."""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        barrier()
+        return a.elapsed_time(b)
+
+    # ---- the all-gather of SURVEY 8(e) inside the timed loop (N > 1): after every step the rank's proposals are packed
+    # into a [B, P, 5] record (double-buffered) and all-gathered over NCCL on a side stream, next to the following step
+    gather = None
+    if world > 1:
+        P = hp.proposals.P
+        rec = [torch.empty((B, P, 5), dtype=torch.float32, device=dev) for _ in range(2)]
+        gout = [torch.empty((world * B, P, 5), dtype=torch.float32, device=dev) for _ in range(2)]
+        s_comm = torch.cuda.Stream()
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        state = {"it": 0}
+
+        def gather():
+            k = state["it"] & 1
+            state["it"] += 1
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev_done[k])                                  # the gather that last used this buffer pair
+            rec[k][:, :, :4].copy_(hp.proposals.props.permute(0, 2, 1))
+            rec[k][:, :, 4].copy_(hp.proposals.scores)
+            s_comm.wait_stream(cur)
+            with torch.cuda.stream(s_comm):
+                dist.all_gather_into_tensor(gout[k], rec[k])
+                ev_done[k].record(s_comm)
+
+        def run_step():
+            graph.replay() if graph is not None else step()
+            gather()
+
+        for _ in range(2):
+            run_step()
+        torch.cuda.current_stream().wait_stream(s_comm)
+    else:
+        def run_step():
+            graph.replay() if graph is not None else step()
+
+    def run_all():
+        run_step()
+
     barrier()
     t_host0 = time.perf_counter()
+    sampler.spin = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        if graph is not None:
-            graph.replay()
-        else:
-            step()
+        run_all()
+    if world > 1:
+        torch.cuda.current_stream().wait_stream(s_comm)                 # the last gather ends inside the timed region
     e1.record()
     barrier()
+    sampler.spin = False
     sampler.window = (t_host0, time.perf_counter())
     ms = e0.elapsed_time(e1)
+    # ---- the same step fed with the reference layout: fp32 NCHW features -> b2d_nchw_to_nhwc (4 launches) -> step
+    nhwc_buf = [torch.empty_like(f, memory_format=torch.channels_last) for f in feats_nchw]
+
+    def step_nchw():
+        for f, o in zip(feats_nchw, nhwc_buf):
+            _C.call("b2d_nchw_to_nhwc", _C.ptr(o), _C.ptr(f), f.shape[0], f.shape[1], f.shape[2], f.shape[3], _C.stream())
+        return hp.step(cls, reg, nhwc_buf, gt, gcount, gl, img_hw)
+
+    step_nchw()
+    torch.cuda.synchronize()
+    graph_nchw = None
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step_nchw()
+            graph_nchw = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_nchw, stream=side):
+                step_nchw()
+        torch.cuda.current_stream().wait_stream(side)
+        graph_nchw.replay()
+    nchw_ms = timed((lambda: graph_nchw.replay()) if graph_nchw is not None else step_nchw, args.steps) / args.steps
+    # ---- strong scaling (N > 1): the global batch of BASELINE config 2 (8 images) split per image over the ranks
+    strong_ms = None
+    if world > 1 and B % world == 0:
+        Bs = B // world
+        hps = fused.TrainHotPath(Bs, grids, dev, gt_ld=K_GT, feat_channels=256, layout=1, overlap=True)
+        sl = slice(0, Bs)
+        args_s = ([t[sl] for t in cls], [t[sl] for t in reg], [f[sl] for f in feats], gt[sl], gcount[sl], gl[sl], img_hw[sl])
+        for _ in range(3):
+            hps.step(*args_s)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            hps.step(*args_s)
+            gs = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gs, stream=side):
+                hps.step(*args_s)
+        torch.cuda.current_stream().wait_stream(side)
+        gs.replay()
+        strong_ms = timed(lambda: gs.replay(), args.steps) / args.steps
+    # ---- what a reference user gets after install(): the reference's own per-image call sequence
+    # (lib/detectors/cascade_rcnn.py:106-131) on the drop-in's reference-signature functions, eager, fp32 NCHW features
+    # as the reference FPN emits them, and channels_last features (install(channels_last=True))
+    dropin = None
+    if rank == 0 and not args.no_dropin:
+        from b200det import refpath
+        seq = refpath.TrainCallSequence(strides, dev)
+        metas = [dict(img_shape=(w["img_shape"][0], w["img_shape"][1], 3), pad_shape=(w["pad_shape"][0], w["pad_shape"][1], 3),
+                      scale_factor=1.0) for _ in range(B)]
+        gtl, gll = [gt[i] for i in range(B)], [gl[i] for i in range(B)]
+        dropin = {}
+        for name, ff in (("nchw", feats_nchw), ("channels_last", feats)):
+            fn = lambda: seq.step(cls, reg, ff, gtl, gll, metas)
+            fn(); fn()
+            torch.cuda.synchronize()
+            n_it = 5
+            t0 = time.perf_counter()
+            for _ in range(n_it):
+                fn()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n_it
+            dropin[name] = {"value": B / dt, "unit": "images/s", "ms_per_step": dt * 1e3}
+        dropin["note"] = "reference call sequence (per-image Python loops of AnchorHead.loss / predict_bboxes_from_output / " \
+                         "bbox_targets / BasicRoIExtractor) on the drop-in functions, eager, host wall clock incl. its syncs"
     # ---- per-stage device times (eager, CUDA events on the launching stream)
     stages = ["proposals", "rpn_targets", "roi_targets", "roi_align"]
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
@@ -284,6 +402,20 @@ def run_b200(args):
         torch.cuda.synchronize()
         bf16_ms = g0.elapsed_time(g1) / args.steps
         del feats16, ra16
+    # ---- the same RoIAlign on ALL 2000 proposals per image ("stress": 16 000 RoIs, 803 MB of output)
+    k2000_ms = None
+    if rank == 0:
+        ra2k = fused.BatchedRoIAlign(B, hp.proposals.P, [(256, g[0], g[1]) for g in grids[:4]], list(strides[:4]), dev, layout=1)
+        for _ in range(2):
+            ra2k(feats, hp.proposals.props, hp.proposals.count)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            ra2k(feats, hp.proposals.props, hp.proposals.count)
+        g1.record()
+        torch.cuda.synchronize()
+        k2000_ms = g0.elapsed_time(g1) / 5
+        del ra2k
     # ---- end-to-end through the public API with HOST buffers (fp32 NCHW, the reference layout):
     # TrainHotPath.step_from_host = pinned host inputs -> H2D -> NCHW->NHWC -> hot path -> D2H of the results
     def e2e_step():
@@ -303,13 +435,28 @@ def run_b200(args):
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1) / n_e2e
+    # the same with the RoI features (the input of the next stage, 205 MB) read back to the host as well
+    e2e_feats_ms = None
+    if rank == 0:
+        hp2 = fused.TrainHotPath(B, grids, dev, gt_ld=K_GT, feat_channels=256, layout=1, overlap=True)
+        fn = lambda: hp2.step_from_host(h_cls, h_reg, h_feat, h_gt, h_gl, gcount, img_hw, with_roi_feats=True)
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        f0.record()
+        for _ in range(3):
+            fn()
+        f1.record()
+        torch.cuda.synchronize()
+        e2e_feats_ms = f0.elapsed_time(f1) / 3
+        del hp2
     sampler.stop_flag = True
     sampler.join(timeout=2)
     # ---- reduce over ranks (max time)
-    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, e2e_ms, nchw_ms, strong_ms or 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms, nchw_ms, strong_ms = float(t[0]), float(t[1]), float(t[2]), (float(t[3]) if strong_ms is not None else None)
     total_imgs = B * world
     value = total_imgs * args.steps / (ms / 1e3)
     e2e_val = total_imgs / (e2e_ms / 1e3)
@@ -336,14 +483,17 @@ def run_b200(args):
         }
         ach = stage_bytes[dom] / (stage_ms[dom] / 1e3) / 1e9
         path_bytes = sum(stage_bytes.values())
-        roofline = {"bound": "hbm", "kernel": {"roi_align": "k_roi_align_win<float>", "proposals": "k_hist..k_merge (K3+K4)",
+        roofline = {"bound": "hbm", "kernel": {"roi_align": "k_roi_align_win<float>", "proposals": "k_rpn_front + k_rpn_back (K3+K4)",
                                                "rpn_targets": "k_assign_colmax/label (K2)", "roi_targets": "k_assign (K2)"}[dom],
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic(dom),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": stage_bytes[dom],
                     "stage_ms": stage_ms, "stage_algorithmic_bytes": stage_bytes,
-                    "stage_ms_note": "eager per-stage CUDA-event times; multi-kernel stages (proposals: 34 launches) are "
-                                     "host-launch-bound there, the step time above is the CUDA-graph replay",
+                    "stage_ms_note": "eager per-stage CUDA-event times (launch gaps included); the step time above is the "
+                                     "CUDA-graph replay",
                     "path_frac": (path_bytes / ((ms / args.steps) / 1e3) / 1e9) / peak,
+                    "roi_align_all_2000_proposals": None if k2000_ms is None else {
+                        "ms": k2000_ms, "rois": int(hp.proposals.count.sum()), "out_bytes": int(hp.proposals.count.sum()) * C * 49 * 4,
+                        "note": "SURVEY 8(d)(ii) stress: every proposal, not the 512 sampled; eager, CUDA events"},
                     "roi_align_bf16_features": None if bf16_ms is None else {
                         "ms": bf16_ms, "algorithmic_bytes": in_bytes // 2 + out_bytes + int(counts.sum()) * 16,
                         "achieved": (in_bytes // 2 + out_bytes + int(counts.sum()) * 16) / (bf16_ms / 1e3) / 1e9,
@@ -374,7 +524,20 @@ def run_b200(args):
                                             "l2": "inputs per step (755 MB/GPU) exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "layout": "pinned host fp32 NCHW (reference layout) -> H2D (copy stream) -> NCHW->NHWC -> hot path -> D2H of proposals/targets"},
-            "gpu_launches": hp.launches * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}),
+            "value_nchw": {"value": total_imgs / (nchw_ms / 1e3), "unit": "images/s", "ms_per_step": nchw_ms,
+                           "note": "the same step fed with fp32 NCHW features (the reference FPN's layout): + 4 x b2d_nchw_to_nhwc; "
+                                   "install(channels_last=True) makes the FPN emit NHWC and removes them"},
+            "dropin": dropin,
+            "strong": None if strong_ms is None else {"global_batch": B, "images_per_gpu": B // world, "ms_per_step": strong_ms,
+                                                      "value": B / (strong_ms / 1e3), "unit": "images/s",
+                                                      "note": "BASELINE config 2: batch 8 split per image over the ranks"},
+            "allgather": None if world == 1 else {"in_timed_loop": True, "bytes_per_rank_and_step": B * hp.proposals.P * 20,
+                                                  "what": "proposals [B, 2000, 5] fp32 per rank, NCCL all_gather on a side stream after every step"},
+            "e2e_with_roi_feats": None if e2e_feats_ms is None else {
+                "value": B / (e2e_feats_ms / 1e3), "unit": "images/s (this rank)", "ms_per_step": e2e_feats_ms,
+                "d2h_bytes_per_step": d2h + B * 512 * 256 * 49 * 4},
+            "gpu_launches": (hp.launches + (1 if world > 1 else 0)) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": sampler.summary()}),
             flush=True)
         os.dup2(2, 1)
     if world > 1:
@@ -391,6 +554,7 @@ if __name__ == "__main__":
                     help="image groups with staggered stream priorities inside one step (fused.TrainHotPath)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the reference-call-sequence measurement")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

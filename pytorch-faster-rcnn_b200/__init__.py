@@ -8,7 +8,7 @@ importlib.import_module("pytorch-faster-rcnn_b200").
 """
 from . import _C  # noqa: F401
 from . import registry
-from . import utils, region, anchor, bbox, heads, fused, workload, dropin, dist  # noqa: F401
+from . import utils, region, anchor, bbox, heads, fused, workload, dropin, dist, refpath  # noqa: F401
 from .anchor import AnchorCreator, anchor_target  # noqa: F401
 from .bbox import bbox_target  # noqa: F401
 from .region import (MaxIoUAssigner, RandomSampler, IoUBalancedNegSampler, BasicRoIExtractor,  # noqa: F401
