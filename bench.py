@@ -173,6 +173,27 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and with it the first-touch placement of its pinned host buffers) to the CPUs local to GPU
+    `index`: at N = 8 the eight H2D streams otherwise cross the socket interconnect.  Best effort, silent on failure."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (int(wd) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 # --------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import torch
@@ -188,6 +209,7 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else 0
     # NCCL prints its version banner on stdout (NCCL_DEBUG=VERSION/WARN): keep fd 1 for the one JSON line
     sys.stdout.flush()
     real_stdout = os.dup(1)
@@ -249,36 +271,48 @@ def run_b200(args):
         barrier()
         return a.elapsed_time(b)
 
-    # ---- the all-gather of SURVEY 8(e) inside the timed loop (N > 1): after every step the rank's proposals are packed
-    # into a [B, P, 5] record (double-buffered) and all-gathered over NCCL on a side stream, next to the following step
-    gather = None
+    # ---- the all-gather of SURVEY 8(e) inside the timed loop (N > 1): the merge kernel itself writes the rank's proposals
+    # as packed [B, P, 5] records (no packing kernel); two graphs alternate between two record buffers, and after every
+    # replay the records are all-gathered over NCCL on a side stream while the next replay already runs
     if world > 1:
         P = hp.proposals.P
-        rec = [torch.empty((B, P, 5), dtype=torch.float32, device=dev) for _ in range(2)]
+        rec = [torch.zeros((B, P, 5), dtype=torch.float32, device=dev) for _ in range(2)]
         gout = [torch.empty((world * B, P, 5), dtype=torch.float32, device=dev) for _ in range(2)]
         s_comm = torch.cuda.Stream()
         ev_done = [torch.cuda.Event() for _ in range(2)]
         state = {"it": 0}
+        graphs = []
+        for k in range(2):
+            fn = (lambda k=k: hp.step(cls, reg, feats, gt, gcount, gl, img_hw, records=rec[k]))
+            fn()
+            torch.cuda.synchronize()
+            if args.no_graph:
+                graphs.append(fn)
+                continue
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, stream=side):
+                    fn()
+            torch.cuda.current_stream().wait_stream(side)
+            graphs.append(g2.replay)
 
-        def gather():
+        def run_step():
             k = state["it"] & 1
             state["it"] += 1
             cur = torch.cuda.current_stream()
-            cur.wait_event(ev_done[k])                                  # the gather that last used this buffer pair
-            rec[k][:, :, :4].copy_(hp.proposals.props.permute(0, 2, 1))
-            rec[k][:, :, 4].copy_(hp.proposals.scores)
+            cur.wait_event(ev_done[k])                                  # the gather that last read rec[k]
+            graphs[k]()
             s_comm.wait_stream(cur)
             with torch.cuda.stream(s_comm):
                 dist.all_gather_into_tensor(gout[k], rec[k])
                 ev_done[k].record(s_comm)
 
-        def run_step():
-            graph.replay() if graph is not None else step()
-            gather()
-
-        for _ in range(2):
+        for _ in range(4):
             run_step()
         torch.cuda.current_stream().wait_stream(s_comm)
+        torch.cuda.synchronize()
     else:
         def run_step():
             graph.replay() if graph is not None else step()
@@ -521,6 +555,7 @@ def run_b200(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": WORKLOAD, "global_batch": total_imgs, "parallelism": "per-image partition, dp%d" % world,
                                             "features": "fp32 NHWC (channels_last) resident in HBM", "cuda_graph": graph is not None, "image_groups": hp.groups,
+                                            "host_cpus_bound_to_gpu_numa_node": numa_cpus,
                                             "l2": "inputs per step (755 MB/GPU) exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "layout": "pinned host fp32 NCHW (reference layout) -> H2D (copy stream) -> NCHW->NHWC -> hot path -> D2H of proposals/targets"},
@@ -532,7 +567,8 @@ def run_b200(args):
                                                       "value": B / (strong_ms / 1e3), "unit": "images/s",
                                                       "note": "BASELINE config 2: batch 8 split per image over the ranks"},
             "allgather": None if world == 1 else {"in_timed_loop": True, "bytes_per_rank_and_step": B * hp.proposals.P * 20,
-                                                  "what": "proposals [B, 2000, 5] fp32 per rank, NCCL all_gather on a side stream after every step"},
+                                                  "what": "proposals [B, 2000, 5] fp32 per rank, written as packed records by the merge kernel; NCCL "
+                                                          "all_gather on a side stream after every step, next to the following step (two alternating graphs)"},
             "e2e_with_roi_feats": None if e2e_feats_ms is None else {
                 "value": B / (e2e_feats_ms / 1e3), "unit": "images/s (this rank)", "ms_per_step": e2e_feats_ms,
                 "d2h_bytes_per_step": d2h + B * 512 * 256 * 49 * 4},

@@ -161,6 +161,8 @@ typedef struct b2d_rpn_cfg {
     float min_size;                 /* scale_factor * min_bbox_size */
     float means[4], stds[4];
     int do_nms;                     /* 0: stop after decode (AnchorHead path) */
+    float* records;                 /* optional DEVICE buffer [B][max_num][5]: (x1, y1, x2, y2, score) per proposal, zero rows past
+                                       count -- the packed record that is all-gathered over NCCL; NULL = not written */
 } b2d_rpn_cfg;
 
 B2D_API size_t b2d_rpn_proposals_workspace_bytes(const b2d_pyramid* pyr_host, int B, const b2d_rpn_cfg* cfg_host);

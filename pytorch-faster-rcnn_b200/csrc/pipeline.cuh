@@ -25,6 +25,7 @@ struct RpnLaunch {
     int raw;                            // 1: plain segmented top-k (no anchors / deltas / decode)
     int dbg;                            // development knob (B2D_DBG)
     float nms_thr, min_size, ms[8];
+    float* rec;                         // optional packed proposal records [B][out_ld][5] (b2d_rpn_cfg::records)
     // workspace
     uint32_t* hist; int* cand_count; int* cand2_count; int* sel_count; int* keep_count; int* thr_bin;
     int* n_cut; int* keep1;             // score-cut NMS: boxes per segment in the first pass, its survivor counts

@@ -424,14 +424,17 @@ __global__ void __launch_bounds__(kBkThreads, 1) k_rpn_back(RpnLaunch p, BackArg
             const long long o = s.soff[l] + r;
             const float4 bx = staged ? s.box[t] : g_box[o];
             pb[rank] = bx.x; pb[p.out_ld + rank] = bx.y; pb[2 * p.out_ld + rank] = bx.z; pb[3 * p.out_ld + rank] = bx.w;
-            ps[rank] = 1.0f / (1.0f + expf(-key2f(key)));
+            const float sc = 1.0f / (1.0f + expf(-key2f(key)));
+            ps[rank] = sc;
             if (pv) pv[rank] = (int)(s.aoff[l] + p.sel_idx[ibase + o]);
+            if (p.rec) { float* q = p.rec + ((long long)b * p.out_ld + rank) * 5; q[0] = bx.x; q[1] = bx.y; q[2] = bx.z; q[3] = bx.w; q[4] = sc; }
         }
     }
     for (int t = nout + crank * kBkThreads + tid; t < p.out_ld; t += kBkCl * kBkThreads) {   // padding slots
         pb[t] = 0.f; pb[p.out_ld + t] = 0.f; pb[2 * p.out_ld + t] = 0.f; pb[3 * p.out_ld + t] = 0.f;
         ps[t] = 0.f;
         if (pv) pv[t] = -1;
+        if (p.rec) { float* q = p.rec + ((long long)b * p.out_ld + t) * 5; q[0] = q[1] = q[2] = q[3] = q[4] = 0.f; }
     }
     if (crank == 0 && tid == 0) a.count[b] = nout;
     if (tid < kMaxLevels && crank == 0 && tid < L) p.keep_count[b * L + tid] = s.keep[tid];

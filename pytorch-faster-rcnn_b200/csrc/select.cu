@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(kSelThreads) k_merge(RpnLaunch p, float* __res
         pb[r] = bx.x; pb[p.out_ld + r] = bx.y; pb[2 * p.out_ld + r] = bx.z; pb[3 * p.out_ld + r] = bx.w;
         scores[(long long)b * p.out_ld + r] = sc;
         if (prov) prov[(long long)b * p.out_ld + r] = pv;
+        if (p.rec) { float* q = p.rec + ((long long)b * p.out_ld + r) * 5; q[0] = bx.x; q[1] = bx.y; q[2] = bx.z; q[3] = bx.w; q[4] = sc; }
     }
     if (threadIdx.x == 0) count[b] = nout;
 }
@@ -469,6 +470,7 @@ __global__ void __launch_bounds__(256) k_merge_rank(RpnLaunch p, float* __restri
         pb[t] = 0.f; pb[p.out_ld + t] = 0.f; pb[2 * p.out_ld + t] = 0.f; pb[3 * p.out_ld + t] = 0.f;
         scores[(long long)b * p.out_ld + t] = 0.f;
         if (prov) prov[(long long)b * p.out_ld + t] = -1;
+        if (p.rec) { float* q = p.rec + ((long long)b * p.out_ld + t) * 5; q[0] = q[1] = q[2] = q[3] = q[4] = 0.f; }
     }
     if (t >= total) return;
     int l = 0;
@@ -505,8 +507,10 @@ __global__ void __launch_bounds__(256) k_merge_rank(RpnLaunch p, float* __restri
     if (rank < nout) {
         const float4 bx = m_box[o];
         pb[rank] = bx.x; pb[p.out_ld + rank] = bx.y; pb[2 * p.out_ld + rank] = bx.z; pb[3 * p.out_ld + rank] = bx.w;
-        scores[(long long)b * p.out_ld + rank] = 1.0f / (1.0f + expf(-key2f(key)));
+        const float sc = 1.0f / (1.0f + expf(-key2f(key)));
+        scores[(long long)b * p.out_ld + rank] = sc;
         if (prov) prov[(long long)b * p.out_ld + rank] = (int)(p.pyr.lv[l].offset + m_idx[o]);
+        if (p.rec) { float* q = p.rec + ((long long)b * p.out_ld + rank) * 5; q[0] = bx.x; q[1] = bx.y; q[2] = bx.z; q[3] = bx.w; q[4] = sc; }
     }
 }
 
@@ -543,6 +547,7 @@ bool rpn_plan(RpnLaunch& p, const b2d_pyramid* pyr, int B, const b2d_rpn_cfg* cf
     p.pre_nms = cfg->pre_nms; p.post_nms = cfg->post_nms; p.max_num = cfg->max_num;
     p.score_mode = cfg->score_mode; p.cls_ch = cfg->num_cls_channels > 0 ? cfg->num_cls_channels : 1;
     p.nms_thr = cfg->nms_thr_f; p.min_size = cfg->min_size; p.do_nms = cfg->do_nms;
+    p.rec = cfg->records;
     for (int i = 0; i < 4; ++i) { p.ms[i] = cfg->means[i]; p.ms[4 + i] = cfg->stds[i]; }
     long long off = 0;
     int wmax = 0;

@@ -91,7 +91,11 @@ class RpnProposals(object):
         v.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.ws.device)
         return v
 
-    def __call__(self, cls_outs, reg_outs, img_hw):
+    def __call__(self, cls_outs, reg_outs, img_hw, records=None):
+        """records: optional fp32 [B, P, 5] tensor that receives (x1, y1, x2, y2, score) rows (zero past count): the
+        packed detection record of SURVEY 8(e), written by the merge itself so that an all-gather can start right
+        after the step without a packing kernel."""
+        self.cfg.records = records.data_ptr() if records is not None else None
         _C.call("b2d_rpn_proposals", _C.ptr(self.props), _C.ptr(self.scores), _C.ptr(self.count), _C.ptr(self.prov),
                 _ptrs(cls_outs), _ptrs(reg_outs), ctypes.byref(self.pyr.c), _C.ptr(img_hw), self.B,
                 ctypes.byref(self.cfg), _C.ptr(self.ws), self.ws.numel(), _C.stream())
@@ -273,7 +277,7 @@ class TrainHotPath(object):
                 ctypes.byref(self.pyr.c), 1, _C.ptr(rt.chosen), _C.ptr(rt.n_chosen), rt.max_num, self.B, _C.stream())
         return rt
 
-    def step(self, cls_outs, reg_outs, feats, gt, gt_count, gt_label, img_hw, feats_ready=None):
+    def step(self, cls_outs, reg_outs, feats, gt, gt_count, gt_label, img_hw, feats_ready=None, records=None):
         """One pass of the hot path over the batch (device-resident inputs).  `feats_ready`: optional
         CUDA event after which `feats` may be read (lets the proposal / target chains start while
         the feature maps are still arriving, see step_from_host)."""
@@ -281,7 +285,7 @@ class TrainHotPath(object):
         if not self.subs:
             if feats_ready is not None:
                 torch.cuda.current_stream().wait_event(feats_ready)
-            props, scores, count = self.proposals(cls_outs, reg_outs, img_hw)
+            props, scores, count = self.proposals(cls_outs, reg_outs, img_hw, records=records)
             rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
             bt = self.roi_targets(gt, gt_count, gt_label, boxes=props, box_count=count)
             self.roi_align(feats, bt.tar_box, bt.n_chosen)
@@ -299,8 +303,11 @@ class TrainHotPath(object):
             for gi, (b0, b1, prop, tgt, ra, st, st_lo) in enumerate(self.subs):
                 st.wait_stream(cur)
                 with torch.cuda.stream(st):
-                    p, _, c = prop([t[b0:b1] for t in cls_outs], [t[b0:b1] for t in reg_outs], img_hw[b0:b1])
+                    p, _, c = prop([t[b0:b1] for t in cls_outs], [t[b0:b1] for t in reg_outs], img_hw[b0:b1],
+                                   records=records[b0:b1] if records is not None else None)
                 if gi == 0 and not rpn_first:
+                    if self.order == "rpn_late":         # behind the proposal stage: next to RoI targets + RoIAlign
+                        self.s_rpn.wait_stream(st)
                     with torch.cuda.stream(self.s_rpn):
                         rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
                 with torch.cuda.stream(st):

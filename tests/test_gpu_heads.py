@@ -700,3 +700,64 @@ def test_multiclass_nms_kernel_vs_oracle_incl_more_than_16384_candidates(mode, n
     keep = oracle.batched_nms(cb, cs, cc.astype(np.int64), 0.6)[:100]
     assert np.array_equal(N(kl), cc[keep])
     assert np.array_equal(N(ks), cs[keep]) and np.array_equal(N(kb), cb[keep])
+
+
+def test_rpn_proposals_packed_records_match_props_and_scores():
+    """b2d_rpn_cfg::records: the merge writes (x1, y1, x2, y2, score) rows, zero past count (the all-gather payload)."""
+    B = 2
+    w = workload.config2(B=B, K=4, channels=8, img_shape=(160, 213), pad_shape=(160, 224))
+    pyr = fused.AnchorPyramid(w["strides"], w["grids"])
+    cfg = dict(pre_nms=300, post_nms=300, max_num=300, nms_iou=0.7, min_bbox_size=0)
+    rp = fused.RpnProposals(pyr, B, cfg, [0, 0, 0, 0], [1, 1, 1, 1], DEV)
+    rec = torch.full((B, rp.P, 5), -7.0, device=DEV)
+    props, scores, count = rp([T(c) for c in w["cls"]], [T(r) for r in w["reg"]], torch.tensor([[160.0, 213.0]] * B, device=DEV),
+                              records=rec)
+    torch.cuda.synchronize()
+    for b in range(B):
+        n = int(count[b])
+        assert np.array_equal(N(rec[b, :n, :4]), N(props[b, :, :n]).T) and np.array_equal(N(rec[b, :n, 4]), N(scores[b, :n]))
+        assert (N(rec[b, n:]) == 0).all()
+
+
+_NCCL_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+import b200det
+from b200det import dist as bdist
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+n_img, M = 6, 5
+mine = bdist.image_partition(n_img, rank, world)
+recs, cnts = [], []
+for g in mine:
+    k = g %% (M + 1)
+    boxes = (torch.arange(k * 4, dtype=torch.float32).view(k, 4) + g).to(dev)
+    sc = (torch.linspace(1, 0.5, k) if k else torch.zeros(0)).to(dev)
+    r, c = bdist.pack_detections(boxes, sc, torch.full((k,), g, device=dev), M)
+    recs.append(r); cnts.append(c)
+rec, cnt = bdist.gather_detections(torch.stack(recs), torch.cat(cnts))
+assert rec.shape == (n_img, M, 6) and cnt.tolist() == [g %% (M + 1) for g in range(n_img)], cnt
+for g in range(n_img):
+    k = g %% (M + 1)
+    assert torch.equal(rec[g, :k, 5].cpu(), torch.full((k,), float(g)))
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_nccl_world2_gather_detections(tmp_path):
+    """SURVEY 8(e) on hardware: the detection all-gather over NCCL (two ranks, two GPUs).  Skipped on a 1-GPU box."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "w.py"
+    script.write_text(_NCCL_WORKER % dict(root=root))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29583")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
