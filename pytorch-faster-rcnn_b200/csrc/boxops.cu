@@ -38,6 +38,7 @@ static void load_knobs() {
     k.roi_pf = geti("B2D_ROI_PF", 0);
     k.roi_order = geti("B2D_ROI_ORDER", 0);
     k.roi_x2 = geti("B2D_ROI_X2", 1);
+    k.roi_bulk_store = geti("B2D_ROI_BULK_STORE", 1);
     k.roi_tma_dev = geti("B2D_ROI_TMA_DEV", 0);
     k.roi_bwd_tile = geti("B2D_ROI_BWD_TILE", 1);
     k.assign_old = getenv("B2D_ASSIGN_OLD") != nullptr;

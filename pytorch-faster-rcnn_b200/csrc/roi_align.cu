@@ -403,9 +403,23 @@ __global__ void __launch_bounds__(NT, MINB) k_roi_align_win(RoiArgs a, float* __
                 }
             }
         }
-        __syncthreads();
         const int ctile = min(CT, C - c0);
         const int total = ctile * bins;                    // multiple of 4 (checked by the launcher)
+        if (a.bulk_store) {
+            // the [ctile][bins] tile is contiguous in shared memory and in HBM: ONE bulk async store (TMA engine) instead
+            // of an LDS.128 + STG.128 per 16 bytes through the LSU pipe, which this kernel keeps 64 % busy (ncu r1j)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned src = (unsigned)__cvta_generic_to_shared(s_tile);
+                float* dstp = o + (long long)c0 * bins;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstp), "r"(src), "r"((unsigned)(total * 4)) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            return;
+        }
+        __syncthreads();
         float4* dst = reinterpret_cast<float4*>(o + (long long)c0 * bins);
         const float4* src = reinterpret_cast<const float4*>(s_tile);
         for (int q = threadIdx.x; q < total / 4; q += NT) dst[q] = src[q];
@@ -522,7 +536,9 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
             const int rc = roi_align_tma_try(a, out, st);
             if (rc != 1) return rc;
         }
-        a.pf_dist = knobs().roi_pf;   // dev knob (L2 prefetch: measured slower, r1)
+        a.pf_dist = knobs().roi_pf;
+        // bulk store of the result tile: needs 16-byte multiples (tile bytes and its offset in the output)
+        a.bulk_store = knobs().roi_bulk_store && ((128ll * bins * 4) % 16 == 0) && (((long long)c.C * bins * 4) % 16 == 0) ? 1 : 0;   // dev knob (L2 prefetch: measured slower, r1)
         auto launch5 = [&](auto kern, int nt, int ct) {
             const size_t smem5 = (size_t)ct * bins * 4 + (size_t)bins * sizeof(BinTab) + 64;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);

@@ -16,6 +16,7 @@ struct RoiArgs {
     const int* counts;
     int tiles;                     // window kernel: > 0 = 1-D grid, channel tiles of a RoI adjacent (bid = r * tiles + tile)
     int pf_dist;                   // window kernel: L2-prefetch the RoI pf_dist CTAs ahead (0 = off)
+    int bulk_store;                // window kernel: result tile leaves as one cp.async.bulk store
 };
 
 // slot r -> (image, coordinates); false if the slot is past the image's count
