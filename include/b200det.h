@@ -165,6 +165,18 @@ typedef struct b2d_rpn_cfg {
                                        count -- the packed record that is all-gathered over NCCL; NULL = not written */
 } b2d_rpn_cfg;
 
+/* The arguments of b2d_roi_targets_fused (below) as one struct, for b2d_rpn_proposals_targets. */
+typedef struct b2d_roi_target_args {
+    int64_t* labels; float* max_iou; long long out_ld;          /* [B][out_ld] assignment of GT rows + proposals */
+    const float* gt; int gt_ld; const int* gt_count; const int64_t* gt_label;
+    float pos_iou, neg_iou, min_pos_iou; int prepend_gt;
+    int* census; int* pos_list; int pos_cap;
+    int* chosen; int* n_chosen; int max_num, pos_num;
+    unsigned long long seed; const unsigned long long* seed_step;
+    float* tar_box; float* tar_gt; float* tar_param; int64_t* tar_label; int64_t* tar_is_gt;
+    float means[4], stds[4];
+} b2d_roi_target_args;
+
 B2D_API size_t b2d_rpn_proposals_workspace_bytes(const b2d_pyramid* pyr_host, int B, const b2d_rpn_cfg* cfg_host);
 /* development aid: byte offset inside the workspace of the globaltimer stamps written when B2D_DBG=10
  * (u64 [B][64 CTAs][16 stamps]) */
@@ -174,6 +186,16 @@ B2D_API size_t b2d_rpn_proposals_debug_offset(const b2d_pyramid* pyr_host, int B
 B2D_API int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const void* const* cls_ptrs_host,
                       const void* const* reg_ptrs_host, const b2d_pyramid* pyr_host, const float* img_hw,
                       int B, const b2d_rpn_cfg* cfg_host, void* workspace, size_t ws_bytes, void* stream);
+
+/* b2d_rpn_proposals followed by bbox_target on its own output (lib/detectors/cascade_rcnn.py:111-126:
+ * predict_bboxes_from_output -> bbox_targets), i.e. b2d_roi_targets_fused with boxes = props, box_count = count.  When
+ * the proposal stage runs as cluster kernels the target stage is the TAIL of the same kernel (assignment spread over
+ * the image's cluster, sampler + encode in its first CTA): no extra launch.  Otherwise the two entry points are called
+ * one after the other; results are identical either way. */
+B2D_API int b2d_rpn_proposals_targets(float* props, float* scores, int* count, int* prov, const void* const* cls_ptrs_host,
+                              const void* const* reg_ptrs_host, const b2d_pyramid* pyr_host, const float* img_hw,
+                              int B, const b2d_rpn_cfg* cfg_host, void* workspace, size_t ws_bytes,
+                              const b2d_roi_target_args* tg_host, void* stream);
 
 /* generic segmented top-k (descending, ties -> lowest index): values [S][ld] with
  * per-segment counts -> idx int32[S][k] (padded -1), out_count int32[S]. */

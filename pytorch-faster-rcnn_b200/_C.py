@@ -34,6 +34,16 @@ class RpnCfg(ctypes.Structure):
                 ("means", c_float * 4), ("stds", c_float * 4), ("do_nms", c_int), ("records", c_void_p)]
 
 
+class RoiTargetArgs(ctypes.Structure):
+    _fields_ = [("labels", c_void_p), ("max_iou", c_void_p), ("out_ld", c_ll), ("gt", c_void_p), ("gt_ld", c_int),
+                ("gt_count", c_void_p), ("gt_label", c_void_p), ("pos_iou", c_float), ("neg_iou", c_float),
+                ("min_pos_iou", c_float), ("prepend_gt", c_int), ("census", c_void_p), ("pos_list", c_void_p),
+                ("pos_cap", c_int), ("chosen", c_void_p), ("n_chosen", c_void_p), ("max_num", c_int), ("pos_num", c_int),
+                ("seed", c_ull), ("seed_step", c_void_p), ("tar_box", c_void_p), ("tar_gt", c_void_p),
+                ("tar_param", c_void_p), ("tar_label", c_void_p), ("tar_is_gt", c_void_p), ("means", c_float * 4),
+                ("stds", c_float * 4)]
+
+
 class RoiCfg(ctypes.Structure):
     _fields_ = [("num_levels", c_int), ("C", c_int), ("PH", c_int), ("PW", c_int), ("sampling_ratio", c_int),
                 ("aligned", c_int), ("layout", c_int), ("finest_scale", c_float), ("H", c_int * MAX_LEVELS),
@@ -76,6 +86,7 @@ _SIGS = {
     "b2d_encode_targets": [_P, _P, _P, _P, _P, _P, _P, c_int, _P, c_ll, _P, c_ll, _P, _P, c_int, _P, _P, c_int,
                            _P, _P, c_int, _P],
     "b2d_rpn_proposals": [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_size_t, _P],
+    "b2d_rpn_proposals_targets": [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_size_t, _P, _P],
     "b2d_topk": [_P, _P, _P, c_ll, _P, c_ll, c_int, c_int, _P, c_size_t, _P],
     "b2d_nms": [_P, _P, _P, _P, c_ll, _P, c_ll, c_int, c_float, c_int, c_int, _P, c_size_t, _P],
     "b2d_roi_align_fwd": [_P, _P, _P, c_ll, _P, _P, c_ll, _P, _P],

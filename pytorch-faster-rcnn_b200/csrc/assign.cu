@@ -10,21 +10,9 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "targets_common.cuh"
 
 namespace b2d {
-
-constexpr int kGtChunk = 512;      // GTs staged in shared memory per pass
-constexpr int kBoxesPerThread = 4;
-
-struct AssignArgs {
-    const float* boxes; long long box_ld; const int* box_count; long long N;
-    int use_pyr;
-    const float* img_hw; float border;
-    const float* gt; int gt_ld; const int* gt_count;
-    float pos_iou, neg_iou, min_pos_iou;
-    int prepend_gt;
-    long long out_ld;
-};
 
 // (in_h, in_w) of inside_grid_mask (lib/region.py:11-13): python float64 reciprocal multiply
 __device__ __forceinline__ void grid_limits(const b2d_level& lv, float img_h, float img_w, int& in_h, int& in_w) {
@@ -434,16 +422,6 @@ __global__ void __launch_bounds__(256) k_label_rows(AssignArgs p, b2d_pyramid py
 // ---- small problems (explicit boxes, N <= 4096: the RoI-target assignment of 2000 proposals) ----
 // colmax + label + census in ONE launch, one CTA per image: the two-pass grid version costs two
 // launches of 16 CTAs whose time is pure launch + global-atomic latency (14 + 14 us, ncu r1e).
-constexpr int kSmallThreads = 1024;
-constexpr int kSmallBoxes = 4;
-
-struct SmallSmem {
-    Box gt[kGtChunk];
-    float ga[kGtChunk];
-    uint32_t mx[kGtChunk];
-    int cnt[3];
-};
-
 // s_lab (optional, shared memory, >= lead + n_b entries): the labels as int32, for the fused kernel below
 __device__ __forceinline__ void assign_small_body(const AssignArgs& p, SmallSmem& sm, int64_t* __restrict__ labels,
                                                   float* __restrict__ out_iou, int* __restrict__ census,
@@ -591,19 +569,6 @@ __global__ void __launch_bounds__(256) k_label_census(int* __restrict__ census, 
 // (max_num - #kept_pos) indices whose label is 0.  Output ascending.
 constexpr int kSampleThreads = 1024;
 constexpr int kSampleSortCap = 4096;
-
-__device__ __forceinline__ uint32_t feistel(uint32_t x, int half_bits, uint64_t seed) {
-    const uint32_t mask = (1u << half_bits) - 1u;
-    uint32_t l = x >> half_bits, r = x & mask;
-#pragma unroll
-    for (int round = 0; round < 4; ++round) {
-        const uint32_t f = mix_key(seed + 0x1000003ull * (uint64_t)(round + 1), r) & mask;
-        const uint32_t nl = r;
-        r = l ^ f;
-        l = nl;
-    }
-    return (l << half_bits) | r;
-}
 
 __global__ void __launch_bounds__(kSampleThreads) k_sample(int* __restrict__ chosen, int* __restrict__ n_chosen,
                                                            const int64_t* __restrict__ labels, long long ld,
@@ -818,186 +783,14 @@ __global__ void __launch_bounds__(128) k_gather_head(GatherArgs p, b2d_pyramid p
 // image, labels / flags in shared memory.  Replaces three dependent launches of 8 CTAs (13 + 17 +
 // 5 us + gaps on the critical path of config 2); the negative walk is one block scan per 4096
 // permutation steps and the ascending output order comes from a flag compaction, not a sort.
-constexpr int kFusedMaxN = kSmallThreads * kSmallBoxes + kGtChunk;     // candidates incl. prepended GT
-constexpr int kFusedPer = (kFusedMaxN + kSmallThreads - 1) / kSmallThreads;
-
-struct FusedArgs {
-    int* chosen; int* n_chosen; int max_num, pos_num;
-    unsigned long long seed;
-    const unsigned long long* seed_step;      // optional device counter added to seed (advanced by b2d_counter_add)
-    const int64_t* gt_label;
-    float* tar_box; float* tar_gt; float* tar_param; int64_t* tar_label; int64_t* tar_is_gt;
-    float ms[8];
-};
-
 __global__ void __launch_bounds__(kSmallThreads) k_roi_targets_small(AssignArgs p, int64_t* __restrict__ labels,
                                                                      float* __restrict__ out_iou,
                                                                      int* __restrict__ census, int* __restrict__ pos_list,
                                                                      int pos_cap, FusedArgs f) {
     __shared__ SmallSmem sm;
-    __shared__ int s_lab[kFusedMaxN];
-    __shared__ unsigned char s_flag[kFusedMaxN];
-    __shared__ int s_chosen[kSmallThreads];
-    __shared__ int s_w[4][32];
-    __shared__ int s_tot, s_red[32];
-    __shared__ unsigned long long s_lo, s_hi;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    assign_small_body(p, sm, labels, out_iou, census, pos_list, pos_cap, s_lab);
-    const int K = p.gt_count[b];
-    const int lead = p.prepend_gt ? K : 0;
-    const int n_tot = lead + (p.box_count ? p.box_count[b] : (int)p.N);
-    const int npos = sm.cnt[0] + lead, nneg = sm.cnt[1];
-    const uint64_t sd = f.seed + (f.seed_step ? *f.seed_step : 0ull) + 0x632BE59BD9B4E019ull * (uint64_t)(b + 1);
-    for (int i = tid; i < n_tot; i += kSmallThreads) s_flag[i] = 0;
-    // ---- positives: all of them, or the pos_num smallest (mix_key(sd, idx) << 32 | idx)
-    const int keep_pos = min(npos, f.pos_num);
-    uint64_t thr = ~0ull;
-    if (npos > f.pos_num) {
-        if (tid == 0) { s_lo = 0ull; s_hi = ~0ull; }
-        __syncthreads();
-        for (int it = 0; it < 64; ++it) {
-            const unsigned long long lo = s_lo, hi = s_hi;
-            if (lo >= hi) break;
-            const unsigned long long mid = lo + (hi - lo) / 2;
-            int c = 0;
-            for (int i = tid; i < n_tot; i += kSmallThreads)
-                if (s_lab[i] > 0) c += ((((uint64_t)mix_key(sd, (uint32_t)i) << 32) | (uint32_t)i) <= mid);
-            c = __reduce_add_sync(0xffffffffu, c);
-            if (lane == 0) s_red[warp] = c;
-            __syncthreads();
-            if (tid == 0) {
-                int tot = 0;
-                for (int w = 0; w < kSmallThreads / 32; ++w) tot += s_red[w];
-                if (tot >= f.pos_num) s_hi = mid; else s_lo = mid + 1;
-            }
-            __syncthreads();
-        }
-        thr = s_lo;
-    }
-    __syncthreads();
-    for (int i = tid; i < n_tot; i += kSmallThreads)
-        if (s_lab[i] > 0 && ((((uint64_t)mix_key(sd, (uint32_t)i) << 32) | (uint32_t)i) <= thr)) s_flag[i] = 1;
-    // ---- negatives: the first want_neg label-0 indices along the keyed Feistel permutation
-    const int want_neg = min(max(f.max_num - keep_pos, 0), nneg);
-    if (want_neg > 0) {
-        int bits = 2;
-        while ((1 << bits) < n_tot) ++bits;
-        if (bits & 1) ++bits;
-        const int half = bits >> 1, dom = 1 << bits;
-        int taken = 0;
-        for (int t0 = 0; t0 < dom && taken < want_neg; t0 += 4 * kSmallThreads) {
-            uint32_t y[4];
-            unsigned m[4];
-            bool hit[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int t = t0 + q * kSmallThreads + tid;
-                y[q] = feistel((uint32_t)t, half, sd ^ 0xA5A5A5A5DEADBEEFull);
-                hit[q] = t < dom && (int)y[q] < n_tot && s_lab[y[q]] == 0;
-                m[q] = __ballot_sync(0xffffffffu, hit[q]);
-                if (lane == 0) s_w[q][warp] = __popc(m[q]);
-            }
-            __syncthreads();
-            if (warp == 0) {                                        // exclusive scan of the 128 warp counts (t order)
-                int v[4], sum = 0;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { v[e] = (&s_w[0][0])[lane * 4 + e]; sum += v[e]; }
-                int incl = sum;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += t;
-                }
-                int run = incl - sum;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { (&s_w[0][0])[lane * 4 + e] = run; run += v[e]; }
-                if (lane == 31) s_tot = incl;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int rank = taken + s_w[q][warp] + __popc(m[q] & ((1u << lane) - 1u));
-                if (hit[q] && rank < want_neg) s_flag[y[q]] = 1;
-            }
-            taken += s_tot;
-            __syncthreads();
-        }
-    }
-    __syncthreads();
-    // ---- ascending compaction of the flags
-    const int total = keep_pos + want_neg;
-    {
-        int c = 0;
-        const int i0 = tid * kFusedPer;
-#pragma unroll
-        for (int e = 0; e < kFusedPer; ++e) c += (i0 + e < n_tot) ? s_flag[i0 + e] : 0;
-        int incl = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (lane == 31) s_red[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const int v = s_red[lane];
-            int iw = v;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, iw, d);
-                if (lane >= d) iw += t;
-            }
-            s_red[lane] = iw - v;
-        }
-        __syncthreads();
-        int pos = s_red[warp] + incl - c;
-#pragma unroll
-        for (int e = 0; e < kFusedPer; ++e)
-            if (i0 + e < n_tot && s_flag[i0 + e]) { if (pos < kSmallThreads) s_chosen[pos] = i0 + e; ++pos; }
-    }
-    __syncthreads();
-    // ---- gather + encode of the sampled rows (k_encode_targets)
-    if (tid == 0) f.n_chosen[b] = total;
-    const int t = tid;
-    if (t >= f.max_num) return;
-    const long long o = (long long)b * 4 * f.max_num;
-    const bool live = t < total;
-    Box bx{0, 0, 0, 0}, gb{0, 0, 0, 0};
-    float prm[4] = {0, 0, 0, 0};
-    int64_t lab_out = 0, isgt = 0;
-    int ci = -1;
-    if (live) {
-        const int i = s_chosen[t];
-        ci = i;
-        const int lab = s_lab[i];
-        if (i < lead) {
-            bx = sm.gt[i];
-            isgt = 1;
-        } else {
-            const float* src = p.boxes + (long long)b * 4 * p.box_ld;
-            const long long ii = i - lead;
-            bx = Box{src[ii], src[p.box_ld + ii], src[2 * p.box_ld + ii], src[3 * p.box_ld + ii]};
-        }
-        const int j = max(lab - 1, 0);                       // negatives point at GT 0 (lib/anchor.py:45-47)
-        gb = sm.gt[j];
-        const float bw = (bx.x2 - bx.x1) + 1.0f, bh = (bx.y2 - bx.y1) + 1.0f;
-        const float gw = (gb.x2 - gb.x1) + 1.0f, gh = (gb.y2 - gb.y1) + 1.0f;
-        const float bcx = (bx.x2 + bx.x1) / 2.0f, bcy = (bx.y2 + bx.y1) / 2.0f;
-        const float gcx = (gb.x2 + gb.x1) / 2.0f, gcy = (gb.y2 + gb.y1) / 2.0f;
-        prm[0] = ((gcx - bcx) / bw - f.ms[0]) / f.ms[4];
-        prm[1] = ((gcy - bcy) / bh - f.ms[1]) / f.ms[5];
-        prm[2] = (logf(gw / bw) - f.ms[2]) / f.ms[6];
-        prm[3] = (logf(gh / bh) - f.ms[3]) / f.ms[7];
-        if (f.gt_label) lab_out = (lab > 0) ? f.gt_label[(long long)b * p.gt_ld + j] : 0;
-        else lab_out = (lab > 0) ? 1 : 0;
-    }
-    const int mn = f.max_num;
-    f.chosen[(long long)b * mn + t] = ci;
-    if (f.tar_box) { f.tar_box[o + t] = bx.x1; f.tar_box[o + mn + t] = bx.y1; f.tar_box[o + 2 * mn + t] = bx.x2; f.tar_box[o + 3 * mn + t] = bx.y2; }
-    if (f.tar_gt) { f.tar_gt[o + t] = gb.x1; f.tar_gt[o + mn + t] = gb.y1; f.tar_gt[o + 2 * mn + t] = gb.x2; f.tar_gt[o + 3 * mn + t] = gb.y2; }
-    if (f.tar_param) { f.tar_param[o + t] = prm[0]; f.tar_param[o + mn + t] = prm[1]; f.tar_param[o + 2 * mn + t] = prm[2]; f.tar_param[o + 3 * mn + t] = prm[3]; }
-    if (f.tar_label) f.tar_label[(long long)b * mn + t] = lab_out;
-    if (f.tar_is_gt) f.tar_is_gt[(long long)b * mn + t] = isgt;
+    __shared__ FusedScratch fs;
+    assign_small_body(p, sm, labels, out_iou, census, pos_list, pos_cap, fs.lab);
+    fused_sample_encode(p, f, sm.gt, fs, sm.cnt[0], sm.cnt[1], blockIdx.x);
 }
 
 __global__ void k_counter_add(unsigned long long* cell, unsigned long long inc) { *cell += inc; }

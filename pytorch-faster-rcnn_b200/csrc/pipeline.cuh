@@ -62,7 +62,9 @@ int rpn_front_launch(const RpnLaunch& p, cudaStream_t st, cudaStream_t side, cud
 int rpn_front_launch_count(const RpnLaunch& p);      // kernels rpn_front_launch issues for this plan (1 or 2)
 // rpn_back.cu: cluster kernel for score cut + sweep mask + scan + merge (one cluster per image)
 bool rpn_back_applicable(const RpnLaunch& p);
-int rpn_back_launch(const RpnLaunch& p, int cut_m, float* props, float* scores, int* count, int* prov, cudaStream_t st);
+int rpn_back_launch(const RpnLaunch& p, int cut_m, float* props, float* scores, int* count, int* prov,
+                    const ::b2d_roi_target_args* tg, cudaStream_t st);
+bool rpn_back_takes_targets(const RpnLaunch& p, const ::b2d_roi_target_args* tg);
 // nms.cu: suppression mask + scan over the sel_* arrays of the launch's segments
 int rpn_nms_launch(const RpnLaunch& p, cudaStream_t st);
 // nms.cu: per image the key of the M-th best selected box over all levels -> n_cut[segment]

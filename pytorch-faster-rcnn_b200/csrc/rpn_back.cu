@@ -30,6 +30,7 @@
 #include "common.cuh"
 #include "nms_common.cuh"
 #include "pipeline.cuh"
+#include "targets_common.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -42,7 +43,25 @@ constexpr int kBkCells = 256;            // x1 cells per level
 constexpr int kBkRows = 2;               // scan: rows per thread (2048 boxes per level)
 constexpr int kBkEntries = 6;            // scan: non-zero words of a row kept in registers
 
+// RoI-target stage as the tail of the kernel (b2d_rpn_proposals_targets); enable == 0: proposals only
+struct BackTargets {
+    int enable;
+    AssignArgs p;
+    FusedArgs f;
+    int64_t* labels; float* out_iou; int* census; int* pos_list; int pos_cap;
+};
+
+// shared memory of the target tail, aliased over BkShared::box (dead after the merge)
+struct TgShared {
+    Box gt[kGtChunk];
+    float ga[kGtChunk];
+    uint32_t cm_local[kGtChunk], cm[kGtChunk];
+    int cnt[4];
+    FusedScratch fs;
+};
+
 struct BackArgs {
+    BackTargets tg;
     float thr, thr_lo, thr_hi, prune;
     int M;                               // score cut: attempt 1 on the M best boxes (0: all boxes at once)
     int use_sweep;                       // 0: dense mask only
@@ -439,6 +458,103 @@ __global__ void __launch_bounds__(kBkThreads, 1) k_rpn_back(RpnLaunch p, BackArg
     if (crank == 0 && tid == 0) a.count[b] = nout;
     if (tid < kMaxLevels && crank == 0 && tid < L) p.keep_count[b * L + tid] = s.keep[tid];
     dbg_stamp(p, b, 32 + crank, 11);
+    if (!a.tg.enable) return;
+
+    // ------------------------------------------------------------------ T: bbox_target on the proposals (lib/bbox.py:6-82)
+    // MaxIoUAssigner over the image's nout proposals, a proposal per thread of the cluster (lib/region.py:75-107: per-GT
+    // column maxima exchanged through distributed shared memory, then labels); GT rows prepended, device-RNG sampler,
+    // gather + encode in the first CTA (fused_sample_encode, the tail of k_roi_targets_small).
+    static_assert(sizeof(TgShared) <= sizeof(float4) * kBkBoxes, "target tail must fit the staged-box area");
+    __threadfence();
+    cl.sync();                                            // the proposals are complete in global memory; s.box is dead
+    TgShared& t = *reinterpret_cast<TgShared*>(s.box);
+    const AssignArgs& ap = a.tg.p;
+    const int K = ap.gt_count[b];
+    const int lead = ap.prepend_gt ? K : 0;
+    const float* g = ap.gt + (long long)b * 4 * ap.gt_ld;
+    const float* src = a.props + (long long)b * 4 * p.out_ld;
+    const uint32_t kNegInf = f2key(-INFINITY);
+    if (tid < 4) t.cnt[tid] = 0;
+    for (int j = tid; j < K; j += kBkThreads) {
+        const Box q{g[j], g[ap.gt_ld + j], g[2 * ap.gt_ld + j], g[3 * ap.gt_ld + j]};
+        t.gt[j] = q; t.ga[j] = area_plus1(q); t.cm_local[j] = kNegInf;
+    }
+    const int i = crank * kBkThreads + tid;               // nout <= 4096 < 8 * 1024: at most one proposal per thread
+    const bool ok = i < nout;
+    Box bx{0.f, 0.f, 0.f, 0.f};
+    if (ok) bx = Box{__ldcg(src + i), __ldcg(src + p.out_ld + i), __ldcg(src + 2 * p.out_ld + i), __ldcg(src + 3 * p.out_ld + i)};
+    const float ba = ok ? area_plus1(bx) : 0.0f;
+    __syncthreads();
+    for (int j = 0; j < K; ++j) {                         // pass 1: per-GT column max, -0 folded to +0
+        uint32_t m = kNegInf;
+        if (ok) m = f2key(iou_plus1(bx, ba, t.gt[j], t.ga[j]) + 0.0f);
+        m = __reduce_max_sync(0xffffffffu, m);
+        if (lane == 0 && m != kNegInf) atomicMax(&t.cm_local[j], m);
+    }
+    cl.sync();
+    for (int j = tid; j < K; j += kBkThreads) {
+        uint32_t m = kNegInf;
+        for (int r = 0; r < kBkCl; ++r) m = max(m, cl.map_shared_rank(&t.cm_local[0], r)[j]);
+        t.cm[j] = m;
+    }
+    __syncthreads();
+    float best = 0.0f, veq = 0.0f;                        // pass 2: labels (lib/region.py:88-107)
+    int arg = 0, eq = -1;
+    if (ok) {
+        for (int j = 0; j < K; ++j) {
+            const float cmj = key2f(t.cm[j]);
+            const float v = iou_plus1(bx, ba, t.gt[j], t.ga[j]);
+            if (j == 0 || v > best) { best = v; arg = j; }                     // first max wins
+            if (eq < 0 && cmj >= ap.min_pos_iou && v == cmj) { eq = j; veq = v; }   // lowest GT wins
+        }
+    }
+    int64_t* lab = a.tg.labels + (long long)b * ap.out_ld;
+    float* oiou = a.tg.out_iou + (long long)b * ap.out_ld;
+    TgShared* t0 = cl.map_shared_rank(&t, 0);             // labels / counts are collected in the first CTA
+    int64_t out_l = -1;
+    if (ok) {
+        int l = -1;
+        if (best < ap.neg_iou) l = 0;
+        if (best >= ap.pos_iou) l = 1;
+        int aa = arg;
+        float out_v = best;
+        if (eq >= 0) { l = 1; aa = eq; out_v = veq; }
+        out_l = (l == 1) ? (int64_t)(aa + 1) : (int64_t)l;
+        lab[lead + i] = out_l; oiou[lead + i] = out_v;
+        t0->fs.lab[lead + i] = (int)out_l;
+    }
+    {
+        const bool is_pos = ok && out_l > 0, is_neg = ok && out_l == 0;
+        const unsigned mp = __ballot_sync(0xffffffffu, is_pos), mn = __ballot_sync(0xffffffffu, is_neg);
+        if (lane == 0) {
+            if (mp) atomicAdd(&t0->cnt[0], __popc(mp));
+            if (mn) atomicAdd(&t0->cnt[1], __popc(mn));
+        }
+        if (a.tg.pos_list) {
+            int* plist = a.tg.pos_list + (long long)b * a.tg.pos_cap;
+            const int slot = warp_alloc(is_pos, &t0->cnt[2]);
+            if (is_pos && slot < a.tg.pos_cap) plist[slot] = lead + i;
+        }
+    }
+    cl.sync();
+    if (crank != 0) return;
+    if (ap.prepend_gt) {                                  // prepended GT rows (lib/bbox.py:27-29): labels 1..K, IoU 1
+        int* plist = a.tg.pos_list ? a.tg.pos_list + (long long)b * a.tg.pos_cap : nullptr;
+        for (int j = tid; j < K; j += kBkThreads) {
+            lab[j] = j + 1; oiou[j] = 1.0f;
+            t.fs.lab[j] = j + 1;
+            if (plist) { const int slot = atomicAdd(&t.cnt[2], 1); if (slot < a.tg.pos_cap) plist[slot] = j; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        a.tg.census[4 * b + 0] = t.cnt[0] + (ap.prepend_gt ? K : 0);
+        a.tg.census[4 * b + 1] = t.cnt[1];
+        a.tg.census[4 * b + 2] = t.cnt[2];
+        a.tg.census[4 * b + 3] = 0;
+    }
+    fused_sample_encode(ap, a.tg.f, t.gt, t.fs, t.cnt[0], t.cnt[1], b);
+    dbg_stamp(p, b, 32 + crank, 9);
 }
 
 static size_t back_smem(const RpnLaunch& p) { return ((sizeof(BkShared) + 15) & ~(size_t)15) + (size_t)p.sel_per_img * 4 + 16; }
@@ -450,8 +566,14 @@ bool rpn_back_applicable(const RpnLaunch& p) {
     return kmax <= kBkThreads * kBkRows && back_smem(p) <= 200 * 1024;
 }
 
+bool rpn_back_takes_targets(const RpnLaunch& p, const ::b2d_roi_target_args* tg) {
+    return tg && rpn_back_applicable(p) && p.out_ld <= kBkCl * kBkThreads && p.out_ld <= kSmallThreads * kSmallBoxes &&
+           tg->gt_ld >= 1 && tg->gt_ld <= kGtChunk && tg->max_num >= 1 && tg->max_num <= kSmallThreads;
+}
+
 // 1: launched; 0: not applicable (the caller runs the multi-kernel path); anything else: error code
-int rpn_back_launch(const RpnLaunch& p, int cut_m, float* props, float* scores, int* count, int* prov, cudaStream_t st) {
+int rpn_back_launch(const RpnLaunch& p, int cut_m, float* props, float* scores, int* count, int* prov,
+                    const ::b2d_roi_target_args* tg, cudaStream_t st) {
     if (!rpn_back_applicable(p)) return 0;
     const size_t smem = back_smem(p);
     BackArgs a;
@@ -461,6 +583,22 @@ int rpn_back_launch(const RpnLaunch& p, int cut_m, float* props, float* scores, 
     a.prune = 1.0f - 0.9f * p.nms_thr;
     a.M = cut_m;
     a.props = props; a.scores = scores; a.count = count; a.prov = prov;
+    if (tg) {
+        if (!rpn_back_takes_targets(p, tg)) return 0;
+        BackTargets& t = a.tg;
+        t.enable = 1;
+        t.p.boxes = props; t.p.box_ld = p.out_ld; t.p.box_count = count; t.p.N = p.out_ld;
+        t.p.use_pyr = 0; t.p.img_hw = nullptr; t.p.border = 0.0f;
+        t.p.gt = tg->gt; t.p.gt_ld = tg->gt_ld; t.p.gt_count = tg->gt_count;
+        t.p.pos_iou = tg->pos_iou; t.p.neg_iou = tg->neg_iou; t.p.min_pos_iou = tg->min_pos_iou;
+        t.p.prepend_gt = tg->prepend_gt; t.p.out_ld = tg->out_ld;
+        t.f.chosen = tg->chosen; t.f.n_chosen = tg->n_chosen; t.f.max_num = tg->max_num; t.f.pos_num = tg->pos_num;
+        t.f.seed = tg->seed; t.f.seed_step = tg->seed_step; t.f.gt_label = tg->gt_label;
+        t.f.tar_box = tg->tar_box; t.f.tar_gt = tg->tar_gt; t.f.tar_param = tg->tar_param; t.f.tar_label = tg->tar_label;
+        t.f.tar_is_gt = tg->tar_is_gt;
+        for (int i = 0; i < 4; ++i) { t.f.ms[i] = tg->means[i]; t.f.ms[4 + i] = tg->stds[i]; }
+        t.labels = tg->labels; t.out_iou = tg->max_iou; t.census = tg->census; t.pos_list = tg->pos_list; t.pos_cap = tg->pos_cap;
+    }
     if (cudaFuncSetAttribute(k_rpn_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;

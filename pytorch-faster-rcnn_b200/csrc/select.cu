@@ -667,9 +667,11 @@ size_t b2d_rpn_proposals_workspace_bytes(const b2d_pyramid* pyr_host, int B, con
     return bytes;
 }
 
-int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const void* const* cls_ptrs_host,
-                      const void* const* reg_ptrs_host, const b2d_pyramid* pyr_host, const float* img_hw, int B,
-                      const b2d_rpn_cfg* cfg_host, void* workspace, size_t ws_bytes, void* stream) {
+// tg != NULL: the RoI-target stage rides on the proposal kernel when it can (*tg_done = 1), else the caller runs it
+static int rpn_proposals_impl(float* props, float* scores, int* count, int* prov, const void* const* cls_ptrs_host,
+                              const void* const* reg_ptrs_host, const b2d_pyramid* pyr_host, const float* img_hw, int B,
+                              const b2d_rpn_cfg* cfg_host, void* workspace, size_t ws_bytes, const b2d_roi_target_args* tg,
+                              int* tg_done, void* stream) {
     B2D_REQUIRE(props && scores && count && cls_ptrs_host && reg_ptrs_host && pyr_host && img_hw && cfg_host,
                 "rpn_proposals: null pointer");
     B2D_REQUIRE(B >= 1 && pyr_host->num_levels >= 1 && pyr_host->num_levels <= B2D_MAX_LEVELS,
@@ -688,7 +690,6 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
     cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
     cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
     int nl = 0;                                           // launches (kernels + memset nodes) of this call
-    cudaMemsetAsync(workspace, 0, p.zero_bytes, st); ++nl;
     // Per-level chains.  hist -> compact -> select -> NMS mask -> scan of one level only depends on that level, and
     // all of them but the mask are small latency-bound grids; run as ONE launch per kernel over all levels the step
     // is the sum of the slowest segment of every kernel (166 us at config 2).  Each level therefore gets its own
@@ -711,14 +712,19 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
             p.sel_per_img * 4 <= 200 * 1024)
             cut_m = (int)(f * p.max_num);
     }
-    // K3 as one cluster kernel (rpn_front.cu) when the plan fits; the per-level chains below otherwise
+    // K3 as one cluster kernel (rpn_front.cu) when the plan fits; the per-level chains below otherwise.  The cluster
+    // kernels keep their histograms / counters in shared memory and clear what they accumulate into themselves:
+    // only the multi-kernel path needs the head of the workspace zeroed.
     bool front_done = false;
+    const bool need_zero = !(knobs().rpn_front && !p.raw && use_back && rpn_front_launch_count(p) > 0);
+    if (need_zero) { cudaMemsetAsync(workspace, 0, p.zero_bytes, st); ++nl; }
     if (knobs().rpn_front && !p.raw) {
         const int rc = ls ? rpn_front_launch(p, st, ls->s[0], ls->fork, ls->join[0])
                           : rpn_front_launch(p, st, nullptr, nullptr, nullptr);
         if (rc == 1) { front_done = true; nl += rpn_front_launch_count(p); }
         else if (rc != 0) return rc;
     }
+    if (!front_done && !need_zero) { cudaMemsetAsync(workspace, 0, p.zero_bytes, st); ++nl; }   // cluster launch unavailable after all
     if (nchains > 1 && !front_done) cudaEventRecord(ls->fork, st);
     for (int c = 0; c < nchains && !front_done; ++c) {
         RpnLaunch q = p;
@@ -749,8 +755,9 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
         if (nchains > 1) { cudaEventRecord(ls->join[c], cs); cudaStreamWaitEvent(st, ls->join[c], 0); }
     }
     if (use_back) {
-        const int rc = rpn_back_launch(p, cut_m, props, scores, count, prov, st);
-        if (rc == 1) { g_last_launches = nl + 1; return B2D_OK; }
+        const bool ride = rpn_back_takes_targets(p, tg);
+        const int rc = rpn_back_launch(p, cut_m, props, scores, count, prov, ride ? tg : nullptr, st);
+        if (rc == 1) { g_last_launches = nl + 1; if (ride && tg_done) *tg_done = 1; return B2D_OK; }
         return rc == 0 ? B2D_ERR_ARG : rc;
     }
     if (front_done && p.do_nms && !cut_m) {
@@ -796,6 +803,36 @@ int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const 
     }
     g_last_launches = nl + 1;
     return check_launch("rpn_proposals");
+}
+
+int b2d_rpn_proposals(float* props, float* scores, int* count, int* prov, const void* const* cls_ptrs_host,
+                      const void* const* reg_ptrs_host, const b2d_pyramid* pyr_host, const float* img_hw, int B,
+                      const b2d_rpn_cfg* cfg_host, void* workspace, size_t ws_bytes, void* stream) {
+    return rpn_proposals_impl(props, scores, count, prov, cls_ptrs_host, reg_ptrs_host, pyr_host, img_hw, B, cfg_host, workspace,
+                              ws_bytes, nullptr, nullptr, stream);
+}
+
+int b2d_rpn_proposals_targets(float* props, float* scores, int* count, int* prov, const void* const* cls_ptrs_host,
+                              const void* const* reg_ptrs_host, const b2d_pyramid* pyr_host, const float* img_hw, int B,
+                              const b2d_rpn_cfg* cfg_host, void* workspace, size_t ws_bytes, const b2d_roi_target_args* tg,
+                              void* stream) {
+    B2D_REQUIRE(tg && tg->labels && tg->max_iou && tg->gt && tg->gt_count && tg->census && tg->chosen && tg->n_chosen,
+                "rpn_proposals_targets: null pointer");
+    int done = 0;
+    const int rc = rpn_proposals_impl(props, scores, count, prov, cls_ptrs_host, reg_ptrs_host, pyr_host, img_hw, B, cfg_host,
+                                      workspace, ws_bytes, tg, &done, stream);
+    if (rc != B2D_OK || done) return rc;
+    RpnLaunch p;
+    size_t need = 0;
+    if (!rpn_plan(p, pyr_host, B, cfg_host, nullptr, &need)) return B2D_ERR_ARG;
+    const int nl = g_last_launches;
+    const int rc2 = b2d_roi_targets_fused(tg->labels, tg->max_iou, tg->out_ld, props, p.out_ld, count, p.out_ld, tg->gt, tg->gt_ld,
+                                          tg->gt_count, tg->gt_label, B, tg->pos_iou, tg->neg_iou, tg->min_pos_iou, tg->prepend_gt,
+                                          tg->census, tg->pos_list, tg->pos_cap, tg->chosen, tg->n_chosen, tg->max_num, tg->pos_num,
+                                          tg->seed, tg->seed_step, tg->tar_box, tg->tar_gt, tg->tar_param, tg->tar_label,
+                                          tg->tar_is_gt, tg->means, tg->stds, stream);
+    g_last_launches = nl + 1;
+    return rc2;
 }
 
 int b2d_last_launch_count(void) { return g_last_launches; }

@@ -91,11 +91,21 @@ class RpnProposals(object):
         v.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.ws.device)
         return v
 
-    def __call__(self, cls_outs, reg_outs, img_hw, records=None):
+    def __call__(self, cls_outs, reg_outs, img_hw, records=None, targets=None):
         """records: optional fp32 [B, P, 5] tensor that receives (x1, y1, x2, y2, score) rows (zero past count): the
         packed detection record of SURVEY 8(e), written by the merge itself so that an all-gather can start right
-        after the step without a packing kernel."""
+        after the step without a packing kernel.
+        targets: optional (BatchedTargets in its fused form, gt, gt_count, gt_label): bbox_target on the proposals in the
+        same library call (b2d_rpn_proposals_targets; the tail of the proposal kernel when that runs as clusters)."""
         self.cfg.records = records.data_ptr() if records is not None else None
+        if targets is not None:
+            bt, gt, gt_count, gt_label = targets
+            ta = bt.target_args(gt, gt_count, gt_label)
+            _C.call("b2d_rpn_proposals_targets", _C.ptr(self.props), _C.ptr(self.scores), _C.ptr(self.count), _C.ptr(self.prov),
+                    _ptrs(cls_outs), _ptrs(reg_outs), ctypes.byref(self.pyr.c), _C.ptr(img_hw), self.B,
+                    ctypes.byref(self.cfg), _C.ptr(self.ws), self.ws.numel(), ctypes.byref(ta), _C.stream())
+            self.launches = int(_C.lib().b2d_last_launch_count())
+            return self.props, self.scores, self.count
         _C.call("b2d_rpn_proposals", _C.ptr(self.props), _C.ptr(self.scores), _C.ptr(self.count), _C.ptr(self.prov),
                 _ptrs(cls_outs), _ptrs(reg_outs), ctypes.byref(self.pyr.c), _C.ptr(img_hw), self.B,
                 ctypes.byref(self.cfg), _C.ptr(self.ws), self.ws.numel(), _C.stream())
@@ -141,6 +151,24 @@ class BatchedTargets(object):
     def reset_step(self):
         """Restart the device sampler's step counter (tests: the same random stream again)."""
         self.step_cell.zero_()
+
+    def target_args(self, gt, gt_count, gt_label):
+        """The arguments of b2d_roi_targets_fused as the struct b2d_rpn_proposals_targets takes (fused form only)."""
+        assert self.fused
+        a = _C.RoiTargetArgs()
+        dp = lambda t: t.data_ptr() if t is not None else None
+        a.labels, a.max_iou, a.out_ld = dp(self.labels), dp(self.iou), self.out_ld
+        a.gt, a.gt_ld, a.gt_count, a.gt_label = dp(gt), self.gt_ld, dp(gt_count), dp(gt_label)
+        a.pos_iou, a.neg_iou, a.min_pos_iou = float(self.pos_iou), float(self.neg_iou), float(self.min_pos)
+        a.prepend_gt, a.census, a.pos_list, a.pos_cap = self.prepend, dp(self.census), dp(self.pos_list), self.out_ld
+        a.chosen, a.n_chosen, a.max_num, a.pos_num = dp(self.chosen), dp(self.n_chosen), self.max_num, self.pos_num
+        a.seed = (self.seed * 1000003 + 0x632BE59BD9B4E019 * self.b0) & 0xFFFFFFFFFFFFFFFF
+        a.seed_step = dp(self.step_cell)
+        a.tar_box, a.tar_gt, a.tar_param = dp(self.tar_box), dp(self.tar_gt), dp(self.tar_param)
+        a.tar_label, a.tar_is_gt = dp(self.tar_label), dp(self.tar_is_gt)
+        for i in range(4):
+            a.means[i], a.stds[i] = self.means[i], self.stds[i]
+        return a
 
     def slice(self, b0, b1):
         return _batch_view(self, b0, b1)
@@ -215,6 +243,7 @@ class TrainHotPath(object):
                  groups=1, overlap=False, order=None):
         z4 = (0.0, 0.0, 0.0, 0.0)
         self.order = order or os.environ.get("B2D_STEP_ORDER", "rpn_first")
+        self.fuse_targets = os.environ.get("B2D_FUSE_TARGETS", "0") != "0"      # bbox_target as the tail of the proposal kernel (measured r2: 258.8 vs 251.2 us separate -> off)
         rpn_proposal = rpn_proposal or dict(pre_nms=2000, post_nms=2000, max_num=2000, nms_iou=0.7, min_bbox_size=0)
         rpn_assigner = rpn_assigner or dict(pos_iou=0.7, neg_iou=0.3, min_pos_iou=0.3)
         rpn_sampler = rpn_sampler or dict(max_num=256, pos_num=128)
@@ -227,8 +256,10 @@ class TrainHotPath(object):
                                           pyramid=self.pyr, border=allowed_border, seed=seed)
         self.roi_targets = BatchedTargets(B, self.proposals.P, gt_ld, rcnn_assigner, rcnn_sampler, z4, rcnn_stds,
                                           device, prepend_gt=True, seed=seed + 1)
-        # one device-side step counter for both samplers, advanced once at the start of step() (graph-replay safe)
-        self.step_cell = torch.zeros(1, dtype=torch.int64, device=device)
+        # one device-side step counter for both samplers (graph-replay safe): starts at 1 and is advanced once per step
+        # AFTER both samplers have read it, on a side stream next to RoIAlign (off the critical path)
+        self.step_cell = torch.ones(1, dtype=torch.int64, device=device)
+        self.s_bump = torch.cuda.Stream(device=device)
         for t in (self.rpn_targets, self.roi_targets):
             t.step_cell, t.auto_bump = self.step_cell, False
         roi_strides = list(strides[:4])
@@ -269,7 +300,7 @@ class TrainHotPath(object):
 
     def reset_step(self):
         """Restart the samplers' step counter (tests: the same random stream again)."""
-        self.step_cell.zero_()
+        self.step_cell.fill_(1)
 
     def _rpn_target_chain(self, cls_outs, reg_outs, gt, gt_count, img_hw):
         rt = self.rpn_targets(gt, gt_count, None, img_hw=img_hw)
@@ -281,13 +312,15 @@ class TrainHotPath(object):
         """One pass of the hot path over the batch (device-resident inputs).  `feats_ready`: optional
         CUDA event after which `feats` may be read (lets the proposal / target chains start while
         the feature maps are still arriving, see step_from_host)."""
-        _C.call("b2d_counter_add", _C.ptr(self.step_cell), 1, _C.stream())      # before the streams fork
         if not self.subs:
             if feats_ready is not None:
                 torch.cuda.current_stream().wait_event(feats_ready)
-            props, scores, count = self.proposals(cls_outs, reg_outs, img_hw, records=records)
+            ride = self.roi_targets.fused and self.fuse_targets
+            props, scores, count = self.proposals(cls_outs, reg_outs, img_hw, records=records,
+                                                  targets=(self.roi_targets, gt, gt_count, gt_label) if ride else None)
             rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
-            bt = self.roi_targets(gt, gt_count, gt_label, boxes=props, box_count=count)
+            bt = self.roi_targets if ride else self.roi_targets(gt, gt_count, gt_label, boxes=props, box_count=count)
+            _C.call("b2d_counter_add", _C.ptr(self.step_cell), 1, _C.stream())      # both samplers have read it
             self.roi_align(feats, bt.tar_box, bt.n_chosen)
         else:
             cur = torch.cuda.current_stream()
@@ -302,26 +335,36 @@ class TrainHotPath(object):
                     rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
             for gi, (b0, b1, prop, tgt, ra, st, st_lo) in enumerate(self.subs):
                 st.wait_stream(cur)
+                ride = tgt.fused and self.fuse_targets
                 with torch.cuda.stream(st):
                     p, _, c = prop([t[b0:b1] for t in cls_outs], [t[b0:b1] for t in reg_outs], img_hw[b0:b1],
-                                   records=records[b0:b1] if records is not None else None)
+                                   records=records[b0:b1] if records is not None else None,
+                                   targets=(tgt, gt[b0:b1], gt_count[b0:b1], gt_label[b0:b1]) if ride else None)
                 if gi == 0 and not rpn_first:
                     if self.order == "rpn_late":         # behind the proposal stage: next to RoI targets + RoIAlign
                         self.s_rpn.wait_stream(st)
                     with torch.cuda.stream(self.s_rpn):
                         rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
                 with torch.cuda.stream(st):
-                    t2 = tgt(gt[b0:b1], gt_count[b0:b1], gt_label[b0:b1], boxes=p, box_count=c)
+                    t2 = tgt if ride else tgt(gt[b0:b1], gt_count[b0:b1], gt_label[b0:b1], boxes=p, box_count=c)
                 st_lo.wait_stream(st)
                 if feats_ready is not None:
                     st_lo.wait_event(feats_ready)
                 with torch.cuda.stream(st_lo):
                     ra([f[b0:b1] for f in feats], t2.tar_box, t2.n_chosen)
+            # the step counter moves on once every sampler of the step has read it: side stream, next to RoIAlign
+            for sub in self.subs:
+                self.s_bump.wait_stream(sub[-2])
+            self.s_bump.wait_stream(self.s_rpn)
+            with torch.cuda.stream(self.s_bump):
+                _C.call("b2d_counter_add", _C.ptr(self.step_cell), 1, _C.stream())
             for sub in self.subs:
                 cur.wait_stream(sub[-1])
             cur.wait_stream(self.s_rpn)
+            cur.wait_stream(self.s_bump)
         self.launches = (sum(sub[2].launches for sub in self.subs) if self.groups > 1 else self.proposals.launches) + \
-            (self.roi_targets.launches + 1) * self.groups + self.rpn_targets.launches + 1 + 1
+            ((0 if (self.roi_targets.fused and self.fuse_targets) else self.roi_targets.launches) + 1) * self.groups + \
+            self.rpn_targets.launches + 1 + 1
         return dict(props=self.proposals.props, scores=self.proposals.scores, prop_count=self.proposals.count,
                     rpn=self.rpn_targets, rpn_tar_cls=self.tar_cls, rpn_tar_reg=self.tar_reg, rcnn=self.roi_targets,
                     roi_feats=self.roi_align.out)

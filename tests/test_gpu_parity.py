@@ -777,3 +777,32 @@ def test_fused_step_is_run_to_run_deterministic():
         else:
             for a, b in zip(ref, snap):
                 assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), it
+
+
+def test_roi_targets_as_tail_of_the_proposal_kernel_equal_the_separate_launch(monkeypatch):
+    """b2d_rpn_proposals_targets: bbox_target riding on k_rpn_back (assignment spread over the image's cluster, sampler
+    + encode in its first CTA) gives bit-identical labels / IoUs / samples / encoded targets to the separate
+    b2d_roi_targets_fused launch, at config-2 sizes."""
+    B, K = 4, 8
+    w = workload.config2(B=B, K=K, channels=16)
+    cls, reg = [T(c) for c in w["cls"]], [T(r) for r in w["reg"]]
+    feats = [T(f).contiguous(memory_format=torch.channels_last) for f in w["feats"]]
+    gt, gl = T(w["gt"]), T(w["gt_label"])
+    gcount = torch.tensor([8, 5, 8, 1], dtype=torch.int32, device=DEV)           # ragged GT counts
+    img_hw = torch.tensor([[800.0, 1333.0]] * B, device=DEV)
+    snaps = []
+    for fuse in ("1", "0"):  # riding on k_rpn_back, separate launch
+        monkeypatch.setenv("B2D_FUSE_TARGETS", fuse)
+        hp = fused.TrainHotPath(B, w["grids"], DEV, gt_ld=K, feat_channels=16, overlap=True)
+        out = hp.step(cls, reg, feats, gt, gcount, gl, img_hw)
+        torch.cuda.synchronize()
+        bt = out["rcnn"]
+        n = N(out["prop_count"])
+        snap = [N(out["props"]), N(bt.n_chosen), N(bt.chosen), N(bt.tar_box), N(bt.tar_gt), N(bt.tar_param), N(bt.tar_label),
+                N(bt.tar_is_gt), N(bt.census)[:, :2]]
+        for b in range(B):
+            kb = int(gcount[b])
+            snap.append(N(bt.labels[b, :kb + n[b]]).copy()); snap.append(N(bt.iou[b, :kb + n[b]]).copy())
+        snaps.append([s.copy() for s in snap])
+    for a, b in zip(*snaps):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
