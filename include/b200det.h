@@ -163,6 +163,9 @@ typedef struct b2d_rpn_cfg {
     int do_nms;                     /* 0: stop after decode (AnchorHead path) */
     float* records;                 /* optional DEVICE buffer [B][max_num][5]: (x1, y1, x2, y2, score) per proposal, zero rows past
                                        count -- the packed record that is all-gathered over NCCL; NULL = not written */
+    void* event_after_select;       /* optional cudaEvent_t recorded on `stream` once the selection stage (K3) has been issued:
+                                       lets a caller start independent work (the RPN-target kernels) behind K3 instead of
+                                       beside it; NULL = none */
 } b2d_rpn_cfg;
 
 /* The arguments of b2d_roi_targets_fused (below) as one struct, for b2d_rpn_proposals_targets. */

@@ -31,7 +31,7 @@ class Pyramid(ctypes.Structure):
 class RpnCfg(ctypes.Structure):
     _fields_ = [("pre_nms", c_int), ("post_nms", c_int), ("max_num", c_int), ("score_mode", c_int),
                 ("num_cls_channels", c_int), ("nms_thr_f", c_float), ("min_size", c_float),
-                ("means", c_float * 4), ("stds", c_float * 4), ("do_nms", c_int), ("records", c_void_p)]
+                ("means", c_float * 4), ("stds", c_float * 4), ("do_nms", c_int), ("records", c_void_p), ("event_after_select", c_void_p)]
 
 
 class RoiTargetArgs(ctypes.Structure):

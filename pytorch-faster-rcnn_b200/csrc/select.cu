@@ -754,6 +754,7 @@ static int rpn_proposals_impl(float* props, float* scores, int* count, int* prov
         }
         if (nchains > 1) { cudaEventRecord(ls->join[c], cs); cudaStreamWaitEvent(st, ls->join[c], 0); }
     }
+    if (cfg_host->event_after_select) cudaEventRecord((cudaEvent_t)cfg_host->event_after_select, st);
     if (use_back) {
         const bool ride = rpn_back_takes_targets(p, tg);
         const int rc = rpn_back_launch(p, cut_m, props, scores, count, prov, ride ? tg : nullptr, st);

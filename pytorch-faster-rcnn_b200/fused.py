@@ -91,13 +91,14 @@ class RpnProposals(object):
         v.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.ws.device)
         return v
 
-    def __call__(self, cls_outs, reg_outs, img_hw, records=None, targets=None):
+    def __call__(self, cls_outs, reg_outs, img_hw, records=None, targets=None, after_select=None):
         """records: optional fp32 [B, P, 5] tensor that receives (x1, y1, x2, y2, score) rows (zero past count): the
         packed detection record of SURVEY 8(e), written by the merge itself so that an all-gather can start right
         after the step without a packing kernel.
         targets: optional (BatchedTargets in its fused form, gt, gt_count, gt_label): bbox_target on the proposals in the
         same library call (b2d_rpn_proposals_targets; the tail of the proposal kernel when that runs as clusters)."""
         self.cfg.records = records.data_ptr() if records is not None else None
+        self.cfg.event_after_select = after_select.cuda_event if after_select is not None else None
         if targets is not None:
             bt, gt, gt_count, gt_label = targets
             ta = bt.target_args(gt, gt_count, gt_label)
@@ -243,6 +244,8 @@ class TrainHotPath(object):
                  groups=1, overlap=False, order=None):
         z4 = (0.0, 0.0, 0.0, 0.0)
         self.order = order or os.environ.get("B2D_STEP_ORDER", "rpn_first")
+        self.ev_select = torch.cuda.Event()
+        self.ev_select.record()                              # (creates the CUDA event behind the handle)
         self.fuse_targets = os.environ.get("B2D_FUSE_TARGETS", "0") != "0"      # bbox_target as the tail of the proposal kernel (measured r2: 258.8 vs 251.2 us separate -> off)
         rpn_proposal = rpn_proposal or dict(pre_nms=2000, post_nms=2000, max_num=2000, nms_iou=0.7, min_bbox_size=0)
         rpn_assigner = rpn_assigner or dict(pos_iou=0.7, neg_iou=0.3, min_pos_iou=0.3)
@@ -336,13 +339,17 @@ class TrainHotPath(object):
             for gi, (b0, b1, prop, tgt, ra, st, st_lo) in enumerate(self.subs):
                 st.wait_stream(cur)
                 ride = tgt.fused and self.fuse_targets
+                ev = self.ev_select if (gi == 0 and self.order == "rpn_after_select") else None
                 with torch.cuda.stream(st):
                     p, _, c = prop([t[b0:b1] for t in cls_outs], [t[b0:b1] for t in reg_outs], img_hw[b0:b1],
                                    records=records[b0:b1] if records is not None else None,
-                                   targets=(tgt, gt[b0:b1], gt_count[b0:b1], gt_label[b0:b1]) if ride else None)
+                                   targets=(tgt, gt[b0:b1], gt_count[b0:b1], gt_label[b0:b1]) if ride else None,
+                                   after_select=ev)
                 if gi == 0 and not rpn_first:
                     if self.order == "rpn_late":         # behind the proposal stage: next to RoI targets + RoIAlign
                         self.s_rpn.wait_stream(st)
+                    if ev is not None:                   # behind the selection kernel, beside NMS / merge / RoI targets
+                        self.s_rpn.wait_event(ev)
                     with torch.cuda.stream(self.s_rpn):
                         rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
                 with torch.cuda.stream(st):
