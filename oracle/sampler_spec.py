@@ -20,11 +20,26 @@ def mix_key(seed, i):
     return (z >> 32) & 0xFFFFFFFF
 
 
+M32 = (1 << 32) - 1
+
+
+def mix32(key, v):
+    """32-bit keyed round function of the Feistel permutation (murmur3-style finaliser)."""
+    h = (v * 0x9E3779B1 + key) & M32
+    h ^= h >> 15
+    h = (h * 0x85EBCA77) & M32
+    h ^= h >> 13
+    h = (h * 0xC2B2AE3D) & M32
+    h ^= h >> 16
+    return h
+
+
 def feistel(x, half_bits, seed):
     mask = (1 << half_bits) - 1
     l, r = x >> half_bits, x & mask
     for rnd in range(4):
-        f = mix_key((seed + 0x1000003 * (rnd + 1)) & M64, r) & mask
+        ks = (seed + 0x1000003 * (rnd + 1)) & M64
+        f = mix32((ks & M32) ^ (ks >> 32), r) & mask
         l, r = r, l ^ f
     return (l << half_bits) | r
 

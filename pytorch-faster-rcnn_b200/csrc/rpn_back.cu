@@ -467,6 +467,7 @@ __global__ void __launch_bounds__(kBkThreads, 1) k_rpn_back(RpnLaunch p, BackArg
     static_assert(sizeof(TgShared) <= sizeof(float4) * kBkBoxes, "target tail must fit the staged-box area");
     __threadfence();
     cl.sync();                                            // the proposals are complete in global memory; s.box is dead
+    dbg_stamp(p, b, 32 + crank, 5);
     TgShared& t = *reinterpret_cast<TgShared*>(s.box);
     const AssignArgs& ap = a.tg.p;
     const int K = ap.gt_count[b];
@@ -491,6 +492,7 @@ __global__ void __launch_bounds__(kBkThreads, 1) k_rpn_back(RpnLaunch p, BackArg
         m = __reduce_max_sync(0xffffffffu, m);
         if (lane == 0 && m != kNegInf) atomicMax(&t.cm_local[j], m);
     }
+    dbg_stamp(p, b, 32 + crank, 6);
     cl.sync();
     for (int j = tid; j < K; j += kBkThreads) {
         uint32_t m = kNegInf;
@@ -536,7 +538,9 @@ __global__ void __launch_bounds__(kBkThreads, 1) k_rpn_back(RpnLaunch p, BackArg
             if (is_pos && slot < a.tg.pos_cap) plist[slot] = lead + i;
         }
     }
+    dbg_stamp(p, b, 32 + crank, 7);
     cl.sync();
+    dbg_stamp(p, b, 32 + crank, 8);
     if (crank != 0) return;
     if (ap.prepend_gt) {                                  // prepended GT rows (lib/bbox.py:27-29): labels 1..K, IoU 1
         int* plist = a.tg.pos_list ? a.tg.pos_list + (long long)b * a.tg.pos_cap : nullptr;

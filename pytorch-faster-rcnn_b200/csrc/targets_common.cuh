@@ -29,12 +29,23 @@ struct SmallSmem {
 };
 
 // ---- device-RNG sampler (spec: DESIGN.md "Samplers"; oracle/sampler_spec.py) ----
+// 32-bit round function of the Feistel permutation (murmur3-style finaliser, keyed): the 4 rounds of a 64-bit
+// splitmix per permutation step were half of the RoI-target kernel's time (r2: ~5 of 11 us sampler + encode).
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t key, uint32_t v) {
+    uint32_t h = v * 0x9E3779B1u + key;
+    h ^= h >> 15; h *= 0x85EBCA77u;
+    h ^= h >> 13; h *= 0xC2B2AE3Du;
+    h ^= h >> 16;
+    return h;
+}
+
 __device__ __forceinline__ uint32_t feistel(uint32_t x, int half_bits, uint64_t seed) {
     const uint32_t mask = (1u << half_bits) - 1u;
     uint32_t l = x >> half_bits, r = x & mask;
 #pragma unroll
     for (int round = 0; round < 4; ++round) {
-        const uint32_t f = mix_key(seed + 0x1000003ull * (uint64_t)(round + 1), r) & mask;
+        const uint64_t ks = seed + 0x1000003ull * (uint64_t)(round + 1);
+        const uint32_t f = mix32((uint32_t)ks ^ (uint32_t)(ks >> 32), r) & mask;
         const uint32_t nl = r;
         r = l ^ f;
         l = nl;
