@@ -398,8 +398,24 @@ def run_b200(args):
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / n_it
             dropin[name] = {"value": B / dt, "unit": "images/s", "ms_per_step": dt * 1e3}
-        dropin["note"] = "reference call sequence (per-image Python loops of AnchorHead.loss / predict_bboxes_from_output / " \
-                         "bbox_targets / BasicRoIExtractor) on the drop-in functions, eager, host wall clock incl. its syncs"
+        # the same sequence with the three per-image loops rebound at the METHOD level (batched.py; what install() binds
+        # onto RPNHead.predict_bboxes_from_output / AnchorHead.loss / BBoxHead.bbox_targets): one batched pass per loop
+        seqb = refpath.BatchedCallSequence(strides, dev)
+        for name, ff in (("batched_nchw", feats_nchw), ("batched_channels_last", feats)):
+            fn = lambda: seqb.step(cls, reg, ff, gtl, gll, metas)
+            fn(); fn()
+            torch.cuda.synchronize()
+            n_it = 20
+            t0 = time.perf_counter()
+            for _ in range(n_it):
+                fn()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n_it
+            dropin[name] = {"value": B / dt, "unit": "images/s", "ms_per_step": dt * 1e3}
+        dropin["note"] = "reference call sequence (AnchorHead.loss targets / predict_bboxes_from_output / bbox_targets / " \
+                         "BasicRoIExtractor) on the drop-in, eager, host wall clock incl. its syncs; nchw / channels_last: " \
+                         "the reference's per-image Python loops on the rebound functions; batched_*: the loops themselves " \
+                         "rebound (one batched pass + one sync each), as install() does"
     # ---- per-stage device times (eager, CUDA events on the launching stream)
     stages = ["proposals", "rpn_targets", "roi_targets", "roi_align"]
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]

@@ -37,7 +37,6 @@ struct Knobs {
     int roi_tma_dev;       // B2D_ROI_TMA_DEV
     int roi_bwd_tile;      // B2D_ROI_BWD_TILE   0: generic backward kernel
     int assign_old;        // B2D_ASSIGN_OLD     1: round-1a assignment kernels in pyramid mode
-    int pdl;               // B2D_PDL            0: no programmatic dependent launch edges
     int debug_sync;        // B2D_DEBUG_SYNC     synchronise after every launch (localise a faulting kernel)
 };
 const Knobs& knobs();

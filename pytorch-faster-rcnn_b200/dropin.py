@@ -121,6 +121,33 @@ def install(lib=None, channels_last=False):
             return heads.predict_single_image(self, cls_outs, reg_outs, ctr_outs, img_meta, test_cfg)
 
         _set(fh.FCOSHead, "predict_single_image", _predict)
+    # the per-image LOOPS themselves: one batched pass when the call is covered, else the reference's loop
+    from . import batched
+    rh = mods["heads.rpn_head"]
+    if rh and hasattr(rh, "RPNHead"):
+        ref_predict_all = rh.RPNHead.predict_bboxes_from_output
+
+        def _predict_all(self, cls_outs, reg_outs, img_metas, test_cfg):
+            out = batched.rpn_predict_fast(self, cls_outs, reg_outs, img_metas, test_cfg)
+            return out if out is not None else ref_predict_all(self, cls_outs, reg_outs, img_metas, test_cfg)
+
+        _set(rh.RPNHead, "predict_bboxes_from_output", _predict_all)
+    if ah and hasattr(ah, "AnchorHead"):
+        ref_loss = ah.AnchorHead.loss
+
+        def _loss(self, cls_outs, reg_outs, gt_bboxes, gt_labels, img_metas, train_cfg):
+            return batched.anchor_head_loss(self, cls_outs, reg_outs, gt_bboxes, gt_labels, img_metas, train_cfg,
+                                            reference_loss=ref_loss)
+
+        _set(ah.AnchorHead, "loss", _loss)
+    if bh and hasattr(bh, "BBoxHead"):
+        ref_bbox_targets = bh.BBoxHead.bbox_targets
+
+        def _bbox_targets(self, img_props, gt_bboxes, gt_labels, train_cfg):
+            out = batched.bbox_targets_fast(self, img_props, gt_bboxes, gt_labels, train_cfg)
+            return out if out is not None else ref_bbox_targets(self, img_props, gt_bboxes, gt_labels, train_cfg)
+
+        _set(bh.BBoxHead, "bbox_targets", _bbox_targets)
     necks = sys.modules.get("lib.necks")
     if channels_last and necks is not None and hasattr(necks, "FPN"):
         _channels_last_fpn(necks)

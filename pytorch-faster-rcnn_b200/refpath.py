@@ -18,7 +18,12 @@ import types
 
 import torch
 
-from . import anchor, bbox, heads, region, utils
+from . import anchor, batched, bbox, heads, region, utils
+
+
+class _Cfg(dict):
+    """Attribute + .get access, like the reference's mmcv ConfigDict."""
+    __getattr__ = dict.__getitem__
 
 
 class TrainCallSequence(object):
@@ -44,6 +49,9 @@ class TrainCallSequence(object):
         self.rcnn_assigner = region.MaxIoUAssigner(a["pos_iou"], a["neg_iou"], a["min_pos_iou"])
         self.rcnn_sampler = region.RandomSampler(s["max_num"], s["pos_num"], rng=sampler_rng)
         self.rpn_ms, self.rcnn_ms = (z4, list(rpn_stds)), (z4, list(rcnn_stds))
+        self.rcnn_head = types.SimpleNamespace(target_means=z4, target_stds=list(rcnn_stds))
+        self.rpn_train_cfg = _Cfg(assigner=self.rpn_assigner, sampler=self.rpn_sampler, allowed_border=allowed_border)
+        self.rcnn_train_cfg = _Cfg(assigner=self.rcnn_assigner, sampler=self.rcnn_sampler)
         self.extractor = region.BasicRoIExtractor(
             [dict(type="RoIAlign", spatial_scale=1.0 / st, sampling_ratio=2) for st in self.strides[:4]], output_size=(7, 7))
 
@@ -88,4 +96,20 @@ class TrainCallSequence(object):
         tar_props = [t[0] for t in tars]
         # roi_extractor
         roi_outs = self.extractor(list(feats), tar_props)
+        return dict(rpn_targets=rpn_tars, props=props, rcnn_targets=tars, roi_feats=roi_outs)
+
+
+class BatchedCallSequence(TrainCallSequence):
+    """The same forward_train sequence with the three loops rebound at the METHOD level, as install() does
+    (batched.py): rpn_head.loss's targets, rpn_head.predict_bboxes_from_output and rcnn_head.bbox_targets are one
+    batched pass each; the RoI extractor call is unchanged."""
+
+    def step(self, cls_outs, reg_outs, feats, gt_bboxes, gt_labels, img_metas):
+        rpn_gt_labels = [torch.full_like(l, 1) for l in gt_labels]                       # cascade_rcnn.py:109
+        rpn_tars = batched.anchor_head_targets(self.head, cls_outs, reg_outs, list(gt_bboxes), rpn_gt_labels, img_metas,
+                                               self.rpn_train_cfg)
+        assert rpn_tars is not None, "batched anchor targets: call not covered"
+        props = batched.rpn_predict_bboxes_from_output(self.head, cls_outs, reg_outs, img_metas, _Cfg(self.rpn_proposal))[0]
+        tars = batched.bbox_head_bbox_targets(self.rcnn_head, props, list(gt_bboxes), list(gt_labels), self.rcnn_train_cfg)
+        roi_outs = self.extractor(list(feats), tars[0])
         return dict(rpn_targets=rpn_tars, props=props, rcnn_targets=tars, roi_feats=roi_outs)

@@ -86,13 +86,33 @@ def _np_discard(idx_tensor, n_discard):
     return np.random.choice(idx_tensor.cpu().numpy(), size=n_discard, replace=False)
 
 
+# The reference builds its sampler from the config dict on EVERY call (lib/anchor.py:29-31, lib/bbox.py:19-20), so a
+# per-instance call counter would restart with every image and the device sampler would walk the same permutation
+# each time.  Samplers without an explicit seed therefore draw their stream index from one process-wide counter
+# (restartable with manual_seed, like torch.manual_seed); an explicit seed= keeps the per-instance counter (tests).
+_auto = {"seed": 0, "calls": 0}
+
+
+def manual_seed(seed):
+    """Restart the process-wide stream of the device samplers that were built without seed=."""
+    _auto["seed"], _auto["calls"] = int(seed), 0
+
+
+def _stream_key(sampler):
+    if sampler.seed is None:
+        _auto["calls"] += 1
+        return (_auto["seed"] * 1000003 + 0x9E3779B97F4A7C15 + _auto["calls"]) & 0xFFFFFFFFFFFFFFFF
+    sampler._calls += 1
+    return (int(sampler.seed) * 1000003 + sampler._calls) & 0xFFFFFFFFFFFFFFFF
+
+
 class RandomSampler(object):
     """lib/region.py:112-126.  rng='device' (default): the library's counter-based
     device sampler (no host sync); rng='numpy': the reference's exact host procedure,
     consuming numpy's global RNG stream identically (parity mode)."""
     default_rng = "device"
 
-    def __init__(self, max_num, pos_num, rng=None, seed=0):
+    def __init__(self, max_num, pos_num, rng=None, seed=None):
         assert pos_num <= max_num
         self.max_num = max_num
         self.pos_num = pos_num
@@ -113,10 +133,8 @@ class RandomSampler(object):
                 _C.stream())
         chosen = torch.empty(self.max_num, dtype=torch.int32, device=dev)
         n_chosen = torch.empty(1, dtype=torch.int32, device=dev)
-        self._calls += 1
         _C.call("b2d_sample_labels", _C.ptr(chosen), _C.ptr(n_chosen), _C.ptr(lab), n, None, None, n, _C.ptr(census),
-                _C.ptr(pos_list), max(n, 1), 1, self.max_num, self.pos_num,
-                (int(self.seed) * 1000003 + self._calls) & 0xFFFFFFFFFFFFFFFF, None, _C.stream())
+                _C.ptr(pos_list), max(n, 1), 1, self.max_num, self.pos_num, _stream_key(self), None, _C.stream())
         out = torch.full_like(lab, -1)
         _C.call("b2d_scatter_sampled", _C.ptr(out), _C.ptr(lab), n, n, _C.ptr(chosen), _C.ptr(n_chosen),
                 self.max_num, 1, _C.stream())
@@ -145,7 +163,7 @@ class IoUBalancedNegSampler(object):
     reference's arguments in the reference's order, one upload, b2d_scatter_sampled."""
     default_rng = "device"
 
-    def __init__(self, max_num, pos_num, num_bins=3, max_iou=0.5, floor_thr=-1, floor_fraction=0, rng=None, seed=0):
+    def __init__(self, max_num, pos_num, num_bins=3, max_iou=0.5, floor_thr=-1, floor_fraction=0, rng=None, seed=None):
         assert max_num >= pos_num
         assert max_iou > 0 and max_iou <= 1
         self.max_num, self.pos_num, self.num_bins, self.max_iou = max_num, pos_num, num_bins, max_iou
@@ -164,10 +182,8 @@ class IoUBalancedNegSampler(object):
         n, dev = int(lab.numel()), lab.device
         if self.rng != "numpy":
             out = torch.empty_like(lab)
-            self._calls += 1
             _C.call("b2d_sample_iou_balanced", _C.ptr(out), _C.ptr(lab), _C.ptr(iou), n, self.max_num, self.pos_num,
-                    self.num_bins, self._lo, self._hi, (int(self.seed) * 1000003 + self._calls) & 0xFFFFFFFFFFFFFFFF,
-                    _C.stream())
+                    self.num_bins, self._lo, self._hi, _stream_key(self), _C.stream())
             return out
         ids = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         _C.call("b2d_iou_bin_ids", _C.ptr(ids), _C.ptr(lab), _C.ptr(iou), n, self.num_bins, self._lo, self._hi, _C.stream())
@@ -519,8 +535,8 @@ class BasicRoIExtractor(nn.Module):
         counts = [int(r.shape[1]) for r in rois_list]
         if self._fusable:
             rois = torch.cat([r.reshape(4, -1) for r in rois_list], dim=1) if len(rois_list) > 1 else rois_list[0]
-            roi_img = torch.cat([torch.full((c,), i, dtype=torch.int32, device=rois.device)
-                                 for i, c in enumerate(counts)]) if len(rois_list) > 1 else None
+            roi_img = torch.from_numpy(np.repeat(np.arange(len(counts), dtype=np.int32), counts)).to(rois.device, non_blocking=True) \
+                if len(rois_list) > 1 else None           # one small upload instead of a fill per image
             l0 = self.roi_layers[0]
             out = roi_align_levels(feats, rois, roi_img, [l.spatial_scale for l in self.roi_layers], self.output_size,
                                    l0.sampling_ratio, l0.aligned, self.finest_scale)

@@ -36,3 +36,15 @@ phase("roi_extractor (NCHW)", lambda: seq.extractor(feats, tp))
 fcl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
 phase("roi_extractor (NHWC)", lambda: seq.extractor(fcl, tp))
 phase("whole step", lambda: seq.step(cls, reg, feats, gtl, gll, metas))
+
+# ---- the loops rebound at the method level (batched.py)
+from b200det import batched
+seqb = refpath.BatchedCallSequence(w["strides"], dev)
+ones = [torch.full_like(l, 1) for l in gll]
+phase("batched anchor targets", lambda: batched.anchor_head_targets(seqb.head, cls, reg, gtl, ones, metas, seqb.rpn_train_cfg), 20)
+bp = phase("batched rpn predict", lambda: batched.rpn_predict_bboxes_from_output(seqb.head, cls, reg, metas, refpath._Cfg(seqb.rpn_proposal))[0], 20)
+bt = phase("batched bbox_targets", lambda: batched.bbox_head_bbox_targets(seqb.rcnn_head, bp, gtl, gll, seqb.rcnn_train_cfg), 20)
+phase("roi_extractor (NCHW)", lambda: seqb.extractor(feats, bt[0]), 20)
+phase("roi_extractor (NHWC)", lambda: seqb.extractor(fcl, bt[0]), 20)
+phase("whole batched step (NCHW)", lambda: seqb.step(cls, reg, feats, gtl, gll, metas), 20)
+phase("whole batched step (NHWC)", lambda: seqb.step(cls, reg, fcl, gtl, gll, metas), 20)

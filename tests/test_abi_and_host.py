@@ -141,9 +141,15 @@ def test_dropin_install_rebinds_reference_names():
     import lib.builder as rb
     import lib.heads.anchor_head as ah
     import lib.heads.rpn_head as rh
+    import lib.heads.bbox_head as bh
     orig = rb.MODULES["MaxIoUAssigner"]
+    ref_loss, ref_tars, ref_pred = ah.AnchorHead.loss, bh.BBoxHead.bbox_targets, rh.RPNHead.predict_bboxes_from_output
     b200det.install(lib)
     try:
+        # the per-image loops themselves (batched.py)
+        assert ah.AnchorHead.loss is not ref_loss and bh.BBoxHead.bbox_targets is not ref_tars
+        assert rh.RPNHead.predict_bboxes_from_output is not ref_pred
+        assert ah.AnchorHead.predict_bboxes_from_output is ref_pred          # only the RPN head's loop is rebound
         assert rb.MODULES["MaxIoUAssigner"] is b200det.region.MaxIoUAssigner
         assert rb.MODULES["RoIAlign"] is b200det.region.RoIAlign
         assert ah.anchor_target is b200det.anchor.anchor_target
@@ -159,6 +165,7 @@ def test_dropin_install_rebinds_reference_names():
     finally:
         b200det.uninstall()
     assert rb.MODULES["MaxIoUAssigner"] is orig
+    assert ah.AnchorHead.loss is ref_loss and bh.BBoxHead.bbox_targets is ref_tars
     assert rh.RPNHead.predict_single_image is not b200det.heads.rpn_predict_single_image
 
 

@@ -761,3 +761,154 @@ def test_nccl_world2_gather_detections(tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+
+# ------------------------------------------------------------------ the per-image LOOPS rebound at the method level (batched.py)
+def _loop_inputs(B=3, K=(3, 6, 1), img_shapes=((250, 310), (256, 320), (200, 333)), pad=(256, 336), channels=16, seed=11):
+    from b200det import refpath
+    rng = np.random.default_rng(seed)
+    strides = workload.STRIDES
+    w = workload.config2(B=B, K=1, seed=seed, channels=channels, img_shape=img_shapes[0], pad_shape=pad)
+    cls, reg = [T(c) for c in w["cls"]], [T(r) for r in w["reg"]]
+    feats = [T(f) for f in w["feats"]]
+    gts = [workload.synth_gt(rng, K[i], *img_shapes[i]) for i in range(B)]
+    gt_bboxes, gt_labels = [T(g[0]) for g in gts], [T(g[1]) for g in gts]
+    metas = [dict(img_shape=(img_shapes[i][0], img_shapes[i][1], 3), pad_shape=(pad[0], pad[1], 3), scale_factor=1.0)
+             for i in range(B)]
+    return refpath, strides, cls, reg, feats, gt_bboxes, gt_labels, metas
+
+
+def test_batched_predict_bboxes_from_output_equals_the_per_image_loop():
+    """batched.rpn_predict_bboxes_from_output (what install() binds onto RPNHead.predict_bboxes_from_output) returns,
+    image by image, exactly what the reference's loop over predict_single_image returns (ragged image sizes)."""
+    from b200det import batched
+    refpath, strides, cls, reg, feats, gt_bboxes, gt_labels, metas = _loop_inputs()
+    seq = refpath.BatchedCallSequence(strides, DEV, rpn_proposal=dict(pre_nms=600, post_nms=300, max_num=500, nms_iou=0.7,
+                                                                      min_bbox_size=0))
+    cfg = refpath._Cfg(seq.rpn_proposal)
+    out = batched.rpn_predict_fast(seq.head, cls, reg, metas, cfg)
+    assert out is not None and len(out) == 3 and out[2] == [None] * 3
+    grids = [tuple(int(v) for v in c.shape[-2:]) for c in cls]
+    anchors = seq.create_anchors(grids)
+    for i in range(3):
+        b, s, _ = bheads.rpn_predict_single_image(seq.head, [c[i] for c in cls], [r[i] for r in reg], anchors, metas[i], cfg)
+        assert out[0][i].shape == b.shape and b.shape[1] > 50
+        assert torch.equal(out[0][i], b) and torch.equal(out[1][i], s)
+    # not covered (per-image size filter with different scale factors): the caller keeps the reference loop
+    metas2 = [dict(m, scale_factor=1.0 + 0.1 * i) for i, m in enumerate(metas)]
+    assert batched.rpn_predict_fast(seq.head, cls, reg, metas2, refpath._Cfg(seq.rpn_proposal, min_bbox_size=4)) is None
+    loop = batched.rpn_predict_bboxes_from_output(seq.head, cls, reg, metas2, refpath._Cfg(seq.rpn_proposal, min_bbox_size=4))
+    assert len(loop[0]) == 3 and loop[0][0].shape[0] == 4
+
+
+def _find_columns(cols, pool):
+    """ascending indices j_0 < j_1 < ... with pool[:, j_k] == cols[:, k] (exact)."""
+    idx, j = [], 0
+    for k in range(cols.shape[1]):
+        while j < pool.shape[1] and not np.array_equal(pool[:, j], cols[:, k]):
+            j += 1
+        assert j < pool.shape[1], "column %d is not a column of [gt; props] in ascending order" % k
+        idx.append(j)
+        j += 1
+    return np.asarray(idx)
+
+
+def test_batched_bbox_targets_equal_the_per_image_semantics():
+    """batched.bbox_head_bbox_targets (bound onto BBoxHead.bbox_targets): per image the result is what bbox_target
+    computes for the SAME sampled set -- columns of [gt; props] in ascending order, labels / GT boxes / deltas /
+    is_gt of lib/bbox.py:27-80, the sampler's cardinalities -- for packed proposals (views of the batched predict) and
+    for re-packed ragged lists; a second call draws a different sample."""
+    from b200det import batched, bbox as bbbox
+    refpath, strides, cls, reg, feats, gt_bboxes, gt_labels, metas = _loop_inputs(K=(3, 6, 1))
+    seq = refpath.BatchedCallSequence(strides, DEV, rpn_proposal=dict(pre_nms=600, post_nms=300, max_num=500, nms_iou=0.7,
+                                                                      min_bbox_size=0),
+                                      rcnn_sampler=dict(max_num=128, pos_num=32))
+    props = batched.rpn_predict_fast(seq.head, cls, reg, metas, refpath._Cfg(seq.rpn_proposal))[0]
+    ragged = [p[:, :p.shape[1] - 7 * i].clone() for i, p in enumerate(props)]       # plain tensors: the re-packing branch
+    assign = bregion.MaxIoUAssigner(0.5, 0.5, 0.5)
+    first = None
+    for plist in (props, ragged, props):
+        res = batched.bbox_targets_fast(seq.rcnn_head, plist, gt_bboxes, gt_labels, seq.rcnn_train_cfg)
+        assert res is not None and len(res) == 5
+        for i in range(3):
+            tp, tb, tl, tpar, tg = [N(r[i]) for r in res]
+            K = gt_bboxes[i].shape[1]
+            pool = np.concatenate([N(gt_bboxes[i]), N(plist[i])], axis=1)
+            lab = np.concatenate([np.arange(1, K + 1), N(assign(plist[i], gt_bboxes[i])[0])])
+            j = _find_columns(tp, pool)
+            assert (lab[j] >= 0).all()
+            npos, nneg = int((lab > 0).sum()), int((lab == 0).sum())
+            kp = min(npos, 32)
+            assert int((lab[j] > 0).sum()) == kp and len(j) == kp + min(128 - kp, nneg)
+            gi = np.maximum(lab[j] - 1, 0)
+            assert np.array_equal(tl, np.where(lab[j] > 0, N(gt_labels[i])[gi], 0))
+            assert np.array_equal(tb, N(gt_bboxes[i])[:, gi]) and np.array_equal(tg, (j < K).astype(np.int64))
+            want = N(butils.bbox2param(T(tp), T(tb), (0., 0., 0., 0.), (0.1, 0.1, 0.2, 0.2)))
+            np.testing.assert_allclose(tpar, want, rtol=1e-5, atol=1e-6)
+        if first is None:
+            first = [N(t) for t in res[0]]
+        elif plist is props:
+            assert any(a.shape != N(b).shape or not np.array_equal(a, N(b)) for a, b in zip(first, res[0])), \
+                "the sampler stream did not advance between two calls"
+    # host-RNG sampler: not covered, the per-image loop is used
+    cfg_np = refpath._Cfg(assigner=seq.rcnn_assigner, sampler=bregion.RandomSampler(128, 32, rng="numpy"))
+    assert batched.bbox_targets_fast(seq.rcnn_head, props, gt_bboxes, gt_labels, cfg_np) is None
+    loop = batched.bbox_head_bbox_targets(seq.rcnn_head, props, gt_bboxes, gt_labels, cfg_np)
+    assert len(loop) == 5 and loop[0][0].shape[0] == 4
+
+
+def test_batched_anchor_targets_are_differentiable_and_equal_the_per_image_semantics():
+    """batched.anchor_head_targets (the target part of AnchorHead.loss): the gradient of tar_cls_out marks the sampled
+    anchors; per image they are inside anchors with labels >= 0 of the reference assignment, in ascending order, with
+    the sampler's cardinalities, and tar_label / tar_param / tar_reg_out are what anchor_target returns for them."""
+    from b200det import batched, anchor as banchor
+    refpath, strides, cls, reg, feats, gt_bboxes, gt_labels, metas = _loop_inputs(K=(3, 6, 1))
+    seq = refpath.BatchedCallSequence(strides, DEV, rpn_sampler=dict(max_num=64, pos_num=16))
+    cls = [c.clone().requires_grad_(True) for c in cls]
+    reg = [r.clone().requires_grad_(True) for r in reg]
+    ones = [torch.full_like(l, 1) for l in gt_labels]
+    tc, tr, tl, tp = batched.anchor_head_targets(seq.head, cls, reg, gt_bboxes, ones, metas, seq.rpn_train_cfg)
+    assert tc.shape[0] == 1 and tr.shape[0] == 4 and tc.shape[1] == tr.shape[1] == tl.shape[0] == tp.shape[1]
+    (tc.sum() + 2.0 * tr.sum()).backward()
+    grids = [tuple(int(v) for v in c.shape[-2:]) for c in cls]
+    anchors = torch.cat([a.view(4, -1) for a in seq.create_anchors(grids)], dim=1)
+    off = 0
+    for i in range(3):
+        g_cls = torch.cat([c.grad[i].reshape(1, -1) for c in cls], dim=1)[0]
+        g_reg = torch.cat([r.grad[i].reshape(4, -1) for r in reg], dim=1)
+        chosen = torch.nonzero(g_cls).view(-1)
+        assert torch.equal(g_cls[chosen], torch.ones_like(g_cls[chosen])) and torch.equal(torch.nonzero(g_reg[0]).view(-1), chosen)
+        hw = metas[i]['img_shape'][:2]
+        in_mask = bregion.inside_anchor_mask(anchors, hw, 0) & torch.cat(
+            [bregion.inside_grid_mask(3, hw, grids[l], st, DEV) for l, st in enumerate(strides)]).bool()
+        lab_in, _ = seq.rpn_assigner(anchors[:, in_mask], gt_bboxes[i])
+        lab = torch.full((anchors.shape[1],), -1, dtype=torch.int64, device=DEV)
+        lab[in_mask] = lab_in
+        lc = lab[chosen]
+        assert bool((lc >= 0).all())
+        npos, nneg = int((lab > 0).sum()), int((lab == 0).sum())
+        kp = min(npos, 16)
+        n = kp + min(64 - kp, nneg)
+        assert int((lc > 0).sum()) == kp and chosen.numel() == n
+        sl = slice(off, off + n)
+        assert torch.equal(tl[sl], (lc > 0).to(torch.int64))
+        gi = (lc - 1).clamp(min=0)
+        want = butils.bbox2param(anchors[:, chosen], gt_bboxes[i][:, gi], (0., 0., 0., 0.), (1., 1., 1., 1.))
+        np.testing.assert_allclose(N(tp[:, sl]), N(want), rtol=1e-5, atol=1e-6)
+        reg_flat = torch.cat([r[i].reshape(4, -1) for r in reg], dim=1)
+        assert torch.equal(tr[:, sl].detach(), reg_flat[:, chosen].detach())
+        off += n
+    assert off == tl.numel()
+    # a RetinaNet-style call (no sampler) is not covered: None -> the reference loop
+    assert batched.anchor_head_targets(seq.head, cls, reg, gt_bboxes, ones, metas, refpath._Cfg(assigner=seq.rpn_assigner)) is None
+
+
+def test_batched_call_sequence_runs_the_whole_forward_train_path():
+    from b200det import refpath
+    rp, strides, cls, reg, feats, gt_bboxes, gt_labels, metas = _loop_inputs()
+    seqb = refpath.BatchedCallSequence(strides, DEV)
+    out = seqb.step(cls, reg, feats, gt_bboxes, gt_labels, metas)
+    n = sum(int(t.shape[1]) for t in out["rcnn_targets"][0])
+    rois = out["roi_feats"]
+    rois = torch.cat(list(rois)) if isinstance(rois, (list, tuple)) else rois
+    assert rois.shape[0] == n and rois.shape[1:] == (16, 7, 7) and bool(torch.isfinite(rois).all())
