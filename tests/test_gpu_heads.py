@@ -797,6 +797,7 @@ def test_batched_predict_bboxes_from_output_equals_the_per_image_loop():
     # not covered (per-image size filter with different scale factors): the caller keeps the reference loop
     metas2 = [dict(m, scale_factor=1.0 + 0.1 * i) for i, m in enumerate(metas)]
     assert batched.rpn_predict_fast(seq.head, cls, reg, metas2, refpath._Cfg(seq.rpn_proposal, min_bbox_size=4)) is None
+    seq.head.predict_single_image = lambda *a: bheads.rpn_predict_single_image(seq.head, *a)     # the head's (rebound) method
     loop = batched.rpn_predict_bboxes_from_output(seq.head, cls, reg, metas2, refpath._Cfg(seq.rpn_proposal, min_bbox_size=4))
     assert len(loop[0]) == 3 and loop[0][0].shape[0] == 4
 
