@@ -871,7 +871,7 @@ int b2d_sample_labels(int* chosen, int* n_chosen, const int64_t* labels, long lo
                 "sample_labels: need 1 <= max_num <= 4096 and pos_num <= max_num");
     B2D_REQUIRE(n < (1ll << 31), "sample_labels: n too large");
     // function attributes are per device: set on every call (a process may drive several GPUs)
-    cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSortCap * 8);
+    B2D_SMEM(k_sample, kSampleSortCap * 8, "k_sample");
     k_sample<<<B, kSampleThreads, kSampleSortCap * 8, (cudaStream_t)stream>>>(
         chosen, n_chosen, labels, ld, count, count_add, n, census, pos_list, pos_cap, max_num, pos_num, seed, seed_step);
     return check_launch("sample_labels");

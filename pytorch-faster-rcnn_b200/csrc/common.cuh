@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "../../include/b200det.h"
 
@@ -40,6 +41,23 @@ struct Knobs {
     int debug_sync;        // B2D_DEBUG_SYNC     synchronise after every launch (localise a faulting kernel)
 };
 const Knobs& knobs();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) with its return code checked (set on every call: it is per device)
+template <typename K>
+inline int set_dyn_smem(K kern, size_t bytes, const char* what) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) return 0;
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s: cudaFuncSetAttribute(%zu B of dynamic shared memory): %s", what, bytes, cudaGetErrorString(e));
+    b2d::set_error(buf);
+    (void)cudaGetLastError();
+    return (int)e;
+}
+#define B2D_SMEM(kern, bytes, what)                          \
+    do {                                                     \
+        const int rc_ = b2d::set_dyn_smem(kern, bytes, what); \
+        if (rc_) return rc_;                                 \
+    } while (0)
 
 #define B2D_REQUIRE(cond, msg)            \
     do {                                  \

@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(1024) k_nms_cut(RpnLaunch p, int M, int zero_c
 
 int rpn_nms_cut_launch(const RpnLaunch& p, int M, cudaStream_t st) {
     const size_t smem = (size_t)p.sel_per_img * 4;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_nms_cut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
+    if (smem > 48 * 1024) B2D_SMEM(k_nms_cut, smem, "k_nms_cut");   // per device
     const int zero_ctas = rpn_nms_sweep_active(p) ? 148 : 0;
     k_nms_cut<<<p.B + zero_ctas, 1024, smem, st>>>(p, M, zero_ctas);
     return check_launch("rpn_nms_cut");
@@ -841,7 +841,7 @@ int b2d_nms(int64_t* keep, int* keep_count, const float* boxes, const float* sco
     uint64_t* mask = (uint64_t*)base; base += al((size_t)S * n_ld * wp * 8);
     int* cnt = (int*)base; base += al((size_t)S * 4);
     uint32_t* nz = (uint32_t*)base;
-    cudaFuncSetAttribute(k_nms_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);   // per device
+    B2D_SMEM(k_nms_sort, kSortCap * 8, "k_nms_sort");   // per device
     if (counts) cudaMemcpyAsync(cnt, counts, sizeof(int) * S, cudaMemcpyDeviceToDevice, st);
     else k_fill_i32<<<cdiv(S, 256), 256, 0, st>>>(cnt, (int)n, S);
     k_nms_sort<<<S, kSelThreads, kSortCap * 8, st>>>(sorted_box, sorted_idx, (const float4*)boxes, scores, n_ld, cnt, n,

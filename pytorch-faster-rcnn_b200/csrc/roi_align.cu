@@ -554,9 +554,10 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
         a.pf_dist = knobs().roi_pf;
         // bulk store of the result tile: needs 16-byte multiples (tile bytes and its offset in the output)
         a.bulk_store = knobs().roi_bulk_store && ((128ll * bins * 4) % 16 == 0) && (((long long)c.C * bins * 4) % 16 == 0) ? 1 : 0;   // dev knob (L2 prefetch: measured slower, r1)
+        int rc5 = 0;
         auto launch5 = [&](auto kern, int nt, int ct) {
             const size_t smem5 = (size_t)ct * bins * 4 + (size_t)bins * sizeof(BinTab) + 64;
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
+            if ((rc5 = set_dyn_smem(kern, smem5, "k_roi_align_win")) != 0) return;
             const int tiles = cdiv(c.C, ct);
             a.tiles = (knobs().roi_order == 1 && R * tiles < (1ll << 31)) ? tiles : 0;
             dim3 grid(a.tiles ? (unsigned)(R * tiles) : (unsigned)R, a.tiles ? 1u : (unsigned)tiles);
@@ -570,13 +571,14 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
         if (c.layout == 1 && knobs().roi_x2 != 0) launch5(k_roi_align_win<float, 128, 128, 6, 4, 1>, 128, 128);
         else if (c.layout == 1) launch5(k_roi_align_win<float, 128, 128, 6, 4>, 128, 128);
         else launch5(k_roi_align_win<__nv_bfloat16, 128, 128, 6, 4>, 128, 128);
+        if (rc5) return rc5;
     } else if (fast) {
         const size_t smem = (size_t)bins * (kCTile + 4) * 4;
         if (c.layout == 1) {
-            cudaFuncSetAttribute(k_roi_align_nhwc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
+            B2D_SMEM(k_roi_align_nhwc<float>, smem, "k_roi_align_nhwc");   // per device
             k_roi_align_nhwc<float><<<(unsigned)R, 256, smem, st>>>(a, out);
         } else {
-            cudaFuncSetAttribute(k_roi_align_nhwc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            B2D_SMEM(k_roi_align_nhwc<__nv_bfloat16>, smem, "k_roi_align_nhwc");
             k_roi_align_nhwc<__nv_bfloat16><<<(unsigned)R, 256, smem, st>>>(a, out);
         }
     } else {

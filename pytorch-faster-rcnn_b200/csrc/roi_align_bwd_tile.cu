@@ -309,7 +309,7 @@ int roi_align_bwd_tile_try(void* const* grad_feat_ptrs_host, const float* grad_o
     a.gout = grad_out; a.meta = meta; a.bucket = bucket; a.bcount = bcount; a.R = R;
     dim3 grid((unsigned)(run * B), (unsigned)(c.C / kCg));
     const size_t smem = 2 * sizeof(float) * kMaxBinsT * kPitch + 2 * kTablesBytes;
-    cudaFuncSetAttribute(k_roi_align_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
+    B2D_SMEM(k_roi_align_bwd_tile, smem, "k_roi_align_bwd_tile");   // per device
     k_roi_align_bwd_tile<<<grid, kBT, smem, st>>>(a);
     return check_launch("roi_align_bwd(tile)");
 }

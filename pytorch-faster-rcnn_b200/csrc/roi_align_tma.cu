@@ -452,8 +452,8 @@ int roi_align_tma_try(const RoiArgs& a, float* out, cudaStream_t st) {
     int sms = 0, dev = 0;                                  // per device, every call (a process may drive several GPUs)
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(k_roi_align_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(k_roi_align_tma<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    B2D_SMEM(k_roi_align_tma<float>, 227 * 1024, "k_roi_align_tma");
+    B2D_SMEM(k_roi_align_tma<__nv_bfloat16>, 227 * 1024, "k_roi_align_tma");
     if (sms <= 0) sms = 1;
     const unsigned grid = (unsigned)(a.R < sms ? a.R : sms);
     RoiArgs b = a;

@@ -603,10 +603,7 @@ int rpn_back_launch(const RpnLaunch& p, int cut_m, float* props, float* scores, 
         for (int i = 0; i < 4; ++i) { t.f.ms[i] = tg->means[i]; t.f.ms[4 + i] = tg->stds[i]; }
         t.labels = tg->labels; t.out_iou = tg->max_iou; t.census = tg->census; t.pos_list = tg->pos_list; t.pos_cap = tg->pos_cap;
     }
-    if (cudaFuncSetAttribute(k_rpn_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
+    if (set_dyn_smem(k_rpn_back, smem, "k_rpn_back") != 0) return 0;      // (error text set; the caller falls back to the multi-kernel chain)
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(kBkCl, (unsigned)p.B, 1);

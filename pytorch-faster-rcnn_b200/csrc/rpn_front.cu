@@ -519,10 +519,7 @@ int rpn_front_launch(const RpnLaunch& p, cudaStream_t st, cudaStream_t side, cud
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return 0;
-    if (cudaFuncSetAttribute(k_rpn_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
+    if (set_dyn_smem(k_rpn_front, smem, "k_rpn_front") != 0) return 0;    // (error text set; the caller falls back to the multi-kernel chain)
     if (ok_dev[dev] == 0) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));

@@ -687,8 +687,8 @@ static int rpn_proposals_impl(float* props, float* scores, int* count, int* prov
     if (p.dbg != 10) p.dbg_t = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     // function attributes are per device: set on every call (a process may drive several GPUs)
-    cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
-    cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
+    B2D_SMEM(k_select, kSortCap * 8, "k_select");
+    B2D_SMEM(k_merge, kSortCap * 8, "k_merge");
     int nl = 0;                                           // launches (kernels + memset nodes) of this call
     // Per-level chains.  hist -> compact -> select -> NMS mask -> scan of one level only depends on that level, and
     // all of them but the mask are small latency-bound grids; run as ONE launch per kernel over all levels the step
@@ -874,7 +874,7 @@ int b2d_topk(int* idx, int* out_count, const float* values, long long ld, const 
     B2D_REQUIRE(idx && out_count && values && S >= 1 && k >= 1, "topk: bad args");
     cudaStream_t st = (cudaStream_t)stream;
     if (n <= kSortCap) {
-        cudaFuncSetAttribute(k_topk_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);   // per device
+        B2D_SMEM(k_topk_small, kSortCap * 8, "k_topk_small");   // per device
         k_topk_small<<<S, kSelThreads, kSortCap * 8, st>>>(idx, out_count, values, ld, counts, n, k);
         return check_launch("topk");
     }
@@ -888,7 +888,7 @@ int b2d_topk(int* idx, int* out_count, const float* values, long long ld, const 
     B2D_REQUIRE(rpn_plan(p, &pyr, S, &cfg, (char*)workspace, &need), "topk: unsupported size");
     B2D_REQUIRE(workspace && ws_bytes >= need, "topk: workspace too small");
     p.cls[0] = values; p.reg[0] = nullptr; p.img_hw = nullptr; p.raw = 1;
-    cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);   // per device
+    B2D_SMEM(k_select, kSortCap * 8, "k_select");   // per device
     cudaMemsetAsync(workspace, 0, p.zero_bytes, st);
     dim3 grid(cdiv(n, kChunk), S);
     k_hist<<<grid, kHcThreads, 0, st>>>(p);

@@ -806,3 +806,53 @@ def test_roi_targets_as_tail_of_the_proposal_kernel_equal_the_separate_launch(mo
         snaps.append([s.copy() for s in snap])
     for a, b in zip(*snaps):
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+# ------------------------------------------------------------------ support limits, AT the limits
+def test_topk_at_the_16384_cap_and_one_above():
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal(50000).astype(np.float32)
+    idx = N(bregion.topk_desc(T(v), 16384))
+    want = np.argsort(-v, kind="stable")[:16384]
+    assert np.array_equal(idx, want)
+    from b200det import _C
+    with pytest.raises(_C.B200DetError):
+        bregion.topk_desc(T(v), 16385)
+
+
+def test_nms_at_the_16384_box_cap_and_one_above():
+    """utils.nms: the kernel up to NMS_MAX_BOXES = 16384 boxes, torchvision above it -- both equal to the oracle."""
+    rng = np.random.default_rng(6)
+    for n in (butils.NMS_MAX_BOXES, butils.NMS_MAX_BOXES + 1):
+        xy = rng.uniform(0, 900, (n, 2)).astype(np.float32)
+        wh = rng.uniform(8, 120, (n, 2)).astype(np.float32)
+        boxes = np.concatenate([xy, xy + wh], axis=1)
+        scores = rng.permutation(n).astype(np.float32) / n
+        keep = N(butils.nms(T(boxes), T(scores), 0.5))
+        want = oracle.nms(boxes, scores, 0.5)
+        assert np.array_equal(keep, want), n
+
+
+@pytest.mark.parametrize("B", [256, 257])
+@pytest.mark.parametrize("knobs", [{}, {"B2D_RPN_FRONT": "0", "B2D_RPN_BACK": "0"}])
+def test_rpn_proposals_at_the_1024_segment_cap(B, knobs, setknob):
+    """B * levels = 1024 is the largest segment table of the item-walking NMS kernels (kItemSegs); 1028 takes the other
+    route.  Tiny 4-level pyramid, every image its own scores; images 0, B/2, B-1 against the oracle."""
+    setknob(**knobs)
+    rng = np.random.default_rng(B)
+    grids, strides = [(12, 16), (6, 8), (3, 4), (2, 2)], (4, 8, 16, 32)
+    pyr = fused.AnchorPyramid(strides, grids)
+    cls = [rng.normal(0, 1, (B, 3) + g).astype(np.float32) for g in grids]
+    reg = [rng.normal(0, 0.2, (B, 12) + g).astype(np.float32) for g in grids]
+    cfg = dict(pre_nms=200, post_nms=100, max_num=150, nms_iou=0.7, min_bbox_size=0)
+    rp = fused.RpnProposals(pyr, B, cfg, [0, 0, 0, 0], [1, 1, 1, 1], DEV)
+    props, scores, count = rp([T(c) for c in cls], [T(r) for r in reg], torch.tensor([[48.0, 64.0]] * B, device=DEV))
+    torch.cuda.synchronize()
+    anc = [oracle.anchor_grid(s, gr, scales=[8]).reshape(4, -1) for s, gr in zip(strides, grids)]
+    offs = np.cumsum([0] + [a.shape[1] for a in anc])
+    for b in (0, B // 2, B - 1):
+        _, _, lv, ix = oracle.rpn_proposals([c[b].reshape(-1) for c in cls], [r[b].reshape(4, -1) for r in reg], anc, cfg,
+                                            [0, 0, 0, 0], [1, 1, 1, 1], (48, 64))
+        n = int(count[b])
+        assert n == lv.shape[0], (B, b)
+        assert np.array_equal(N(rp.prov[b, :n]), offs[lv] + ix), (B, b)
