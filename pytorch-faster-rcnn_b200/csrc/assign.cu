@@ -789,6 +789,7 @@ __global__ void __launch_bounds__(kSmallThreads) k_roi_targets_small(AssignArgs 
                                                                      int pos_cap, FusedArgs f) {
     __shared__ SmallSmem sm;
     __shared__ FusedScratch fs;
+    pdl_wait();                                         // the proposals (no-op unless launched as a programmatic dependent)
     assign_small_body(p, sm, labels, out_iou, census, pos_list, pos_cap, fs.lab);
     fused_sample_encode(p, f, sm.gt, fs, sm.cnt[0], sm.cnt[1], blockIdx.x);
 }
@@ -949,7 +950,20 @@ int b2d_roi_targets_fused(int64_t* labels, float* max_iou, long long out_ld, con
     f.gt_label = gt_label;
     f.tar_box = tar_box; f.tar_gt = tar_gt; f.tar_param = tar_param; f.tar_label = tar_label; f.tar_is_gt = tar_is_gt;
     for (int i = 0; i < 4; ++i) { f.ms[i] = means_host ? means_host[i] : 0.0f; f.ms[4 + i] = stds_host ? stds_host[i] : 1.0f; }
-    k_roi_targets_small<<<B, kSmallThreads, 0, (cudaStream_t)stream>>>(a, labels, max_iou, census, pos_list, pos_cap, f);
+    if (knobs().pdl) {
+        // set up while the stream predecessor (the proposal kernel, which calls pdl_launch_dependents) still runs
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)B, 1, 1); cfg.blockDim = dim3(kSmallThreads, 1, 1); cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, k_roi_targets_small, a, labels, max_iou, census, pos_list, pos_cap, f);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
+    } else {
+        k_roi_targets_small<<<B, kSmallThreads, 0, (cudaStream_t)stream>>>(a, labels, max_iou, census, pos_list, pos_cap, f);
+    }
     return check_launch("roi_targets_fused");
 }
 

@@ -39,6 +39,7 @@ struct Knobs {
     int roi_bwd_tile;      // B2D_ROI_BWD_TILE   0: generic backward kernel
     int assign_old;        // B2D_ASSIGN_OLD     1: round-1a assignment kernels in pyramid mode
     int debug_sync;        // B2D_DEBUG_SYNC     synchronise after every launch (localise a faulting kernel)
+    int pdl;               // B2D_PDL            1: programmatic dependent launch edges front -> back -> RoI targets (default 0)
 };
 const Knobs& knobs();
 
@@ -58,6 +59,13 @@ inline int set_dyn_smem(K kern, size_t bytes, const char* what) {
         const int rc_ = b2d::set_dyn_smem(kern, bytes, what); \
         if (rc_) return rc_;                                 \
     } while (0)
+
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// become resident while its stream predecessor still runs, once every CTA of the predecessor has executed
+// pdl_launch_dependents() (or exited); pdl_wait() blocks until the predecessor has COMPLETED and its writes are visible.
+// Both are no-ops for a kernel that was launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 #define B2D_REQUIRE(cond, msg)            \
     do {                                  \

@@ -106,6 +106,8 @@ __device__ __forceinline__ int count_before(const uint32_t* k, int n, uint32_t k
 }
 
 __global__ void __launch_bounds__(kBkThreads, 1) k_rpn_back(RpnLaunch p, BackArgs a) {
+    pdl_wait();                                         // the selection kernel's lists (no-op unless launched as its programmatic dependent)
+    pdl_launch_dependents();                            // the RoI-target kernel behind us may be set up now
     cg::cluster_group cl = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char s_raw[];
     BkShared& s = *reinterpret_cast<BkShared*>(s_raw);
@@ -610,10 +612,12 @@ int rpn_back_launch(const RpnLaunch& p, int cut_m, float* props, float* scores, 
     cfg.blockDim = dim3(kBkThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kBkCl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = knobs().pdl ? 2 : 1;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, k_rpn_back, p, a);
     if (e != cudaSuccess) {
         set_error(cudaGetErrorString(e));

@@ -142,6 +142,7 @@ __device__ void group_select(cg::cluster_group& cl, FrShared& s, bool work, int 
 }
 
 __global__ void __launch_bounds__(kFrThreads, 1) k_rpn_front(RpnLaunch p, FrontPlan fp) {
+    pdl_launch_dependents();                            // k_rpn_back may be set up while this kernel runs (it waits for our completion)
     cg::cluster_group cl = cg::this_cluster();
     extern __shared__ __align__(16) uint64_t s_buf[];   // [0, cap): the owner's candidate list; [cap, 2 cap): local staging
     __shared__ FrShared s;

@@ -40,6 +40,10 @@ orders = {
     "img,level,morton": np.lexsort((morton(cx, cy), lv, im)),
     "level,img,y,x": np.lexsort((cx, cy.astype(int), im, lv)),
     "random": np.random.default_rng(0).permutation(r.shape[1]),
+    # longest-processing-time-first: the cost of a CTA grows with the window size, i.e. with the RoI's size in cells
+    "cells desc (LPT)": np.argsort(-((r[2] - r[0]) / stride) * ((r[3] - r[1]) / stride), kind="stable"),
+    "cells asc": np.argsort(((r[2] - r[0]) / stride) * ((r[3] - r[1]) / stride), kind="stable"),
+    "img, cells desc": np.lexsort((-((r[2] - r[0]) / stride) * ((r[3] - r[1]) / stride), im)),
 }
 cfg = hp.roi_align.cfg
 outbuf = torch.empty((r.shape[1], 256, 7, 7), device=dev)
