@@ -4,6 +4,7 @@ dropin.install() can rebind the loops themselves and not only the functions they
   rpn_predict_bboxes_from_output   AnchorHead.predict_bboxes_from_output  lib/heads/anchor_head.py:268-289  (on RPNHead)
   bbox_head_bbox_targets           BBoxHead.bbox_targets                  lib/heads/bbox_head.py:47-52
   anchor_head_targets / _loss      AnchorHead.loss (the target part)      lib/heads/anchor_head.py:152-199
+  bbox_head_refine_bboxes          BBoxHead.refine_bboxes                 lib/heads/bbox_head.py:94-96   (cascade stage loop)
 
 Each one packs its per-image arguments into the image-major batch layout of fused.py, runs the batched kernels once
 (one host synchronisation per call, for the ragged result sizes) and hands back exactly the per-image lists the
@@ -287,3 +288,57 @@ def anchor_head_loss(self, cls_outs, reg_outs, gt_bboxes, gt_labels, img_metas, 
             raise _C.B200DetError("anchor_head_loss: call not covered by the batched path and no reference loop given")
         return reference_loss(self, cls_outs, reg_outs, gt_bboxes, gt_labels, img_metas, train_cfg)
     return self.calc_loss(*tars, train_cfg)
+
+
+# ------------------------------------------------------------------------------------------------ cascade refinement
+def refine_bboxes_fast(self, props, labels, reg_outs, is_gts=None, img_metas=None):
+    """BBoxHead.refine_bboxes (multi_apply over refine_bboxes_single_image, lib/heads/bbox_head.py:94-120) for all
+    images in one b2d_refine_bboxes launch: per image the non-GT columns, decoded with the stage's means / stds and
+    clamped to img_shape.  Returns the list of [4, s_i - #gt_i] tensors, or None when the call is not covered."""
+    B = len(props)
+    if B == 0 or not _all_cuda_f32(props, reg_outs) or len(labels) != B or len(reg_outs) != B:
+        return None
+    if img_metas is not None and (not isinstance(img_metas, list) or len(img_metas) != B):
+        return None
+    if is_gts is not None and (not isinstance(is_gts, list) or len(is_gts) != B):
+        return None
+    dev = props[0].device
+    C = 1 if self.reg_class_agnostic else int(self.num_classes)
+    if any(int(r.shape[1]) != 4 * C or int(r.shape[0]) != int(p.shape[1]) for r, p in zip(reg_outs, props)):
+        return None
+    pk, ns = _pack_cols(props)
+    ld = int(pk.shape[2])
+    pad = lambda t, n: t if int(t.shape[0]) == ld else F.pad(t, (0, 0) * (t.dim() - 1) + (0, ld - n))
+    lab = torch.stack([pad(l.to(torch.int64).view(-1), n) for l, n in zip(labels, ns)]).contiguous()
+    reg = torch.stack([pad(r, n) for r, n in zip(reg_outs, ns)]).contiguous()
+    gtf = None
+    if is_gts is not None:
+        gtf = torch.stack([pad(g.to(torch.int64).view(-1), n) for g, n in zip(is_gts, ns)]).contiguous()
+    counts = _upload_i32(ns, dev)
+    out = torch.empty((B, 4, ld), dtype=torch.float32, device=dev)
+    out_count = torch.empty(B, dtype=torch.int32, device=dev)
+    clamp = img_metas is not None
+    hw = _img_hw(img_metas, dev) if clamp else None
+    with torch.no_grad():
+        _C.call("b2d_refine_bboxes", _C.ptr(out), _C.ptr(out_count), _C.ptr(pk), ld, _C.ptr(counts), ld, _C.ptr(lab),
+                _C.ptr(reg), C, _C.ptr(gtf), _C.host_f4(self.target_means, [0, 0, 0, 0]),
+                _C.host_f4(self.target_stds, [1, 1, 1, 1]), int(clamp), _C.ptr(hw), B, _C.stream())
+        no = out_count.tolist() if gtf is not None else ns   # the one synchronisation (only when GT columns are dropped)
+    res = []
+    for i, n in enumerate(no):
+        r = out[i][:, :n]
+        r._b2d_batch = (out, out_count if gtf is not None else counts, i, B)
+        res.append(r)
+    return res
+
+
+def bbox_head_refine_bboxes(self, props, labels, reg_outs, is_gts=None, img_metas=None):
+    """Method form of BBoxHead.refine_bboxes."""
+    out = refine_bboxes_fast(self, props, labels, reg_outs, is_gts, img_metas)
+    if out is not None:
+        return out
+    from . import heads
+    nb = len(props)
+    is_gts = is_gts if isinstance(is_gts, list) else [is_gts] * nb
+    img_metas = img_metas if isinstance(img_metas, list) else [img_metas] * nb
+    return [heads.refine_bboxes_single_image(self, p, l, r, g, m) for p, l, r, g, m in zip(props, labels, reg_outs, is_gts, img_metas)]

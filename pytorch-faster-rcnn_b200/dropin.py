@@ -148,6 +148,13 @@ def install(lib=None, channels_last=False):
             return out if out is not None else ref_bbox_targets(self, img_props, gt_bboxes, gt_labels, train_cfg)
 
         _set(bh.BBoxHead, "bbox_targets", _bbox_targets)
+        ref_refine = bh.BBoxHead.refine_bboxes
+
+        def _refine(self, props, labels, reg_outs, is_gts=None, img_metas=None):
+            out = batched.refine_bboxes_fast(self, props, labels, reg_outs, is_gts, img_metas)
+            return out if out is not None else ref_refine(self, props, labels, reg_outs, is_gts, img_metas)
+
+        _set(bh.BBoxHead, "refine_bboxes", _refine)
     necks = sys.modules.get("lib.necks")
     if channels_last and necks is not None and hasattr(necks, "FPN"):
         _channels_last_fpn(necks)

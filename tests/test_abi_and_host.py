@@ -148,6 +148,7 @@ def test_dropin_install_rebinds_reference_names():
     try:
         # the per-image loops themselves (batched.py)
         assert ah.AnchorHead.loss is not ref_loss and bh.BBoxHead.bbox_targets is not ref_tars
+        assert bh.BBoxHead.refine_bboxes.__name__ == "_refine"
         assert rh.RPNHead.predict_bboxes_from_output is not ref_pred
         assert ah.AnchorHead.predict_bboxes_from_output is ref_pred          # only the RPN head's loop is rebound
         assert rb.MODULES["MaxIoUAssigner"] is b200det.region.MaxIoUAssigner

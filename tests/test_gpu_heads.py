@@ -913,3 +913,33 @@ def test_batched_call_sequence_runs_the_whole_forward_train_path():
     rois = out["roi_feats"]
     rois = torch.cat(list(rois)) if isinstance(rois, (list, tuple)) else rois
     assert rois.shape[0] == n and rois.shape[1:] == (16, 7, 7) and bool(torch.isfinite(rois).all())
+
+
+def test_batched_refine_bboxes_equals_the_per_image_loop():
+    """batched.refine_bboxes_fast (bound onto BBoxHead.refine_bboxes, the cascade stage loop's last step): ragged
+    per-image lists, GT columns dropped, per-class deltas -- image by image what refine_bboxes_single_image returns."""
+    from b200det import batched
+    rng = np.random.default_rng(31)
+    me = types.SimpleNamespace(reg_class_agnostic=False, num_classes=21, target_means=[0.0] * 4, target_stds=[0.05, 0.05, 0.1, 0.1])
+    ns = (512, 300, 417)
+    props, labels, regs, gts, metas = [], [], [], [], []
+    for i, n in enumerate(ns):
+        xy = rng.uniform(0, 500, (2, n)); wh = rng.uniform(8, 200, (2, n))
+        props.append(T(np.concatenate([xy, xy + wh]).astype(np.float32)))
+        labels.append(T(rng.integers(0, 21, n).astype(np.int64)))
+        regs.append(T((0.3 * rng.standard_normal((n, 84))).astype(np.float32)))
+        g = np.zeros(n, np.int64); g[:5 + i] = 1
+        gts.append(T(g)); metas.append(dict(img_shape=(600 + 10 * i, 800 - 7 * i, 3)))
+    out = batched.refine_bboxes_fast(me, props, labels, regs, gts, metas)
+    assert out is not None and len(out) == 3
+    for i in range(3):
+        want = bheads.refine_bboxes_single_image(me, props[i], labels[i], regs[i], gts[i], metas[i])
+        assert out[i].shape == want.shape == (4, ns[i] - 5 - i) and torch.equal(out[i], want)
+    # class-agnostic, no GT flags, no clamp
+    me2 = types.SimpleNamespace(reg_class_agnostic=True, num_classes=21, target_means=[0.0] * 4, target_stds=[0.1, 0.1, 0.2, 0.2])
+    regs4 = [r[:, :4].contiguous() for r in regs]
+    out2 = batched.refine_bboxes_fast(me2, props, labels, regs4, None, None)
+    for i in range(3):
+        assert torch.equal(out2[i], bheads.refine_bboxes_single_image(me2, props[i], labels[i], regs4[i], None, None))
+    # the refined proposals feed the next stage's batched bbox_targets without re-packing
+    assert out[0]._b2d_batch[0] is out[1]._b2d_batch[0]
