@@ -99,8 +99,10 @@ class ClockSampler(threading.Thread):
     def summary(self):
         rows = self.rows
         inside = [r for r in rows if self.window and self.window[0] <= r[0] <= self.window[1]]
-        use = inside
-        if not use and self.window and rows:             # the region is a few ms: fall back to the samples closest to it
+        lw = getattr(self, "load_window", None)
+        loaded = [r for r in rows if lw and lw[0] <= r[0] <= lw[1]]      # timed region + the untimed continuation of the same load
+        use = inside or loaded
+        if not use and self.window and rows:             # fall back to the samples closest to the region
             mid = 0.5 * (self.window[0] + self.window[1])
             use = sorted(rows, key=lambda r: abs(r[0] - mid))[:8]
         if not use:
@@ -109,7 +111,9 @@ class ClockSampler(threading.Thread):
         mx = [r[2] for r in use]
         reasons = sorted({k for r in use for k in r[3]})
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(sm), samples_in_timed_region=len(inside), source="nvml" if self.nvml is not None else "nvidia-smi")
+                    samples=len(sm), samples_in_timed_region=len(inside), samples_under_load=len(loaded),
+                    mean_sample_interval_ms=(1e3 * (rows[-1][0] - rows[0][0]) / max(len(rows) - 1, 1)) if len(rows) > 1 else None,
+                    source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 def touched_cell_bytes(rois_b4n, counts, grids, strides, C, finest=56.0):
@@ -320,9 +324,14 @@ def run_b200(args):
     def run_all():
         run_step()
 
+    # wake the clock sampler BEFORE the region and wait until it is spinning: on boxes with a coarse timer its 0.5 ms idle
+    # sleep lasts longer than the whole timed region (seen: 0 samples inside although a query takes 3 us)
+    sampler.spin = True
+    n_rows, t_wake = len(sampler.rows), time.perf_counter()
+    while len(sampler.rows) < n_rows + 3 and time.perf_counter() - t_wake < 0.5:
+        time.sleep(0.001)
     barrier()
     t_host0 = time.perf_counter()
-    sampler.spin = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -331,9 +340,21 @@ def run_b200(args):
         torch.cuda.current_stream().wait_stream(s_comm)                 # the last gather ends inside the timed region
     e1.record()
     barrier()
-    sampler.spin = False
     sampler.window = (t_host0, time.perf_counter())
     ms = e0.elapsed_time(e1)
+    # The timed region is a few milliseconds; where an NVML query takes longer than that (box-dependent) no sample can
+    # fall inside it.  The identical load is therefore kept up, UNTIMED, for another ~60 ms while the sampler keeps
+    # spinning; those samples are reported separately (clocks.samples_under_load) and only used when the region has none.
+    t_load0 = time.perf_counter()
+    while time.perf_counter() - t_load0 < 0.06:
+        for _ in range(args.steps):
+            run_all()
+        torch.cuda.synchronize()
+    if world > 1:
+        torch.cuda.current_stream().wait_stream(s_comm)
+    barrier()
+    sampler.spin = False
+    sampler.load_window = (t_host0, time.perf_counter())
     # ---- the same step fed with the reference layout: fp32 NCHW features -> b2d_nchw_to_nhwc (4 launches) -> step
     nhwc_buf = [torch.empty_like(f, memory_format=torch.channels_last) for f in feats_nchw]
 
