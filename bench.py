@@ -343,10 +343,9 @@ def run_b200(args):
     sampler.window = (t_host0, time.perf_counter())
     ms = e0.elapsed_time(e1)
     # The timed region is a few milliseconds; where an NVML query takes longer than that (box-dependent) no sample can
-    # fall inside it.  The identical load is therefore kept up, UNTIMED, for another ~60 ms while the sampler keeps
+    # fall inside it.  The identical load is therefore kept up, UNTIMED, for ~240 more steps while the sampler keeps
     # spinning; those samples are reported separately (clocks.samples_under_load) and only used when the region has none.
-    t_load0 = time.perf_counter()
-    while time.perf_counter() - t_load0 < 0.06:
+    for _ in range(max(1, 240 // max(args.steps, 1))):   # a FIXED count (every rank issues the same collectives): ~240 more steps
         for _ in range(args.steps):
             run_all()
         torch.cuda.synchronize()
