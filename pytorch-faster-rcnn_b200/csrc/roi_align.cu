@@ -547,7 +547,11 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
         // TMA-ring kernel (roi_align_tma.cu): opt-in with B2D_ROI_TMA=1.  Bit-identical, but measured slower than
         // the L1-path kernel below on config 2 (380 vs 159 us, round 1: issue-bound consumers).
         const int use_tma = knobs().roi_tma;
-        if (use_tma) {
+        if (use_tma == 2) {                               // tensor-map band kernel (roi_align_tband.cu)
+            const int nimg = batched_ld > 0 ? (int)(R / batched_ld) : (1 << 20);     // image-index bound of the 4-D tensor map
+            const int rc = roi_align_tband_try(a, out, nimg, st);
+            if (rc != 1) return rc;
+        } else if (use_tma) {
             const int rc = roi_align_tma_try(a, out, st);
             if (rc != 1) return rc;
         }

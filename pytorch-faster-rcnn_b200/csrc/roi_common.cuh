@@ -79,5 +79,7 @@ __device__ __forceinline__ RoiGeom roi_geom(float x1, float y1, float x2, float 
 // not eligible (the caller then uses the L1-path kernels of roi_align.cu).
 struct RoiArgs;
 int roi_align_tma_try(const RoiArgs& a, float* out, cudaStream_t st);
+// tensor-map TMA band kernel (roi_align_tband.cu): same contract; B = images in the feature tensors (upper bound)
+int roi_align_tband_try(const RoiArgs& a, float* out, int B, cudaStream_t st);
 
 }  // namespace b2d
