@@ -5,6 +5,7 @@ dropin.install() can rebind the loops themselves and not only the functions they
   bbox_head_bbox_targets           BBoxHead.bbox_targets                  lib/heads/bbox_head.py:47-52
   anchor_head_targets / _loss      AnchorHead.loss (the target part)      lib/heads/anchor_head.py:152-199
   bbox_head_refine_bboxes          BBoxHead.refine_bboxes                 lib/heads/bbox_head.py:94-96   (cascade stage loop)
+  anchor_head_predict_fast         AnchorHead.predict_bboxes_from_output  lib/heads/anchor_head.py:268-289  (dense heads, test path)
 
 Each one packs its per-image arguments into the image-major batch layout of fused.py, runs the batched kernels once
 (one host synchronisation per call, for the ragged result sizes) and hands back exactly the per-image lists the
@@ -342,3 +343,55 @@ def bbox_head_refine_bboxes(self, props, labels, reg_outs, is_gts=None, img_meta
     is_gts = is_gts if isinstance(is_gts, list) else [is_gts] * nb
     img_metas = img_metas if isinstance(img_metas, list) else [img_metas] * nb
     return [heads.refine_bboxes_single_image(self, p, l, r, g, m) for p, l, r, g, m in zip(props, labels, reg_outs, is_gts, img_metas)]
+
+
+# ------------------------------------------------------------------------------------------------ dense-head test path
+def anchor_head_predict_fast(self, cls_outs, reg_outs, img_metas, test_cfg):
+    """AnchorHead.predict_bboxes_from_output for a dense (RetinaNet-style) head: the per-level best-class top-k, decode,
+    clamp and size filter of ALL images as one batched K3 call (b2d_rpn_proposals, score_mode 2 / 3, do_nms 0); the class
+    scores of the selected anchors are gathered per image and go through utils.multiclass_nms (one library call per
+    image, as in heads.anchor_head_predict_single_image).  Returns [[bbox [4,k]]*B, [score [k]]*B, [label [k]]*B] or None."""
+    from . import utils
+    B = len(img_metas)
+    cf = _closed_form(self, len(cls_outs))
+    if cf is None or B == 0 or not _all_cuda_f32(cls_outs, reg_outs) or int(cls_outs[0].shape[0]) != B:
+        return None
+    sfs = [float(m.get('scale_factor', 1.0)) for m in img_metas]
+    min_bbox = float(_get(test_cfg, 'min_bbox_size', 0) or 0)
+    if min_bbox > 0 and any(s != sfs[0] for s in sfs):
+        return None
+    strides, scales, ratios, center_lt = cf
+    dev = cls_outs[0].device
+    C = int(self.cls_channels)
+    grids = tuple(tuple(int(v) for v in c.shape[-2:]) for c in cls_outs)
+    key = (B, grids, int(_get(test_cfg, 'pre_nms', 0)), min_bbox, sfs[0], str(dev), C, bool(self.use_sigmoid))
+    cache = _cache(self, '_b2d_pred_batch_cache')
+    rp = cache.get(key)
+    if rp is None:
+        pyr = fused.AnchorPyramid(strides, grids, scales, ratios, center_lt)
+        sel_cfg = dict(pre_nms=int(_get(test_cfg, 'pre_nms', 0)), post_nms=0, max_num=0, nms_iou=0.5, min_bbox_size=min_bbox)
+        try:
+            rp = fused.RpnProposals(pyr, B, sel_cfg, self.target_means, self.target_stds, dev,
+                                    score_mode=2 if self.use_sigmoid else 3, cls_channels=C, do_nms=False, scale_factor=sfs[0])
+        except _C.B200DetError:
+            return None
+        cache[key] = rp
+    cls, reg = [c.contiguous() for c in cls_outs], [r.contiguous() for r in reg_outs]
+    with torch.no_grad():
+        props, _, count = rp(cls, reg, _img_hw(img_metas, dev))
+        ns = count.tolist()                               # the one synchronisation of the selection
+        flat = torch.cat([c.reshape(B, C, -1) for c in cls], dim=2)              # [B, C, total] logits
+    if self.use_sigmoid:
+        label_set, adjust = list(range(0, self.num_classes - 1)), 1
+    else:
+        label_set, adjust = list(range(1, self.num_classes)), 0
+    out = [[], [], []]
+    for i, n in enumerate(ns):
+        boxes = props[i][:, :n]
+        picked = flat[i].index_select(1, rp.prov[i, :n].to(torch.int64))
+        score = picked.sigmoid() if self.use_sigmoid else picked.softmax(dim=0)
+        kb, ks, kl = utils.multiclass_nms(boxes.t().contiguous(), score.t().contiguous(), label_set, _get(test_cfg, 'nms_iou'),
+                                          _get(test_cfg, 'min_score'), _get(test_cfg, 'max_per_img'),
+                                          mode=_get(test_cfg, 'nms_type', 'official'))
+        out[0].append(kb.t()); out[1].append(ks); out[2].append(kl + adjust)
+    return out

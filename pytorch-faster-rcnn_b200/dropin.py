@@ -133,6 +133,16 @@ def install(lib=None, channels_last=False):
 
         _set(rh.RPNHead, "predict_bboxes_from_output", _predict_all)
     if ah and hasattr(ah, "AnchorHead"):
+        ref_predict_dense = ah.AnchorHead.predict_bboxes_from_output
+
+        def _predict_dense(self, cls_outs, reg_outs, img_metas, test_cfg):
+            # RPNHead has its own binding above; GA-RPN / other subclasses with their own predict_single_image keep the loop
+            out = None
+            if type(self).predict_single_image is heads.anchor_head_predict_single_image:
+                out = batched.anchor_head_predict_fast(self, cls_outs, reg_outs, img_metas, test_cfg)
+            return out if out is not None else ref_predict_dense(self, cls_outs, reg_outs, img_metas, test_cfg)
+
+        _set(ah.AnchorHead, "predict_bboxes_from_output", _predict_dense)
         ref_loss = ah.AnchorHead.loss
 
         def _loss(self, cls_outs, reg_outs, gt_bboxes, gt_labels, img_metas, train_cfg):

@@ -150,7 +150,7 @@ def test_dropin_install_rebinds_reference_names():
         assert ah.AnchorHead.loss is not ref_loss and bh.BBoxHead.bbox_targets is not ref_tars
         assert bh.BBoxHead.refine_bboxes.__name__ == "_refine"
         assert rh.RPNHead.predict_bboxes_from_output is not ref_pred
-        assert ah.AnchorHead.predict_bboxes_from_output is ref_pred          # only the RPN head's loop is rebound
+        assert ah.AnchorHead.predict_bboxes_from_output is not ref_pred      # dense heads: batched selection
         assert rb.MODULES["MaxIoUAssigner"] is b200det.region.MaxIoUAssigner
         assert rb.MODULES["RoIAlign"] is b200det.region.RoIAlign
         assert ah.anchor_target is b200det.anchor.anchor_target

@@ -943,3 +943,30 @@ def test_batched_refine_bboxes_equals_the_per_image_loop():
         assert torch.equal(out2[i], bheads.refine_bboxes_single_image(me2, props[i], labels[i], regs4[i], None, None))
     # the refined proposals feed the next stage's batched bbox_targets without re-packing
     assert out[0]._b2d_batch[0] is out[1]._b2d_batch[0]
+
+
+@pytest.mark.parametrize("use_sigmoid", [True, False])
+def test_batched_dense_head_predict_equals_the_per_image_loop(use_sigmoid):
+    """batched.anchor_head_predict_fast (bound onto AnchorHead.predict_bboxes_from_output for dense heads): image by image
+    exactly what the loop over anchor_head_predict_single_image returns (3 images of different sizes, 9 anchors x 6
+    classes, per-level top-300, official multiclass NMS)."""
+    from b200det import batched, anchor as banchor
+    rng = np.random.default_rng(41)
+    strides, scales, ratios = [8, 16, 32], [4, 4 * 2 ** (1 / 3), 4 * 2 ** (2 / 3)], [0.5, 1.0, 2.0]
+    grids = [(40, 52), (20, 26), (10, 13)]
+    C, B = (6, 3) if use_sigmoid else (7, 3)
+    creators = [banchor.AnchorCreator(base=s, scales=scales, aspect_ratios=ratios) for s in strides]
+    head = types.SimpleNamespace(anchor_strides=strides, anchor_scales=scales, anchor_ratios=ratios, target_means=[0.0] * 4,
+                                 target_stds=[1.0] * 4, use_sigmoid=use_sigmoid, cls_channels=C,
+                                 num_classes=C + 1 if use_sigmoid else C, anchor_creators=creators)
+    cls = [T(rng.standard_normal((B, 9 * C) + g).astype(np.float32) * 2.0 - 1.0) for g in grids]
+    reg = [T((0.3 * rng.standard_normal((B, 36) + g)).astype(np.float32)) for g in grids]
+    metas = [dict(img_shape=(300 + 9 * i, 400 - 11 * i, 3), scale_factor=1.0) for i in range(B)]
+    cfg = dict(pre_nms=300, min_bbox_size=0, min_score=0.3, nms_iou=0.5, max_per_img=100)
+    out = batched.anchor_head_predict_fast(head, cls, reg, metas, cfg)
+    assert out is not None and len(out) == 3 and len(out[0]) == B
+    anchors = [torch.empty((4, 9) + g, device=DEV) for g in grids]
+    for i in range(B):
+        b, s, l = bheads.anchor_head_predict_single_image(head, [c[i] for c in cls], [r[i] for r in reg], anchors, metas[i], cfg)
+        assert b.shape[1] > 5
+        assert torch.equal(out[0][i], b) and torch.equal(out[1][i], s) and torch.equal(out[2][i], l)
