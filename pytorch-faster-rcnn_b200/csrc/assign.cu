@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(kSampleThreads) k_sample(int* __restrict__ cho
             __syncthreads();
             if (threadIdx.x == 0) {
                 int tot = 0;
-                for (int w = 0; w < kSampleThreads / 32; ++w) tot += s_warp[w];
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_warp[w];
                 if (tot >= pos_num) s_hi = mid; else s_lo = mid + 1;
             }
             __syncthreads();
@@ -644,6 +644,41 @@ __global__ void __launch_bounds__(kSampleThreads) k_sample(int* __restrict__ cho
         const long long dom = 1ll << bits;
         if (threadIdx.x == 0) s_take = 0;
         __syncthreads();
+        if (blockDim.x <= 256) {
+            // slim launch (128 threads: a CTA that fits the hole one retiring RoIAlign CTA leaves, see fused.TrainHotPath):
+            // 4 permutation steps per thread and round, so that 4 label loads are in flight per thread; same order by t
+            __shared__ int s_cnt4[4][8];
+            const int nw = blockDim.x >> 5, wq = threadIdx.x >> 5;
+            for (long long t0 = 0; t0 < dom; t0 += 4ll * blockDim.x) {
+                uint32_t y[4];
+                bool hit[4];
+                unsigned m[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const long long t = t0 + (long long)q * blockDim.x + threadIdx.x;
+                    y[q] = feistel((uint32_t)t, half, sd ^ 0xA5A5A5A5DEADBEEFull);
+                    hit[q] = t < dom && ((long long)y[q] < n_b) && (lab[y[q]] == 0);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    m[q] = __ballot_sync(0xffffffffu, hit[q]);
+                    if (lane_id() == 0) s_cnt4[q][wq] = __popc(m[q]);
+                }
+                __syncthreads();
+                int before = s_take, tot = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int mine = before + tot;
+                    for (int w = 0; w < nw; ++w) { if (w < wq) mine += s_cnt4[q][w]; tot += s_cnt4[q][w]; }
+                    const int rank = mine + __popc(m[q] & ((1u << lane_id()) - 1u));
+                    if (hit[q] && rank < want_neg) s_sort[keep_pos + rank] = (uint64_t)y[q];
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) s_take += tot;
+                __syncthreads();
+                if (s_take >= want_neg) break;
+            }
+        } else
         for (long long t0 = 0; t0 < dom; t0 += blockDim.x) {
             const uint32_t y = feistel((uint32_t)(t0 + threadIdx.x), half, sd ^ 0xA5A5A5A5DEADBEEFull);
             const bool hit = ((long long)y < n_b) && (lab[y] == 0);
@@ -658,7 +693,7 @@ __global__ void __launch_bounds__(kSampleThreads) k_sample(int* __restrict__ cho
             __syncthreads();
             if (threadIdx.x == 0) {
                 int tot = 0;
-                for (int w = 0; w < kSampleThreads / 32; ++w) tot += s_warp[w];
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_warp[w];
                 s_take += tot;
             }
             __syncthreads();
@@ -873,7 +908,8 @@ int b2d_sample_labels(int* chosen, int* n_chosen, const int64_t* labels, long lo
     B2D_REQUIRE(n < (1ll << 31), "sample_labels: n too large");
     // function attributes are per device: set on every call (a process may drive several GPUs)
     B2D_SMEM(k_sample, kSampleSortCap * 8, "k_sample");
-    k_sample<<<B, kSampleThreads, kSampleSortCap * 8, (cudaStream_t)stream>>>(
+    const int threads = (knobs().sample_threads == 128 || knobs().sample_threads == 256) ? knobs().sample_threads : kSampleThreads;
+    k_sample<<<B, threads, kSampleSortCap * 8, (cudaStream_t)stream>>>(
         chosen, n_chosen, labels, ld, count, count_add, n, census, pos_list, pos_cap, max_num, pos_num, seed, seed_step);
     return check_launch("sample_labels");
 }

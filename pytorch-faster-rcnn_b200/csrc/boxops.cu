@@ -42,6 +42,7 @@ static void load_knobs() {
     k.roi_tma_dev = geti("B2D_ROI_TMA_DEV", 0);
     k.roi_bwd_tile = geti("B2D_ROI_BWD_TILE", 1);
     k.assign_old = getenv("B2D_ASSIGN_OLD") != nullptr;
+    k.sample_threads = geti("B2D_SAMPLE_THREADS", 1024);
     k.pdl = geti("B2D_PDL", 0);           // measured r2: 258 vs 250 us per step with the edges on
     k.debug_sync = getenv("B2D_DEBUG_SYNC") != nullptr;
     g_knobs = k;

@@ -39,6 +39,7 @@ struct Knobs {
     int roi_bwd_tile;      // B2D_ROI_BWD_TILE   0: generic backward kernel
     int assign_old;        // B2D_ASSIGN_OLD     1: round-1a assignment kernels in pyramid mode
     int debug_sync;        // B2D_DEBUG_SYNC     synchronise after every launch (localise a faulting kernel)
+    int sample_threads;    // B2D_SAMPLE_THREADS 128 / 256: slim k_sample CTAs (default 1024)
     int pdl;               // B2D_PDL            1: programmatic dependent launch edges front -> back -> RoI targets (default 0)
 };
 const Knobs& knobs();

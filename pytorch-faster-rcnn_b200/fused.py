@@ -174,7 +174,8 @@ class BatchedTargets(object):
     def slice(self, b0, b1):
         return _batch_view(self, b0, b1)
 
-    def __call__(self, gt, gt_count, gt_label=None, boxes=None, box_count=None, img_hw=None):
+    def __call__(self, gt, gt_count, gt_label=None, boxes=None, box_count=None, img_hw=None, tail_stream=None):
+        """tail_stream: optional stream for the sampler + encode kernels (they start when the assignment is done)."""
         pyr = ctypes.byref(self.pyr.c) if boxes is None else None
         box_ld = boxes.shape[-1] if boxes is not None else 0
         if self.auto_bump:
@@ -197,6 +198,15 @@ class BatchedTargets(object):
         cnt, cnt_add = (box_count, gt_count) if (self.prepend and box_count is not None) else \
             ((None, gt_count) if self.prepend else (box_count, None))
         n = self.N if cnt is None else 0
+        if tail_stream is not None:
+            tail_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(tail_stream):
+                self._sample_encode(cnt, cnt_add, n, base_seed, boxes, box_ld, pyr, gt, gt_count, gt_label)
+            return self
+        self._sample_encode(cnt, cnt_add, n, base_seed, boxes, box_ld, pyr, gt, gt_count, gt_label)
+        return self
+
+    def _sample_encode(self, cnt, cnt_add, n, base_seed, boxes, box_ld, pyr, gt, gt_count, gt_label):
         _C.call("b2d_sample_labels", _C.ptr(self.chosen), _C.ptr(self.n_chosen), _C.ptr(self.labels), self.out_ld,
                 _C.ptr(cnt), _C.ptr(cnt_add), n, _C.ptr(self.census), _C.ptr(self.pos_list), self.out_ld, self.B,
                 self.max_num, self.pos_num, base_seed, _C.ptr(self.step_cell), _C.stream())
@@ -299,6 +309,11 @@ class TrainHotPath(object):
             # while the proposal chains sit in hist / compact / select (latency-bound, ~50 us, SMs idle): lowest
             # priority (the small critical kernels always get their SM slots) but enqueued first, see step()
             self.s_rpn = torch.cuda.Stream(device=device, priority=int(os.environ.get("B2D_RPN_PRIO", "0")))
+            # optional: the sampler / encode / gather tail of the RPN-target chain on its own stream ABOVE RoIAlign in
+            # priority (B2D_RPN_TAIL_PRIO, e.g. -5), with slim sampler CTAs (B2D_SAMPLE_THREADS=128) that fit the hole a
+            # retiring RoIAlign CTA leaves -- so that the tail is not starved when RoIAlign starts before K2 has finished
+            tp = os.environ.get("B2D_RPN_TAIL_PRIO", "")
+            self.s_tail = torch.cuda.Stream(device=device, priority=int(tp)) if tp else None
         self.launches = 0
 
     def reset_step(self):
@@ -306,9 +321,14 @@ class TrainHotPath(object):
         self.step_cell.fill_(1)
 
     def _rpn_target_chain(self, cls_outs, reg_outs, gt, gt_count, img_hw):
-        rt = self.rpn_targets(gt, gt_count, None, img_hw=img_hw)
-        _C.call("b2d_gather_head_outputs", _C.ptr(self.tar_cls), _C.ptr(self.tar_reg), _ptrs(cls_outs), _ptrs(reg_outs),
-                ctypes.byref(self.pyr.c), 1, _C.ptr(rt.chosen), _C.ptr(rt.n_chosen), rt.max_num, self.B, _C.stream())
+        tail = getattr(self, "s_tail", None)
+        rt = self.rpn_targets(gt, gt_count, None, img_hw=img_hw, tail_stream=tail)
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(tail if tail is not None else cur):
+            _C.call("b2d_gather_head_outputs", _C.ptr(self.tar_cls), _C.ptr(self.tar_reg), _ptrs(cls_outs), _ptrs(reg_outs),
+                    ctypes.byref(self.pyr.c), 1, _C.ptr(rt.chosen), _C.ptr(rt.n_chosen), rt.max_num, self.B, _C.stream())
+        if tail is not None:
+            cur.wait_stream(tail)                        # the chain's stream ends where its tail ends (joins below see both)
         return rt
 
     def step(self, cls_outs, reg_outs, feats, gt, gt_count, gt_label, img_hw, feats_ready=None, records=None):

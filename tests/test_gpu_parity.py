@@ -628,9 +628,11 @@ def test_targets_numpy_rng_mode_vs_reference():
     assert np.array_equal(N(bregion.IoUBalancedNegSampler(256, 64, rng="numpy")(T(g["rs_in"]), T(g["ib_iou"]), None, None)), g["ib_out"])
 
 
-@pytest.mark.parametrize("n,max_num,pos_num", [(3000, 256, 64), (3000, 256, 2000), (100, 256, 128), (20000, 512, 128)])
-def test_device_sampler_matches_its_spec_and_properties(n, max_num, pos_num):
+@pytest.mark.parametrize("threads", ["1024", "128"])
+@pytest.mark.parametrize("n,max_num,pos_num", [(3000, 256, 64), (3000, 256, 2000), (100, 256, 128), (20000, 512, 128), (268569, 256, 128)])
+def test_device_sampler_matches_its_spec_and_properties(n, max_num, pos_num, threads, setknob):
     from oracle import sampler_spec
+    setknob(B2D_SAMPLE_THREADS=threads)                  # 128: the slim CTA form (4 permutation steps per thread and round)
     rng = np.random.default_rng(n + max_num)
     labels = rng.choice([-1, 0, 0, 0, 1, 2, 3], n).astype(np.int64)
     pos_num = min(pos_num, max_num)
