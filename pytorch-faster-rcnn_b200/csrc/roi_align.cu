@@ -275,8 +275,13 @@ __global__ void __launch_bounds__(NT, MINB) k_roi_align_win(RoiArgs a, float* __
     static_assert(!X2 || (sizeof(FT) == 4 && V == 4), "packed path: fp32 features, 4 channels per lane");
     using Tab = BinTab;
     extern __shared__ __align__(16) float s_tile[];                      // [CT][bins] (+ bin table behind it)
-    const long long r = a.tiles > 0 ? blockIdx.x / a.tiles : blockIdx.x;
+    long long r = a.tiles > 0 ? blockIdx.x / a.tiles : blockIdx.x;
     const int tile = a.tiles > 0 ? blockIdx.x % a.tiles : blockIdx.y;
+    if (a.sel_m > 1) {                                  // heterogeneous split: this kernel takes the RoIs with r % m != 0
+        const long long q = r / (a.sel_m - 1);
+        r = q * a.sel_m + 1 + (r - q * (a.sel_m - 1));
+        if (r >= a.R) return;
+    }
     const b2d_roi_cfg& c = a.cfg;
     float x1, y1, x2, y2;
     int img;
@@ -547,11 +552,31 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
         // TMA-ring kernel (roi_align_tma.cu): opt-in with B2D_ROI_TMA=1.  Bit-identical, but measured slower than
         // the L1-path kernel below on config 2 (380 vs 159 us, round 1: issue-bound consumers).
         const int use_tma = knobs().roi_tma;
+        cudaStream_t side = nullptr;
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+        bool hetero = false;
         if (use_tma == 2) {                               // tensor-map band kernel (roi_align_tband.cu)
             const int nimg = batched_ld > 0 ? (int)(R / batched_ld) : (1 << 20);     // image-index bound of the 4-D tensor map
             const int rc = roi_align_tband_try(a, out, nimg, st);
             if (rc != 1) return rc;
-        } else if (use_tma) {
+        } else if (use_tma == 3 && c.layout == 1 && R >= 64 && roi_hetero_streams(&side, &ev_fork, &ev_join)) {
+            // heterogeneous: one persistent tensor-map CTA per SM (97 KB of shared memory, 24 K registers) takes every m-th
+            // RoI; the window kernel below takes the others and finds room for 4 CTAs beside it (smem-bound in-flight
+            // bytes + register-bound in-flight bytes on the same SM)
+            const int m = knobs().roi_tma_dev >= 2 ? knobs().roi_tma_dev : 4;
+            const int nimg = batched_ld > 0 ? (int)(R / batched_ld) : (1 << 20);
+            int sms = 148, dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            RoiArgs t = a;
+            t.sel_m = m;
+            cudaEventRecord(ev_fork, st);
+            cudaStreamWaitEvent(side, ev_fork, 0);
+            const int rc = roi_align_tband_try(t, out, nimg, side, sms);
+            if (rc == B2D_OK) { a.sel_m = m; hetero = true; }
+            else if (rc != 1) return rc;
+            cudaEventRecord(ev_join, side);
+        } else if (use_tma == 1) {
             const int rc = roi_align_tma_try(a, out, st);
             if (rc != 1) return rc;
         }
@@ -564,8 +589,9 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
             if ((rc5 = set_dyn_smem(kern, smem5, "k_roi_align_win")) != 0) return;
             const int tiles = cdiv(c.C, ct);
             a.tiles = (knobs().roi_order == 1 && R * tiles < (1ll << 31)) ? tiles : 0;
-            dim3 grid(a.tiles ? (unsigned)(R * tiles) : (unsigned)R, a.tiles ? 1u : (unsigned)tiles);
-            kern<<<grid, nt, smem5, st>>>(a, out);
+            const long long Rw = a.sel_m > 1 ? R - (R + a.sel_m - 1) / a.sel_m : R;       // RoIs of this kernel
+            dim3 grid(a.tiles ? (unsigned)(Rw * tiles) : (unsigned)Rw, a.tiles ? 1u : (unsigned)tiles);
+            if (Rw > 0) kern<<<grid, nt, smem5, st>>>(a, out);
         };
         // 128 threads x 4 channels = 128 channels per CTA, 6 CTAs/SM: fastest of the measured
         // (threads, channels/CTA, CTAs/SM, channels/thread) points -- (256,256,2,4) 200 us,
@@ -576,6 +602,7 @@ static int roi_align_launch(float* out, const void* const* feat_ptrs_host, const
         else if (c.layout == 1) launch5(k_roi_align_win<float, 128, 128, 6, 4>, 128, 128);
         else launch5(k_roi_align_win<__nv_bfloat16, 128, 128, 6, 4>, 128, 128);
         if (rc5) return rc5;
+        if (hetero) cudaStreamWaitEvent(st, ev_join, 0);
     } else if (fast) {
         const size_t smem = (size_t)bins * (kCTile + 4) * 4;
         if (c.layout == 1) {

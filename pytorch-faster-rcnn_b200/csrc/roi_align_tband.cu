@@ -151,12 +151,16 @@ __global__ void __launch_bounds__(kTbThreads, 2) k_roi_align_tband(RoiArgs a, co
     int* s_rows = reinterpret_cast<int*>(s_tab + bins);                  // [PH][4] feature rows of the band, [PH] counts behind
     int* s_nrows = s_rows + 8 * 4;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_nrows + 8);          // full[4], empty[4]   (8-byte aligned: offsets are multiples of 16)
-    const long long r = blockIdx.x;
-    const int tile = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles = c.C / kTbCT, step = a.sel_m > 1 ? a.sel_m : 1;
+    const long long n_units = ((a.R + step - 1) / step) * tiles;
+    // one unit = (RoI, channel tile); an ordinary launch has one CTA per unit, the heterogeneous launch one CTA per SM
+    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const long long r = (unit / tiles) * step;
+    const int tile = (int)(unit % tiles);
     float x1, y1, x2, y2;
     int img;
-    if (!roi_fetch(a, r, img, x1, y1, x2, y2)) return;
+    if (!roi_fetch(a, r, img, x1, y1, x2, y2)) continue;
     int lvl;
     if (a.levels) lvl = a.levels[r];
     else lvl = c.num_levels > 1 ? roi_level(x1, y1, x2, y2, c.finest_scale, c.num_levels) : 0;
@@ -274,6 +278,9 @@ __global__ void __launch_bounds__(kTbThreads, 2) k_roi_align_tband(RoiArgs a, co
                      "r"((unsigned)(kTbCT * bins * 4)) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        for (int k = 0; k < 8; ++k) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(s_bar + k)) : "memory");
+    }
+    __syncthreads();                                     // tile, tables and barriers are reused by the next unit
     }
 }
 
@@ -295,7 +302,27 @@ static EncodeFn encode_fn() {
 }  // namespace
 
 // returns B2D_OK if it handled the launch, 1 if the configuration is not eligible
-int roi_align_tband_try(const RoiArgs& a, float* out, int B, cudaStream_t st) {
+bool roi_hetero_streams(cudaStream_t* side, cudaEvent_t* fork, cudaEvent_t* join) {
+    struct Set { cudaStream_t s; cudaEvent_t f, j; bool made, ok; };
+    static Set table[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    Set& t = table[dev];
+    if (!t.made) {
+        t.made = true;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        t.ok = cudaStreamCreateWithPriority(&t.s, cudaStreamNonBlocking, hi) == cudaSuccess &&
+               cudaEventCreateWithFlags(&t.f, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&t.j, cudaEventDisableTiming) == cudaSuccess;
+        if (!t.ok) cudaGetLastError();
+    }
+    if (!t.ok) return false;
+    *side = t.s; *fork = t.f; *join = t.j;
+    return true;
+}
+
+int roi_align_tband_try(const RoiArgs& a, float* out, int B, cudaStream_t st, int persistent_ctas) {
     const b2d_roi_cfg& c = a.cfg;
     const int bins = c.PH * c.PW;
     if (c.layout != 1 || c.sampling_ratio != 2 || bins > kMaxBinsTb || c.PH > 8 || (c.C % kTbCT) != 0 || B < 1) return 1;
@@ -319,7 +346,9 @@ int roi_align_tband_try(const RoiArgs& a, float* out, int B, cudaStream_t st) {
     }
     const size_t smem = (size_t)kRingBytes + (size_t)kTbCT * bins * 4 + (size_t)bins * sizeof(TbBin) + (8 * 4 + 8) * 4 + 8 * 8 + 64;
     B2D_SMEM(k_roi_align_tband, smem, "k_roi_align_tband");
-    dim3 grid((unsigned)a.R, (unsigned)(c.C / kTbCT));
+    const int step = a.sel_m > 1 ? a.sel_m : 1;
+    const long long n_units = ((a.R + step - 1) / step) * (c.C / kTbCT);
+    const unsigned grid = (unsigned)(persistent_ctas > 0 && persistent_ctas < n_units ? persistent_ctas : n_units);
     k_roi_align_tband<<<grid, kTbThreads, smem, st>>>(a, maps, out);
     return check_launch("roi_align_fwd(tband)");
 }

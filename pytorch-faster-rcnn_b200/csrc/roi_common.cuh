@@ -17,6 +17,7 @@ struct RoiArgs {
     int tiles;                     // window kernel: > 0 = 1-D grid, channel tiles of a RoI adjacent (bid = r * tiles + tile)
     int pf_dist;                   // window kernel: L2-prefetch the RoI pf_dist CTAs ahead (0 = off)
     int bulk_store;                // window kernel: result tile leaves as one cp.async.bulk store
+    int sel_m;                     // > 1: heterogeneous split -- the tensor-map kernel takes the RoIs r % sel_m == 0, the window kernel the others
 };
 
 // slot r -> (image, coordinates); false if the slot is past the image's count
@@ -80,6 +81,8 @@ __device__ __forceinline__ RoiGeom roi_geom(float x1, float y1, float x2, float 
 struct RoiArgs;
 int roi_align_tma_try(const RoiArgs& a, float* out, cudaStream_t st);
 // tensor-map TMA band kernel (roi_align_tband.cu): same contract; B = images in the feature tensors (upper bound)
-int roi_align_tband_try(const RoiArgs& a, float* out, int B, cudaStream_t st);
+int roi_align_tband_try(const RoiArgs& a, float* out, int B, cudaStream_t st, int persistent_ctas = 0);
+// side stream + fork / join events for the heterogeneous launch (created once per device); false if unavailable
+bool roi_hetero_streams(cudaStream_t* side, cudaEvent_t* fork, cudaEvent_t* join);
 
 }  // namespace b2d

@@ -463,11 +463,12 @@ def _ring_case(seed, C, K, B=2):
     return grids, feats, rois, img
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("mode", ["1", "2", "3"])
 @pytest.mark.parametrize("C,K", [(256, 700), (128, 333)])
 def test_roi_align_tma_ring_bit_exact_vs_oracle(C, K, mode, setknob):
     """The two opt-in TMA forms of K5 -- 1: bulk-copy row ring (roi_align_tma.cu), 2: tensor-map band kernel
-    (roi_align_tband.cu, cp.async.bulk.tensor.4d / UTMALDG; RoIs wider than 16 cells take its in-kernel window path)."""
+    (roi_align_tband.cu, cp.async.bulk.tensor.4d / UTMALDG; RoIs wider than 16 cells take its in-kernel window path),
+    3: heterogeneous launch (a persistent band CTA per SM takes every m-th RoI beside the window kernel)."""
     setknob(B2D_ROI_TMA=mode)                                             # opt-in kernels
     grids, feats, rois, img = _ring_case(11, C, K)
     fs = [T(f).contiguous(memory_format=torch.channels_last) for f in feats]
