@@ -329,6 +329,21 @@ B2D_API int b2d_nchw_to_nhwc(float* dst, const float* src, int B, int C, int H, 
 B2D_API int b2d_roi_levels(int* levels, const float* rois, long long roi_ld, long long R, float finest_scale,
                    int num_levels, void* stream);
 
+/* ---- sparse host -> device feature transfer for the RoI extractor (csrc/roi_fetch.cu).
+ * BasicRoIExtractor (lib/region.py:299-375) reads only the cells under the bilinear taps of the RoIs.  When the
+ * pyramid is channels-last in PINNED (mapped) HOST memory, b2d_roi_mark_cells writes a bitmap with one bit per
+ * (level, image, y, x) -- levels in order, each padded to whole 32-bit words, b2d_roi_cell_bitmap_bytes in total --
+ * holding the tap rectangle of every RoI (rois [B][4][ld], counts int32[B], as b2d_roi_align_fwd_batched; the same
+ * level map and sample geometry, so every cell RoIAlign reads is marked), and b2d_fetch_marked_cells copies the
+ * marked cells from src (device-visible pointers of the host tensors, [B,H,W,C] per level) to the same offsets of
+ * dst (device tensors of the same shape) with SM-issued loads; *moved_cells (device, may be NULL) is incremented by
+ * the number of cells copied.  Needs cfg.layout 1 or 2 and a fixed sampling_ratio. */
+B2D_API size_t b2d_roi_cell_bitmap_bytes(int B, const b2d_roi_cfg* cfg_host);
+B2D_API int b2d_roi_mark_cells(void* bitmap, const float* rois, long long ld, const int* counts, int B,
+                       const b2d_roi_cfg* cfg_host, void* stream);
+B2D_API int b2d_fetch_marked_cells(void* const* dst_ptrs_host, const void* const* src_ptrs_host, const void* bitmap,
+                           int B, const b2d_roi_cfg* cfg_host, unsigned long long* moved_cells, void* stream);
+
 /* ---- K7: RoIPool (torchvision.ops.roi_pool semantics), single level, NCHW fp32.
  * argmax int32 [R,C,PH,PW] (index into the H*W plane, -1 = empty). */
 B2D_API int b2d_roi_pool_fwd(float* out, int* argmax, const float* feat, int B, int C, int H, int W, const float* rois,

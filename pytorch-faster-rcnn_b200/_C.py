@@ -106,6 +106,8 @@ _SIGS = {
     "b2d_sample_iou_balanced": [_P, _P, _P, c_ll, c_int, c_int, c_int, _P, _P, c_ull, _P],
     "b2d_sampled_ce_fwd": [_P, _P, c_ll, c_int, c_int, c_int, _P, c_ll, _P],
     "b2d_sampled_ce_bwd": [_P, _P, _P, c_ll, c_int, c_int, c_int, _P, c_ll, _P],
+    "b2d_roi_mark_cells": [_P, _P, c_ll, _P, c_int, _P, _P],
+    "b2d_fetch_marked_cells": [_P, _P, _P, c_int, _P, _P, _P],
     "b2d_roi_pool_bwd": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_ll, _P, c_ll, c_float, c_int, c_int, _P,
                          c_size_t, _P],
 }
@@ -120,6 +122,7 @@ _SIZE_FNS = {
     "b2d_anchor_loss_workspace_bytes": [_P, c_int],
     "b2d_multiclass_nms_workspace_bytes": [c_int],
     "b2d_sampled_ce_workspace_bytes": [],
+    "b2d_roi_cell_bitmap_bytes": [c_int, _P],
 }
 EXPORTS = sorted(list(_SIGS) + list(_SIZE_FNS) + ["b2d_last_error_string", "b2d_version", "b2d_reload_knobs", "b2d_last_launch_count"])
 

@@ -25,6 +25,15 @@ def _ptrs(tensors):
     return arr
 
 
+def pinned_channels_last(t):
+    """Pinned host copy of a [B,C,H,W] tensor in channels_last memory format (NHWC strides): the host-side layout
+    TrainHotPath.step_from_host fetches sparsely."""
+    B, C, H, W = t.shape
+    h = torch.empty((B, H, W, C), dtype=t.dtype, pin_memory=True).permute(0, 3, 1, 2)
+    h.copy_(t)
+    return h
+
+
 def _batch_view(obj, b0, b1, rows_per_image=None):
     """Shallow copy of a batched stage object restricted to images [b0, b1): every tensor
     attribute is re-sliced along dim 0 (views, no copies), so a sub-batch can run on its own
@@ -240,6 +249,24 @@ class BatchedRoIAlign(object):
                 self.B, ctypes.byref(self.cfg), _C.stream())
         return self.out
 
+    def fetch_touched(self, dev_feats, host_feats, rois, counts):
+        """Bring the cells these RoIs read -- and only those -- from channels-last PINNED HOST feature maps into the
+        device maps (b2d_roi_mark_cells + b2d_fetch_marked_cells, csrc/roi_fetch.cu): 59 % of the pyramid at config 2.
+        Returns the device counter of cells moved so far (cumulative)."""
+        if not hasattr(self, "_bitmap"):
+            n = _C.lib().b2d_roi_cell_bitmap_bytes(self.B, ctypes.byref(self.cfg))
+            self._bitmap = torch.zeros(n, dtype=torch.uint8, device=self.out.device)
+            self.cells_moved = torch.zeros(1, dtype=torch.int64, device=self.out.device)
+        for d, h in zip(dev_feats, host_feats):
+            if not (h.is_pinned() and d.is_cuda and d.shape == h.shape and d.dtype == h.dtype and d.stride() == h.stride()
+                    and h.is_contiguous(memory_format=torch.channels_last)):
+                raise _C.B200DetError("fetch_touched: host maps must be pinned channels_last tensors matching the device maps")
+        _C.call("b2d_roi_mark_cells", _C.ptr(self._bitmap), _C.ptr(rois), self.ld, _C.ptr(counts), self.B,
+                ctypes.byref(self.cfg), _C.stream())
+        _C.call("b2d_fetch_marked_cells", _ptrs(dev_feats), _ptrs(host_feats), _C.ptr(self._bitmap), self.B,
+                ctypes.byref(self.cfg), _C.ptr(self.cells_moved), _C.stream())
+        return self.cells_moved
+
 
 class TrainHotPath(object):
     """faster_rcnn_r50_fpn train path (BASELINE config 2): RPN proposals (K3+K4), RPN
@@ -331,10 +358,12 @@ class TrainHotPath(object):
             cur.wait_stream(tail)                        # the chain's stream ends where its tail ends (joins below see both)
         return rt
 
-    def step(self, cls_outs, reg_outs, feats, gt, gt_count, gt_label, img_hw, feats_ready=None, records=None):
+    def step(self, cls_outs, reg_outs, feats, gt, gt_count, gt_label, img_hw, feats_ready=None, records=None,
+             before_roi_align=None):
         """One pass of the hot path over the batch (device-resident inputs).  `feats_ready`: optional
         CUDA event after which `feats` may be read (lets the proposal / target chains start while
-        the feature maps are still arriving, see step_from_host)."""
+        the feature maps are still arriving, see step_from_host).  `before_roi_align(rois, counts)`: optional
+        callable run on RoIAlign's stream once the sampled RoIs exist (step_from_host: fetch of the touched cells)."""
         if not self.subs:
             if feats_ready is not None:
                 torch.cuda.current_stream().wait_event(feats_ready)
@@ -344,6 +373,8 @@ class TrainHotPath(object):
             rt = self._rpn_target_chain(cls_outs, reg_outs, gt, gt_count, img_hw)
             bt = self.roi_targets if ride else self.roi_targets(gt, gt_count, gt_label, boxes=props, box_count=count)
             _C.call("b2d_counter_add", _C.ptr(self.step_cell), 1, _C.stream())      # both samplers have read it
+            if before_roi_align is not None:
+                before_roi_align(bt.tar_box, bt.n_chosen)
             self.roi_align(feats, bt.tar_box, bt.n_chosen)
         else:
             cur = torch.cuda.current_stream()
@@ -378,6 +409,10 @@ class TrainHotPath(object):
                 if feats_ready is not None:
                     st_lo.wait_event(feats_ready)
                 with torch.cuda.stream(st_lo):
+                    if before_roi_align is not None:
+                        if self.groups != 1:
+                            raise _C.B200DetError("before_roi_align needs groups == 1")
+                        before_roi_align(t2.tar_box, t2.n_chosen)
                     ra([f[b0:b1] for f in feats], t2.tar_box, t2.n_chosen)
             # the step counter moves on once every sampler of the step has read it: side stream, next to RoIAlign
             for sub in self.subs:
@@ -398,7 +433,7 @@ class TrainHotPath(object):
 
     # ------------------------------------------------------------------ host-buffer entry
     def step_from_host(self, h_cls, h_reg, h_feats, h_gt, h_gt_label, gt_count, img_hw, h_out=None,
-                       with_roi_feats=False):
+                       with_roi_feats=False, sparse=None):
         """End-to-end form of step(): inputs are pinned HOST tensors in the reference's layout
         (head maps [B,A*C,H,W] / [B,4A,H,W], FPN features fp32 NCHW [B,C,H,W], GT [B,4,K] and
         labels [B,K]); results land in pinned host tensors (`h_out`, allocated on first use).
@@ -407,8 +442,21 @@ class TrainHotPath(object):
         feature level is transposed to NHWC (b2d_nchw_to_nhwc) while the next one is still in
         flight, and only RoIAlign waits for the features.  gt_count / img_hw are device tensors.
         The RoI features (the input of the next GPU stage, 205 MB at config 2) stay on the device
-        unless with_roi_feats is set; a one-element probe of them is always read back."""
+        unless with_roi_feats is set; a one-element probe of them is always read back.
+
+        `sparse` (default: chosen by the layout of h_feats): when the host feature maps are channels_last
+        ([B,C,H,W] tensors with NHWC strides, what `install(channels_last=True)` makes the FPN emit) they are not
+        copied at all -- once the sampled RoIs exist, the cells under their bilinear taps are fetched straight from
+        the pinned host maps by the SMs (BatchedRoIAlign.fetch_touched) and RoIAlign reads those.  Same results,
+        ~0.6 of the bytes over PCIe at config 2.  NCHW host maps take the full copy + transposition."""
         dev, B = self.device, self.B
+        cl = all(t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
+                 for t in h_feats)
+        if sparse is None:
+            sparse = cl and all(t.is_pinned() for t in h_feats)
+        if sparse:
+            return self._step_from_host_sparse(h_cls, h_reg, h_feats, h_gt, h_gt_label, gt_count, img_hw, h_out,
+                                               with_roi_feats)
         if not hasattr(self, "_stage"):
             st = dict(cls=[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in h_cls],
                       reg=[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in h_reg],
@@ -423,17 +471,7 @@ class TrainHotPath(object):
             self._stage = st
         st = self._stage
         if h_out is None:
-            if not hasattr(self, "_h_out"):
-                pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()
-                rt, bt = self.rpn_targets, self.roi_targets
-                self._h_out = dict(props=pin(self.proposals.props), scores=pin(self.proposals.scores),
-                                   prop_count=pin(self.proposals.count), rpn_label=pin(rt.tar_label),
-                                   rpn_param=pin(rt.tar_param), rpn_tar_cls=pin(self.tar_cls), rpn_tar_reg=pin(self.tar_reg),
-                                   roi_label=pin(bt.tar_label), roi_param=pin(bt.tar_param), roi_count=pin(bt.n_chosen),
-                                   roi_probe=torch.empty(1).pin_memory())
-                if with_roi_feats:
-                    self._h_out["roi_feats"] = pin(self.roi_align.out)
-            h_out = self._h_out
+            h_out = self._host_results(with_roi_feats)
         cur = torch.cuda.current_stream()
         sc, sx = st["s_copy"], st["s_xpose"]
         sc.wait_stream(cur)
@@ -456,6 +494,23 @@ class TrainHotPath(object):
             st["ev_ready"].record(sx)
         cur.wait_event(st["ev_heads"])
         out = self.step(st["cls"], st["reg"], st["nhwc"], st["gt"], gt_count, st["gl"], img_hw, feats_ready=st["ev_ready"])
+        return self._read_back(out, h_out)
+
+    def _host_results(self, with_roi_feats):
+        if not hasattr(self, "_h_out"):
+            pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            rt, bt = self.rpn_targets, self.roi_targets
+            self._h_out = dict(props=pin(self.proposals.props), scores=pin(self.proposals.scores),
+                               prop_count=pin(self.proposals.count), rpn_label=pin(rt.tar_label),
+                               rpn_param=pin(rt.tar_param), rpn_tar_cls=pin(self.tar_cls), rpn_tar_reg=pin(self.tar_reg),
+                               roi_label=pin(bt.tar_label), roi_param=pin(bt.tar_param), roi_count=pin(bt.n_chosen),
+                               roi_probe=torch.empty(1).pin_memory())
+        if with_roi_feats and "roi_feats" not in self._h_out:
+            self._h_out["roi_feats"] = torch.empty(self.roi_align.out.shape, dtype=self.roi_align.out.dtype).pin_memory()
+        return self._h_out
+
+    @staticmethod
+    def _read_back(out, h_out):
         pairs = [("props", out["props"]), ("scores", out["scores"]), ("prop_count", out["prop_count"]),
                  ("rpn_label", out["rpn"].tar_label), ("rpn_param", out["rpn"].tar_param),
                  ("rpn_tar_cls", out["rpn_tar_cls"]), ("rpn_tar_reg", out["rpn_tar_reg"]),
@@ -466,6 +521,39 @@ class TrainHotPath(object):
             if k in h_out:
                 h_out[k].copy_(t, non_blocking=True)
         return h_out
+
+    def _step_from_host_sparse(self, h_cls, h_reg, h_feats, h_gt, h_gt_label, gt_count, img_hw, h_out, with_roi_feats):
+        """step_from_host for channels_last pinned host feature maps: GT + head maps by H2D copy (33 MB at config 2),
+        proposal / target chains, then only the cells the sampled RoIs touch are fetched from the host maps."""
+        dev = self.device
+        if self.groups != 1:
+            raise _C.B200DetError("step_from_host(sparse): image groups are not supported")
+        if not hasattr(self, "_stage_sparse"):
+            self._stage_sparse = dict(
+                cls=[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in h_cls],
+                reg=[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in h_reg],
+                # zero-filled once: cells no RoI has touched yet are never read, but stay finite for debuggers
+                nhwc=[torch.zeros(t.shape, dtype=t.dtype, device=dev).contiguous(memory_format=torch.channels_last)
+                      for t in h_feats],
+                gt=torch.empty(h_gt.shape, dtype=h_gt.dtype, device=dev),
+                gl=torch.empty(h_gt_label.shape, dtype=h_gt_label.dtype, device=dev),
+                s_copy=torch.cuda.Stream(device=dev), ev_heads=torch.cuda.Event())
+        st = self._stage_sparse
+        if h_out is None:
+            h_out = self._host_results(with_roi_feats)
+        cur = torch.cuda.current_stream()
+        sc = st["s_copy"]
+        sc.wait_stream(cur)
+        with torch.cuda.stream(sc):
+            st["gt"].copy_(h_gt, non_blocking=True)
+            st["gl"].copy_(h_gt_label, non_blocking=True)
+            for d, h in zip(st["cls"] + st["reg"], list(h_cls) + list(h_reg)):
+                d.copy_(h, non_blocking=True)
+            st["ev_heads"].record(sc)
+        cur.wait_event(st["ev_heads"])
+        fetch = lambda rois, counts: self.roi_align.fetch_touched(st["nhwc"], h_feats, rois, counts)
+        out = self.step(st["cls"], st["reg"], st["nhwc"], st["gt"], gt_count, st["gl"], img_hw, before_roi_align=fetch)
+        return self._read_back(out, h_out)
 
 
 class CascadeHotPath(object):

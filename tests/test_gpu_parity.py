@@ -785,6 +785,110 @@ def test_fused_step_is_run_to_run_deterministic():
                 assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), it
 
 
+def _tap_cells(rois, img, grids, strides, B, finest=56.0):
+    """Exact set of (level, image, y, x) cells under the 2x2-per-bin bilinear taps of 7x7 RoIAlign (numpy restatement of
+    torchvision's pre_calc_for_bilinear_interpolate index arithmetic, fp32)."""
+    masks = [np.zeros((B,) + tuple(g), bool) for g in grids]
+    r = rois.astype(np.float32)
+    s = np.sqrt(((r[2] - r[0]) + np.float32(1)) * ((r[3] - r[1]) + np.float32(1)))
+    lv = np.clip(np.floor(np.log2(s / np.float32(finest) + np.float32(1e-6))), 0, len(grids) - 1).astype(int)
+    for i in range(r.shape[1]):
+        l = lv[i]
+        H, W = grids[l]
+        sc = np.float32(1.0 / strides[l])
+        sx, sy = r[0, i] * sc, r[1, i] * sc
+        bw = np.maximum(r[2, i] * sc - sx, np.float32(1)) / np.float32(7)
+        bh = np.maximum(r[3, i] * sc - sy, np.float32(1)) / np.float32(7)
+        def axis(st, b, n):
+            out = set()
+            for p in range(7):
+                for k in range(2):
+                    v = st + np.float32(p) * b + (np.float32(k) + np.float32(0.5)) * b / np.float32(2)
+                    v = max(v, np.float32(0))
+                    lo = int(v)
+                    if lo >= n - 1:
+                        lo = hi = n - 1
+                    else:
+                        hi = lo + 1
+                    out.update((lo, hi))
+            return sorted(out)
+        ys, xs = axis(sy, bh, H), axis(sx, bw, W)
+        masks[l][img[i]][np.ix_(ys, xs)] = True
+    return masks
+
+
+def test_mark_and_fetch_touched_cells_cover_every_tap(setknob):
+    """b2d_roi_mark_cells / b2d_fetch_marked_cells (sparse host -> device transfer of the RoI extractor's inputs): the
+    bitmap holds every cell under a bilinear tap (exact numpy restatement) and little more (tap rectangle vs tap set);
+    exactly the marked cells are copied from pinned channels_last host maps; RoIAlign on a NaN-poisoned device pyramid
+    that received only those cells is bit-identical to RoIAlign on the whole pyramid."""
+    import ctypes
+    grids, feats, rois, img = _ring_case(21, 64, 600)
+    B, strides = feats[0].shape[0], [4, 8, 16, 32]
+    order = np.argsort(img, kind="stable")
+    rois, img = rois[:, order], img[order]
+    ld = int(np.bincount(img, minlength=B).max())
+    rb = np.zeros((B, 4, ld), np.float32)
+    counts = np.bincount(img, minlength=B).astype(np.int32)
+    for b in range(B):
+        rb[b, :, :counts[b]] = rois[:, img == b]
+    ra = fused.BatchedRoIAlign(B, ld, [(64,) + tuple(g) for g in grids], strides, DEV, layout=1)
+    h_feats = [fused.pinned_channels_last(torch.from_numpy(f)) for f in feats]
+    full = [h.to(DEV) for h in h_feats]
+    want = N(ra(full, T(rb), T(counts))).copy()
+    poisoned = [torch.full_like(f, float("nan")) for f in full]
+    moved = ra.fetch_touched(poisoned, h_feats, T(rb), T(counts))
+    got = N(ra(poisoned, T(rb), T(counts)))
+    for b in range(B):
+        sl = slice(b * ld, b * ld + counts[b])
+        assert np.array_equal(bits(got[sl]), bits(want[sl]))
+    # bitmap against the exact tap set
+    words = N(ra._bitmap).view(np.uint32)
+    exact = _tap_cells(rois, img, grids, strides, B)
+    w0, n_marked, n_exact = 0, 0, 0
+    for l, g in enumerate(grids):
+        cells = B * g[0] * g[1]
+        nw = (cells + 31) // 32
+        bitsl = np.unpackbits(words[w0:w0 + nw].view(np.uint8), bitorder="little")[:cells].astype(bool).reshape((B,) + tuple(g))
+        assert (bitsl | ~exact[l]).all(), "a tap cell is not marked (level %d)" % l
+        copied = ~torch.isnan(poisoned[l]).any(1).cpu().numpy()            # [B,H,W]: cells that received data
+        assert np.array_equal(copied, bitsl), "copied cells != marked cells (level %d)" % l
+        assert np.array_equal(N(poisoned[l]).transpose(0, 2, 3, 1)[bitsl], feats[l].transpose(0, 2, 3, 1)[bitsl])
+        n_marked += int(bitsl.sum()); n_exact += int(exact[l].sum()); w0 += nw
+    assert int(moved[0]) == n_marked
+    assert n_marked <= 1.6 * n_exact                                      # rectangles of RoIs with bins > 2 cells have holes
+
+
+def test_step_from_host_sparse_fetch_equals_full_copy():
+    """TrainHotPath.step_from_host: channels_last pinned host feature maps (sparse fetch of the touched cells) and NCHW
+    pinned host maps (full copy + transposition) give bit-identical results, RoI features included."""
+    B, K = 2, 8
+    w = workload.config2(B=B, K=K, channels=32)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_cls, h_reg = [pin(c) for c in w["cls"]], [pin(r) for r in w["reg"]]
+    h_gt, h_gl = pin(w["gt"]), pin(w["gt_label"])
+    h_nchw = [pin(f) for f in w["feats"]]
+    h_nhwc = [fused.pinned_channels_last(torch.from_numpy(f)) for f in w["feats"]]
+    gcount = torch.full((B,), K, dtype=torch.int32, device=DEV)
+    img_hw = torch.tensor([[800.0, 1333.0]] * B, device=DEV)
+    snaps = []
+    for h_feats in (h_nchw, h_nhwc):
+        hp = fused.TrainHotPath(B, w["grids"], DEV, gt_ld=K, feat_channels=32, overlap=True)
+        for it in range(2):                                               # second pass: stale cells of pass 1 in the device maps
+            hp.reset_step()
+            out = hp.step_from_host(h_cls, h_reg, h_feats, h_gt, h_gl, gcount, img_hw, with_roi_feats=True)
+            torch.cuda.synchronize()
+        snaps.append({k: v.clone() for k, v in out.items()})
+        if h_feats is h_nhwc:
+            assert hasattr(hp, "_stage_sparse") and not hasattr(hp, "_stage")
+            cells = int(hp.roi_align.cells_moved[0]) / 2
+            total = B * sum(g[0] * g[1] for g in w["grids"][:4])
+            assert 0.3 * total < cells < 0.8 * total                      # config 2: ~0.6 of the pyramid
+    assert set(snaps[0]) == set(snaps[1])
+    for k in snaps[0]:
+        assert torch.equal(snaps[0][k].view(torch.uint8), snaps[1][k].view(torch.uint8)), k
+
+
 def test_roi_targets_as_tail_of_the_proposal_kernel_equal_the_separate_launch(monkeypatch):
     """b2d_rpn_proposals_targets: bbox_target riding on k_rpn_back (assignment spread over the image's cluster, sampler
     + encode in its first CTA) gives bit-identical labels / IoUs / samples / encoded targets to the separate
