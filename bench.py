@@ -569,7 +569,13 @@ def run_b200(args):
     barrier()
     e2e_sparse_ms = f0.elapsed_time(f1) / n_e2e
     cells_step = (int(hp_s.roi_align.cells_moved[0]) - cells0) / n_e2e
-    h2d_sparse = sum(t.numel() * t.element_size() for t in h_cls + h_reg + [h_gt, h_gl]) + int(cells_step * 256 * 4)
+    h2d_sparse = sum(t.numel() * t.element_size() for t in h_cls + [h_gt, h_gl]) + int(cells_step * 256 * 4)
+    if getattr(hp_s, "last_reg_zero_copy", False):
+        # regression deltas are read at the selected anchors only, from the mapped host maps: 4 values per anchor of the
+        # per-level top-k and per RPN sample, counted as the 32-byte sectors such reads move over PCIe
+        h2d_sparse += B * (sum(min(2000, n) for n in hp_s.pyr.level_sizes) + 256) * 4 * 32
+    else:
+        h2d_sparse += sum(t.numel() * t.element_size() for t in h_reg)
     # the same with the RoI features (the input of the next stage, 205 MB) read back to the host as well
     e2e_feats_ms = None
     if rank == 0:

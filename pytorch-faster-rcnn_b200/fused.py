@@ -523,15 +523,18 @@ class TrainHotPath(object):
         return h_out
 
     def _step_from_host_sparse(self, h_cls, h_reg, h_feats, h_gt, h_gt_label, gt_count, img_hw, h_out, with_roi_feats):
-        """step_from_host for channels_last pinned host feature maps: GT + head maps by H2D copy (33 MB at config 2),
-        proposal / target chains, then only the cells the sampled RoIs touch are fetched from the host maps."""
+        """step_from_host for channels_last pinned host feature maps: GT + objectness maps by H2D copy (8.6 MB at
+        config 2), proposal / target chains, then only the cells the sampled RoIs touch are fetched from the host maps.
+        The regression maps (34 MB) are not copied either when they are pinned: the kernels read them only at the
+        selected anchors (k_rpn_front's decode of the per-level top-k, b2d_gather_head_outputs at the 256 samples) and
+        take those 4-byte values straight from the mapped host maps (`self.reg_zero_copy`, default on)."""
         dev = self.device
         if self.groups != 1:
             raise _C.B200DetError("step_from_host(sparse): image groups are not supported")
         if not hasattr(self, "_stage_sparse"):
             self._stage_sparse = dict(
                 cls=[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in h_cls],
-                reg=[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in h_reg],
+                reg=None,
                 # zero-filled once: cells no RoI has touched yet are never read, but stay finite for debuggers
                 nhwc=[torch.zeros(t.shape, dtype=t.dtype, device=dev).contiguous(memory_format=torch.channels_last)
                       for t in h_feats],
@@ -544,15 +547,20 @@ class TrainHotPath(object):
         cur = torch.cuda.current_stream()
         sc = st["s_copy"]
         sc.wait_stream(cur)
+        zc_reg = getattr(self, "reg_zero_copy", True) and all(t.is_pinned() and t.is_contiguous() for t in h_reg)
+        if not zc_reg and st["reg"] is None:
+            st["reg"] = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in h_reg]
         with torch.cuda.stream(sc):
             st["gt"].copy_(h_gt, non_blocking=True)
             st["gl"].copy_(h_gt_label, non_blocking=True)
-            for d, h in zip(st["cls"] + st["reg"], list(h_cls) + list(h_reg)):
+            for d, h in zip(st["cls"] + ([] if zc_reg else st["reg"]), list(h_cls) + ([] if zc_reg else list(h_reg))):
                 d.copy_(h, non_blocking=True)
             st["ev_heads"].record(sc)
         cur.wait_event(st["ev_heads"])
         fetch = lambda rois, counts: self.roi_align.fetch_touched(st["nhwc"], h_feats, rois, counts)
-        out = self.step(st["cls"], st["reg"], st["nhwc"], st["gt"], gt_count, st["gl"], img_hw, before_roi_align=fetch)
+        out = self.step(st["cls"], list(h_reg) if zc_reg else st["reg"], st["nhwc"], st["gt"], gt_count, st["gl"], img_hw,
+                        before_roi_align=fetch)
+        self.last_reg_zero_copy = zc_reg
         return self._read_back(out, h_out)
 
 

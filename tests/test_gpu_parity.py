@@ -872,8 +872,9 @@ def test_step_from_host_sparse_fetch_equals_full_copy():
     gcount = torch.full((B,), K, dtype=torch.int32, device=DEV)
     img_hw = torch.tensor([[800.0, 1333.0]] * B, device=DEV)
     snaps = []
-    for h_feats in (h_nchw, h_nhwc):
+    for h_feats, zc_reg in ((h_nchw, False), (h_nhwc, True), (h_nhwc, False)):
         hp = fused.TrainHotPath(B, w["grids"], DEV, gt_ld=K, feat_channels=32, overlap=True)
+        hp.reg_zero_copy = zc_reg                                         # regression maps read in place from the host / copied
         for it in range(2):                                               # second pass: stale cells of pass 1 in the device maps
             hp.reset_step()
             out = hp.step_from_host(h_cls, h_reg, h_feats, h_gt, h_gl, gcount, img_hw, with_roi_feats=True)
@@ -884,9 +885,11 @@ def test_step_from_host_sparse_fetch_equals_full_copy():
             cells = int(hp.roi_align.cells_moved[0]) / 2
             total = B * sum(g[0] * g[1] for g in w["grids"][:4])
             assert 0.3 * total < cells < 0.8 * total                      # config 2: ~0.6 of the pyramid
-    assert set(snaps[0]) == set(snaps[1])
-    for k in snaps[0]:
-        assert torch.equal(snaps[0][k].view(torch.uint8), snaps[1][k].view(torch.uint8)), k
+            assert hp.last_reg_zero_copy == zc_reg
+    for other in snaps[1:]:
+        assert set(snaps[0]) == set(other)
+        for k in snaps[0]:
+            assert torch.equal(snaps[0][k].view(torch.uint8), other[k].view(torch.uint8)), k
 
 
 def test_roi_targets_as_tail_of_the_proposal_kernel_equal_the_separate_launch(monkeypatch):
