@@ -144,6 +144,12 @@ def touched_cell_bytes(rois_b4n, counts, grids, strides, C, finest=56.0):
     return total
 
 
+def workload_config(world):
+    """`config` of the JSON line: the workload only (identical for both arms; what the B200 arm does with it is `run_config`)."""
+    return {"workload": WORKLOAD, "global_batch": IMGS_PER_GPU * world, "parallelism": "per-image partition, dp%d" % world,
+            "l2": "inputs per step (755 MB/GPU) exceed the 126 MB L2; no flush needed"}
+
+
 # --------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference's CPU implementation of the path, timed on the host cores: the oracle
@@ -156,22 +162,27 @@ def run_reference(args):
     from b200det import workload  # host-side input generator only
     oracle.set_num_threads(os.cpu_count())
     cores = oracle.num_threads()
-    w = workload.config2(B=1, K=K_GT)
+    # one step = one GPU's batch (8 images) run image by image, as the reference's per-image loops do; with more than ~25
+    # steps requested the sample shrinks to 2 images per step so that the run stays within a few minutes
+    imgs = IMGS_PER_GPU if (args.steps + max(args.warmup, 1)) <= 25 else 2
+    w = workload.config2(B=imgs, K=K_GT)
     path = opipe.ImagePath(w["grids"], w["strides"], w["img_shape"])
-    imgs = 1
-    args_img = ([c[0] for c in w["cls"]], [r[0] for r in w["reg"]], [f[0] for f in w["feats"]], w["gt"][0], w["gt_label"][0])
+    per_img = [([c[b] for c in w["cls"]], [r[b] for r in w["reg"]], [f[b] for f in w["feats"]], w["gt"][b], w["gt_label"][b])
+               for b in range(imgs)]
     for _ in range(max(args.warmup, 1)):
-        path.run(*args_img)
+        for a in per_img:
+            path.run(*a)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        path.run(*args_img, seed=i)
+        for a in per_img:
+            path.run(*a, seed=i)
     dt = time.perf_counter() - t0
     val = imgs * args.steps / dt
-    sample = "1 image per step (of the 8-image batch), %d steps; C port of the reference path with OpenMP" % args.steps
+    sample = "%d images per step (one GPU's batch of the workload), %d steps; C port of the reference path with OpenMP" % (imgs, args.steps)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(max(int(args.gpus), 1)),
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -662,10 +673,9 @@ def run_b200(args):
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "global_batch": total_imgs, "parallelism": "per-image partition, dp%d" % world,
-                                            "features": "fp32 NHWC (channels_last) resident in HBM", "cuda_graph": graph is not None, "image_groups": hp.groups,
-                                            "host_cpus_bound_to_gpu_numa_node": numa_cpus,
-                                            "l2": "inputs per step (755 MB/GPU) exceed the 126 MB L2; no flush needed"},
+            "data": "synthetic", "config": workload_config(world),
+            "run_config": {"features": "fp32 NHWC (channels_last) resident in HBM", "cuda_graph": graph is not None,
+                           "image_groups": hp.groups, "host_cpus_bound_to_gpu_numa_node": numa_cpus},
             "e2e": {"value": e2e_sparse_val, "unit": "images/s", "h2d_bytes_per_step": h2d_sparse, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_sparse_ms,
                     "layout": "TrainHotPath.step_from_host on pinned host buffers, feature maps fp32 channels_last (NHWC strides; what "
