@@ -40,7 +40,7 @@ static void load_knobs() {
     k.roi_x2 = geti("B2D_ROI_X2", 1);
     k.roi_bulk_store = geti("B2D_ROI_BULK_STORE", 1);
     k.roi_tma_dev = geti("B2D_ROI_TMA_DEV", 0);
-    k.roi_bwd_tile = geti("B2D_ROI_BWD_TILE", 1);
+    k.roi_bwd_tile = geti("B2D_ROI_BWD_TILE", 2);
     k.assign_old = getenv("B2D_ASSIGN_OLD") != nullptr;
     k.sample_threads = geti("B2D_SAMPLE_THREADS", 1024);
     k.pdl = geti("B2D_PDL", 0);           // measured r2: 258 vs 250 us per step with the edges on

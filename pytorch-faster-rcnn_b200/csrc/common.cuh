@@ -36,7 +36,7 @@ struct Knobs {
     int roi_x2;            // B2D_ROI_X2         0: scalar adds in k_roi_align_win
     int roi_bulk_store;    // B2D_ROI_BULK_STORE 0: result tile through LDS + STG instead of one bulk async store
     int roi_tma_dev;       // B2D_ROI_TMA_DEV
-    int roi_bwd_tile;      // B2D_ROI_BWD_TILE   0: generic backward kernel
+    int roi_bwd_tile;      // B2D_ROI_BWD_TILE   2: patch form (default), 1: tile-gather form, 0: generic backward kernel
     int assign_old;        // B2D_ASSIGN_OLD     1: round-1a assignment kernels in pyramid mode
     int debug_sync;        // B2D_DEBUG_SYNC     synchronise after every launch (localise a faulting kernel)
     int sample_threads;    // B2D_SAMPLE_THREADS 128 / 256: slim k_sample CTAs (default 1024)

@@ -20,7 +20,7 @@
 // HBM roofline: grad_out read (50 176 B/RoI, ~4x from L2: a RoI overlaps ~4 tiles) + every gradient cell written once.
 #include <cstring>
 
-#include "roi_common.cuh"
+#include "roi_bwd_common.cuh"
 
 namespace b2d {
 namespace {
@@ -28,69 +28,7 @@ namespace {
 constexpr int kT = 16;                 // tile side in cells
 constexpr int kCg = 128;               // channels per CTA
 constexpr int kBT = 512;               // threads per CTA: warp w owns tile row w, lane l channels 4l .. 4l + 3
-constexpr int kMaxS = 16;              // samples per axis (PH * 2, PW * 2 <= 16)
 constexpr int kPitch = kCg + 4;        // shared-memory pitch of a bin row (floats)
-constexpr int kMaxBinsT = 64;
-
-struct __align__(16) BwdMeta {
-    int img, lvl, y0, y1;
-    int x0, x1; float sx, sy;
-    float bw, bh; int _p0, _p1;
-};
-
-struct MetaArgs {
-    b2d_roi_cfg cfg;
-    const float* rois; long long roi_ld; const int* roi_img; const int* levels; long long R;
-};
-
-__global__ void __launch_bounds__(256) k_bwd_meta(MetaArgs a, BwdMeta* __restrict__ meta) {
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.R) return;
-    const b2d_roi_cfg& c = a.cfg;
-    const float x1 = a.rois[r], y1 = a.rois[a.roi_ld + r], x2 = a.rois[2 * a.roi_ld + r], y2 = a.rois[3 * a.roi_ld + r];
-    BwdMeta m;
-    m.img = a.roi_img ? a.roi_img[r] : 0;
-    m.lvl = a.levels ? a.levels[r] : (c.num_levels > 1 ? roi_level(x1, y1, x2, y2, c.finest_scale, c.num_levels) : 0);
-    const int H = c.H[m.lvl], W = c.W[m.lvl];
-    const RoiGeom g = roi_geom(x1, y1, x2, y2, c.spatial_scale[m.lvl], c.PH, c.PW, 2, c.aligned);
-    m.sx = g.sx; m.sy = g.sy; m.bw = g.bw; m.bh = g.bh;
-    // cell bounding box of all taps (sample positions need not be monotone for malformed RoIs: take min / max)
-    int y0 = H, y1c = -1, x0 = W, x1c = -1;
-    for (int s = 0; s < 2 * c.PH; ++s) {
-        const AxisTap t = axis_tap(g.sy, g.bh, s >> 1, s & 1, 2, H);
-        if (t.valid) { y0 = min(y0, t.lo); y1c = max(y1c, t.hi); }
-    }
-    for (int s = 0; s < 2 * c.PW; ++s) {
-        const AxisTap t = axis_tap(g.sx, g.bw, s >> 1, s & 1, 2, W);
-        if (t.valid) { x0 = min(x0, t.lo); x1c = max(x1c, t.hi); }
-    }
-    m.y0 = y0; m.y1 = y1c; m.x0 = x0; m.x1 = x1c; m._p0 = m._p1 = 0;
-    meta[r] = m;
-}
-
-// bucket[(img * L + lvl) * R + k] = k-th RoI (ascending) of that feature map; bcount[img * L + lvl]
-__global__ void __launch_bounds__(256) k_bwd_bucket(const BwdMeta* __restrict__ meta, long long R, int L,
-                                                    int* __restrict__ bucket, int* __restrict__ bcount) {
-    __shared__ int s_warp[8], s_base;
-    const int img = blockIdx.x / L, lvl = blockIdx.x - img * L;
-    int* out = bucket + (long long)blockIdx.x * R;
-    if (threadIdx.x == 0) s_base = 0;
-    __syncthreads();
-    for (long long r0 = 0; r0 < R; r0 += 256) {
-        const long long r = r0 + threadIdx.x;
-        const bool hit = r < R && meta[r].img == img && meta[r].lvl == lvl;
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = __popc(m);
-        __syncthreads();
-        int before = s_base;
-        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += s_warp[w];
-        if (hit) out[before + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = (int)r;
-        __syncthreads();
-        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_warp[w]; s_base += t; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) bcount[blockIdx.x] = s_base;
-}
 
 struct TileArgs {
     b2d_roi_cfg cfg;
@@ -98,6 +36,7 @@ struct TileArgs {
     const float* gout; const BwdMeta* meta; const int* bucket; const int* bcount;
     long long R;
     int tile_off[kMaxLevels + 1], tiles_x[kMaxLevels];
+    const int* guard;                  // non-NULL: run only if *guard != 0 (fallback of the patch form, roi_align_bwd_patch.cu)
 };
 
 struct __align__(8) ColTerm { float w; int off; };     // column weight, float offset of its bin column in s_g
@@ -118,6 +57,7 @@ __global__ void __launch_bounds__(kBT, 1) k_roi_align_bwd_tile(TileArgs a) {
     float (*s_g)[kMaxBinsT * kPitch] = reinterpret_cast<float (*)[kMaxBinsT * kPitch]>(s_dyn);
     Tables* s_tab = reinterpret_cast<Tables*>(s_dyn + 2 * sizeof(float) * kMaxBinsT * kPitch);
     __shared__ int s_list[kBT], s_n, s_warp[kBT / 32];
+    if (a.guard && *a.guard == 0) return;
     const b2d_roi_cfg& c = a.cfg;
     const int tiles_per_img = a.tile_off[c.num_levels];
     const int img = blockIdx.x / tiles_per_img;
@@ -273,6 +213,9 @@ __global__ void __launch_bounds__(kBT, 1) k_roi_align_bwd_tile(TileArgs a) {
 
 }  // namespace
 
+int roi_align_bwd_tile_launch(void* const* grad_feat_ptrs_host, const float* grad_out, long long R, int B, const b2d_roi_cfg& c,
+                              const void* meta, const int* bucket, const int* bcount, const int* guard, cudaStream_t st);
+
 size_t roi_align_bwd_tile_workspace(long long R, int B, int L) {
     const size_t r = (size_t)(R > 0 ? R : 1);
     return r * sizeof(BwdMeta) + 256 + (size_t)B * L * r * 4 + 256 + (size_t)B * L * 4 + 256;
@@ -295,6 +238,12 @@ int roi_align_bwd_tile_try(void* const* grad_feat_ptrs_host, const float* grad_o
     ma.cfg = c; ma.rois = rois; ma.roi_ld = roi_ld; ma.roi_img = roi_img; ma.levels = levels; ma.R = R;
     k_bwd_meta<<<cdiv(R, 256), 256, 0, st>>>(ma, meta);
     k_bwd_bucket<<<B * c.num_levels, 256, 0, st>>>(meta, R, c.num_levels, bucket, bcount);
+    return roi_align_bwd_tile_launch(grad_feat_ptrs_host, grad_out, R, B, c, meta, bucket, bcount, nullptr, st);
+}
+
+// the tile kernel alone, on a meta / bucket table that already exists; guard: see TileArgs
+int roi_align_bwd_tile_launch(void* const* grad_feat_ptrs_host, const float* grad_out, long long R, int B, const b2d_roi_cfg& c,
+                              const void* meta, const int* bucket, const int* bcount, const int* guard, cudaStream_t st) {
     TileArgs a;
     memset(&a, 0, sizeof(a));
     a.cfg = c;
@@ -306,7 +255,7 @@ int roi_align_bwd_tile_try(void* const* grad_feat_ptrs_host, const float* grad_o
         run += a.tiles_x[l] * cdiv(c.H[l], kT);
     }
     a.tile_off[c.num_levels] = run;
-    a.gout = grad_out; a.meta = meta; a.bucket = bucket; a.bcount = bcount; a.R = R;
+    a.gout = grad_out; a.meta = (const BwdMeta*)meta; a.bucket = bucket; a.bcount = bcount; a.R = R; a.guard = guard;
     dim3 grid((unsigned)(run * B), (unsigned)(c.C / kCg));
     const size_t smem = 2 * sizeof(float) * kMaxBinsT * kPitch + 2 * kTablesBytes;
     B2D_SMEM(k_roi_align_bwd_tile, smem, "k_roi_align_bwd_tile");   // per device

@@ -19,6 +19,11 @@ namespace b2d {
 
 // roi_align_bwd_tile.cu
 size_t roi_align_bwd_tile_workspace(long long R, int B, int L);
+// patch form (roi_align_bwd_patch.cu): its workspace begins with the tile form's tables, so either can use it
+size_t roi_align_bwd_patch_workspace(long long R, int B, const b2d_roi_cfg& c);
+int roi_align_bwd_patch_try(void* const* grad_feat_ptrs_host, const float* grad_out, const float* rois, long long roi_ld,
+                            const int* roi_img, const int* levels, long long R, int B, const b2d_roi_cfg& c, void* workspace,
+                            cudaStream_t st);
 int roi_align_bwd_tile_try(void* const* grad_feat_ptrs_host, const float* grad_out, const float* rois, long long roi_ld,
                            const int* roi_img, const int* levels, long long R, int B, const b2d_roi_cfg& c, void* workspace,
                            cudaStream_t st);
@@ -274,7 +279,13 @@ static size_t bwd_levels_bytes(long long R) { return (((size_t)(R > 0 ? R : 1) *
 
 size_t b2d_roi_align_bwd_workspace_bytes(long long R, int B, const b2d_roi_cfg* cfg_host) {
     const int L = cfg_host ? cfg_host->num_levels : B2D_MAX_LEVELS;
-    return bwd_levels_bytes(R) + roi_align_bwd_tile_workspace(R, B > 0 ? B : 1, L);   // level ids + tile-kernel tables
+    size_t n = roi_align_bwd_tile_workspace(R, B > 0 ? B : 1, L);                     // tile-kernel tables
+    if (cfg_host && cfg_host->layout == 1 && cfg_host->sampling_ratio == 2 && cfg_host->num_levels >= 1 &&
+        cfg_host->num_levels <= B2D_MAX_LEVELS) {
+        const size_t p = roi_align_bwd_patch_workspace(R, B > 0 ? B : 1, *cfg_host);  // + bitmaps + patch scratch
+        if (p > n) n = p;
+    }
+    return bwd_levels_bytes(R) + n;                                                   // level ids in front
 }
 
 int b2d_roi_align_bwd(void* const* grad_feat_ptrs_host, const float* grad_out, const float* rois, long long roi_ld,
@@ -288,8 +299,13 @@ int b2d_roi_align_bwd(void* const* grad_feat_ptrs_host, const float* grad_out, c
                 "roi_align_bwd: needs a fixed sampling_ratio with PH*sr, PW*sr <= 16");
     B2D_REQUIRE(workspace && ws_bytes >= b2d_roi_align_bwd_workspace_bytes(R, B, cfg_host), "roi_align_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    {   // tile-gather kernel (roi_align_bwd_tile.cu) for NHWC fp32 gradients with 2x2 samples; B2D_ROI_BWD_TILE=0 forces
-        // the generic, torchvision-bit-identical kernel below
+    {   // NHWC fp32 gradients with 2x2 samples: patch form (B2D_ROI_BWD_TILE=2, default), tile-gather form (=1);
+        // B2D_ROI_BWD_TILE=0 forces the generic, torchvision-bit-identical kernel below
+        if (knobs().roi_bwd_tile >= 2) {                  // patch form ("sorted scatter", roi_align_bwd_patch.cu): default
+            const int rc = roi_align_bwd_patch_try(grad_feat_ptrs_host, grad_out, rois, roi_ld, roi_img, levels, R, B, c,
+                                                   (char*)workspace + bwd_levels_bytes(R), st);
+            if (rc != 1) return rc;
+        }
         if (knobs().roi_bwd_tile != 0) {
             const int rc = roi_align_bwd_tile_try(grad_feat_ptrs_host, grad_out, rois, roi_ld, roi_img, levels, R, B, c,
                                                   (char*)workspace + bwd_levels_bytes(R), st);
