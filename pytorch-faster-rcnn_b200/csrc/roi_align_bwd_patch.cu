@@ -7,11 +7,10 @@
 // with WY[y][ph] = the bilinear row weights of the two samples of bin row ph that land on feature row y (WX likewise):
 // the weights of the <= 4 taps of a bin that share a cell are added BEFORE the multiply (2-3 terms per cell instead of
 // 6-7 tap terms).  Patches of different RoIs overlap (43 % of the touched cells at config 2), so:
-//   k_bwd_meta / k_bwd_bucket   per-RoI geometry, ascending RoI lists per (image, level)          (roi_bwd_common.cuh)
-//   k_bwd_scan      exclusive prefix of the patch areas = scratch slot of every (RoI, cell); raises `fallback` if the
-//                   patches do not fit the scratch
-//   k_bwd_mark      bitmaps `any` (cell lies in some patch) and `multi` (in two or more) -- integer atomicOr only, the
-//                   result does not depend on the order
+//   k_bwd_meta_mark per-RoI geometry (roi_bwd_common.cuh) and the bitmaps `any` (cell lies in some patch) / `multi` (in two
+//                   or more) -- integer atomicOr only, the result does not depend on the order
+//   k_bwd_bucket_scan  ascending RoI lists per (image, level); in its last block the exclusive prefix of the patch areas
+//                   = scratch slot of every (RoI, cell), raising `fallback` if the patches do not fit the scratch
 //   k_bwd_patch     one CTA per (RoI, 128 channels): grad_out[roi] / 4 staged as [bin][channel], the row / column
 //                   weight lists built once, then a warp walks its rows of the patch and writes every cell exactly once:
 //                   straight into grad_feat if no other patch covers it, else into its scratch slot
@@ -61,20 +60,40 @@ __device__ __forceinline__ long long patch_area(const BwdMeta& m) {
     return (m.y1 >= m.y0 && m.x1 >= m.x0) ? (long long)(m.y1 - m.y0 + 1) * (m.x1 - m.x0 + 1) : 0;
 }
 
-__global__ void __launch_bounds__(1024) k_bwd_scan(const BwdMeta* __restrict__ meta, long long R, long long cap_cells,
-                                                   long long* __restrict__ poff, int* __restrict__ flags) {
+// blocks 0 .. B * L - 1: the ascending RoI list of one (image, level) (k_bwd_bucket with 1024 threads); the last block: the
+// exclusive prefix of the patch areas and the fallback flag
+__global__ void __launch_bounds__(1024) k_bwd_bucket_scan(const BwdMeta* __restrict__ meta, long long R, int L, int n_maps,
+                                                          int* __restrict__ bucket, int* __restrict__ bcount, long long cap_cells,
+                                                          long long* __restrict__ poff, int* __restrict__ flags) {
     __shared__ long long s_w[32];
     __shared__ long long s_base;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if ((int)blockIdx.x < n_maps) {
+        const int img = blockIdx.x / L, lvl = blockIdx.x - img * L;
+        int* out = bucket + (long long)blockIdx.x * R;
+        for (long long r0 = 0; r0 < R; r0 += 1024) {
+            const long long r = r0 + threadIdx.x;
+            bool hit = false;
+            if (r < R) { const int4 h = *reinterpret_cast<const int4*>(meta + r); hit = h.x == img && h.y == lvl; }
+            const unsigned bm = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_w[warp] = __popc(bm);
+            __syncthreads();
+            long long before = s_base;
+            for (int w = 0; w < warp; ++w) before += s_w[w];
+            if (hit) out[before + __popc(bm & ((1u << lane) - 1u))] = (int)r;
+            __syncthreads();
+            if (threadIdx.x == 0) { long long t = 0; for (int w = 0; w < 32; ++w) t += s_w[w]; s_base += t; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) bcount[blockIdx.x] = (int)s_base;
+        return;
+    }
     for (long long r0 = 0; r0 < R; r0 += 1024) {
         const long long r = r0 + threadIdx.x;
         long long a = 0;
-        if (r < R) {
-            const BwdMeta m = meta[r];
-            a = patch_area(m);
-        }
+        if (r < R) a = patch_area(meta[r]);
         long long inc = a;
         for (int d = 1; d < 32; d <<= 1) {
             const long long t = __shfl_up_sync(0xffffffffu, inc, d);
@@ -95,13 +114,13 @@ __global__ void __launch_bounds__(1024) k_bwd_scan(const BwdMeta* __restrict__ m
     }
 }
 
-// one warp per RoI; lanes over the rows of its patch
-__global__ void __launch_bounds__(256) k_bwd_mark(PatchArgs a) {
-    if (a.flags[0]) return;
+// one warp per RoI: its geometry record, then the rows of its patch into the `any` / `multi` bitmaps (lanes over rows)
+__global__ void __launch_bounds__(256) k_bwd_meta_mark(MetaArgs ma, PatchArgs a, BwdMeta* __restrict__ meta) {
     const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= a.R) return;
-    const BwdMeta m = a.meta[r];
+    const BwdMeta m = bwd_meta_of(ma, r);
+    if (lane == 0) meta[r] = m;
     if (patch_area(m) == 0) return;
     const int H = a.cfg.H[m.lvl], W = a.cfg.W[m.lvl];
     unsigned* ab = a.anyb + a.word0[m.lvl];
@@ -443,10 +462,7 @@ int roi_align_bwd_patch_try(void* const* grad_feat_ptrs_host, const float* grad_
     MetaArgs ma;
     memset(&ma, 0, sizeof(ma));
     ma.cfg = c; ma.rois = rois; ma.roi_ld = roi_ld; ma.roi_img = roi_img; ma.levels = levels; ma.R = R;
-    k_bwd_meta<<<cdiv(R, 256), 256, 0, st>>>(ma, meta);
-    k_bwd_bucket<<<B * c.num_levels, 256, 0, st>>>(meta, R, c.num_levels, bucket, bcount);
     a.cap_cells = patch_budget_cells(R);
-    k_bwd_scan<<<1, 1024, 0, st>>>(meta, R, a.cap_cells, poff, flags);
     if (cudaMemsetAsync(anyb, 0, 2 * align256((size_t)words * 4 + 16), st) != cudaSuccess) return check_launch("roi_align_bwd(patch memset)");
     int run = 0;
     for (int l = 0; l < c.num_levels; ++l) {
@@ -458,7 +474,9 @@ int roi_align_bwd_patch_try(void* const* grad_feat_ptrs_host, const float* grad_
     a.tile_off[c.num_levels] = run;
     a.gout = grad_out; a.meta = meta; a.poff = poff; a.anyb = anyb; a.multi = multi; a.scratch = scratch; a.flags = flags;
     a.bucket = bucket; a.bcount = bcount; a.R = R;
-    k_bwd_mark<<<cdiv(R * 32, 256), 256, 0, st>>>(a);
+    k_bwd_meta_mark<<<cdiv(R * 32, 256), 256, 0, st>>>(ma, a, meta);
+    k_bwd_bucket_scan<<<B * c.num_levels + 1, 1024, 0, st>>>(meta, R, c.num_levels, B * c.num_levels, bucket, bcount, a.cap_cells,
+                                                            poff, flags);
     const size_t smem = (size_t)c.PH * c.PW * kPPitch * 4 + 2 * kMaxDim * kMaxTerms * sizeof(Term) + 2 * kMaxDim * 4;
     B2D_SMEM(k_bwd_patch, smem, "k_bwd_patch");
     k_bwd_patch<<<dim3((unsigned)R, (unsigned)(c.C / kPCg)), kPT, smem, st>>>(a);

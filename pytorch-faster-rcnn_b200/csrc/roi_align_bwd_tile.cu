@@ -36,6 +36,7 @@ struct TileArgs {
     const float* gout; const BwdMeta* meta; const int* bucket; const int* bcount;
     long long R;
     int tile_off[kMaxLevels + 1], tiles_x[kMaxLevels];
+    unsigned n_tiles;                  // tiles x images (grid.x of the ordinary launch)
     const int* guard;                  // non-NULL: run only if *guard != 0 (fallback of the patch form, roi_align_bwd_patch.cu)
 };
 
@@ -58,10 +59,13 @@ __global__ void __launch_bounds__(kBT, 1) k_roi_align_bwd_tile(TileArgs a) {
     Tables* s_tab = reinterpret_cast<Tables*>(s_dyn + 2 * sizeof(float) * kMaxBinsT * kPitch);
     __shared__ int s_list[kBT], s_n, s_warp[kBT / 32];
     if (a.guard && *a.guard == 0) return;
+    // one tile per CTA in the ordinary launch; the guarded fallback launch is persistent (a few CTAs per SM striding over
+    // the tiles), so that it costs a microsecond when the guard says there is nothing to do
+    for (unsigned bx = blockIdx.x; bx < a.n_tiles; bx += gridDim.x) {
     const b2d_roi_cfg& c = a.cfg;
     const int tiles_per_img = a.tile_off[c.num_levels];
-    const int img = blockIdx.x / tiles_per_img;
-    int t = blockIdx.x - img * tiles_per_img, lvl = 0;
+    const int img = bx / tiles_per_img;
+    int t = bx - img * tiles_per_img, lvl = 0;
     for (int q = 1; q < c.num_levels; ++q) if (t >= a.tile_off[q]) lvl = q;
     t -= a.tile_off[lvl];
     const int H = c.H[lvl], W = c.W[lvl], C = c.C, bins = c.PH * c.PW;
@@ -209,6 +213,8 @@ __global__ void __launch_bounds__(kBT, 1) k_roi_align_bwd_tile(TileArgs a) {
         for (int x = 0; x < kT; ++x)
             if (tx0 + x < W) *reinterpret_cast<float4*>(g + (long long)x * C) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
     }
+    __syncthreads();                                     // shared lists / buffers are reused by the next tile
+    }
 }
 
 }  // namespace
@@ -256,7 +262,16 @@ int roi_align_bwd_tile_launch(void* const* grad_feat_ptrs_host, const float* gra
     }
     a.tile_off[c.num_levels] = run;
     a.gout = grad_out; a.meta = (const BwdMeta*)meta; a.bucket = bucket; a.bcount = bcount; a.R = R; a.guard = guard;
-    dim3 grid((unsigned)(run * B), (unsigned)(c.C / kCg));
+    a.n_tiles = (unsigned)(run * B);
+    unsigned gx = a.n_tiles;
+    if (guard) {                                         // persistent: one wave
+        int sms = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const unsigned wave = (unsigned)cdiv(sms, c.C / kCg);
+        if (gx > wave) gx = wave;
+    }
+    dim3 grid(gx, (unsigned)(c.C / kCg));
     const size_t smem = 2 * sizeof(float) * kMaxBinsT * kPitch + 2 * kTablesBytes;
     B2D_SMEM(k_roi_align_bwd_tile, smem, "k_roi_align_bwd_tile");   // per device
     k_roi_align_bwd_tile<<<grid, kBT, smem, st>>>(a);

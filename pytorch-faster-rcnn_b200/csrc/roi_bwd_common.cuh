@@ -19,9 +19,7 @@ struct MetaArgs {
     const float* rois; long long roi_ld; const int* roi_img; const int* levels; long long R;
 };
 
-static __global__ void __launch_bounds__(256) k_bwd_meta(MetaArgs a, BwdMeta* __restrict__ meta) {
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.R) return;
+__device__ __forceinline__ BwdMeta bwd_meta_of(const MetaArgs& a, long long r) {
     const b2d_roi_cfg& c = a.cfg;
     const float x1 = a.rois[r], y1 = a.rois[a.roi_ld + r], x2 = a.rois[2 * a.roi_ld + r], y2 = a.rois[3 * a.roi_ld + r];
     BwdMeta m;
@@ -41,7 +39,13 @@ static __global__ void __launch_bounds__(256) k_bwd_meta(MetaArgs a, BwdMeta* __
         if (t.valid) { x0 = min(x0, t.lo); x1c = max(x1c, t.hi); }
     }
     m.y0 = y0; m.y1 = y1c; m.x0 = x0; m.x1 = x1c; m._p0 = m._p1 = 0;
-    meta[r] = m;
+    return m;
+}
+
+static __global__ void __launch_bounds__(256) k_bwd_meta(MetaArgs a, BwdMeta* __restrict__ meta) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    meta[r] = bwd_meta_of(a, r);
 }
 
 // bucket[(img * L + lvl) * R + k] = k-th RoI (ascending) of that feature map; bcount[img * L + lvl]
