@@ -581,6 +581,33 @@ def run_b200(args):
     e2e_sparse_ms = f0.elapsed_time(f1) / n_e2e
     cells_step = (int(hp_s.roi_align.cells_moved[0]) - cells0) / n_e2e
     h2d_sparse = sum(t.numel() * t.element_size() for t in h_cls + [h_gt, h_gl]) + int(cells_step * 256 * 4)
+    # the same with two host batches in flight: two TrainHotPath instances on two streams, called alternately, so that the
+    # objectness copy + chains of one batch run under the other's cell fetch (the PCIe link stays busy); secondary number
+    e2e_if2_ms = None
+    if rank == 0 and world == 1:
+        pair = [(hp_s, torch.cuda.Stream(device=dev)),
+                (fused.TrainHotPath(B, grids, dev, gt_ld=K_GT, feat_channels=256, layout=1, overlap=True, seed=7), torch.cuda.Stream(device=dev))]
+        cur0 = torch.cuda.current_stream()
+
+        def two_host_batches(n):
+            for _, st_ in pair:
+                st_.wait_stream(cur0)
+            for i in range(n):
+                hp_i, st_ = pair[i % 2]
+                with torch.cuda.stream(st_):
+                    hp_i.step_from_host(h_cls, h_reg, h_feat_cl, h_gt, h_gl, gcount, img_hw)
+            for _, st_ in pair:
+                cur0.wait_stream(st_)
+
+        two_host_batches(4)
+        torch.cuda.synchronize()
+        n2 = 2 * max(2, n_e2e // 2)
+        f0.record()
+        two_host_batches(n2)
+        f1.record()
+        torch.cuda.synchronize()
+        e2e_if2_ms = f0.elapsed_time(f1) / n2
+        del pair
     if getattr(hp_s, "last_reg_zero_copy", False):
         # regression deltas are read at the selected anchors only, from the mapped host maps: 4 values per anchor of the
         # per-level top-k and per RPN sample, counted as the 32-byte sectors such reads move over PCIe
@@ -684,6 +711,9 @@ def run_b200(args):
                               "from the mapped host maps by b2d_fetch_marked_cells, the rest never crosses PCIe -> RoIAlign -> D2H of "
                               "proposals / targets.  Results bit-identical to e2e_nchw (tests)." % (
                                   cells_step / float(B * sum(g[0] * g[1] for g in grids[:4])))},
+            "e2e_in_flight_2": None if e2e_if2_ms is None else {
+                "value": B / (e2e_if2_ms / 1e3), "unit": "images/s", "ms_per_step": e2e_if2_ms, "batches_in_flight": 2,
+                "note": "two TrainHotPath instances on two streams, step_from_host called alternately (total time / steps)"},
             "e2e_nchw": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                          "ms_per_step": e2e_ms, "layout": "the same call with pinned host fp32 NCHW feature maps (the reference FPN's default "
                                                           "layout): H2D of the whole pyramid (copy stream) -> NCHW->NHWC -> hot path -> D2H; "
