@@ -461,16 +461,23 @@ def run_b200(args):
                       scale_factor=1.0) for _ in range(B)]
         gtl, gll = [gt[i] for i in range(B)], [gl[i] for i in range(B)]
         dropin = {}
+
+        def host_median(fn, n_it):
+            """median host wall time of one call, device work included (a scheduling hiccup of the host does not
+            triple a 1 ms measurement, as it does with a mean over 20 calls)"""
+            ts = []
+            for _ in range(n_it):
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            return float(np.median(ts))
+
         for name, ff in (("nchw", feats_nchw), ("channels_last", feats)):
             fn = lambda: seq.step(cls, reg, ff, gtl, gll, metas)
             fn(); fn()
             torch.cuda.synchronize()
-            n_it = 5
-            t0 = time.perf_counter()
-            for _ in range(n_it):
-                fn()
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / n_it
+            dt = host_median(fn, 5)
             dropin[name] = {"value": B / dt, "unit": "images/s", "ms_per_step": dt * 1e3}
         # the same sequence with the three per-image loops rebound at the METHOD level (batched.py; what install() binds
         # onto RPNHead.predict_bboxes_from_output / AnchorHead.loss / BBoxHead.bbox_targets): one batched pass per loop
@@ -479,15 +486,10 @@ def run_b200(args):
             fn = lambda: seqb.step(cls, reg, ff, gtl, gll, metas)
             fn(); fn()
             torch.cuda.synchronize()
-            n_it = 20
-            t0 = time.perf_counter()
-            for _ in range(n_it):
-                fn()
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / n_it
+            dt = host_median(fn, 20)
             dropin[name] = {"value": B / dt, "unit": "images/s", "ms_per_step": dt * 1e3}
         dropin["note"] = "reference call sequence (AnchorHead.loss targets / predict_bboxes_from_output / bbox_targets / " \
-                         "BasicRoIExtractor) on the drop-in, eager, host wall clock incl. its syncs; nchw / channels_last: " \
+                         "BasicRoIExtractor) on the drop-in, eager, median host wall clock per call incl. its syncs; nchw / channels_last: " \
                          "the reference's per-image Python loops on the rebound functions; batched_*: the loops themselves " \
                          "rebound (one batched pass + one sync each), as install() does"
     # ---- per-stage device times (eager, CUDA events on the launching stream)

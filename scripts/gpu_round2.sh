@@ -12,6 +12,7 @@ N="ncu --set full --clock-control none --import-source on"
 $N -k regex:k_roi_align_win -s 3 -c 1 -o gpurun_out/prof_${tag}_roi $B > gpurun_out/ncu_a.log 2>&1; echo rc=$?
 $N -k regex:'k_rpn_front|k_rpn_back' -s 6 -c 3 -o gpurun_out/prof_${tag}_rpn $B > gpurun_out/ncu_b.log 2>&1; echo rc=$?
 $N -k regex:'k_label_rows|k_colmax_rect|k_roi_targets_small|k_sample|k_encode_targets|k_gather_head' -s 12 -c 6 -o gpurun_out/prof_${tag}_tgt $B > gpurun_out/ncu_c.log 2>&1; echo rc=$?
+$N -k regex:'k_fetch_cells|k_roi_mark' -c 2 -o gpurun_out/prof_${tag}_fetch $B > gpurun_out/ncu_d.log 2>&1; echo rc=$?
 python scripts/timeline.py 1 > gpurun_out/timeline_$tag.txt 2>&1; echo tl_rc=$?
 python scripts/bench_rpn.py "B2D_DBG=10" > gpurun_out/rpn_phases_$tag.txt 2>&1; echo ph_rc=$?
 python scripts/bench_roi_order.py > gpurun_out/roi_order_$tag.txt 2>&1; echo ord_rc=$?
