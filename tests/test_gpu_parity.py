@@ -900,6 +900,33 @@ def test_mark_and_fetch_touched_cells_cover_every_tap(setknob):
     assert n_marked <= 1.6 * n_exact                                      # rectangles of RoIs with bins > 2 cells have holes
 
 
+def test_mark_and_fetch_ragged_counts_bf16_single_level():
+    """Sparse transfer at its edges: an image without RoIs, a single-level extractor, bf16 channels_last maps (a cell is
+    C * 2 bytes), C = 8 (one 16-byte chunk per cell): RoIAlign on the fetched cells == RoIAlign on the whole map."""
+    rng = np.random.default_rng(11)
+    B, C, H, W, ld = 3, 8, 40, 60, 16
+    feat = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    counts = np.array([16, 0, 5], np.int32)
+    rb = np.zeros((B, 4, ld), np.float32)
+    for b in range(B):
+        x1 = rng.uniform(-10, 400, ld); y1 = rng.uniform(-10, 280, ld)
+        rb[b] = np.stack([x1, y1, x1 + rng.uniform(1, 200, ld), y1 + rng.uniform(1, 150, ld)])
+    for layout, dt in ((1, torch.float32), (2, torch.bfloat16)):
+        ra = fused.BatchedRoIAlign(B, ld, [(C, H, W)], [8], DEV, layout=layout)
+        h = fused.pinned_channels_last(torch.from_numpy(feat).to(dt))
+        full = [h.to(DEV)]
+        want = N(ra([full[0]], T(rb), T(counts))).copy()
+        part = [torch.full_like(full[0], float("nan"))]
+        moved = ra.fetch_touched(part, [h], T(rb), T(counts))
+        got = N(ra(part, T(rb), T(counts)))
+        for b in range(B):
+            sl = slice(b * ld, b * ld + counts[b])
+            assert np.array_equal(bits(got[sl]), bits(want[sl]))
+        touched = ~torch.isnan(part[0].float()).any(1).cpu().numpy()
+        assert not touched[1].any(), "image without RoIs: nothing fetched"
+        assert int(moved[0]) == int(touched.sum()) and 0 < int(moved[0]) < B * H * W
+
+
 def test_step_from_host_sparse_fetch_equals_full_copy():
     """TrainHotPath.step_from_host: channels_last pinned host feature maps (sparse fetch of the touched cells) and NCHW
     pinned host maps (full copy + transposition) give bit-identical results, RoI features included."""
