@@ -42,6 +42,51 @@ __global__ void k_fetch(const float4* __restrict__ src, float4* __restrict__ dst
     }
 }
 
+// TMA variant: one elected thread per CTA moves the marked cells of a bitmap word with bulk async copies, host -> shared
+// memory (mbarrier completion), shared memory -> device; two word buffers so that the loads of one word overlap the stores
+// of the previous one
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(32) k_fetch_tma(const char* __restrict__ src, char* __restrict__ dst, const unsigned* __restrict__ bits,
+                                                  int n_words) {
+    extern __shared__ __align__(128) char buf[];                  // [2][32][1024]
+    __shared__ uint64_t bar[2];
+    if (threadIdx.x != 0) return;
+    for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    unsigned phase[2] = {0, 0};
+    int it = 0;
+    for (int wd = blockIdx.x; wd < n_words; wd += gridDim.x) {
+        unsigned m = bits[wd];
+        if (!m) continue;
+        const int b = it & 1;
+        ++it;
+        char* slot = buf + b * 32 * 1024;
+        // the stores that last read this buffer must have finished reading it (at most one older group may be pending)
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        const int n = __popc(m);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar[b])), "r"(n * 1024) : "memory");
+        unsigned mm = m;
+        for (int k = 0; mm; ++k) {
+            const int c = __ffs(mm) - 1; mm &= mm - 1;
+            const char* s = src + ((long long)wd * 32 + c) * 1024;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(slot + k * 1024)),
+                         "l"(s), "r"(1024), "r"(smem_u32(&bar[b])) : "memory");
+        }
+        unsigned ok = 0;
+        while (!ok)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(&bar[b])), "r"(phase[b]) : "memory");
+        phase[b] ^= 1;
+        mm = m;
+        for (int k = 0; mm; ++k) {
+            const int c = __ffs(mm) - 1; mm &= mm - 1;
+            char* d = dst + ((long long)wd * 32 + c) * 1024;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d), "r"(smem_u32(slot + k * 1024)), "r"(1024) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 int main(int argc, char** argv) {
     const int B = 8, H = 200, W = 336;
     const long long cells = (long long)B * H * W;          // level 0 of the config-2 pyramid, 8 images
@@ -92,6 +137,13 @@ int main(int argc, char** argv) {
             time(name, (double)bytes, [&] { k_fetch<4><<<ctas, threads>>>((const float4*)hd, (float4*)d, d_dense, n_words); });
             snprintf(name, sizeof name, "zero-copy sparse U=4 %4d CTAs x %4d", ctas, threads);
             time(name, set * 1024.0, [&] { k_fetch<4><<<ctas, threads>>>((const float4*)hd, (float4*)d, d_sparse, n_words); });
+        }
+    CK(cudaFuncSetAttribute(k_fetch_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    for (int ctas : {148, 296, 444})
+        for (int pass = 0; pass < 2; ++pass) {
+            char name[128];
+            snprintf(name, sizeof name, "TMA bulk %s %4d CTAs (1 thread, 2 x 32 KB)", pass ? "sparse" : "dense ", ctas);
+            time(name, pass ? set * 1024.0 : (double)bytes, [&] { k_fetch_tma<<<ctas, 32, 65536>>>((const char*)hd, (char*)d, pass ? d_sparse : d_dense, n_words); });
         }
     time("zero-copy sparse U=1  592 CTAs x 1024", set * 1024.0, [&] { k_fetch<1><<<592, 1024>>>((const float4*)hd, (float4*)d, d_sparse, n_words); });
     time("zero-copy sparse U=2  592 CTAs x 1024", set * 1024.0, [&] { k_fetch<2><<<592, 1024>>>((const float4*)hd, (float4*)d, d_sparse, n_words); });
