@@ -333,8 +333,8 @@ B2D_API int b2d_roi_levels(int* levels, const float* rois, long long roi_ld, lon
  * BasicRoIExtractor (lib/region.py:299-375) reads only the cells under the bilinear taps of the RoIs.  When the
  * pyramid is channels-last in PINNED (mapped) HOST memory, b2d_roi_mark_cells writes a bitmap with one bit per
  * (level, image, y, x) -- levels in order, each padded to whole 32-bit words, b2d_roi_cell_bitmap_bytes in total --
- * holding the tap rectangle of every RoI (rois [B][4][ld], counts int32[B], as b2d_roi_align_fwd_batched; the same
- * level map and sample geometry, so every cell RoIAlign reads is marked), and b2d_fetch_marked_cells copies the
+ * holding the cells under the bilinear taps of every RoI (rois [B][4][ld], counts int32[B], as
+ * b2d_roi_align_fwd_batched; the same level map and sample geometry, so exactly the cells RoIAlign reads are marked), and b2d_fetch_marked_cells copies the
  * marked cells from src (device-visible pointers of the host tensors, [B,H,W,C] per level) to the same offsets of
  * dst (device tensors of the same shape) with SM-issued loads; *moved_cells (device, may be NULL) is incremented by
  * the number of cells copied.  Needs cfg.layout 1 or 2 and a fixed sampling_ratio. */

@@ -8,9 +8,10 @@
 // PCIe 5 x16 link against 55 GB/s for cudaMemcpyAsync of everything (scripts/zc_probe.cu,
 // profiles/r2m_zc_probe.txt), so the step ships 0.59 of the bytes at 0.93 of the speed.
 //
-//   k_roi_mark   one warp per RoI slot: level map + tap rectangle of the RoI (the same roi_level /
-//                roi_geom / axis_tap as the RoIAlign kernels, so the rectangle is a superset of
-//                every cell they read), OR-ed into a bitmap with one bit per (level, image, y, x).
+//   k_roi_mark   one warp per RoI slot: level map + the cells under the RoI's bilinear taps -- (rows
+//                under a tap) x (columns under a tap), from the same roi_level / roi_geom / axis_tap as
+//                the RoIAlign kernels, so exactly the cells they read -- OR-ed into a bitmap with one
+//                bit per (level, image, y, x).
 //   k_fetch_cells one warp per bitmap word (32 cells): every marked cell is copied from the mapped
 //                host tensor to the same offset of the device tensor (NHWC), several cells in flight
 //                per warp; the number of cells moved is counted for the byte accounting of bench.py.
@@ -46,27 +47,41 @@ __global__ void __launch_bounds__(256) k_roi_mark(RoiArgs a, unsigned* __restric
     else lvl = c.num_levels > 1 ? roi_level(x1, y1, x2, y2, c.finest_scale, c.num_levels) : 0;
     const int H = c.H[lvl], W = c.W[lvl];
     const RoiGeom g = roi_geom(x1, y1, x2, y2, c.spatial_scale[lvl], c.PH, c.PW, c.sampling_ratio, c.aligned);
-    // extent of the taps over every (bin, sample) of each axis: no monotonicity assumed (aligned=True may give
-    // negative bin sizes); invalid samples still have clamped cell indices, which the kernels may read with weight 0
-    int ylo = H, yhi = -1, xlo = W, xhi = -1;
+    // rows: the extent of the taps (no monotonicity assumed: aligned=True may give negative bin sizes; invalid samples still
+    // have clamped cell indices, which the kernels read with weight 0); a lane takes the rows ylo + lane, + 32, ...
+    int ylo = H, yhi = -1;
     for (int p = 0; p < c.PH; ++p)
         for (int i = 0; i < g.gy; ++i) {
             const AxisTap t = axis_tap(g.sy, g.bh, p, i, g.gy, H);
             ylo = min(ylo, t.lo); yhi = max(yhi, t.hi);
         }
-    for (int p = 0; p < c.PW; ++p)
-        for (int i = 0; i < g.gx; ++i) {
-            const AxisTap t = axis_tap(g.sx, g.bw, p, i, g.gx, W);
-            xlo = min(xlo, t.lo); xhi = max(xhi, t.hi);
-        }
     unsigned* lb = bits + f.word0[lvl];
     for (int y = ylo + lane; y <= yhi; y += 32) {
-        const long long c0 = ((long long)img * H + y) * W + xlo, c1 = c0 + (xhi - xlo);
-        for (long long wd = c0 >> 5; wd <= (c1 >> 5); ++wd) {
-            const int b0 = wd == (c0 >> 5) ? (int)(c0 & 31) : 0, b1 = wd == (c1 >> 5) ? (int)(c1 & 31) : 31;
-            const unsigned m = (b1 == 31 ? 0xffffffffu : ((1u << (b1 + 1)) - 1u)) & ~((1u << b0) - 1u);
-            atomicOr(lb + wd, m);
-        }
+        // exactly the tap cells: (rows under a tap) x (columns under a tap) -- RoIs with bins wider than two cells have
+        // rows and columns no sample touches
+        bool tap_row = false;
+        for (int p = 0; p < c.PH && !tap_row; ++p)
+            for (int i = 0; i < g.gy; ++i) {
+                const AxisTap t = axis_tap(g.sy, g.bh, p, i, g.gy, H);
+                tap_row = tap_row || t.lo == y || t.hi == y;
+            }
+        if (!tap_row) continue;
+        const long long row0 = ((long long)img * H + y) * W;
+        long long cur = -1;                                  // pending bitmap word and its bits
+        unsigned m = 0;
+        for (int p = 0; p < c.PW; ++p)
+            for (int i = 0; i < g.gx; ++i) {
+                const AxisTap t = axis_tap(g.sx, g.bw, p, i, g.gx, W);
+                for (int k = 0; k < 2; ++k) {
+                    const long long cell = row0 + (k ? t.hi : t.lo);
+                    if ((cell >> 5) != cur) {
+                        if (m) atomicOr(lb + cur, m);
+                        cur = cell >> 5; m = 0;
+                    }
+                    m |= 1u << (cell & 31);
+                }
+            }
+        if (m) atomicOr(lb + cur, m);
     }
 }
 
