@@ -571,6 +571,60 @@ def test_roi_align_backward_patch_form_blocks_and_fallback(setknob):
     assert np.array_equal(bits(grads_of(big, "2")), bits(grads_of(big, "1"))), "fallback must be the tile kernel's result"
 
 
+def test_roi_align_backward_full_size_properties(setknob):
+    """K6 at BASELINE config-2 / 3 geometry (the sampled RoIs of a 2-image step, 256 channels, full pyramid): the patch
+    form against the tile form (rounding only), run-to-run bit-identical, exactly linear under a power-of-two scaling of
+    the incoming gradient, and the size-independent checksum of the operator: every counted sample's four bilinear
+    weights sum to one, so sum over all cells of grad_feat[:, c] == sum over (RoI, bin) of grad_out[:, c] x (fraction of
+    the bin's 4 samples that lie on the map)."""
+    B, K, C = 2, 8, 256
+    w = workload.config2(B=B, K=K, channels=C)
+    hp = fused.TrainHotPath(B, w["grids"], DEV, gt_ld=K, feat_channels=C)
+    cls, reg = [T(c) for c in w["cls"]], [T(r) for r in w["reg"]]
+    feats = [T(f).contiguous(memory_format=torch.channels_last) for f in w["feats"]]
+    gcount = torch.full((B,), K, dtype=torch.int32, device=DEV)
+    img_hw = torch.tensor([[800.0, 1333.0]] * B, device=DEV)
+    out = hp.step(cls, reg, feats, T(w["gt"]), gcount, T(w["gt_label"]), img_hw)
+    bt = out["rcnn"]
+    rois = torch.cat([bt.tar_box[b, :, :int(bt.n_chosen[b])] for b in range(B)], 1).contiguous()
+    roi_img = torch.cat([torch.full((int(bt.n_chosen[b]),), b, dtype=torch.int32, device=DEV) for b in range(B)])
+    R = rois.shape[1]
+    assert R == B * 512
+    go = torch.randn((R, C, 7, 7), device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+
+    def grads(form, g):
+        setknob(B2D_ROI_BWD_TILE=form)
+        fs = [f.detach().clone().requires_grad_(True) for f in feats]
+        bregion.roi_align_levels(fs, rois, roi_img, scales).backward(g)
+        return [f.grad for f in fs]
+
+    gp, gt_ = grads("2", go), grads("1", go)
+    for a, b in zip(gp, gt_):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=5e-6)
+    for a, b in zip(gp, grads("2", go)):
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), "run-to-run deterministic"
+    for a, b in zip(gp, grads("2", go * 4.0)):
+        assert torch.equal((a * 4.0).view(torch.int32), b.view(torch.int32)), "linear under exact scaling"
+    # checksum: a sample is dropped only if it lies beyond the map (y < -1 or y > H: thin RoIs at the image border, whose
+    # size is raised to one cell); vy / vx = fraction of a bin's two samples per axis that count
+    r = N(rois)
+    lv = oracle.level_map(r)
+    sc = np.array([1 / 4, 1 / 8, 1 / 16, 1 / 32], np.float32)[lv]
+    Hs, Ws = np.array([g[0] for g in w["grids"]])[lv], np.array([g[1] for g in w["grids"]])[lv]
+    frac = []
+    for lo, hi, size in ((r[1], r[3], Hs), (r[0], r[2], Ws)):
+        st = lo * sc
+        b = np.maximum(hi * sc - st, np.float32(1)) / np.float32(7)
+        pos = st[:, None, None] + np.arange(7, dtype=np.float32)[None, :, None] * b[:, None, None] + \
+            (np.arange(2, dtype=np.float32)[None, None, :] + np.float32(0.5)) * b[:, None, None] / np.float32(2)
+        frac.append(((pos >= -1) & (pos <= size[:, None, None])).mean(2))                 # [R, 7]
+    wgt = torch.from_numpy(frac[0][:, :, None] * frac[1][:, None, :]).to(DEV)              # [R, 7, 7]
+    total = sum(g.double().sum(dim=(0, 2, 3)) for g in gp)                # [C]
+    want = (go.double() * wgt[:, None].double()).sum(dim=(0, 2, 3))
+    torch.testing.assert_close(total, want, rtol=1e-6, atol=1e-3)
+
+
 def test_roi_align_reference_layout_takes_fast_kernels():
     """fp32 NCHW features (the reference's FPN output layout, lib/necks.py) are transposed once and go through the same
     K5 / K6 kernels as channels_last inputs: identical forward bits, identical gradients (returned for the NCHW input)."""
