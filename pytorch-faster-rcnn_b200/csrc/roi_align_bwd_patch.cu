@@ -189,22 +189,30 @@ __global__ void __launch_bounds__(kPT, 6) k_bwd_patch(PatchArgs a) {
     const int nrows = m.y1 - m.y0 + 1, ncols = m.x1 - m.x0 + 1;
     // ---- grad_out[r][cg * 128 + tid][bins] / 4 -> [bin][channel]
     {
-        // the [128 channels][bins] block of this CTA is contiguous: element e = 128 i + tid, read coalesced (a warp load = 4
-        // sectors; one thread per channel would touch 32 sectors per load and bound the kernel by L1 sector requests),
-        // 32 loads in flight; (channel, bin) of e advance incrementally
+        // the [128 channels][bins] block of this CTA is contiguous: element e = 128 i + tid, i < bins, read coalesced (a warp
+        // load = 4 sectors; one thread per channel would touch 32 sectors per load and bound the kernel by L1 sector
+        // requests), 16 loads in flight; the shared-memory address of e advances incrementally (e += 128: channel += 128 /
+        // bins, bin += 128 % bins with one wrap)
         const float* go = a.gout + ((long long)r * C + (long long)cg * kPCg) * bins + tid;
-        const int total = kPCg * bins, dch = kPT / bins, db = kPT % bins;
-        int ch = tid / bins, b = tid % bins;
-        for (int e0 = 0; e0 < total; e0 += 32 * kPT) {
-            float v[32];
+        const int dch = kPT / bins, db = kPT % bins;
+        const int step = db * kPPitch + dch, wrap = 1 - bins * kPPitch;
+        int b = tid % bins, addr = b * kPPitch + tid / bins;
+        int i = 0;
+        for (; i + 16 <= bins; i += 16) {
+            float v[16];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] = (e0 + k * kPT + tid < total) ? __ldg(go + e0 + k * kPT) : 0.0f;
+            for (int k = 0; k < 16; ++k) v[k] = __ldg(go + (i + k) * kPT);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                if (e0 + k * kPT + tid < total) sg[b * kPPitch + ch] = v[k] * 0.25f;
-                ch += dch; b += db;
-                if (b >= bins) { b -= bins; ++ch; }
+            for (int k = 0; k < 16; ++k) {
+                sg[addr] = v[k] * 0.25f;
+                addr += step; b += db;
+                if (b >= bins) { b -= bins; addr += wrap; }
             }
+        }
+        for (; i < bins; ++i) {
+            sg[addr] = __ldg(go + i * kPT) * 0.25f;
+            addr += step; b += db;
+            if (b >= bins) { b -= bins; addr += wrap; }
         }
     }
     const unsigned sg_lane = (unsigned)__cvta_generic_to_shared(sg + lane * 4);
