@@ -36,7 +36,7 @@ namespace {
 constexpr int kPT = 128;               // threads per patch CTA: 4 warps, lane = 4 channels
 constexpr int kPCg = 128;              // channels per CTA
 constexpr int kPPitch = kPCg + 4;      // shared-memory pitch of a bin row (floats)
-constexpr int kMaxDim = 64;            // patch rows / columns per block of the weight lists
+constexpr int kMaxDim = 32;            // patch rows / columns per block of the weight lists
 constexpr int kMaxTerms = 8;           // PH, PW <= 8
 constexpr int kMT = 16;                // merge tile side
 constexpr int kMThreads = 512;         // merge CTA: warp = tile row
@@ -171,7 +171,7 @@ __device__ __forceinline__ void patch_row(const Term* __restrict__ rt, const Ter
     }
 }
 
-__global__ void __launch_bounds__(kPT, 6) k_bwd_patch(PatchArgs a) {
+__global__ void __launch_bounds__(kPT, 7) k_bwd_patch(PatchArgs a) {
     extern __shared__ __align__(16) float s_dyn[];
     if (a.flags[0]) return;
     const b2d_roi_cfg& c = a.cfg;
@@ -220,17 +220,17 @@ __global__ void __launch_bounds__(kPT, 6) k_bwd_patch(PatchArgs a) {
     float* gl = a.grad[m.lvl] + (long long)cg * kPCg + lane * 4;
     float* sl = a.scratch + (long long)cg * kPCg + lane * 4;
     const long long p0 = a.poff[r];
-    // the patch in blocks of 64 x 64 cells (one block for every RoI the level map places; thin RoIs clamped at the image
-    // border can be a few hundred cells long)
+    // the patch in blocks of 32 x 32 cells (one block for almost every RoI the level map places; thin RoIs clamped at the
+    // image border can be a few hundred cells long)
     for (int yb = 0; yb < nrows; yb += kMaxDim) {
         for (int xb = 0; xb < ncols; xb += kMaxDim) {
             const int bh = min(kMaxDim, nrows - yb), bw = min(kMaxDim, ncols - xb);
             __syncthreads();                                         // staged gradients visible / previous block done
-            // ---- weight lists: thread k < 64 does block row k, thread 64 + k block column k
+            // ---- weight lists: thread k < kMaxDim does block row k, thread kMaxDim + k block column k
             {
-                const int ax = tid >> 6, k = tid & 63;
+                const int ax = tid / kMaxDim, k = tid % kMaxDim;
                 const int n = ax ? bw : bh;
-                if (k < n) {
+                if (ax < 2 && k < n) {
                     const int coord = (ax ? m.x0 + xb : m.y0 + yb) + k, P = ax ? c.PW : c.PH, size = ax ? W : H;
                     const float start = ax ? m.sx : m.sy, bin = ax ? m.bw : m.bh;
                     const int step = (ax ? kPPitch : c.PW * kPPitch) * 4;
