@@ -167,11 +167,26 @@ __global__ void __launch_bounds__(kFrThreads, 1) k_rpn_front(RpnLaunch p, FrontP
     chunk = (chunk + 3) & ~3;
     const int start = min(n, my * chunk), end = min(n, start + chunk);
 
+    dbg_stamp(p, b, dbg_cta, 9);                           // kernel entry
     uint32_t key[kFrPer];
+    if (p.score_mode == 0 && !identity) {
+        // sigmoid RPN (every FPN config of the reference): all 25 loads of a thread in flight at once.  Through the generic
+        // load_logit() below the score-mode branches keep the compiler from batching them: 25 dependent L2 round trips,
+        // 8 us from kernel entry to the first histogram pass (globaltimer stamps) against 1.5 us here.
+        float v[kFrPer];
 #pragma unroll
-    for (int q = 0; q < kFrPer; ++q) {
-        const int i = start + q * kFrThreads + tid;
-        key[q] = i < end ? (identity ? 0xffffffffu : f2key(load_logit(cls, n, i, p.score_mode, p.cls_ch))) : 0u;
+        for (int q = 0; q < kFrPer; ++q) {
+            const int i = start + q * kFrThreads + tid;
+            v[q] = i < end ? __ldg(cls + i) : 0.0f;
+        }
+#pragma unroll
+        for (int q = 0; q < kFrPer; ++q) key[q] = (start + q * kFrThreads + tid < end) ? f2key(v[q]) : 0u;
+    } else {
+#pragma unroll
+        for (int q = 0; q < kFrPer; ++q) {
+            const int i = start + q * kFrThreads + tid;
+            key[q] = i < end ? (identity ? 0xffffffffu : f2key(load_logit(cls, n, i, p.score_mode, p.cls_ch))) : 0u;
+        }
     }
     dbg_stamp(p, b, dbg_cta, 0);
     for (int t = tid; t < kHistBins; t += kFrThreads) s.h[t] = 0u;
@@ -257,14 +272,20 @@ __global__ void __launch_bounds__(kFrThreads, 1) k_rpn_front(RpnLaunch p, FrontP
         all += c;
     }
     const int nA = (int)(all & 0xffffu), nB = (int)(all >> 16);
+    const float* reg_pf = seg_reg(p, b, lq);
     if (cnt != 0u && !(tie && (cnt & 0xffffu) == 0u)) {   // one thread in four holds a candidate at all
         uint32_t pa = before & 0xffffu, pb = before >> 16;
 #pragma unroll
         for (int q = 0; q < kFrPer; ++q) {
             if (q < nv && key[q] >= blo) {
-                const uint64_t c = make_comp(key[q], (uint32_t)(start + q * kFrThreads + tid));
+                const int idx = start + q * kFrThreads + tid;
+                const uint64_t c = make_comp(key[q], (uint32_t)idx);
                 if (key[q] > bhi) stage[pa++] = c;
                 else if (!tie) stage[kFrCap - 1 - (pb++)] = c;
+                // the candidate's four deltas are read by the decode below, after the sort: ask L2 for them now (the step's
+                // inputs are cold in L2 -- the previous RoIAlign streamed 600 MB through it: -2 us, scripts/bench_rpn_cold.py)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) asm volatile("prefetch.global.L2 [%0];" ::"l"(reg_pf + (long long)e * n + idx));
             }
         }
     }

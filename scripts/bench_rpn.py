@@ -17,6 +17,8 @@ img_hw = torch.tensor([[800.0, 1333.0]] * B, device=dev)
 hp = fused.TrainHotPath(B, w["grids"], dev, gt_ld=K, feat_channels=256, layout=1)
 hp.proposals.ws.zero_()
 step = lambda: hp.proposals(cls, reg, img_hw)
+COLD = os.environ.get("RPN_COLD") == "1"            # a 512 MB write before every profiled replay: L2 as RoIAlign leaves it
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if COLD else None
 ref = None
 for setting in (sys.argv[1:] or [""]):
     kv = dict(x.split("=") for x in setting.split(";") if x)
@@ -44,7 +46,9 @@ for setting in (sys.argv[1:] or [""]):
     print("[%s] proposals graph: %.1f us/replay  same_as_first=%s" % (setting, e0.elapsed_time(e1) / 50 * 1e3, same))
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for _ in range(2): g.replay()
+        for _ in range(2):
+            if COLD: flush.zero_(); torch.cuda.synchronize()
+            g.replay()
         torch.cuda.synchronize()
     ev = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events()
                  if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda r: r[0])
