@@ -34,6 +34,7 @@ struct RpnLaunch {
     uint32_t* nz;                       // NMS: per selected box, bitmap of its non-zero mask words (nms.cu)
     size_t zero_bytes, dbg_off;
     uint64_t* cand; uint64_t* cand2;
+    float* red;                         // score_mode 2 with several class channels: [level][B][n_l] best class logit (k_class_max)
     float4* sel_box; uint32_t* sel_key; int* sel_idx;
     float4* kept_box; uint32_t* kept_key; int* kept_idx;   // NMS survivors, compacted in score order
     uint64_t* mask;

@@ -597,10 +597,35 @@ bool rpn_plan(RpnLaunch& p, const b2d_pyramid* pyr, int B, const b2d_rpn_cfg* cf
     p.kept_key = (uint32_t*)carve(kept * 4);
     p.kept_idx = (int*)carve(kept * 4);
     p.mask = (uint64_t*)carve(cfg->do_nms ? (size_t)B * p.mask_per_img * 8 : 0);
+    p.red = (float*)carve((cfg->score_mode == 2 && p.cls_ch > 1) ? (size_t)B * pyr->total * 4 : 0);
     p.dbg_off = o;
     p.dbg_t = (unsigned long long*)carve((size_t)B * kDbgCtas * kDbgStamps * 8);
     *bytes = o;
     return true;
+}
+
+// Sigmoid anchor heads with many class channels (RetinaNet: 9 anchors x 80 classes = 64 MB of logits per image): the best
+// class logit of every anchor, computed by the whole GPU in one coalesced pass (channel loop per thread, same fmaxf order as
+// load_logit mode 2).  The selection kernels then run on the reduced map with score_mode 0 -- inside k_rpn_front the
+// 8 CTAs that own an image would pull those 64 MB through 8 SMs (147 us for the stage; 60 us with this pass in front).
+__global__ void __launch_bounds__(256) k_class_max(RpnLaunch p, int B) {
+    const int l = blockIdx.y;
+    const long long n = p.n[l], total = (long long)B * n;
+    const float* cls = p.cls[l];
+    float* out = p.red + (long long)B * p.pyr.lv[l].offset;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long b = t / n, i = t - b * n;
+        const float* src = cls + b * n * p.cls_ch + i;
+        float m = src[0];
+        int c = 1;
+        for (; c + 4 <= p.cls_ch; c += 4) {
+            const float v0 = src[(long long)c * n], v1 = src[(long long)(c + 1) * n], v2 = src[(long long)(c + 2) * n],
+                        v3 = src[(long long)(c + 3) * n];
+            m = fmaxf(fmaxf(fmaxf(fmaxf(m, v0), v1), v2), v3);
+        }
+        for (; c < p.cls_ch; ++c) m = fmaxf(m, src[(long long)c * n]);
+        out[t] = m;
+    }
 }
 
 }  // namespace b2d
@@ -686,10 +711,19 @@ static int rpn_proposals_impl(float* props, float* scores, int* count, int* prov
     p.dbg = knobs().dbg;
     if (p.dbg != 10) p.dbg_t = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
+    int nl = 0;                                           // launches (kernels + memset nodes) of this call
+    if (p.score_mode == 2 && p.cls_ch > 1 && p.red) {     // many class channels: reduce once, then select on the reduced map
+        int sms = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        k_class_max<<<dim3(sms * 8, p.L), 256, 0, st>>>(p, B);
+        ++nl;
+        for (int l = 0; l < p.L; ++l) p.cls[l] = p.red + (long long)B * p.pyr.lv[l].offset;
+        p.score_mode = 0; p.cls_ch = 1;
+    }
     // function attributes are per device: set on every call (a process may drive several GPUs)
     B2D_SMEM(k_select, kSortCap * 8, "k_select");
     B2D_SMEM(k_merge, kSortCap * 8, "k_merge");
-    int nl = 0;                                           // launches (kernels + memset nodes) of this call
     // Per-level chains.  hist -> compact -> select -> NMS mask -> scan of one level only depends on that level, and
     // all of them but the mask are small latency-bound grids; run as ONE launch per kernel over all levels the step
     // is the sum of the slowest segment of every kernel (166 us at config 2).  Each level therefore gets its own
