@@ -79,6 +79,7 @@ for st, pat in stage_kernel.items():
         if pat in rec["kernel"] and "dram_read_MB" in rec:
             traffic[st] = int((rec["dram_read_MB"] + rec["dram_write_MB"]) * 1e6)
             break
-traffic["source"] = "profiles/%s_ncu_full.csv" % tag
-json.dump(traffic, open("profiles/traffic.json", "w"), indent=1)
+if traffic:                                      # a report without the step's dominant kernel (e.g. a K6-only capture) leaves it alone
+    traffic["source"] = "profiles/%s_ncu_full.csv" % tag
+    json.dump(traffic, open("profiles/traffic.json", "w"), indent=1)
 print("wrote profiles/%s_*" % tag)
