@@ -68,13 +68,17 @@ def test_atss_batched_vs_oracle_ragged():
     rng = np.random.default_rng(7)
     strides, pad, img = [8, 16, 32, 64, 128], (800, 1344), (800, 1333)
     grids = [(-(-pad[0] // s), -(-pad[1] // s)) for s in strides]
-    counts = [1, 16, 64, 5]
+    counts = [1, 16, 64, 5, 8]
     B, ld = len(counts), 64
     gt = np.zeros((B, 4, ld), np.float32)
     gl = np.zeros((B, ld), np.int64)
     for b, k in enumerate(counts):
         bb, ll = workload.synth_gt(rng, k, *img)
         gt[b, :, :k], gl[b, :k] = bb, ll
+    # image 4: GTs whose centres sit in the corners / on the borders of the image (the candidate search scans a window
+    # around the centre's cell: clipped windows must still hold the 9 nearest cells of every level)
+    gt[4, :, :8] = np.array([[0, 0, 30, 30], [1300, 770, 1332, 799], [0, 760, 12, 799], [1320, 0, 1332, 9], [600, 0, 700, 6],
+                             [0, 300, 5, 500], [1326, 100, 1332, 700], [2, 2, 1330, 797]], np.float32).T
     cls, reg, ctr = bheads.atss_assign(grids, strides, T(gt), torch.tensor(counts, dtype=torch.int32, device=DEV), T(gl),
                                        torch.tensor([[800.0, 1333.0]] * B, device=DEV))
     for b, k in enumerate(counts):
