@@ -234,6 +234,18 @@ B2D_API int b2d_multiclass_candidates(float* cand_box, float* nms_box, float* ca
                               int strict, int cap, void* stream);
 /* utils.batched_nms (lib/utils.py:211-221): out [n][4] = bbox + fp32(label * max(bbox)) -- the boxes handed to nms */
 B2D_API int b2d_batched_nms_boxes(float* out, const float* bbox, const int64_t* label, long long n, void* stream);
+/* GA-RPN call sites (GARPNHead.predict_bboxes_single_image, lib/heads/guided_head.py:621-669): guided anchors are explicit
+ * per-location boxes [4][n_l] with a location mask (torch.bool [n_l]) per level.  b2d_ga_pack_scores writes the logits of all
+ * levels as rows of one [L][ld] array with -inf at masked / padded places (the input of ONE segmented b2d_topk over the
+ * levels); b2d_ga_decode gathers anchor + deltas of the selected places, decodes and clamps them (utils.param2bbox with
+ * img_size, lib/utils.py:83-120) into box [L][k][4] (row-major, the layout b2d_nms takes), score = sigmoid(logit) or -inf
+ * for masked rows and for boxes below min_size, nvalid int32[L] = selected unmasked places per level. */
+B2D_API int b2d_ga_pack_scores(float* out, long long ld, const void* const* cls_ptrs_host, const void* const* mask_ptrs_host,
+                       const int* n_host, int L, void* stream);
+B2D_API int b2d_ga_decode(float* box, float* score, int* nvalid, const int* idx, const float* packed, long long ld, int k,
+                  const void* const* cls_ptrs_host, const void* const* mask_ptrs_host, const void* const* anchor_ptrs_host,
+                  const void* const* reg_ptrs_host, const int* n_host, int L, const float* means_host, const float* stds_host,
+                  float img_h, float img_w, float min_size, void* stream);
 /* ScalableRoICrop.scale_bbox (lib/region.py:220-225) on [4][ld] boxes */
 B2D_API int b2d_scale_rois(float* out, const float* rois, long long ld, long long n, float scale, void* stream);
 /* IoUBalancedNegSampler (lib/region.py:128-172).  Bins are given HIGHEST IoU range first (the reference's walk order),

@@ -106,6 +106,8 @@ _SIGS = {
     "b2d_sample_iou_balanced": [_P, _P, _P, c_ll, c_int, c_int, c_int, _P, _P, c_ull, _P],
     "b2d_sampled_ce_fwd": [_P, _P, c_ll, c_int, c_int, c_int, _P, c_ll, _P],
     "b2d_sampled_ce_bwd": [_P, _P, _P, c_ll, c_int, c_int, c_int, _P, c_ll, _P],
+    "b2d_ga_pack_scores": [_P, c_ll, _P, _P, _P, c_int, _P],
+    "b2d_ga_decode": [_P, _P, _P, _P, _P, c_ll, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_float, c_float, c_float, _P],
     "b2d_roi_mark_cells": [_P, _P, c_ll, _P, c_int, _P, _P],
     "b2d_fetch_marked_cells": [_P, _P, _P, c_int, _P, _P, _P],
     "b2d_roi_pool_bwd": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_ll, _P, c_ll, c_float, c_int, c_int, _P,

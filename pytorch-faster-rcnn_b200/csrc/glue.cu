@@ -373,6 +373,51 @@ __global__ void __launch_bounds__(256) k_ce_bwd(CeArgs p, float* __restrict__ gr
     for (int c = 0; c < p.C; ++c) put(c, g * (expf(ce_logit(p, r, c) - m) / s - (c == (int)t ? 1.0f : 0.0f)));
 }
 
+// ---- GA-RPN call sites (lib/heads/guided_head.py:621-669): explicit per-location anchors + a location mask ----
+struct GaLevels {
+    const float* cls[kMaxLevels];          // [n_l] logits
+    const unsigned char* mask[kMaxLevels]; // [n_l] torch.bool
+    const float* anchor[kMaxLevels];       // [4][n_l]
+    const float* reg[kMaxLevels];          // [4][n_l]
+    int n[kMaxLevels];
+    int L;
+};
+
+// out[l][i] = logit of location i of level l if it is inside the level and unmasked, else -inf (one launch for all levels)
+__global__ void __launch_bounds__(256) k_ga_pack_scores(GaLevels g, float* __restrict__ out, long long ld) {
+    const int l = blockIdx.y;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ld; i += (long long)gridDim.x * blockDim.x)
+        out[(long long)l * ld + i] = (i < g.n[l] && g.mask[l][i]) ? g.cls[l][i] : -INFINITY;
+}
+
+// per selected location (l, j) of the segmented top-k: gather its anchor and deltas, decode + clamp (utils.param2bbox with
+// img_size), sigmoid score; rows whose location is masked out (-inf logit, they sort last) or missing (-1) are invalid.
+// A box below min_size keeps its row but gets score -inf: the NMS behind this sorts it to the end of its level.
+__global__ void __launch_bounds__(256) k_ga_decode(GaLevels g, const int* __restrict__ idx, const float* __restrict__ packed,
+                                                   long long ld, int k, float4 ms_lo, float4 ms_hi, float img_h, float img_w,
+                                                   float min_size, float* __restrict__ box /* [L][k][4] */,
+                                                   float* __restrict__ score /* [L][k] */, int* __restrict__ nvalid /* [L] */) {
+    const int l = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    const int i = idx[(long long)l * k + j];
+    const float logit = i >= 0 ? packed[(long long)l * ld + i] : -INFINITY;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sc = -INFINITY;
+    if (i >= 0 && logit > -INFINITY) {
+        const long long n = g.n[l];
+        const Box a{g.anchor[l][i], g.anchor[l][n + i], g.anchor[l][2 * n + i], g.anchor[l][3 * n + i]};
+        const float ms[8] = {ms_lo.x, ms_lo.y, ms_lo.z, ms_lo.w, ms_hi.x, ms_hi.y, ms_hi.z, ms_hi.w};
+        const Box d = decode_box(a, g.reg[l][i], g.reg[l][n + i], g.reg[l][2 * n + i], g.reg[l][3 * n + i], ms, true, img_h, img_w);
+        o = make_float4(d.x1, d.y1, d.x2, d.y2);
+        const bool small = min_size > 0.0f && !(((d.x2 - d.x1) + 1.0f >= min_size) && ((d.y2 - d.y1) + 1.0f >= min_size));
+        sc = small ? -INFINITY : 1.0f / (1.0f + expf(-logit));
+        atomicAdd(&nvalid[l], 1);
+    }
+    reinterpret_cast<float4*>(box)[(long long)l * k + j] = o;
+    score[(long long)l * k + j] = sc;
+}
+
 }  // namespace b2d
 
 using namespace b2d;
@@ -512,5 +557,45 @@ int b2d_sampled_ce_bwd(float* grad, const float* scale, const float* logits, lon
     k_ce_bwd<<<cdiv(rows, 256), 256, 0, (cudaStream_t)stream>>>(p, grad, scale);
     return check_launch("sampled_ce_bwd");
 }
+
+static bool ga_fill(GaLevels& g, const void* const* cls, const void* const* mask, const void* const* anchor, const void* const* reg,
+                    const int* n_host, int L) {
+    if (!cls || !mask || !n_host || L < 1 || L > kMaxLevels) return false;
+    memset(&g, 0, sizeof(g));
+    g.L = L;
+    for (int l = 0; l < L; ++l) {
+        g.cls[l] = (const float*)cls[l]; g.mask[l] = (const unsigned char*)mask[l];
+        g.anchor[l] = anchor ? (const float*)anchor[l] : nullptr; g.reg[l] = reg ? (const float*)reg[l] : nullptr;
+        g.n[l] = n_host[l];
+        if (!g.cls[l] || !g.mask[l] || g.n[l] < 0) return false;
+    }
+    return true;
+}
+
+int b2d_ga_pack_scores(float* out, long long ld, const void* const* cls_ptrs_host, const void* const* mask_ptrs_host,
+                       const int* n_host, int L, void* stream) {
+    GaLevels g;
+    B2D_REQUIRE(out && ld >= 1 && ga_fill(g, cls_ptrs_host, mask_ptrs_host, nullptr, nullptr, n_host, L), "ga_pack_scores: bad args");
+    k_ga_pack_scores<<<dim3(cdiv(ld, 256), L), 256, 0, (cudaStream_t)stream>>>(g, out, ld);
+    return check_launch("ga_pack_scores");
+}
+
+int b2d_ga_decode(float* box, float* score, int* nvalid, const int* idx, const float* packed, long long ld, int k,
+                  const void* const* cls_ptrs_host, const void* const* mask_ptrs_host, const void* const* anchor_ptrs_host,
+                  const void* const* reg_ptrs_host, const int* n_host, int L, const float* means_host, const float* stds_host,
+                  float img_h, float img_w, float min_size, void* stream) {
+    GaLevels g;
+    B2D_REQUIRE(box && score && nvalid && idx && packed && k >= 1 && anchor_ptrs_host && reg_ptrs_host && means_host && stds_host &&
+                ga_fill(g, cls_ptrs_host, mask_ptrs_host, anchor_ptrs_host, reg_ptrs_host, n_host, L), "ga_decode: bad args");
+    for (int l = 0; l < L; ++l) B2D_REQUIRE(g.anchor[l] && g.reg[l], "ga_decode: null level pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(nvalid, 0, sizeof(int) * L, st) != cudaSuccess) return check_launch("ga_decode(memset)");
+    k_ga_decode<<<dim3(cdiv(k, 256), L), 256, 0, st>>>(g, idx, packed, ld, k,
+                                                      make_float4(means_host[0], means_host[1], means_host[2], means_host[3]),
+                                                      make_float4(stds_host[0], stds_host[1], stds_host[2], stds_host[3]),
+                                                      img_h, img_w, min_size, box, score, nvalid);
+    return check_launch("ga_decode");
+}
+
 
 }  // extern "C"

@@ -66,7 +66,7 @@ def install(lib=None, channels_last=False):
         raise RuntimeError("import the reference package `lib` before calling install()")
     mods = {n: sys.modules.get("lib." + n) for n in
             ("anchor", "bbox", "region", "utils", "builder", "heads.anchor_head", "heads.rpn_head",
-             "heads.bbox_head", "heads.fcos_head", "heads.retina_head", "heads.rcnn_head",
+             "heads.bbox_head", "heads.fcos_head", "heads.retina_head", "heads.rcnn_head", "heads.guided_head",
              "detectors.cascade_rcnn")}
     util_names = ["calc_iou", "elem_iou", "bbox2param", "param2bbox", "batched_param2bbox", "clamp_bbox",
                   "batched_nms", "multiclass_nms"]
@@ -103,6 +103,14 @@ def install(lib=None, channels_last=False):
         _set(mods["heads.rpn_head"], "tvops", types.SimpleNamespace(nms=utils.nms))
         if hasattr(mods["heads.rpn_head"], "RPNHead"):   # a9: the whole per-level loop as one fused K3 + K4 call
             _set(mods["heads.rpn_head"].RPNHead, "predict_single_image", heads.rpn_predict_single_image)
+    gh = mods["heads.guided_head"]                      # GA-RPN (imported only where mmdet's DeformConv exists)
+    if gh:
+        _set(gh, "tvops", types.SimpleNamespace(nms=utils.nms))
+        if hasattr(gh, "anchor_target"):
+            _set(gh, "anchor_target", anchor.anchor_target)
+        if hasattr(gh, "GARPNHead"):                     # explicit guided anchors + location masks
+            _set(gh.GARPNHead, "predict_bboxes_single_image", heads.ga_rpn_predict_single_image)
+            _set(gh.GARPNHead, "rpn_target_single_image", heads.ga_rpn_target_single_image)
     if mods["heads.fcos_head"] and hasattr(mods["heads.fcos_head"], "AnchorCreator"):
         _set(mods["heads.fcos_head"], "AnchorCreator", anchor.AnchorCreator)
     # head methods that are part of the path: rebind on the classes

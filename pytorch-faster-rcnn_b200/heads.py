@@ -184,6 +184,84 @@ def rpn_predict_single_image(self, level_cls_outs, level_reg_outs, level_anchors
     return props[0][:, :k].clone(), scores[0][:k].clone(), None
 
 
+# ---------------------------------------------------------------------------------- GA-RPN call sites
+def ga_rpn_predict_single_image(self, cls_outs, reg_outs, anchors, in_masks, img_meta, cfg):
+    """Method form of GARPNHead.predict_bboxes_single_image (lib/heads/guided_head.py:621-669): guided anchors are
+    explicit per-location boxes `anchors[l]` [4,H,W] with a location mask `in_masks[l]` [1,H,W]; per level the unmasked
+    places with the best objectness (top `pre_nms`), delta decode + clamp, min-size filter, NMS, `post_nms` cut, then
+    the best `max_num` over all levels.  Returns `(bbox [4,k], score [k], None)`.
+    All levels go through the kernels TOGETHER: one packed [L, ld] score array (masked places -inf), ONE segmented top-k,
+    ONE gather + decode launch, ONE segmented NMS (levels = segments), one host read of the survivor counts.  Selection
+    happens on the logit (sigmoid is monotone), ties go to the lowest index; where the reference slices with the
+    misspelt `cfg.pos_nms` (:656-657, an AttributeError as soon as it is reached) this uses `post_nms`."""
+    from . import utils
+    dev = cls_outs[0].device
+    _C.require_cuda(*cls_outs)
+    L = len(cls_outs)
+    get = (lambda k, d=0: cfg.get(k, d)) if hasattr(cfg, "get") else (lambda k, d=0: getattr(cfg, k, d))
+    pre, post, max_num = int(get('pre_nms') or 0), int(get('post_nms') or 0), int(get('max_num') or 0)
+    img_h, img_w = float(img_meta['img_shape'][0]), float(img_meta['img_shape'][1])
+    min_size = float(np.float32(float(img_meta.get('scale_factor', 1.0)) * float(get('min_bbox_size', 0) or 0)))
+    cls = [_C.f32c(c).reshape(-1) for c in cls_outs]
+    reg = [_C.f32c(r).reshape(4, -1) for r in reg_outs]
+    anc = [_C.f32c(a).reshape(4, -1) for a in anchors]
+    msk = [m.reshape(-1).to(torch.bool).contiguous() for m in in_masks]
+    ns = [int(c.numel()) for c in cls]
+    ld = max(ns)
+    k = min(pre, ld) if pre > 0 else ld
+    if k > 16384:
+        raise _C.B200DetError("ga_rpn_predict: at most 16384 candidates per level (pre_nms = %d, level of %d places)" % (pre, ld))
+    n_host = (_C.c_int * _C.MAX_LEVELS)(*ns)
+    packed = torch.empty((L, ld), dtype=torch.float32, device=dev)
+    _C.call("b2d_ga_pack_scores", _C.ptr(packed), ld, _ptrs(cls), _ptrs(msk), n_host, L, _C.stream())
+    idx = torch.empty((L, k), dtype=torch.int32, device=dev)
+    cnt = torch.empty(L, dtype=torch.int32, device=dev)
+    lens = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
+    ws = utils._workspace(_C.lib().b2d_topk_workspace_bytes(ld, L, k), dev, "topk")
+    _C.call("b2d_topk", _C.ptr(idx), _C.ptr(cnt), _C.ptr(packed), ld, _C.ptr(lens), ld, L, k, _C.ptr(ws), ws.numel(), _C.stream())
+    box = torch.empty((L, k, 4), dtype=torch.float32, device=dev)
+    score = torch.empty((L, k), dtype=torch.float32, device=dev)
+    nvalid = torch.empty(L, dtype=torch.int32, device=dev)
+    _C.call("b2d_ga_decode", _C.ptr(box), _C.ptr(score), _C.ptr(nvalid), _C.ptr(idx), _C.ptr(packed), ld, k, _ptrs(cls), _ptrs(msk),
+            _ptrs(anc), _ptrs(reg), n_host, L, _C.host_f4(self.target_means, [0, 0, 0, 0]), _C.host_f4(self.target_stds, [1, 1, 1, 1]),
+            img_h, img_w, min_size, _C.stream())
+    keep = torch.empty((L, k), dtype=torch.int64, device=dev)
+    kept = torch.empty(L, dtype=torch.int32, device=dev)
+    ws2 = utils._workspace(_C.lib().b2d_nms_workspace_bytes(k, L), dev, "nms")
+    _C.call("b2d_nms", _C.ptr(keep), _C.ptr(kept), _C.ptr(box), _C.ptr(score), k, _C.ptr(nvalid), k, L,
+            _C.floor_f32(float(get('nms_iou', 0.7))), 0, 0, _C.ptr(ws2), ws2.numel(), _C.stream())
+    # survivors in (level, score) order = the reference's concatenation; boxes below min_size carry score -inf and end
+    # their level's list
+    slot = torch.arange(k, device=dev)[None, :]
+    kept_score = torch.gather(score, 1, keep.clamp(0, k - 1))          # (rows past a level's count are not written)
+    ok = (slot < kept[:, None]) & (kept_score > float("-inf"))
+    if post > 0:
+        ok &= slot < post
+    lv, js = torch.nonzero(ok, as_tuple=True)                # the one host synchronisation of the call
+    src = keep[lv, js]
+    out_score = score[lv, src]
+    out_box = box[lv, src].t().contiguous()
+    if max_num > 0 and int(out_score.numel()) > max_num:
+        from . import region
+        top = region.topk_desc(out_score, max_num).to(torch.int64)
+        out_score, out_box = out_score[top], out_box[:, top].contiguous()
+    return out_box, out_score, None
+
+
+def ga_rpn_target_single_image(self, cls_outs, reg_outs, anchors, in_masks, gt_bbox, gt_label, img_meta, cfg):
+    """Method form of GARPNHead.rpn_target_single_image (lib/heads/guided_head.py:557-572): anchor_target on the guided
+    anchors of all levels, restricted to the location mask (K2 with explicit boxes + sampler + K8, anchor.anchor_target)."""
+    from . import anchor as banchor
+    cls_out = torch.cat([c.reshape(1, -1) for c in cls_outs], dim=1)
+    reg_out = torch.cat([r.reshape(4, -1) for r in reg_outs], dim=1)
+    all_anchors = torch.cat([a.reshape(4, -1) for a in anchors], dim=1)
+    in_mask = torch.cat([m.reshape(-1) for m in in_masks]).to(torch.bool)
+    get = (lambda k, d=None: cfg.get(k, d)) if hasattr(cfg, "get") else (lambda k, d=None: getattr(cfg, k, d))
+    return banchor.anchor_target(cls_out, reg_out, 1, all_anchors[:, in_mask], in_mask, gt_bbox, None,
+                                 assigner=get('assigner'), sampler=get('sampler'),
+                                 target_means=self.target_means, target_stds=self.target_stds)
+
+
 # ---------------------------------------------------------------------------------- RetinaNet test path (BASELINE config 4)
 def anchor_head_predict_single_image(self, level_cls_outs, level_reg_outs, level_anchors, img_meta, test_cfg):
     """Method form of AnchorHead.predict_single_image (lib/heads/anchor_head.py:207-258), same arguments and return

@@ -618,10 +618,60 @@ def g_heads2():
     save("heads2", **out)
 
 
+def g_garpn():
+    """GA-RPN call sites (lib/heads/guided_head.py:557-669): GARPNHead.rpn_target_single_image and
+    GARPNHead.predict_bboxes_single_image, called as the reference defines them on a stand-in `self` that carries the two
+    attributes they read (target_means / target_stds).  The module imports mmdet's DeformConv at import time (stubbed by
+    ref_shim); neither function touches it.  Guided anchors are explicit per-location boxes with a location mask."""
+    import importlib
+    import types
+    gh = importlib.import_module("lib.heads.guided_head")
+    rng = np.random.default_rng(SEED + 31)
+    H, W = 160, 213
+    grids, strides = [(20, 28), (10, 14), (5, 7), (3, 4)], [8, 16, 32, 64]
+    gt, gl = synth_gt(rng, 4, H, W)
+    cls = [rng.normal(0, 1.5, (1,) + g).astype(np.float32) for g in grids]
+    reg = [rng.normal(0, 0.3, (4,) + g).astype(np.float32) for g in grids]
+    anchors, masks = [], []
+    for g, s in zip(grids, strides):
+        ys, xs = np.meshgrid(np.arange(g[0]), np.arange(g[1]), indexing="ij")
+        cx, cy = xs * s + s / 2.0, ys * s + s / 2.0
+        w = np.exp(rng.uniform(np.log(1.0 * s), np.log(8.0 * s), g))
+        h = np.exp(rng.uniform(np.log(1.0 * s), np.log(8.0 * s), g))
+        anchors.append(np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2]).astype(np.float32))
+        masks.append(rng.random((1,) + g) > 0.35)
+    out = dict(gt=gt, gl=gl, n_levels=np.array(len(grids)))
+    for l in range(len(grids)):
+        out["cls%d" % l], out["reg%d" % l], out["anc%d" % l], out["mask%d" % l] = cls[l], reg[l], anchors[l], masks[l]
+    meta = dict(img_shape=(H, W, 3), pad_shape=(160, 224, 3), scale_factor=1.0)
+    for i, (means, stds, cfg) in enumerate([
+            ((0., 0., 0., 0.), (1., 1., 1., 1.), dict(pre_nms=200, post_nms=0, max_num=100, nms_iou=0.7, min_bbox_size=0)),
+            ((0., 0., 0., 0.), (0.07, 0.07, 0.14, 0.14), dict(pre_nms=60, post_nms=0, max_num=0, nms_iou=0.5, min_bbox_size=12)),
+            ((0., 0., 0., 0.), (1., 1., 1., 1.), dict(pre_nms=0, post_nms=0, max_num=300, nms_iou=0.8, min_bbox_size=0))]):
+        me = types.SimpleNamespace(target_means=list(means), target_stds=list(stds))
+        b, sc, _ = gh.GARPNHead.predict_bboxes_single_image(
+            me, [T(c).clone() for c in cls], [T(r).clone() for r in reg], [T(a).clone() for a in anchors],
+            [T(m).clone() for m in masks], meta, ref_shim.AttrDict(cfg))
+        out["pred_box%d" % i], out["pred_score%d" % i] = b, sc
+        out["pred_cfg%d" % i] = np.array(json.dumps(dict(cfg, means=means, stds=stds)))
+        print("ga-rpn predict", i, tuple(b.shape))
+    tcfg = ref_shim.AttrDict(assigner=dict(type="MaxIoUAssigner", pos_iou=0.5, neg_iou=0.3, min_pos_iou=0.3),
+                             sampler=dict(type="RandomSampler", max_num=64, pos_num=32))
+    me = types.SimpleNamespace(target_means=[0., 0., 0., 0.], target_stds=[0.07, 0.07, 0.14, 0.14])
+    np.random.seed(SEED)
+    r = gh.GARPNHead.rpn_target_single_image(
+        me, [T(c).clone() for c in cls], [T(x).clone() for x in reg], [T(a).clone() for a in anchors],
+        [T(m).clone() for m in masks], T(gt), None, meta, tcfg)
+    for k, v in zip(("tar_cls", "tar_reg", "tar_lab", "tar_anc", "tar_box", "tar_par"), r):
+        out[k] = v
+    print("ga-rpn target: %d samples, %d positive" % (int(r[2].numel()), int((r[2] > 0).sum())))
+    save("garpn", **out)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     gens = dict(anchors=g_anchors, iou_assign=g_iou_assign, deltas=g_deltas, nms=g_nms, rpn=g_rpn, roi=g_roi,
-                targets=g_targets, atss=g_atss, heads=g_heads, loss=g_loss, c4=g_c4, heads2=g_heads2)
+                targets=g_targets, atss=g_atss, heads=g_heads, loss=g_loss, c4=g_c4, heads2=g_heads2, garpn=g_garpn)
     for k, fn in gens.items():
         if not only or k in only:
             fn()

@@ -142,6 +142,8 @@ def test_dropin_install_rebinds_reference_names():
     import lib.heads.anchor_head as ah
     import lib.heads.rpn_head as rh
     import lib.heads.bbox_head as bh
+    import lib.heads.guided_head as gh                                      # (mmdet's DeformConv stubbed by ref_shim)
+    ref_ga_pred = gh.GARPNHead.predict_bboxes_single_image
     orig = rb.MODULES["MaxIoUAssigner"]
     ref_loss, ref_tars, ref_pred = ah.AnchorHead.loss, bh.BBoxHead.bbox_targets, rh.RPNHead.predict_bboxes_from_output
     b200det.install(lib)
@@ -161,6 +163,9 @@ def test_dropin_install_rebinds_reference_names():
         assert ah.AnchorHead.predict_single_image is b200det.heads.anchor_head_predict_single_image
         assert sys.modules["lib.utils"].tv.ops.nms is b200det.utils.nms
         assert sys.modules["lib.bbox"].bbox_target is b200det.bbox.bbox_target
+        assert gh.GARPNHead.predict_bboxes_single_image is b200det.heads.ga_rpn_predict_single_image
+        assert gh.GARPNHead.rpn_target_single_image is b200det.heads.ga_rpn_target_single_image
+        assert gh.tvops.nms is b200det.utils.nms
         built = rb.build_module(dict(type="MaxIoUAssigner", pos_iou=0.7, neg_iou=0.3, min_pos_iou=0.3))
         assert isinstance(built, b200det.region.MaxIoUAssigner)
     finally:
@@ -168,6 +173,7 @@ def test_dropin_install_rebinds_reference_names():
     assert rb.MODULES["MaxIoUAssigner"] is orig
     assert ah.AnchorHead.loss is ref_loss and bh.BBoxHead.bbox_targets is ref_tars
     assert rh.RPNHead.predict_single_image is not b200det.heads.rpn_predict_single_image
+    assert gh.GARPNHead.predict_bboxes_single_image is ref_ga_pred
 
 
 def test_dropin_keeps_gradients_and_cpu_tensors_on_the_reference_path():

@@ -1,6 +1,7 @@
 """GPU parity of the head-side rows and of BASELINE configs 3-5:
 cascade refine / 3-stage targets, RetinaNet dense assignment + per-level top-k NMS, ATSS.
 Compared with golden vectors from the unmodified reference and with the CPU oracle."""
+import json
 import types
 
 import numpy as np
@@ -243,6 +244,39 @@ def test_rcnn_detect_batched_vs_oracle(mode, agnostic):
             assert np.array_equal(N(ol[b, :k]), kl)
             np.testing.assert_allclose(N(os_[b, :k]), ks, rtol=1e-5, atol=1e-7)
             np.testing.assert_allclose(N(ob[b, :, :k]), kb, rtol=1e-5, atol=1e-3)
+
+
+# ------------------------------------------------------------------ GA-RPN call sites
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_ga_rpn_predict_vs_reference(i):
+    """GARPNHead.predict_bboxes_single_image (lib/heads/guided_head.py:621-669) on explicit guided anchors + location masks:
+    golden from the unmodified reference function (tests/golden/make_golden.py g_garpn); cfg 0: top-k + NMS + max_num,
+    cfg 1: target stds, min-size filter, no max_num, cfg 2: no per-level top-k."""
+    g = load_golden("garpn")
+    L = int(g["n_levels"])
+    cfg = json.loads(str(g["pred_cfg%d" % i]))
+    head = types.SimpleNamespace(target_means=cfg.pop("means"), target_stds=cfg.pop("stds"))
+    b, s, extra = bheads.ga_rpn_predict_single_image(
+        head, [T(g["cls%d" % l]) for l in range(L)], [T(g["reg%d" % l]) for l in range(L)], [T(g["anc%d" % l]) for l in range(L)],
+        [T(g["mask%d" % l]) for l in range(L)], dict(img_shape=(160, 213, 3), pad_shape=(160, 224, 3), scale_factor=1.0), cfg)
+    assert extra is None and tuple(b.shape) == g["pred_box%d" % i].shape
+    np.testing.assert_allclose(N(s), g["pred_score%d" % i], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N(b), g["pred_box%d" % i], rtol=1e-5, atol=1e-3)
+
+
+def test_ga_rpn_target_vs_reference():
+    """GARPNHead.rpn_target_single_image (lib/heads/guided_head.py:557-572) with the reference's host RNG stream."""
+    g = load_golden("garpn")
+    L = int(g["n_levels"])
+    head = types.SimpleNamespace(target_means=[0., 0., 0., 0.], target_stds=[0.07, 0.07, 0.14, 0.14])
+    cfg = dict(assigner=bregion.MaxIoUAssigner(0.5, 0.3, 0.3), sampler=bregion.RandomSampler(64, 32, rng="numpy"))
+    np.random.seed(2019)
+    r = bheads.ga_rpn_target_single_image(
+        head, [T(g["cls%d" % l]) for l in range(L)], [T(g["reg%d" % l]) for l in range(L)], [T(g["anc%d" % l]) for l in range(L)],
+        [T(g["mask%d" % l]) for l in range(L)], T(g["gt"]), None, dict(img_shape=(160, 213, 3)), cfg)
+    for got, name in zip(r, ("tar_cls", "tar_reg", "tar_lab", "tar_anc", "tar_box")):
+        assert np.array_equal(N(got), g[name]), name
+    np.testing.assert_allclose(N(r[5]), g["tar_par"], rtol=1e-5, atol=1e-5)
 
 
 # ------------------------------------------------------------------ SURVEY 8(f-4)
